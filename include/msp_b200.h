@@ -1,0 +1,261 @@
+/*
+ * msp_b200.h — C ABI of libmsp_b200.so: the B200 (sm_100a) kernels behind the training / evaluation
+ * hot path of aielte-research/MedSegPretrainImageNet.
+ *
+ * The reference is pure Python on stock PyTorch; "the interface each entry point replaces" is
+ * therefore the ATen op(s) the reference's nn.Modules / losses / metrics dispatch to (SURVEY.md
+ * §2.3, §8a).  Citations are `reference/src/...:line`.
+ *
+ * Conventions
+ *  - All pointers are DEVICE pointers unless marked host.  The caller owns every buffer
+ *    (PyTorch's caching allocator in the shipped host code); the library allocates nothing.
+ *  - All calls are asynchronous on `stream` (a cudaStream_t passed as void*), never touch the
+ *    default stream implicitly and never synchronise.
+ *  - Activations are NHWC bf16 ("pixel-major"): element (n,h,w,c) of a tensor with pixel stride
+ *    `cs` lives at ((n*H + h)*W + w)*cs + c.  A pixel stride larger than C lets several
+ *    producers write channel slices of one concat buffer (zero-copy torch.cat(dim=1),
+ *    reference blocks.py:628,635).  Channel counts and pixel strides are multiples of 8.
+ *  - Return value 0 = ok, <0 = error (see MSP_ERR_*); msp_last_error() gives a thread-local text.
+ *    There is no CPU fallback: unsupported shapes return MSP_ERR_UNSUPPORTED.
+ */
+#ifndef MSP_B200_H
+#define MSP_B200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MSP_ABI_VERSION 1
+
+const char* msp_last_error(void);
+int msp_version(void);
+/* number of kernels launched by this library on the calling process so far (bench "gpu_launches") */
+long long msp_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------
+ * Convolution (implicit GEMM on tcgen05 tensor cores, TMEM accumulators, TMA-staged tiles).
+ * Replaces nn.Conv2d forward / autograd dgrad / wgrad:
+ *   classification/models.py:43-46,161-179,234-253 ; segmentation/models/blocks.py:458,518,590 ;
+ *   segmentation/models/unet_models.py:440-445 (cuDNN / mkldnn_convolution in the reference).
+ * ------------------------------------------------------------------------------------------ */
+typedef struct msp_conv_desc {
+  int32_t N, H, W;          /* input batch / height / width                                   */
+  int32_t C;                /* input channels as stored (multiple of 8; zero-padded if needed) */
+  int32_t x_cs;             /* input pixel stride in elements (>= C, multiple of 8)            */
+  int32_t Ho, Wo;           /* output height / width                                           */
+  int32_t K;                /* output channels (multiple of 8)                                 */
+  int32_t y_cs;             /* output pixel stride in elements (>= K, multiple of 8)           */
+  int32_t KH, KW;           /* filter size                                                     */
+  int32_t stride;           /* 1 or 2                                                          */
+  int32_t pad_t, pad_l;     /* top / left zero padding (bottom/right implied by Ho, Wo)        */
+  int32_t relu;             /* fprop: apply ReLU in the epilogue (conv -> ReLU without BN)     */
+} msp_conv_desc;
+
+/* OIHW fp32 master weights -> bf16 [K][KH*KW][Cpad] (fprop/wgrad operand) and, if w_dgrad != NULL,
+ * bf16 [Cpad][KH*KW][Kpad] (dgrad operand).  Cpad/Kpad >= C/K, multiples of 8, padding zero-filled. */
+int msp_pack_weights(const float* w_oihw, int K, int C, int KH, int KW, int Cpad, int Kpad,
+                     void* w_fprop, void* w_dgrad, void* stream);
+
+/* y = conv(x, w) (+ bias) (ReLU optional).  If ch_sum / ch_sqsum are non-NULL the per-output-channel
+ * sum and sum of squares of the (bf16-rounded) outputs over N*Ho*Wo are ADDED to them (fp32, [K]) —
+ * the BatchNorm batch statistics (blocks.py:462, classification/models.py:47) come for free. */
+int msp_conv_fprop(const msp_conv_desc* d, const void* x, const void* w_fprop, const float* bias,
+                   void* y, float* ch_sum, float* ch_sqsum, void* stream);
+
+/* dx = conv_transpose(dy, w): gradient w.r.t. the input.  `w_dgrad` is the second output of
+ * msp_pack_weights.  dx has d->C channels at pixel stride d->x_cs; dy has d->K channels at d->y_cs. */
+int msp_conv_dgrad(const msp_conv_desc* d, const void* dy, const void* w_dgrad, void* dx,
+                   int accumulate /* dx += result (residual gradient already in dx) */, void* stream);
+
+/* dw[K][KH*KW][Cpad] (fp32, packed like w_fprop) = sum over pixels of dy^T * im2col(x).
+ * The buffer is zeroed by the call; split-K partial sums are combined with fp32 atomics. */
+int msp_conv_wgrad(const msp_conv_desc* d, const void* x, const void* dy, float* dw_packed,
+                   void* stream);
+
+/* packed fp32 [K][KH*KW][Cpad] -> OIHW fp32 [K][C][KH][KW] (the layout of nn.Conv2d.weight.grad);
+ * also reduces bias grad if requested elsewhere. */
+int msp_unpack_wgrad(const float* dw_packed, int K, int C, int KH, int KW, int Cpad, float* dw_oihw,
+                     void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Layout conversion at the module boundary (reference tensors are NCHW fp32).
+ * ------------------------------------------------------------------------------------------ */
+int msp_nchw_f32_to_nhwc_bf16(const float* x, int N, int C, int H, int W, int Cpad, void* y,
+                              void* stream);
+int msp_nhwc_bf16_to_nchw_f32(const void* x, int N, int C, int H, int W, int x_cs, float* y,
+                              void* stream);
+int msp_nchw_f32_grad_to_nhwc_bf16(const float* g, int N, int C, int H, int W, int g_cs_out,
+                                   void* y, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * BatchNorm2d (train + eval) fused with activation / residual.  Replaces nn.BatchNorm2d + nn.ReLU +
+ * the zero-fill / stride-2 shortcut + DropPath multiply of the ResNet blocks
+ * (classification/models.py:203-212, 277-290) and BN+ReLU of ConvBlock (blocks.py:458-488).
+ * ------------------------------------------------------------------------------------------ */
+/* sums -> mean / invstd, running-stat update (momentum, unbiased var) like torch (eps 1e-5). */
+int msp_bn_finalize(const float* ch_sum, const float* ch_sqsum, int C, double count, float eps,
+                    float momentum, float* mean, float* invstd, float* running_mean,
+                    float* running_var, void* stream);
+
+#define MSP_ACT_NONE 0
+#define MSP_ACT_RELU 1
+#define MSP_ACT_SIGMOID 2
+
+typedef struct msp_bn_act_desc {
+  int32_t N, H, W, C;       /* shape of x / y                                                  */
+  int32_t x_cs, y_cs;       /* pixel strides                                                   */
+  int32_t act;              /* MSP_ACT_*                                                       */
+  /* optional residual r: out = act( scale[n] * bn(x) + r ), r taken from a tensor of shape
+   * (N, H*r_stride, W*r_stride, r_C) at pixel stride r_cs, sub-sampled by r_stride, channels
+   * >= r_C read as zero (zero-fill shortcut, classification/models.py:257-274).               */
+  int32_t r_C, r_cs, r_stride;
+} msp_bn_act_desc;
+
+/* y = act( s[n] * (gamma*(x-mean)*invstd + beta) + residual ).  sample_scale may be NULL (=1). */
+int msp_bn_act_fwd(const msp_bn_act_desc* d, const void* x, const float* mean, const float* invstd,
+                   const float* gamma, const float* beta, const float* sample_scale,
+                   const void* residual, void* y, void* stream);
+
+/* Backward pass 1: with g = dy * act'(y) (ReLU mask recomputed from y; sigmoid from y),
+ * accumulates sum_g[c] += sum s[n]*g, sum_gx[c] += sum s[n]*g*xhat (fp32 [C]); if dres != NULL also
+ * writes the residual-branch gradient (g itself) — strided / channel-truncated like the forward. */
+int msp_bn_act_bwd_reduce(const msp_bn_act_desc* d, const void* x, const void* y, const void* dy,
+                          const float* mean, const float* invstd, const float* sample_scale,
+                          float* sum_g, float* sum_gx, void* stream);
+/* Backward pass 2: dx = gamma*invstd*( s*g - sum_g/M - xhat*sum_gx/M ); M = N*H*W (x world size
+ * when the sums were all-reduced: pass the global count).  dres (optional, same shape as the
+ * residual tensor) receives g added into the sub-sampled positions (others untouched).          */
+int msp_bn_act_bwd_apply(const msp_bn_act_desc* d, const void* x, const void* y, const void* dy,
+                         const float* mean, const float* invstd, const float* gamma,
+                         const float* sample_scale, const float* sum_g, const float* sum_gx,
+                         double count, void* dx, void* dres, int dres_accumulate, void* stream);
+/* eval-mode BN uses running stats: same forward with mean=running_mean, invstd=rsqrt(var+eps):   */
+int msp_bn_eval_prepare(const float* running_var, int C, float eps, float* invstd, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Pooling / resampling (nn.MaxPool2d classification/models.py:56, unet_models.py:452;
+ * nn.Upsample(scale_factor=2) nearest blocks.py:532,615; AdaptiveAvgPool2d models.py:73).
+ * ------------------------------------------------------------------------------------------ */
+/* idx (optional, uint8 [N][Ho][Wo][C]) receives the in-window arg-max (first max in scan order,
+ * like ATen) for the backward pass. */
+int msp_maxpool_fwd(const void* x, int N, int H, int W, int C, int x_cs, int k, int stride, int pad,
+                    void* y, void* idx, int Ho, int Wo, int y_cs, void* stream);
+/* dx (+)= gather of dy over the windows whose arg-max is this pixel (no atomics). */
+int msp_maxpool_bwd(const void* idx, const void* dy, int N, int H, int W, int C, int k, int stride,
+                    int pad, int Ho, int Wo, int dy_cs, void* dx, int dx_cs, int accumulate,
+                    void* stream);
+int msp_upsample2x_fwd(const void* x, int N, int H, int W, int C, int x_cs, void* y, int y_cs,
+                       void* stream);
+int msp_upsample2x_bwd(const void* dy, int N, int H, int W, int C, int dy_cs, void* dx, int dx_cs,
+                       void* stream);
+int msp_avgpool_fwd(const void* x, int N, int HW, int C, int x_cs, void* y, void* stream);
+int msp_avgpool_bwd(const void* dy, int N, int HW, int C, void* dx, int dx_cs, void* stream);
+/* y[.., off:off+C] = x (channel-slice copy into a concat buffer) and its inverse for gradients. */
+int msp_copy_channels(const void* x, long long P, int C, int x_cs, void* y, int y_cs, void* stream);
+/* out[c] = sum over P pixels of x[p][c] (fp32; conv bias gradients). out is zeroed by the call. */
+int msp_channel_sum(const void* x, long long P, int C, int cs, float* out, void* stream);
+/* generic elementwise helpers on NHWC bf16 */
+int msp_add_relu_fwd(const void* a, const void* b, long long P, int C, int a_cs, int b_cs, void* y,
+                     int y_cs, void* stream);
+int msp_relu_bwd(const void* y, const void* dy, long long P, int C, int y_cs, int dy_cs, void* dx,
+                 int dx_cs, void* stream);
+int msp_add(const void* a, const void* b, long long P, int C, int a_cs, int b_cs, void* y, int y_cs,
+            void* stream);
+/* attention gate tail (blocks.py:624-628): out[.., off:] = skip * up2(p);  and backward. */
+int msp_gate_mul_fwd(const void* skip, const void* p, int N, int H, int W, int C, int skip_cs,
+                     int p_cs, void* y, int y_cs, void* stream);
+int msp_gate_mul_bwd(const void* skip, const void* p, const void* dy, int N, int H, int W, int C,
+                     int skip_cs, int p_cs, int dy_cs, void* dskip, int dskip_cs,
+                     int dskip_accumulate, void* dp, int dp_cs, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Heads and losses.
+ * ------------------------------------------------------------------------------------------ */
+/* Final 1x1 conv with <= 8 output channels + activation, NHWC bf16 in -> NCHW fp32 out
+ * (unet_models.py:442-445 + :685-686).  act: 0 none, 1 sigmoid, 2 softmax(dim=1). */
+int msp_final_conv_act_fwd(const void* x, int N, int H, int W, int C, int x_cs, const float* w,
+                           const float* bias, int K, int act, float* logits_nchw, float* prob_nchw,
+                           void* stream);
+/* given dL/dprob (NCHW fp32) -> dlogits (through act), dx (NHWC bf16), dw [K][C], db [K] (atomics,
+ * zeroed by the call) */
+int msp_final_conv_act_bwd(const void* x, int N, int H, int W, int C, int x_cs, const float* w,
+                           int K, int act, const float* prob_nchw, const float* dprob_nchw,
+                           void* dx, int dx_cs, float* dw, float* db, void* stream);
+
+/* Dice loss (segmentation/losses/losses.py:34-58).  For each (group g, class c):
+ *   I = sum y*p, Y = sum y, S = sum p^2   with y = (mask == c + label_offset),
+ * groups = 1 (batchwise) or N;  loss = 1 - mean_{g, c >= class_start} (2I+eps)/(Y+S+eps).
+ * prob is NCHW fp32 [N][Cp][HW]; mask int64 [N][HW].  If two_class != 0 (requires Cp == 1) the classes
+ * are [1-p, p] (losses.py:46-49); the `include_background=False`, one-channel branch (losses.py:50-52)
+ * is Cp == 1, two_class = 0, label_offset = 1.
+ * Outputs: sums fp64 [G][Ceff][3] (zeroed by the call), coef fp32 [G][Ceff][2] = the per-class gradient
+ * coefficients consumed by msp_dice_bwd (dL/dp = a*y + b*p), loss fp32 [1]. */
+int msp_dice_fwd(const float* prob, const int64_t* mask, int N, int Cp, long long HW, int two_class,
+                 int label_offset, int batchwise, int class_start, float eps, double* sums,
+                 float* coef, float* loss, void* stream);
+/* dprob = gscale * dL/dprob (NCHW fp32, every element written). */
+int msp_dice_bwd(const float* prob, const int64_t* mask, int N, int Cp, long long HW, int two_class,
+                 int label_offset, int batchwise, const float* coef, float gscale, float* dprob,
+                 void* stream);
+/* pixel-wise CE on probabilities (classification/losses.py:27-40, apply_softmax=False):
+ * loss_sum (fp64 [1], zeroed by the call) = sum over pixels of -sum_c clamp(nan_to_num(log p_c),-100)*t_c
+ * with t = one-hot(label) clamped to [smooth/C, 1-smooth/C] when smooth != 0; dprob (optional) =
+ * gscale * d loss_sum / d prob.  label int64 [N][HW]. */
+int msp_ce_prob_fwd_bwd(const float* prob, const int64_t* label, int N, int C, long long HW,
+                        float smooth, float gscale, double* loss_sum, float* dprob, void* stream);
+/* BCE sum: clamp_log = 0 -> classification/losses.py:4-11 (plain logs, autograd gradient);
+ * clamp_log = 1 -> torch.nn.BCELoss (utils/default_dict.py:10; logs clamped at -100,
+ * gradient (p-y)/max(p(1-p),1e-12)).  target fp32, same shape as prob. */
+int msp_bce_fwd_bwd(const float* prob, const float* target, long long numel, int clamp_log,
+                    float gscale, double* loss_sum, float* dprob, void* stream);
+/* classification head loss: F.cross_entropy(logits[N][C], label[N], label_smoothing)
+ * (classification/losses.py:24-25): loss_sum fp64 [1] = sum of per-row losses; dlogits (optional) =
+ * gscale * d loss_sum / d logits. */
+int msp_softmax_ce_fwd_bwd(const float* logits, const int64_t* label, int N, int C, float smooth,
+                           float gscale, double* loss_sum, float* dlogits, void* stream);
+/* out[0] = (float)(in[0] * scale): turns a loss sum into the mean without a host round trip. */
+int msp_scale_to_float(const double* in, double scale, float* out, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Metrics (metrics/metrics.py:61-95, metrics/multiclass_metrics.py:90-107, 424-446).
+ * ------------------------------------------------------------------------------------------ */
+/* Binary confusion counts, single pass.  pred fp32 [N][C][HW], target [N][C][HW] (int64 or fp32,
+ * target_is_float).  per_channel=0: out int64[6] = {TP,TN,FP,FN,class_count,nan_count} over all
+ * elements; per_channel=1: out int64[C][6].  `pred >= thr`, `target == 1`; NaN targets counted
+ * (the caller subtracts nan_count*multiplicity from TN like metrics.py:69,76).  out is zeroed. */
+int msp_confusion_binary(const float* pred, const void* target, int target_is_float, int N, int C,
+                         long long HW, float thr, int per_channel, long long* out, void* stream);
+/* Multi-class: cm[t][p] += 1 with p = argmax_c pred[n][c][hw] (first max wins), t = target
+ * (int64 [N][HW]) or argmax of a one-hot target (target_is_onehot, fp32 [N][C][HW]).
+ * cm int64 [C][C], zeroed by the call. */
+int msp_confusion_multiclass(const float* pred, const void* target, int target_is_onehot, int N,
+                             int C, long long HW, long long* cm, void* stream);
+/* number of rows whose label is among the top-k scores (torch.topk tie order: lower index first)*/
+int msp_topk_hits(const float* pred, const int64_t* label, int N, int C, long long HW, int k,
+                  long long* hits, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Robustness distances (robustness/distance.py:3-10, robustness/eval.py:16-28).
+ * q, k: fp32 [N][D] row-major.  For every row i: positive pair (q_i, k_i), negative pair
+ * (q_i, k_perm(i)) with perm = [1,0,N-1,N-2,...,2].  out fp32 [6][N]:
+ *   0 cos(q,k1) 1 cos(q,k0) 2 l2(q,k1) 3 l2(q,k0) 4 1-pearson(q,k1) 5 1-pearson(q,k0).
+ * pooled_hw > 1: inputs are [N][C][pooled_hw] feature maps and the spatial mean is taken first
+ * (D = C), fused into the same pass.
+ * ------------------------------------------------------------------------------------------ */
+int msp_rowpair_distances(const float* q, const float* k, int N, long long D, int pooled_hw,
+                          float* out, void* stream);
+/* scores[m][d][i] = max(0, pos - neg + margins[m]) from the table above; out fp32 [M][3][N] */
+int msp_triplet_hinge(const float* dist, int N, const float* margins, int M, float* out,
+                      void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Optimiser-side helpers (train_model.py:93-107): fused multi-tensor L2 norm is left to the host
+ * framework in this round.
+ * ------------------------------------------------------------------------------------------ */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MSP_B200_H */

@@ -1,0 +1,862 @@
+// HBM-bound NHWC bf16 kernels: layout conversion, fused BatchNorm(+act+residual) forward/backward,
+// pooling, nearest up-sampling, attention-gate product, channel-slice copies.
+// All use 16-byte vector accesses (8 bf16 channels per thread), coalesced along channels.
+//
+// Replaces (reference): nn.BatchNorm2d + nn.ReLU + zero-fill/stride-2 shortcut + DropPath
+// (classification/models.py:203-212,257-290), ConvBlock BN+act (segmentation/models/blocks.py:458-488),
+// nn.MaxPool2d (classification/models.py:56; unet_models.py:452), nn.Upsample (blocks.py:532,615),
+// skip*p and torch.cat (blocks.py:624-628,635).
+#include "msp_common.cuh"
+#include "../../include/msp_b200.h"
+
+extern void msp_count_launch(int n);
+
+namespace {
+
+struct F8 {
+  float v[8];
+};
+__device__ __forceinline__ F8 load_bf16x8(const __nv_bfloat16* p) {
+  uint4 u = *reinterpret_cast<const uint4*>(p);
+  F8 r;
+  float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), c = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
+  r.v[0] = a.x; r.v[1] = a.y; r.v[2] = b.x; r.v[3] = b.y;
+  r.v[4] = c.x; r.v[5] = c.y; r.v[6] = d.x; r.v[7] = d.y;
+  return r;
+}
+__device__ __forceinline__ void store_bf16x8(__nv_bfloat16* p, const F8& f) {
+  uint4 u;
+  u.x = pack_bf16x2(f.v[0], f.v[1]);
+  u.y = pack_bf16x2(f.v[2], f.v[3]);
+  u.z = pack_bf16x2(f.v[4], f.v[5]);
+  u.w = pack_bf16x2(f.v[6], f.v[7]);
+  *reinterpret_cast<uint4*>(p) = u;
+}
+__device__ __forceinline__ F8 load_f32x8(const float* p) {
+  F8 r;
+  float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
+  r.v[0] = a.x; r.v[1] = a.y; r.v[2] = a.z; r.v[3] = a.w;
+  r.v[4] = b.x; r.v[5] = b.y; r.v[6] = b.z; r.v[7] = b.w;
+  return r;
+}
+
+inline int grid_for(long long work_items, int per_block, int max_waves = 8) {
+  long long b = (work_items + per_block - 1) / per_block;
+  long long cap = (long long)msp_num_sms() * max_waves;
+  if (b > cap) b = cap;
+  if (b < 1) b = 1;
+  return (int)b;
+}
+// threads per block such that blockDim % V == 0 (V = 8-channel vectors per pixel)
+inline int threads_for_vecs(int V) {
+  if (V >= 256) return 256;
+  return V * (256 / V);
+}
+
+// ---------------------------------------------------------------------------------------------
+// layout conversion
+// ---------------------------------------------------------------------------------------------
+// NCHW fp32 -> NHWC bf16 via a 32x32 smem transpose of (c, hw) per image
+__global__ void nchw_to_nhwc_kernel(const float* __restrict__ x, int C, long long HW, int Cpad,
+                                    __nv_bfloat16* __restrict__ y) {
+  __shared__ float tile[32][33];
+  const int n = blockIdx.z;
+  const long long hw0 = (long long)blockIdx.x * 32;
+  const int c0 = blockIdx.y * 32;
+  const float* xn = x + (long long)n * C * HW;
+  __nv_bfloat16* yn = y + (long long)n * HW * Cpad;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int c = c0 + i;
+    const long long hw = hw0 + threadIdx.x;
+    tile[i][threadIdx.x] = (c < C && hw < HW) ? xn[(long long)c * HW + hw] : 0.f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const long long hw = hw0 + i;
+    const int c = c0 + threadIdx.x;
+    if (hw < HW && c < Cpad) yn[hw * Cpad + c] = __float2bfloat16_rn(tile[threadIdx.x][i]);
+  }
+}
+// NHWC bf16 (pixel stride cs) -> NCHW fp32
+__global__ void nhwc_to_nchw_kernel(const __nv_bfloat16* __restrict__ x, int C, long long HW, int cs,
+                                    float* __restrict__ y) {
+  __shared__ float tile[32][33];
+  const int n = blockIdx.z;
+  const long long hw0 = (long long)blockIdx.x * 32;
+  const int c0 = blockIdx.y * 32;
+  const __nv_bfloat16* xn = x + (long long)n * HW * cs;
+  float* yn = y + (long long)n * C * HW;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const long long hw = hw0 + i;
+    const int c = c0 + threadIdx.x;
+    tile[i][threadIdx.x] = (hw < HW && c < C) ? __bfloat162float(xn[hw * cs + c]) : 0.f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int c = c0 + i;
+    const long long hw = hw0 + threadIdx.x;
+    if (c < C && hw < HW) yn[(long long)c * HW + hw] = tile[threadIdx.x][i];
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// BatchNorm
+// ---------------------------------------------------------------------------------------------
+__global__ void bn_finalize_kernel(const float* __restrict__ s1, const float* __restrict__ s2, int C,
+                                   double count, float eps, float momentum, float* mean,
+                                   float* invstd, float* rmean, float* rvar) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const double m = (double)s1[c] / count;
+  double var = (double)s2[c] / count - m * m;
+  if (var < 0) var = 0;
+  mean[c] = (float)m;
+  invstd[c] = (float)(1.0 / sqrt(var + (double)eps));
+  if (rmean != nullptr) {
+    const double unb = count > 1 ? var * count / (count - 1) : var;
+    rmean[c] = (1.f - momentum) * rmean[c] + momentum * (float)m;
+    rvar[c] = (1.f - momentum) * rvar[c] + momentum * (float)unb;
+  }
+}
+__global__ void bn_eval_prepare_kernel(const float* __restrict__ rvar, int C, float eps,
+                                       float* invstd) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c < C) invstd[c] = 1.f / sqrtf(rvar[c] + eps);
+}
+
+__device__ __forceinline__ float act_fwd(float x, int act) {
+  if (act == MSP_ACT_RELU) return fmaxf(x, 0.f);
+  if (act == MSP_ACT_SIGMOID) return 1.f / (1.f + __expf(-x));
+  return x;
+}
+// derivative of act expressed through the stored output y
+__device__ __forceinline__ float act_bwd(float y, float dy, int act) {
+  if (act == MSP_ACT_RELU) return y > 0.f ? dy : 0.f;
+  if (act == MSP_ACT_SIGMOID) return dy * y * (1.f - y);
+  return dy;
+}
+
+__global__ void bn_act_fwd_kernel(const msp_bn_act_desc d, const __nv_bfloat16* __restrict__ x,
+                                  const float* __restrict__ mean, const float* __restrict__ invstd,
+                                  const float* __restrict__ gamma, const float* __restrict__ beta,
+                                  const float* __restrict__ sscale,
+                                  const __nv_bfloat16* __restrict__ res,
+                                  __nv_bfloat16* __restrict__ y) {
+  const int V = d.C >> 3;
+  const int cg = threadIdx.x % V, pl = threadIdx.x / V, ppb = blockDim.x / V;
+  const int c = cg * 8;
+  float sc[8], sh[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const float g = gamma ? gamma[c + j] : 1.f, b = beta ? beta[c + j] : 0.f;
+    sc[j] = g * invstd[c + j];
+    sh[j] = b - mean[c + j] * sc[j];
+  }
+  const long long HW = (long long)d.H * d.W;
+  const long long P = (long long)d.N * HW;
+  const bool has_res = res != nullptr && c < d.r_C;
+  for (long long pix = (long long)blockIdx.x * ppb + pl; pix < P; pix += (long long)gridDim.x * ppb) {
+    F8 a = load_bf16x8(x + pix * d.x_cs + c);
+    const int n = (int)(pix / HW);
+    const float s = sscale ? sscale[n] : 1.f;
+    F8 r;
+    if (has_res) {
+      long long rp = pix;
+      if (d.r_stride > 1) {
+        const long long hw = pix - (long long)n * HW;
+        const int h = (int)(hw / d.W), w = (int)(hw - (long long)h * d.W);
+        rp = ((long long)n * d.H * d.r_stride + (long long)h * d.r_stride) * ((long long)d.W * d.r_stride) +
+             (long long)w * d.r_stride;
+      }
+      r = load_bf16x8(res + rp * d.r_cs + c);
+    }
+    F8 o;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float t = fmaf(a.v[j], sc[j], sh[j]) * s;
+      if (has_res) t += r.v[j];
+      o.v[j] = act_fwd(t, d.act);
+    }
+    store_bf16x8(y + pix * d.y_cs + c, o);
+  }
+}
+
+// pass 1 of the backward: per-channel sum(s*g) and sum(s*g*xhat)
+__global__ void bn_act_bwd_reduce_kernel(const msp_bn_act_desc d, const __nv_bfloat16* __restrict__ x,
+                                         const __nv_bfloat16* __restrict__ y,
+                                         const __nv_bfloat16* __restrict__ dy,
+                                         const float* __restrict__ mean,
+                                         const float* __restrict__ invstd,
+                                         const float* __restrict__ sscale, float* sum_g,
+                                         float* sum_gx) {
+  extern __shared__ float red[];  // [blockDim][16] would be too big; reduce by pixel-lane below
+  const int V = d.C >> 3;
+  const int cg = threadIdx.x % V, pl = threadIdx.x / V, ppb = blockDim.x / V;
+  const int c = cg * 8;
+  float mu[8], is[8], a1[8], a2[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    mu[j] = mean[c + j];
+    is[j] = invstd[c + j];
+    a1[j] = 0.f;
+    a2[j] = 0.f;
+  }
+  const long long HW = (long long)d.H * d.W;
+  const long long P = (long long)d.N * HW;
+  for (long long pix = (long long)blockIdx.x * ppb + pl; pix < P; pix += (long long)gridDim.x * ppb) {
+    F8 xv = load_bf16x8(x + pix * d.x_cs + c);
+    F8 yv = load_bf16x8(y + pix * d.y_cs + c);
+    F8 gv = load_bf16x8(dy + pix * d.y_cs + c);
+    const float s = sscale ? sscale[(int)(pix / HW)] : 1.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float g = act_bwd(yv.v[j], gv.v[j], d.act) * s;
+      a1[j] += g;
+      a2[j] = fmaf(g, (xv.v[j] - mu[j]) * is[j], a2[j]);
+    }
+  }
+  // block reduction over pixel lanes: red[pl][cg*16 + j]
+  float* mine = red + ((long long)pl * V + cg) * 16;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    mine[j] = a1[j];
+    mine[8 + j] = a2[j];
+  }
+  __syncthreads();
+  if (pl == 0) {
+    for (int l = 1; l < ppb; ++l) {
+      const float* o = red + ((long long)l * V + cg) * 16;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        a1[j] += o[j];
+        a2[j] += o[8 + j];
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      atomicAdd(sum_g + c + j, a1[j]);
+      atomicAdd(sum_gx + c + j, a2[j]);
+    }
+  }
+}
+
+__global__ void bn_act_bwd_apply_kernel(const msp_bn_act_desc d, const __nv_bfloat16* __restrict__ x,
+                                        const __nv_bfloat16* __restrict__ y,
+                                        const __nv_bfloat16* __restrict__ dy,
+                                        const float* __restrict__ mean,
+                                        const float* __restrict__ invstd,
+                                        const float* __restrict__ gamma,
+                                        const float* __restrict__ sscale,
+                                        const float* __restrict__ sum_g,
+                                        const float* __restrict__ sum_gx, float inv_count,
+                                        __nv_bfloat16* __restrict__ dx, __nv_bfloat16* dres,
+                                        int dres_acc) {
+  const int V = d.C >> 3;
+  const int cg = threadIdx.x % V, pl = threadIdx.x / V, ppb = blockDim.x / V;
+  const int c = cg * 8;
+  float mu[8], is[8], k0[8], k1[8], k2[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    mu[j] = mean[c + j];
+    is[j] = invstd[c + j];
+    const float gi = (gamma ? gamma[c + j] : 1.f) * is[j];
+    k0[j] = gi;
+    k1[j] = gi * sum_g[c + j] * inv_count;
+    k2[j] = gi * sum_gx[c + j] * inv_count;
+  }
+  const long long HW = (long long)d.H * d.W;
+  const long long P = (long long)d.N * HW;
+  const bool has_res = dres != nullptr && c < d.r_C;
+  for (long long pix = (long long)blockIdx.x * ppb + pl; pix < P; pix += (long long)gridDim.x * ppb) {
+    F8 xv = load_bf16x8(x + pix * d.x_cs + c);
+    F8 yv = load_bf16x8(y + pix * d.y_cs + c);
+    F8 gv = load_bf16x8(dy + pix * d.y_cs + c);
+    const int n = (int)(pix / HW);
+    const float s = sscale ? sscale[n] : 1.f;
+    F8 o, g;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      g.v[j] = act_bwd(yv.v[j], gv.v[j], d.act);
+      const float xh = (xv.v[j] - mu[j]) * is[j];
+      o.v[j] = k0[j] * s * g.v[j] - k1[j] - xh * k2[j];
+    }
+    store_bf16x8(dx + pix * d.x_cs + c, o);
+    if (has_res) {
+      long long rp = pix;
+      if (d.r_stride > 1) {
+        const long long hw = pix - (long long)n * HW;
+        const int h = (int)(hw / d.W), w = (int)(hw - (long long)h * d.W);
+        rp = ((long long)n * d.H * d.r_stride + (long long)h * d.r_stride) * ((long long)d.W * d.r_stride) +
+             (long long)w * d.r_stride;
+      }
+      __nv_bfloat16* rpz = dres + rp * d.r_cs + c;
+      if (dres_acc) {
+        F8 old = load_bf16x8(rpz);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) g.v[j] += old.v[j];
+      }
+      store_bf16x8(rpz, g);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// pooling / resampling
+// ---------------------------------------------------------------------------------------------
+__global__ void maxpool_fwd_kernel(const __nv_bfloat16* __restrict__ x, int N, int H, int W, int C,
+                                   int x_cs, int k, int s, int pad, __nv_bfloat16* __restrict__ y,
+                                   uint8_t* __restrict__ idx, int Ho, int Wo, int y_cs) {
+  const int V = C >> 3;
+  const long long total = (long long)N * Ho * Wo * V;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int cg = (int)(i % V);
+    long long p = i / V;
+    const int wo = (int)(p % Wo); p /= Wo;
+    const int ho = (int)(p % Ho);
+    const int n = (int)(p / Ho);
+    float best[8];
+    int bi[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { best[j] = -INFINITY; bi[j] = 0; }
+    for (int r = 0; r < k; ++r) {
+      const int h = ho * s - pad + r;
+      if (h < 0 || h >= H) continue;
+      for (int q = 0; q < k; ++q) {
+        const int w = wo * s - pad + q;
+        if (w < 0 || w >= W) continue;
+        F8 v = load_bf16x8(x + (((long long)n * H + h) * W + w) * x_cs + cg * 8);
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          if (v.v[j] > best[j] || v.v[j] != v.v[j]) { best[j] = v.v[j]; bi[j] = r * k + q; }
+      }
+    }
+    F8 o;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) o.v[j] = best[j];
+    const long long op = ((long long)n * Ho + ho) * Wo + wo;
+    store_bf16x8(y + op * y_cs + cg * 8, o);
+    if (idx) {
+      uint2 u;
+      u.x = (uint32_t)bi[0] | ((uint32_t)bi[1] << 8) | ((uint32_t)bi[2] << 16) | ((uint32_t)bi[3] << 24);
+      u.y = (uint32_t)bi[4] | ((uint32_t)bi[5] << 8) | ((uint32_t)bi[6] << 16) | ((uint32_t)bi[7] << 24);
+      *reinterpret_cast<uint2*>(idx + op * C + cg * 8) = u;
+    }
+  }
+}
+// gather formulation: every input pixel sums dy of the windows whose arg-max it is
+__global__ void maxpool_bwd_kernel(const uint8_t* __restrict__ idx, const __nv_bfloat16* __restrict__ dy,
+                                   int N, int H, int W, int C, int k, int s, int pad, int Ho, int Wo,
+                                   int dy_cs, __nv_bfloat16* __restrict__ dx, int dx_cs, int acc) {
+  const int V = C >> 3;
+  const long long total = (long long)N * H * W * V;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int cg = (int)(i % V);
+    long long p = i / V;
+    const int w = (int)(p % W); p /= W;
+    const int h = (int)(p % H);
+    const int n = (int)(p / H);
+    float a[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) a[j] = 0.f;
+    // windows (ho, wo) with ho*s - pad <= h < ho*s - pad + k
+    const int ho_lo = (h + pad - k + 1) <= 0 ? 0 : (h + pad - k + s) / s;
+    const int wo_lo = (w + pad - k + 1) <= 0 ? 0 : (w + pad - k + s) / s;
+    for (int ho = ho_lo; ho <= (h + pad) / s && ho < Ho; ++ho) {
+      const int r = h + pad - ho * s;
+      for (int wo = wo_lo; wo <= (w + pad) / s && wo < Wo; ++wo) {
+        const int q = w + pad - wo * s;
+        const int me = r * k + q;
+        const long long op = ((long long)n * Ho + ho) * Wo + wo;
+        const uint2 u = *reinterpret_cast<const uint2*>(idx + op * C + cg * 8);
+        F8 g = load_bf16x8(dy + op * dy_cs + cg * 8);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const uint32_t b = ((j < 4 ? u.x : u.y) >> ((j & 3) * 8)) & 0xFFu;
+          if ((int)b == me) a[j] += g.v[j];
+        }
+      }
+    }
+    __nv_bfloat16* o = dx + (((long long)n * H + h) * W + w) * dx_cs + cg * 8;
+    F8 r8;
+    if (acc) {
+      F8 old = load_bf16x8(o);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) r8.v[j] = old.v[j] + a[j];
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) r8.v[j] = a[j];
+    }
+    store_bf16x8(o, r8);
+  }
+}
+
+__global__ void upsample2x_fwd_kernel(const __nv_bfloat16* __restrict__ x, int N, int H, int W, int C,
+                                      int x_cs, __nv_bfloat16* __restrict__ y, int y_cs) {
+  const int V = C >> 3;
+  const int H2 = 2 * H, W2 = 2 * W;
+  const long long total = (long long)N * H2 * W2 * V;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int cg = (int)(i % V);
+    long long p = i / V;
+    const int w = (int)(p % W2); p /= W2;
+    const int h = (int)(p % H2);
+    const int n = (int)(p / H2);
+    const uint4 v = *reinterpret_cast<const uint4*>(
+        x + (((long long)n * H + (h >> 1)) * W + (w >> 1)) * x_cs + cg * 8);
+    *reinterpret_cast<uint4*>(y + (((long long)n * H2 + h) * W2 + w) * y_cs + cg * 8) = v;
+  }
+}
+__global__ void upsample2x_bwd_kernel(const __nv_bfloat16* __restrict__ dy, int N, int H, int W, int C,
+                                      int dy_cs, __nv_bfloat16* __restrict__ dx, int dx_cs) {
+  const int V = C >> 3;
+  const int W2 = 2 * W;
+  const long long total = (long long)N * H * W * V;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int cg = (int)(i % V);
+    long long p = i / V;
+    const int w = (int)(p % W); p /= W;
+    const int h = (int)(p % H);
+    const int n = (int)(p / H);
+    const __nv_bfloat16* b = dy + (((long long)n * 2 * H + 2 * h) * W2 + 2 * w) * dy_cs + cg * 8;
+    F8 a = load_bf16x8(b), b1 = load_bf16x8(b + dy_cs), c0 = load_bf16x8(b + (long long)W2 * dy_cs),
+       c1 = load_bf16x8(b + (long long)W2 * dy_cs + dy_cs);
+    F8 o;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) o.v[j] = (a.v[j] + b1.v[j]) + (c0.v[j] + c1.v[j]);
+    store_bf16x8(dx + (((long long)n * H + h) * W + w) * dx_cs + cg * 8, o);
+  }
+}
+
+__global__ void avgpool_fwd_kernel(const __nv_bfloat16* __restrict__ x, int N, int HW, int C, int x_cs,
+                                   __nv_bfloat16* __restrict__ y) {
+  const int V = C >> 3;
+  const long long total = (long long)N * V;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int cg = (int)(i % V);
+    const int n = (int)(i / V);
+    float a[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) a[j] = 0.f;
+    for (int p = 0; p < HW; ++p) {
+      F8 v = load_bf16x8(x + ((long long)n * HW + p) * x_cs + cg * 8);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) a[j] += v.v[j];
+    }
+    F8 o;
+    const float inv = 1.f / (float)HW;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) o.v[j] = a[j] * inv;
+    store_bf16x8(y + (long long)n * C + cg * 8, o);
+  }
+}
+__global__ void avgpool_bwd_kernel(const __nv_bfloat16* __restrict__ dy, int N, int HW, int C,
+                                   __nv_bfloat16* __restrict__ dx, int dx_cs) {
+  const int V = C >> 3;
+  const long long total = (long long)N * HW * V;
+  const float inv = 1.f / (float)HW;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int cg = (int)(i % V);
+    const long long p = i / V;
+    const int n = (int)(p / HW);
+    F8 g = load_bf16x8(dy + (long long)n * C + cg * 8);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) g.v[j] *= inv;
+    store_bf16x8(dx + p * dx_cs + cg * 8, g);
+  }
+}
+
+// generic 2-input elementwise on channel slices. op: 0 copy(a), 1 relu(a+b), 2 a+b,
+// 3 relu_bwd (a = y, b = dy)
+template <int OP>
+__global__ void ew2_kernel(const __nv_bfloat16* __restrict__ a, const __nv_bfloat16* __restrict__ b,
+                           long long P, int C, int a_cs, int b_cs, __nv_bfloat16* __restrict__ y,
+                           int y_cs) {
+  const int V = C >> 3;
+  const long long total = P * V;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int cg = (int)(i % V);
+    const long long p = i / V;
+    if (OP == 0) {
+      *reinterpret_cast<uint4*>(y + p * y_cs + cg * 8) =
+          *reinterpret_cast<const uint4*>(a + p * a_cs + cg * 8);
+    } else {
+      F8 av = load_bf16x8(a + p * a_cs + cg * 8), bv = load_bf16x8(b + p * b_cs + cg * 8), o;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        if (OP == 1) o.v[j] = fmaxf(av.v[j] + bv.v[j], 0.f);
+        else if (OP == 2) o.v[j] = av.v[j] + bv.v[j];
+        else o.v[j] = av.v[j] > 0.f ? bv.v[j] : 0.f;
+      }
+      store_bf16x8(y + p * y_cs + cg * 8, o);
+    }
+  }
+}
+
+__global__ void gate_mul_fwd_kernel(const __nv_bfloat16* __restrict__ skip,
+                                    const __nv_bfloat16* __restrict__ pg, int N, int H, int W, int C,
+                                    int skip_cs, int p_cs, __nv_bfloat16* __restrict__ y, int y_cs) {
+  const int V = C >> 3;
+  const int Hp = H >> 1, Wp = W >> 1;
+  const long long total = (long long)N * H * W * V;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int cg = (int)(i % V);
+    long long p = i / V;
+    const long long pix = p;
+    const int w = (int)(p % W); p /= W;
+    const int h = (int)(p % H);
+    const int n = (int)(p / H);
+    F8 s = load_bf16x8(skip + pix * skip_cs + cg * 8);
+    F8 g = load_bf16x8(pg + (((long long)n * Hp + (h >> 1)) * Wp + (w >> 1)) * p_cs + cg * 8);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s.v[j] *= g.v[j];
+    store_bf16x8(y + pix * y_cs + cg * 8, s);
+  }
+}
+// one thread per low-res pixel x 8 channels: dp = sum_{2x2} dy*skip ; dskip = dy * p
+__global__ void gate_mul_bwd_kernel(const __nv_bfloat16* __restrict__ skip,
+                                    const __nv_bfloat16* __restrict__ pg,
+                                    const __nv_bfloat16* __restrict__ dy, int N, int H, int W, int C,
+                                    int skip_cs, int p_cs, int dy_cs, __nv_bfloat16* __restrict__ dskip,
+                                    int dskip_cs, int dskip_acc, __nv_bfloat16* __restrict__ dp,
+                                    int dp_cs) {
+  const int V = C >> 3;
+  const int Hp = H >> 1, Wp = W >> 1;
+  const long long total = (long long)N * Hp * Wp * V;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int cg = (int)(i % V);
+    long long p = i / V;
+    const long long ppix = p;
+    const int wp = (int)(p % Wp); p /= Wp;
+    const int hp = (int)(p % Hp);
+    const int n = (int)(p / Hp);
+    F8 g = load_bf16x8(pg + ppix * p_cs + cg * 8);
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+#pragma unroll
+    for (int dh = 0; dh < 2; ++dh)
+#pragma unroll
+      for (int dw = 0; dw < 2; ++dw) {
+        const long long pix = ((long long)n * H + 2 * hp + dh) * W + 2 * wp + dw;
+        F8 d = load_bf16x8(dy + pix * dy_cs + cg * 8);
+        F8 s = load_bf16x8(skip + pix * skip_cs + cg * 8);
+        F8 o;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          acc[j] = fmaf(d.v[j], s.v[j], acc[j]);
+          o.v[j] = d.v[j] * g.v[j];
+        }
+        __nv_bfloat16* dst = dskip + pix * dskip_cs + cg * 8;
+        if (dskip_acc) {
+          F8 old = load_bf16x8(dst);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) o.v[j] += old.v[j];
+        }
+        store_bf16x8(dst, o);
+      }
+    F8 o;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) o.v[j] = acc[j];
+    store_bf16x8(dp + ppix * dp_cs + cg * 8, o);
+  }
+}
+
+// per-channel sum over pixels of an NHWC bf16 tensor -> fp32 (bias gradients)
+__global__ void channel_sum_kernel(const __nv_bfloat16* __restrict__ x, long long P, int C, int cs,
+                                   float* out) {
+  extern __shared__ float red[];
+  const int V = C >> 3;
+  const int cg = threadIdx.x % V, pl = threadIdx.x / V, ppb = blockDim.x / V;
+  float a[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) a[j] = 0.f;
+  for (long long pix = (long long)blockIdx.x * ppb + pl; pix < P; pix += (long long)gridDim.x * ppb) {
+    F8 v = load_bf16x8(x + pix * cs + cg * 8);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) a[j] += v.v[j];
+  }
+  float* mine = red + ((long long)pl * V + cg) * 8;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) mine[j] = a[j];
+  __syncthreads();
+  if (pl == 0) {
+    for (int l = 1; l < ppb; ++l) {
+      const float* o = red + ((long long)l * V + cg) * 8;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) a[j] += o[j];
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) atomicAdd(out + cg * 8 + j, a[j]);
+  }
+}
+
+}  // namespace
+
+#define ST ((cudaStream_t)stream)
+#define REQ_C8(C, cs, what)                                                                  \
+  MSP_REQUIRE((C) > 0 && (C) % 8 == 0 && (cs) % 8 == 0 && (cs) >= (C),                        \
+              what ": channels (%d) and pixel stride (%d) must be multiples of 8", (int)(C), \
+              (int)(cs))
+
+extern "C" int msp_nchw_f32_to_nhwc_bf16(const float* x, int N, int C, int H, int W, int Cpad,
+                                         void* y, void* stream) {
+  MSP_REQUIRE(x && y && N > 0 && C > 0 && Cpad >= C, "nchw_to_nhwc: bad arguments");
+  const long long HW = (long long)H * W;
+  dim3 grid((unsigned)((HW + 31) / 32), (unsigned)((Cpad + 31) / 32), (unsigned)N);
+  nchw_to_nhwc_kernel<<<grid, dim3(32, 8), 0, ST>>>(x, C, HW, Cpad, (__nv_bfloat16*)y);
+  MSP_CHECK_LAUNCH();
+  msp_count_launch(1);
+  return MSP_OK;
+}
+extern "C" int msp_nhwc_bf16_to_nchw_f32(const void* x, int N, int C, int H, int W, int x_cs,
+                                         float* y, void* stream) {
+  MSP_REQUIRE(x && y && N > 0 && C > 0 && x_cs >= C, "nhwc_to_nchw: bad arguments");
+  const long long HW = (long long)H * W;
+  dim3 grid((unsigned)((HW + 31) / 32), (unsigned)((C + 31) / 32), (unsigned)N);
+  nhwc_to_nchw_kernel<<<grid, dim3(32, 8), 0, ST>>>((const __nv_bfloat16*)x, C, HW, x_cs, y);
+  MSP_CHECK_LAUNCH();
+  msp_count_launch(1);
+  return MSP_OK;
+}
+extern "C" int msp_nchw_f32_grad_to_nhwc_bf16(const float* g, int N, int C, int H, int W,
+                                              int g_cs_out, void* y, void* stream) {
+  return msp_nchw_f32_to_nhwc_bf16(g, N, C, H, W, g_cs_out, y, stream);
+}
+
+extern "C" int msp_bn_finalize(const float* ch_sum, const float* ch_sqsum, int C, double count,
+                               float eps, float momentum, float* mean, float* invstd,
+                               float* running_mean, float* running_var, void* stream) {
+  MSP_REQUIRE(ch_sum && ch_sqsum && mean && invstd && C > 0 && count > 0, "bn_finalize: bad arguments");
+  MSP_REQUIRE((running_mean == nullptr) == (running_var == nullptr),
+              "bn_finalize: need both running buffers or none");
+  bn_finalize_kernel<<<(C + 127) / 128, 128, 0, ST>>>(ch_sum, ch_sqsum, C, count, eps, momentum, mean,
+                                                      invstd, running_mean, running_var);
+  MSP_CHECK_LAUNCH();
+  msp_count_launch(1);
+  return MSP_OK;
+}
+extern "C" int msp_bn_eval_prepare(const float* running_var, int C, float eps, float* invstd,
+                                   void* stream) {
+  MSP_REQUIRE(running_var && invstd && C > 0, "bn_eval_prepare: bad arguments");
+  bn_eval_prepare_kernel<<<(C + 127) / 128, 128, 0, ST>>>(running_var, C, eps, invstd);
+  MSP_CHECK_LAUNCH();
+  msp_count_launch(1);
+  return MSP_OK;
+}
+
+static int check_bn_desc(const msp_bn_act_desc* d) {
+  MSP_REQUIRE(d && d->N > 0 && d->H > 0 && d->W > 0, "bn_act: empty tensor");
+  REQ_C8(d->C, d->x_cs, "bn_act(x)");
+  REQ_C8(d->C, d->y_cs, "bn_act(y)");
+  MSP_REQUIRE(d->C <= 2048, "bn_act: C=%d > 2048 unsupported", d->C);
+  MSP_REQUIRE(d->act >= 0 && d->act <= 2, "bn_act: bad activation");
+  return MSP_OK;
+}
+
+extern "C" int msp_bn_act_fwd(const msp_bn_act_desc* d, const void* x, const float* mean,
+                              const float* invstd, const float* gamma, const float* beta,
+                              const float* sample_scale, const void* residual, void* y, void* stream) {
+  int rc = check_bn_desc(d);
+  if (rc) return rc;
+  MSP_REQUIRE(x && y && mean && invstd, "bn_act_fwd: null pointer");
+  if (residual) {
+    MSP_REQUIRE(d->r_C > 0 && d->r_C % 8 == 0 && d->r_cs % 8 == 0 && d->r_stride >= 1,
+                "bn_act_fwd: bad residual description");
+  }
+  const int V = d->C / 8, T = threads_for_vecs(V), ppb = T / V;
+  const long long P = (long long)d->N * d->H * d->W;
+  bn_act_fwd_kernel<<<grid_for(P, ppb * 4), T, 0, ST>>>(
+      *d, (const __nv_bfloat16*)x, mean, invstd, gamma, beta, sample_scale,
+      (const __nv_bfloat16*)residual, (__nv_bfloat16*)y);
+  MSP_CHECK_LAUNCH();
+  msp_count_launch(1);
+  return MSP_OK;
+}
+
+extern "C" int msp_bn_act_bwd_reduce(const msp_bn_act_desc* d, const void* x, const void* y,
+                                     const void* dy, const float* mean, const float* invstd,
+                                     const float* sample_scale, float* sum_g, float* sum_gx,
+                                     void* stream) {
+  int rc = check_bn_desc(d);
+  if (rc) return rc;
+  MSP_REQUIRE(x && y && dy && mean && invstd && sum_g && sum_gx, "bn_act_bwd_reduce: null pointer");
+  const int V = d->C / 8, T = threads_for_vecs(V), ppb = T / V;
+  const long long P = (long long)d->N * d->H * d->W;
+  MSP_CHECK_CUDA(cudaMemsetAsync(sum_g, 0, sizeof(float) * d->C, ST));
+  MSP_CHECK_CUDA(cudaMemsetAsync(sum_gx, 0, sizeof(float) * d->C, ST));
+  const size_t smem = (size_t)T * 16 * sizeof(float);
+  bn_act_bwd_reduce_kernel<<<grid_for(P, ppb * 8, 4), T, smem, ST>>>(
+      *d, (const __nv_bfloat16*)x, (const __nv_bfloat16*)y, (const __nv_bfloat16*)dy, mean, invstd,
+      sample_scale, sum_g, sum_gx);
+  MSP_CHECK_LAUNCH();
+  msp_count_launch(1);
+  return MSP_OK;
+}
+
+extern "C" int msp_bn_act_bwd_apply(const msp_bn_act_desc* d, const void* x, const void* y,
+                                    const void* dy, const float* mean, const float* invstd,
+                                    const float* gamma, const float* sample_scale, const float* sum_g,
+                                    const float* sum_gx, double count, void* dx, void* dres,
+                                    int dres_accumulate, void* stream) {
+  int rc = check_bn_desc(d);
+  if (rc) return rc;
+  MSP_REQUIRE(x && y && dy && mean && invstd && sum_g && sum_gx && dx && count > 0,
+              "bn_act_bwd_apply: null pointer");
+  const int V = d->C / 8, T = threads_for_vecs(V), ppb = T / V;
+  const long long P = (long long)d->N * d->H * d->W;
+  bn_act_bwd_apply_kernel<<<grid_for(P, ppb * 4), T, 0, ST>>>(
+      *d, (const __nv_bfloat16*)x, (const __nv_bfloat16*)y, (const __nv_bfloat16*)dy, mean, invstd,
+      gamma, sample_scale, sum_g, sum_gx, (float)(1.0 / count), (__nv_bfloat16*)dx,
+      (__nv_bfloat16*)dres, dres_accumulate);
+  MSP_CHECK_LAUNCH();
+  msp_count_launch(1);
+  return MSP_OK;
+}
+
+extern "C" int msp_maxpool_fwd(const void* x, int N, int H, int W, int C, int x_cs, int k, int stride,
+                               int pad, void* y, void* idx, int Ho, int Wo, int y_cs, void* stream) {
+  REQ_C8(C, x_cs, "maxpool_fwd(x)");
+  REQ_C8(C, y_cs, "maxpool_fwd(y)");
+  MSP_REQUIRE(x && y && k >= 1 && k <= 15 && stride >= 1 && pad >= 0, "maxpool_fwd: bad arguments");
+  const long long total = (long long)N * Ho * Wo * (C / 8);
+  maxpool_fwd_kernel<<<grid_for(total, 256), 256, 0, ST>>>((const __nv_bfloat16*)x, N, H, W, C, x_cs, k,
+                                                           stride, pad, (__nv_bfloat16*)y,
+                                                           (uint8_t*)idx, Ho, Wo, y_cs);
+  MSP_CHECK_LAUNCH();
+  msp_count_launch(1);
+  return MSP_OK;
+}
+extern "C" int msp_maxpool_bwd(const void* idx, const void* dy, int N, int H, int W, int C, int k,
+                               int stride, int pad, int Ho, int Wo, int dy_cs, void* dx, int dx_cs,
+                               int accumulate, void* stream) {
+  REQ_C8(C, dy_cs, "maxpool_bwd(dy)");
+  REQ_C8(C, dx_cs, "maxpool_bwd(dx)");
+  MSP_REQUIRE(idx && dy && dx, "maxpool_bwd: null pointer");
+  const long long total = (long long)N * H * W * (C / 8);
+  maxpool_bwd_kernel<<<grid_for(total, 256), 256, 0, ST>>>((const uint8_t*)idx, (const __nv_bfloat16*)dy,
+                                                           N, H, W, C, k, stride, pad, Ho, Wo, dy_cs,
+                                                           (__nv_bfloat16*)dx, dx_cs, accumulate);
+  MSP_CHECK_LAUNCH();
+  msp_count_launch(1);
+  return MSP_OK;
+}
+extern "C" int msp_upsample2x_fwd(const void* x, int N, int H, int W, int C, int x_cs, void* y,
+                                  int y_cs, void* stream) {
+  REQ_C8(C, x_cs, "upsample2x_fwd(x)");
+  REQ_C8(C, y_cs, "upsample2x_fwd(y)");
+  const long long total = (long long)N * 4 * H * W * (C / 8);
+  upsample2x_fwd_kernel<<<grid_for(total, 256), 256, 0, ST>>>((const __nv_bfloat16*)x, N, H, W, C, x_cs,
+                                                              (__nv_bfloat16*)y, y_cs);
+  MSP_CHECK_LAUNCH();
+  msp_count_launch(1);
+  return MSP_OK;
+}
+extern "C" int msp_upsample2x_bwd(const void* dy, int N, int H, int W, int C, int dy_cs, void* dx,
+                                  int dx_cs, void* stream) {
+  REQ_C8(C, dy_cs, "upsample2x_bwd(dy)");
+  REQ_C8(C, dx_cs, "upsample2x_bwd(dx)");
+  const long long total = (long long)N * H * W * (C / 8);
+  upsample2x_bwd_kernel<<<grid_for(total, 256), 256, 0, ST>>>((const __nv_bfloat16*)dy, N, H, W, C,
+                                                              dy_cs, (__nv_bfloat16*)dx, dx_cs);
+  MSP_CHECK_LAUNCH();
+  msp_count_launch(1);
+  return MSP_OK;
+}
+extern "C" int msp_avgpool_fwd(const void* x, int N, int HW, int C, int x_cs, void* y, void* stream) {
+  REQ_C8(C, x_cs, "avgpool_fwd");
+  const long long total = (long long)N * (C / 8);
+  avgpool_fwd_kernel<<<grid_for(total, 128), 128, 0, ST>>>((const __nv_bfloat16*)x, N, HW, C, x_cs,
+                                                           (__nv_bfloat16*)y);
+  MSP_CHECK_LAUNCH();
+  msp_count_launch(1);
+  return MSP_OK;
+}
+extern "C" int msp_avgpool_bwd(const void* dy, int N, int HW, int C, void* dx, int dx_cs, void* stream) {
+  REQ_C8(C, dx_cs, "avgpool_bwd");
+  const long long total = (long long)N * HW * (C / 8);
+  avgpool_bwd_kernel<<<grid_for(total, 256), 256, 0, ST>>>((const __nv_bfloat16*)dy, N, HW, C,
+                                                           (__nv_bfloat16*)dx, dx_cs);
+  MSP_CHECK_LAUNCH();
+  msp_count_launch(1);
+  return MSP_OK;
+}
+
+template <int OP>
+static int launch_ew2(const void* a, const void* b, long long P, int C, int a_cs, int b_cs, void* y,
+                      int y_cs, void* stream) {
+  REQ_C8(C, a_cs, "elementwise(a)");
+  REQ_C8(C, y_cs, "elementwise(y)");
+  if (OP != 0) REQ_C8(C, b_cs, "elementwise(b)");
+  MSP_REQUIRE(a && y && (OP == 0 || b) && P > 0, "elementwise: bad arguments");
+  ew2_kernel<OP><<<grid_for(P * (C / 8), 256), 256, 0, ST>>>(
+      (const __nv_bfloat16*)a, (const __nv_bfloat16*)b, P, C, a_cs, b_cs, (__nv_bfloat16*)y, y_cs);
+  MSP_CHECK_LAUNCH();
+  msp_count_launch(1);
+  return MSP_OK;
+}
+extern "C" int msp_copy_channels(const void* x, long long P, int C, int x_cs, void* y, int y_cs,
+                                 void* stream) {
+  return launch_ew2<0>(x, nullptr, P, C, x_cs, x_cs, y, y_cs, stream);
+}
+extern "C" int msp_add_relu_fwd(const void* a, const void* b, long long P, int C, int a_cs, int b_cs,
+                                void* y, int y_cs, void* stream) {
+  return launch_ew2<1>(a, b, P, C, a_cs, b_cs, y, y_cs, stream);
+}
+extern "C" int msp_add(const void* a, const void* b, long long P, int C, int a_cs, int b_cs, void* y,
+                       int y_cs, void* stream) {
+  return launch_ew2<2>(a, b, P, C, a_cs, b_cs, y, y_cs, stream);
+}
+extern "C" int msp_relu_bwd(const void* y, const void* dy, long long P, int C, int y_cs, int dy_cs,
+                            void* dx, int dx_cs, void* stream) {
+  return launch_ew2<3>(y, dy, P, C, y_cs, dy_cs, dx, dx_cs, stream);
+}
+
+extern "C" int msp_gate_mul_fwd(const void* skip, const void* p, int N, int H, int W, int C,
+                                int skip_cs, int p_cs, void* y, int y_cs, void* stream) {
+  REQ_C8(C, skip_cs, "gate_mul_fwd(skip)");
+  REQ_C8(C, p_cs, "gate_mul_fwd(p)");
+  REQ_C8(C, y_cs, "gate_mul_fwd(y)");
+  MSP_REQUIRE(H % 2 == 0 && W % 2 == 0, "gate_mul_fwd: H, W must be even");
+  const long long total = (long long)N * H * W * (C / 8);
+  gate_mul_fwd_kernel<<<grid_for(total, 256), 256, 0, ST>>>((const __nv_bfloat16*)skip,
+                                                            (const __nv_bfloat16*)p, N, H, W, C,
+                                                            skip_cs, p_cs, (__nv_bfloat16*)y, y_cs);
+  MSP_CHECK_LAUNCH();
+  msp_count_launch(1);
+  return MSP_OK;
+}
+extern "C" int msp_gate_mul_bwd(const void* skip, const void* p, const void* dy, int N, int H, int W,
+                                int C, int skip_cs, int p_cs, int dy_cs, void* dskip, int dskip_cs,
+                                int dskip_accumulate, void* dp, int dp_cs, void* stream) {
+  REQ_C8(C, skip_cs, "gate_mul_bwd(skip)");
+  REQ_C8(C, dy_cs, "gate_mul_bwd(dy)");
+  MSP_REQUIRE(H % 2 == 0 && W % 2 == 0 && dskip && dp, "gate_mul_bwd: bad arguments");
+  const long long total = (long long)N * (H / 2) * (W / 2) * (C / 8);
+  gate_mul_bwd_kernel<<<grid_for(total, 256), 256, 0, ST>>>(
+      (const __nv_bfloat16*)skip, (const __nv_bfloat16*)p, (const __nv_bfloat16*)dy, N, H, W, C,
+      skip_cs, p_cs, dy_cs, (__nv_bfloat16*)dskip, dskip_cs, dskip_accumulate, (__nv_bfloat16*)dp,
+      dp_cs);
+  MSP_CHECK_LAUNCH();
+  msp_count_launch(1);
+  return MSP_OK;
+}
+extern "C" int msp_channel_sum(const void* x, long long P, int C, int cs, float* out, void* stream) {
+  REQ_C8(C, cs, "channel_sum");
+  MSP_REQUIRE(C <= 2048 && out && x, "channel_sum: bad arguments");
+  const int V = C / 8, T = threads_for_vecs(V), ppb = T / V;
+  MSP_CHECK_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * C, ST));
+  channel_sum_kernel<<<grid_for(P, ppb * 8, 4), T, (size_t)T * 8 * sizeof(float), ST>>>(
+      (const __nv_bfloat16*)x, P, C, cs, out);
+  MSP_CHECK_LAUNCH();
+  msp_count_launch(1);
+  return MSP_OK;
+}

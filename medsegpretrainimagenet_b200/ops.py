@@ -1,0 +1,448 @@
+"""Thin, autograd-free Python wrappers over the C ABI (include/msp_b200.h).
+
+Activations are bf16 tensors of logical shape (N, H, W, C) whose last dimension is contiguous and whose
+pixel stride (`t.stride(2)`) may exceed C: a channel slice `buf[..., a:b]` of a wider buffer is a valid
+operand, which is how torch.cat(dim=1) of the reference (blocks.py:628,635) becomes zero-copy.
+PyTorch is used only for device memory and the current stream.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import BnActDesc, ConvDesc, call
+
+ACT_NONE, ACT_RELU, ACT_SIGMOID = 0, 1, 2
+_BF16 = torch.bfloat16
+
+
+def ceil8(c: int) -> int:
+    return (c + 7) // 8 * 8
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _p(t: Optional[torch.Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+def _chk_nhwc(t: torch.Tensor, name: str) -> Tuple[int, int, int, int, int]:
+    if t.dtype != _BF16 or t.dim() != 4 or not t.is_cuda:
+        raise ValueError(f"{name}: expected a CUDA bf16 (N,H,W,C) tensor, got {t.dtype} {tuple(t.shape)}")
+    n, h, w, c = t.shape
+    cs = t.stride(2)
+    if t.stride(3) != 1 or t.stride(1) != w * cs or (n > 1 and t.stride(0) != h * w * cs):
+        raise ValueError(f"{name}: not a pixel-major NHWC view (strides {t.stride()})")
+    return n, h, w, c, cs
+
+
+def new_act(n: int, h: int, w: int, c: int, device, zero: bool = False) -> torch.Tensor:
+    f = torch.zeros if zero else torch.empty
+    return f((n, h, w, c), dtype=_BF16, device=device)
+
+
+# ------------------------------------------------------------------------------------------------
+# layout conversion
+# ------------------------------------------------------------------------------------------------
+def nchw_to_nhwc(x: torch.Tensor, cpad: Optional[int] = None) -> torch.Tensor:
+    """fp32 NCHW -> bf16 NHWC with the channel dimension zero-padded to `cpad` (default ceil8(C))."""
+    x = x.contiguous()
+    if x.dtype != torch.float32:
+        x = x.float()
+    n, c, h, w = x.shape
+    cpad = ceil8(c) if cpad is None else cpad
+    y = new_act(n, h, w, cpad, x.device)
+    call("msp_nchw_f32_to_nhwc_bf16", _p(x), n, c, h, w, cpad, _p(y), _stream())
+    return y
+
+
+def nhwc_to_nchw(x: torch.Tensor, c: Optional[int] = None) -> torch.Tensor:
+    n, h, w, cc, cs = _chk_nhwc(x, "nhwc_to_nchw")
+    c = cc if c is None else c
+    y = torch.empty((n, c, h, w), dtype=torch.float32, device=x.device)
+    call("msp_nhwc_bf16_to_nchw_f32", _p(x), n, c, h, w, cs, _p(y), _stream())
+    return y
+
+
+# ------------------------------------------------------------------------------------------------
+# convolution
+# ------------------------------------------------------------------------------------------------
+def pack_weights(w: torch.Tensor, need_dgrad: bool = True):
+    """OIHW fp32 -> (bf16 [K8][taps][C8] for fprop, bf16 [C8][taps][K8] for dgrad)."""
+    w = w.detach()
+    if w.dtype != torch.float32 or not w.is_contiguous():
+        w = w.float().contiguous()
+    k, c, kh, kw = w.shape
+    c8, k8 = ceil8(c), ceil8(k)
+    if k8 != k:
+        raise ValueError("conv: output channels must be a multiple of 8")
+    wf = torch.empty((k, kh * kw, c8), dtype=_BF16, device=w.device)
+    wd = torch.empty((c8, kh * kw, k8), dtype=_BF16, device=w.device) if need_dgrad else None
+    call("msp_pack_weights", _p(w), k, c, kh, kw, c8, k8, _p(wf), _p(wd), _stream())
+    return wf, wd
+
+
+def conv_out_size(h: int, w: int, kh: int, kw: int, stride: int, padding) -> Tuple[int, int, int, int]:
+    """-> (Ho, Wo, pad_t, pad_l); padding is an int, (ph, pw) or 'same' (torch semantics: for even
+    kernels the extra padding goes to the bottom/right, blocks.py:518 probe in SURVEY App. B)."""
+    if padding == "same":
+        if stride != 1:
+            raise ValueError("padding='same' needs stride 1")
+        return h, w, (kh - 1) // 2, (kw - 1) // 2
+    if isinstance(padding, int):
+        ph = pw = padding
+    else:
+        ph, pw = padding
+    return (h + 2 * ph - kh) // stride + 1, (w + 2 * pw - kw) // stride + 1, ph, pw
+
+
+def _conv_desc(n, h, w, c, x_cs, ho, wo, k, y_cs, kh, kw, stride, pad_t, pad_l, relu=0) -> ConvDesc:
+    return ConvDesc(n, h, w, c, x_cs, ho, wo, k, y_cs, kh, kw, stride, pad_t, pad_l, relu)
+
+
+def conv_fprop(x, wf, bias, k, kh, kw, stride, pad_t, pad_l, ho, wo, relu=False, out=None, stats=None):
+    """y = conv(x, w) [+ bias] [ReLU]; if `stats` (fp32 [2, K], zeroed by the caller) is given the
+    per-channel sum / sum of squares of y are accumulated into it (BatchNorm batch statistics)."""
+    n, h, w, c, x_cs = _chk_nhwc(x, "conv_fprop(x)")
+    if out is None:
+        out = new_act(n, ho, wo, k, x.device)
+    _, _, _, ko, y_cs = _chk_nhwc(out, "conv_fprop(out)")
+    assert ko == k and wf.shape[2] == c, (ko, k, tuple(wf.shape), c)
+    d = _conv_desc(n, h, w, c, x_cs, ho, wo, k, y_cs, kh, kw, stride, pad_t, pad_l, int(relu))
+    s1 = s2 = None
+    if stats is not None:
+        s1, s2 = stats[0].data_ptr(), stats[1].data_ptr()
+    call("msp_conv_fprop", C.byref(d), _p(x), _p(wf), _p(bias), _p(out), s1, s2, _stream())
+    return out
+
+
+def conv_dgrad(dy, wd, x_shape, kh, kw, stride, pad_t, pad_l, out=None, accumulate=False):
+    """dx = conv_transpose(dy, w); x_shape = (N, H, W, C8)."""
+    n, ho, wo, k, y_cs = _chk_nhwc(dy, "conv_dgrad(dy)")
+    _, h, w, c = x_shape
+    if out is None:
+        out = new_act(n, h, w, c, dy.device)
+        accumulate = False
+    _, _, _, _, x_cs = _chk_nhwc(out, "conv_dgrad(out)")
+    d = _conv_desc(n, h, w, c, x_cs, ho, wo, k, y_cs, kh, kw, stride, pad_t, pad_l)
+    call("msp_conv_dgrad", C.byref(d), _p(dy), _p(wd), _p(out), int(accumulate), _stream())
+    return out
+
+
+def conv_wgrad(x, dy, c_true, kh, kw, stride, pad_t, pad_l) -> torch.Tensor:
+    """-> dW in the OIHW fp32 layout of nn.Conv2d.weight.grad."""
+    n, h, w, c, x_cs = _chk_nhwc(x, "conv_wgrad(x)")
+    _, ho, wo, k, y_cs = _chk_nhwc(dy, "conv_wgrad(dy)")
+    d = _conv_desc(n, h, w, c, x_cs, ho, wo, k, y_cs, kh, kw, stride, pad_t, pad_l)
+    dwp = torch.empty((k, kh * kw, c), dtype=torch.float32, device=x.device)
+    call("msp_conv_wgrad", C.byref(d), _p(x), _p(dy), _p(dwp), _stream())
+    dw = torch.empty((k, c_true, kh, kw), dtype=torch.float32, device=x.device)
+    call("msp_unpack_wgrad", _p(dwp), k, c_true, kh, kw, c, _p(dw), _stream())
+    return dw
+
+
+def channel_sum(x: torch.Tensor) -> torch.Tensor:
+    n, h, w, c, cs = _chk_nhwc(x, "channel_sum")
+    out = torch.empty((c,), dtype=torch.float32, device=x.device)
+    call("msp_channel_sum", _p(x), n * h * w, c, cs, _p(out), _stream())
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+# BatchNorm (+ activation + residual)
+# ------------------------------------------------------------------------------------------------
+def bn_finalize(stats, count, eps, momentum, running_mean=None, running_var=None):
+    c = stats.shape[1]
+    mi = torch.empty((2, c), dtype=torch.float32, device=stats.device)
+    call("msp_bn_finalize", stats[0].data_ptr(), stats[1].data_ptr(), c, float(count), float(eps),
+         float(momentum), mi[0].data_ptr(), mi[1].data_ptr(), _p(running_mean), _p(running_var), _stream())
+    return mi
+
+
+def bn_eval_stats(running_mean, running_var, eps):
+    c = running_mean.shape[0]
+    mi = torch.empty((2, c), dtype=torch.float32, device=running_mean.device)
+    mi[0].copy_(running_mean)
+    call("msp_bn_eval_prepare", _p(running_var), c, float(eps), mi[1].data_ptr(), _stream())
+    return mi
+
+
+def _bn_desc(x, y, act, res, r_stride):
+    n, h, w, c, x_cs = _chk_nhwc(x, "bn_act(x)")
+    _, _, _, _, y_cs = _chk_nhwc(y, "bn_act(y)")
+    r_c = r_cs = 0
+    if res is not None:
+        _, _, _, r_c, r_cs = _chk_nhwc(res, "bn_act(residual)")
+        r_c = min(r_c, c)
+    return BnActDesc(n, h, w, c, x_cs, y_cs, act, r_c, r_cs, r_stride)
+
+
+def bn_act_fwd(x, mi, gamma, beta, act, residual=None, r_stride=1, sample_scale=None, out=None):
+    if out is None:
+        out = new_act(x.shape[0], x.shape[1], x.shape[2], x.shape[3], x.device)
+    d = _bn_desc(x, out, act, residual, r_stride)
+    call("msp_bn_act_fwd", C.byref(d), _p(x), mi[0].data_ptr(), mi[1].data_ptr(), _p(gamma), _p(beta),
+         _p(sample_scale), _p(residual), _p(out), _stream())
+    return out
+
+
+def bn_act_bwd_reduce(x, y, dy, mi, act, sample_scale=None):
+    d = _bn_desc(x, y, act, None, 1)
+    _chk_nhwc(dy, "bn_act_bwd(dy)")
+    assert dy.stride(2) == y.stride(2), "dy must share the pixel stride of y"
+    sums = torch.empty((2, x.shape[3]), dtype=torch.float32, device=x.device)
+    call("msp_bn_act_bwd_reduce", C.byref(d), _p(x), _p(y), _p(dy), mi[0].data_ptr(), mi[1].data_ptr(),
+         _p(sample_scale), sums[0].data_ptr(), sums[1].data_ptr(), _stream())
+    return sums
+
+
+def bn_act_bwd_apply(x, y, dy, mi, gamma, act, sums, count, residual_like=None, r_stride=1,
+                     sample_scale=None, dres=None, dres_accumulate=False):
+    n, h, w, c = x.shape
+    if x.stride(2) == c:
+        dx = new_act(n, h, w, c, x.device)
+    else:  # x is a channel slice of a wider buffer: dx must share its pixel stride
+        dx = torch.empty((n, h, w, x.stride(2)), dtype=_BF16, device=x.device)[..., :c]
+    d = _bn_desc(x, y, act, residual_like if dres is None else dres, r_stride)
+    call("msp_bn_act_bwd_apply", C.byref(d), _p(x), _p(y), _p(dy), mi[0].data_ptr(), mi[1].data_ptr(),
+         _p(gamma), _p(sample_scale), sums[0].data_ptr(), sums[1].data_ptr(), float(count), _p(dx),
+         _p(dres), int(dres_accumulate), _stream())
+    return dx
+
+
+# ------------------------------------------------------------------------------------------------
+# pooling / resampling / elementwise
+# ------------------------------------------------------------------------------------------------
+def maxpool_fwd(x, k, stride, pad, want_idx=True):
+    n, h, w, c, cs = _chk_nhwc(x, "maxpool(x)")
+    ho, wo = (h + 2 * pad - k) // stride + 1, (w + 2 * pad - k) // stride + 1
+    y = new_act(n, ho, wo, c, x.device)
+    idx = torch.empty((n, ho, wo, c), dtype=torch.uint8, device=x.device) if want_idx else None
+    call("msp_maxpool_fwd", _p(x), n, h, w, c, cs, k, stride, pad, _p(y), _p(idx), ho, wo, c, _stream())
+    return y, idx
+
+
+def maxpool_bwd(idx, dy, x_shape, k, stride, pad):
+    n, h, w, c = x_shape
+    _, ho, wo, _, dy_cs = _chk_nhwc(dy, "maxpool_bwd(dy)")
+    dx = new_act(n, h, w, c, dy.device)
+    call("msp_maxpool_bwd", _p(idx), _p(dy), n, h, w, c, k, stride, pad, ho, wo, dy_cs, _p(dx), c, 0,
+         _stream())
+    return dx
+
+
+def upsample2x_fwd(x, out=None):
+    n, h, w, c, cs = _chk_nhwc(x, "upsample2x(x)")
+    if out is None:
+        out = new_act(n, 2 * h, 2 * w, c, x.device)
+    call("msp_upsample2x_fwd", _p(x), n, h, w, c, cs, _p(out), out.stride(2), _stream())
+    return out
+
+
+def upsample2x_bwd(dy):
+    n, h2, w2, c, cs = _chk_nhwc(dy, "upsample2x_bwd(dy)")
+    dx = new_act(n, h2 // 2, w2 // 2, c, dy.device)
+    call("msp_upsample2x_bwd", _p(dy), n, h2 // 2, w2 // 2, c, cs, _p(dx), c, _stream())
+    return dx
+
+
+def avgpool_fwd(x):
+    n, h, w, c, cs = _chk_nhwc(x, "avgpool(x)")
+    y = new_act(n, 1, 1, c, x.device)
+    call("msp_avgpool_fwd", _p(x), n, h * w, c, cs, _p(y), _stream())
+    return y
+
+
+def avgpool_bwd(dy, h, w):
+    n, _, _, c, _ = _chk_nhwc(dy, "avgpool_bwd(dy)")
+    dyc = dy if dy.stride(2) == c else dy.contiguous()
+    dx = new_act(n, h, w, c, dy.device)
+    call("msp_avgpool_bwd", _p(dyc), n, h * w, c, _p(dx), c, _stream())
+    return dx
+
+
+def copy_channels(x, out):
+    n, h, w, c, cs = _chk_nhwc(x, "copy_channels(x)")
+    _, _, _, co, ocs = _chk_nhwc(out, "copy_channels(out)")
+    assert co == c
+    call("msp_copy_channels", _p(x), n * h * w, c, cs, _p(out), ocs, _stream())
+    return out
+
+
+def _ew2(name, a, b, out=None):
+    n, h, w, c, a_cs = _chk_nhwc(a, name + "(a)")
+    _, _, _, _, b_cs = _chk_nhwc(b, name + "(b)")
+    if out is None:
+        out = new_act(n, h, w, c, a.device)
+    call(name, _p(a), _p(b), n * h * w, c, a_cs, b_cs, _p(out), out.stride(2), _stream())
+    return out
+
+
+def add_relu(a, b, out=None):
+    return _ew2("msp_add_relu_fwd", a, b, out)
+
+
+def add(a, b, out=None):
+    return _ew2("msp_add", a, b, out)
+
+
+def relu_bwd(y, dy, out=None):
+    return _ew2("msp_relu_bwd", y, dy, out)
+
+
+def gate_mul_fwd(skip, p, out=None):
+    n, h, w, c, s_cs = _chk_nhwc(skip, "gate_mul(skip)")
+    _, _, _, _, p_cs = _chk_nhwc(p, "gate_mul(p)")
+    if out is None:
+        out = new_act(n, h, w, c, skip.device)
+    call("msp_gate_mul_fwd", _p(skip), _p(p), n, h, w, c, s_cs, p_cs, _p(out), out.stride(2), _stream())
+    return out
+
+
+def gate_mul_bwd(skip, p, dy):
+    n, h, w, c, s_cs = _chk_nhwc(skip, "gate_mul_bwd(skip)")
+    _, _, _, _, p_cs = _chk_nhwc(p, "gate_mul_bwd(p)")
+    _, _, _, _, dy_cs = _chk_nhwc(dy, "gate_mul_bwd(dy)")
+    dskip = new_act(n, h, w, c, skip.device)
+    dp = new_act(n, h // 2, w // 2, c, skip.device)
+    call("msp_gate_mul_bwd", _p(skip), _p(p), _p(dy), n, h, w, c, s_cs, p_cs, dy_cs, _p(dskip), c, 0,
+         _p(dp), c, _stream())
+    return dskip, dp
+
+
+# ------------------------------------------------------------------------------------------------
+# heads / losses
+# ------------------------------------------------------------------------------------------------
+HEAD_ACT = {None: 0, "none": 0, "sigmoid": 1, "softmax": 2}
+
+
+def final_conv_act_fwd(x, w2d, bias, act: int, want_logits=False):
+    n, h, w, c, cs = _chk_nhwc(x, "final_conv(x)")
+    k = w2d.shape[0]
+    prob = torch.empty((n, k, h, w), dtype=torch.float32, device=x.device)
+    logits = torch.empty_like(prob) if want_logits else None
+    call("msp_final_conv_act_fwd", _p(x), n, h, w, c, cs, _p(w2d), _p(bias), k, act, _p(logits), _p(prob),
+         _stream())
+    return prob, logits
+
+
+def final_conv_act_bwd(x, w2d, act: int, prob, dprob, need_dx=True, has_bias=True):
+    n, h, w, c, cs = _chk_nhwc(x, "final_conv_bwd(x)")
+    k = w2d.shape[0]
+    dx = new_act(n, h, w, c, x.device) if need_dx else None
+    dw = torch.empty((k, c), dtype=torch.float32, device=x.device)
+    db = torch.empty((k,), dtype=torch.float32, device=x.device) if has_bias else None
+    call("msp_final_conv_act_bwd", _p(x), n, h, w, c, cs, _p(w2d), k, act, _p(prob), _p(dprob), _p(dx), c,
+         _p(dw), _p(db), _stream())
+    return dx, dw, db
+
+
+def dice_fwd(prob, mask, two_class, label_offset, batchwise, class_start, eps):
+    n, cp = prob.shape[0], prob.shape[1]
+    hw = prob[0, 0].numel()
+    ceff = 2 if two_class else cp
+    g = 1 if batchwise else n
+    sums = torch.empty((g, ceff, 3), dtype=torch.float64, device=prob.device)
+    coef = torch.empty((g, ceff, 2), dtype=torch.float32, device=prob.device)
+    loss = torch.empty((), dtype=torch.float32, device=prob.device)
+    call("msp_dice_fwd", _p(prob), _p(mask), n, cp, hw, int(two_class), int(label_offset), int(batchwise),
+         int(class_start), float(eps), _p(sums), _p(coef), _p(loss), _stream())
+    return loss, coef, sums
+
+
+def dice_bwd(prob, mask, two_class, label_offset, batchwise, coef, gscale):
+    n, cp = prob.shape[0], prob.shape[1]
+    hw = prob[0, 0].numel()
+    dprob = torch.empty_like(prob)
+    call("msp_dice_bwd", _p(prob), _p(mask), n, cp, hw, int(two_class), int(label_offset), int(batchwise),
+         _p(coef), float(gscale), _p(dprob), _stream())
+    return dprob
+
+
+def _sum_to_mean(loss_sum, scale):
+    out = torch.empty((), dtype=torch.float32, device=loss_sum.device)
+    call("msp_scale_to_float", _p(loss_sum), float(scale), _p(out), _stream())
+    return out
+
+
+def ce_prob(prob, label, smooth, gscale, want_grad=True):
+    n, c = prob.shape[0], prob.shape[1]
+    hw = prob[0, 0].numel()
+    ls = torch.empty((1,), dtype=torch.float64, device=prob.device)
+    dprob = torch.empty_like(prob) if want_grad else None
+    call("msp_ce_prob_fwd_bwd", _p(prob), _p(label), n, c, hw, float(smooth), float(gscale), _p(ls),
+         _p(dprob), _stream())
+    return ls, dprob
+
+
+def bce(prob, target, clamp_log, gscale, want_grad=True):
+    ls = torch.empty((1,), dtype=torch.float64, device=prob.device)
+    dprob = torch.empty_like(prob) if want_grad else None
+    call("msp_bce_fwd_bwd", _p(prob), _p(target), prob.numel(), int(clamp_log), float(gscale), _p(ls),
+         _p(dprob), _stream())
+    return ls, dprob
+
+
+def softmax_ce(logits, label, smooth, gscale, want_grad=True):
+    n, c = logits.shape
+    ls = torch.empty((1,), dtype=torch.float64, device=logits.device)
+    dl = torch.empty_like(logits) if want_grad else None
+    call("msp_softmax_ce_fwd_bwd", _p(logits), _p(label), n, c, float(smooth), float(gscale), _p(ls),
+         _p(dl), _stream())
+    return ls, dl
+
+
+# ------------------------------------------------------------------------------------------------
+# metrics / robustness
+# ------------------------------------------------------------------------------------------------
+def confusion_binary(pred, target, thr, per_channel):
+    """pred fp32 (N, C, *spatial); target same shape (int64 or fp32).  -> int64 [6] or [C, 6] =
+    TP, TN, FP, FN, positives, NaN targets."""
+    n, c = pred.shape[0], pred.shape[1]
+    hw = pred[0, 0].numel() if n > 0 else 0
+    out = torch.empty((c, 6) if per_channel else (6,), dtype=torch.int64, device=pred.device)
+    is_float = target.dtype == torch.float32
+    call("msp_confusion_binary", _p(pred), _p(target), int(is_float), n, c, hw, float(thr), int(per_channel),
+         _p(out), _stream())
+    return out
+
+
+def confusion_multiclass(pred, target, onehot):
+    n, c = pred.shape[0], pred.shape[1]
+    hw = pred[0, 0].numel() if n > 0 else 0
+    cm = torch.empty((c, c), dtype=torch.int64, device=pred.device)
+    call("msp_confusion_multiclass", _p(pred), _p(target), int(onehot), n, c, hw, _p(cm), _stream())
+    return cm
+
+
+def topk_hits(pred, label, k):
+    n, c = pred.shape[0], pred.shape[1]
+    hw = pred[0, 0].numel() if n > 0 else 0
+    hits = torch.empty((1,), dtype=torch.int64, device=pred.device)
+    call("msp_topk_hits", _p(pred), _p(label), n, c, hw, k, _p(hits), _stream())
+    return hits
+
+
+def rowpair_distances(q, k, pooled_hw=0):
+    """q, k fp32 [N, D] (or [N, C, hw] with pooled_hw = hw).  -> fp32 [6, N]."""
+    n = q.shape[0]
+    d = q.shape[1] if pooled_hw > 1 else q[0].numel()
+    out = torch.empty((6, n), dtype=torch.float32, device=q.device)
+    call("msp_rowpair_distances", _p(q), _p(k), n, d, int(pooled_hw), _p(out), _stream())
+    return out
+
+
+def triplet_hinge(dist, margins):
+    n = dist.shape[1]
+    m = margins.numel()
+    out = torch.empty((m, 3, n), dtype=torch.float32, device=dist.device)
+    call("msp_triplet_hinge", _p(dist), n, _p(margins), m, _p(out), _stream())
+    return out
+
+
+launch_count = _lib.launch_count

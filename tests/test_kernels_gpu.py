@@ -1,0 +1,292 @@
+"""GPU parity of every C-ABI kernel against plain fp32 PyTorch on the CPU (same seeded inputs, already
+rounded to bf16 where the kernel consumes bf16, so the only differences are accumulation order and the
+bf16 rounding of the outputs).  Tolerances are written next to each check."""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+DEV = "cuda"
+
+
+def _ops():
+    from medsegpretrainimagenet_b200 import ops
+    return ops
+
+
+def _bf(x):
+    return x.to(torch.bfloat16).float()
+
+
+def _to_nhwc(x_nchw, cpad=None):
+    """CPU fp32 NCHW -> CUDA bf16 NHWC (host-side permutation, independent of the kernel under test)."""
+    n, c, h, w = x_nchw.shape
+    cpad = cpad or (c + 7) // 8 * 8
+    y = torch.zeros((n, h, w, cpad), dtype=torch.bfloat16)
+    y[..., :c] = x_nchw.permute(0, 2, 3, 1).to(torch.bfloat16)
+    return y.to(DEV)
+
+
+def _from_nhwc(y, c=None):
+    y = y.float().cpu()
+    if c is not None:
+        y = y[..., :c]
+    return y.permute(0, 3, 1, 2).contiguous()
+
+
+def _close(got, ref, rel, what):
+    scale = ref.abs().max().item() + 1e-12
+    err = (got - ref).abs().max().item()
+    assert err <= rel * scale, f"{what}: max abs err {err:.4g} vs scale {scale:.4g} (rel {err / scale:.3g} > {rel})"
+
+
+def _ref_conv(x, w, b, stride, padding):
+    if padding == "same":
+        kh, kw = w.shape[2:]
+        x = F.pad(x, ((kw - 1) // 2, kw - 1 - (kw - 1) // 2, (kh - 1) // 2, kh - 1 - (kh - 1) // 2))
+        padding = 0
+    return F.conv2d(x, w, b, stride=stride, padding=padding)
+
+
+CONV_CASES = [
+    # N, H, W, C, K, k, stride, padding
+    (2, 16, 16, 64, 64, 3, 1, 1),
+    (2, 14, 14, 256, 256, 3, 1, 1),
+    (1, 56, 56, 64, 64, 3, 1, 1),
+    (2, 8, 8, 256, 64, 1, 1, 0),
+    (4, 7, 7, 2048, 512, 1, 1, 0),
+    (2, 16, 16, 128, 128, 3, 2, 1),
+    (3, 28, 28, 128, 128, 3, 2, 1),
+    (2, 64, 64, 3, 64, 7, 2, 3),
+    (2, 64, 64, 1, 64, 7, 2, 3),
+    (2, 16, 16, 64, 32, 2, 1, "same"),
+    (2, 16, 16, 64, 128, 2, 2, 0),
+    (1, 4, 256, 16, 16, 3, 1, 1),
+    (2, 32, 32, 32, 16, 3, 1, 1),
+    (16, 1, 1, 2048, 1000, 1, 1, 0),
+    (2, 20, 24, 96, 40, 3, 1, 1),
+    (1, 130, 130, 16, 16, 3, 1, 1),
+]
+
+
+@pytest.mark.parametrize("case", CONV_CASES, ids=lambda c: "x".join(map(str, c)))
+def test_conv_fprop_dgrad_wgrad(case):
+    ops = _ops()
+    n, h, w, c, k, ks, stride, padding = case
+    g = torch.Generator().manual_seed(100 + CONV_CASES.index(case))
+    x = _bf(torch.randn((n, c, h, w), generator=g))
+    wt = _bf(torch.randn((k, c, ks, ks), generator=g) / math.sqrt(c * ks * ks))
+    bias = torch.randn((k,), generator=g)
+    x.requires_grad_(True)
+    wt.requires_grad_(True)
+    ref = _ref_conv(x, wt, bias, stride, padding)
+    dy = _bf(torch.randn(ref.shape, generator=g))
+    ref.backward(dy)
+
+    ho, wo, pt, pl = ops.conv_out_size(h, w, ks, ks, stride, padding)
+    assert (ho, wo) == tuple(ref.shape[2:])
+    xd = _to_nhwc(x.detach())
+    wf, wd = ops.pack_weights(wt.detach().to(DEV))
+    stats = torch.zeros((2, k), dtype=torch.float32, device=DEV)
+    y = ops.conv_fprop(xd, wf, bias.to(DEV), k, ks, ks, stride, pt, pl, ho, wo, stats=stats)
+    torch.cuda.synchronize()
+    got = _from_nhwc(y)
+    # bf16 output rounding (2^-9 relative) + fp32 accumulation-order noise
+    _close(got, ref.detach(), 6e-3, "fprop")
+    # fused BatchNorm statistics are the sums of the bf16-rounded outputs
+    yb = y.float().cpu().reshape(-1, k)
+    _close(stats[0].cpu(), yb.sum(0), 1e-3, "ch_sum")
+    _close(stats[1].cpu(), (yb * yb).sum(0), 1e-3, "ch_sqsum")
+
+    # ReLU epilogue without bias
+    y2 = ops.conv_fprop(xd, wf, None, k, ks, ks, stride, pt, pl, ho, wo, relu=True)
+    _close(_from_nhwc(y2), torch.relu(ref.detach() - bias.view(1, -1, 1, 1)), 6e-3, "fprop+relu")
+
+    dyd = _to_nhwc(dy)
+    dx = ops.conv_dgrad(dyd, wd, tuple(xd.shape), ks, ks, stride, pt, pl)
+    _close(_from_nhwc(dx, c), x.grad, 6e-3, "dgrad")
+    # accumulate form: dx2 = base + dgrad
+    base = _bf(torch.randn((n, c, h, w), generator=g))
+    dx2 = _to_nhwc(base)
+    ops.conv_dgrad(dyd, wd, tuple(xd.shape), ks, ks, stride, pt, pl, out=dx2, accumulate=True)
+    _close(_from_nhwc(dx2, c), x.grad + base, 1e-2, "dgrad(accumulate)")
+
+    dw = ops.conv_wgrad(xd, dyd, c, ks, ks, stride, pt, pl)
+    # fp32 accumulation over up to N*Ho*Wo pixels, fp32 atomics across split-K
+    _close(dw.cpu(), wt.grad, 2e-3, "wgrad")
+
+
+def test_conv_concat_slices():
+    """Operands that are channel slices of wider buffers (zero-copy concat, blocks.py:628,635)."""
+    ops = _ops()
+    g = torch.Generator().manual_seed(7)
+    n, h, w, c, k = 2, 16, 16, 32, 64
+    x = _bf(torch.randn((n, c, h, w), generator=g))
+    wt = _bf(torch.randn((k, c, 3, 3), generator=g) / 17.0)
+    ref = F.conv2d(x, wt, None, padding=1)
+    xin = torch.zeros((n, h, w, 96), dtype=torch.bfloat16, device=DEV)
+    xin[..., 40:72] = _to_nhwc(x)
+    out = torch.full((n, h, w, 160), 3.0, dtype=torch.bfloat16, device=DEV)
+    wf, _ = ops.pack_weights(wt.to(DEV), need_dgrad=False)
+    ops.conv_fprop(xin[..., 40:72], wf, None, k, 3, 3, 1, 1, 1, h, w, out=out[..., 64:128])
+    _close(_from_nhwc(out[..., 64:128]), ref, 6e-3, "fprop into slice")
+    assert (out[..., :64] == 3).all() and (out[..., 128:] == 3).all(), "wrote outside the channel slice"
+
+
+def test_layout_roundtrip():
+    ops = _ops()
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn((3, 5, 17, 23), generator=g)
+    y = ops.nchw_to_nhwc(x.to(DEV))
+    assert y.shape == (3, 17, 23, 8)
+    assert torch.equal(y[..., :5].cpu(), x.permute(0, 2, 3, 1).to(torch.bfloat16))
+    assert (y[..., 5:] == 0).all()
+    back = ops.nhwc_to_nchw(y, 5)
+    assert torch.equal(back.cpu(), _bf(x))
+
+
+@pytest.mark.parametrize("shape", [(4, 8, 8, 64), (2, 7, 9, 24), (2, 4, 4, 2048)])
+@pytest.mark.parametrize("act", [0, 1, 2])
+def test_bn_act_fwd_bwd(shape, act):
+    ops = _ops()
+    n, h, w, c = shape
+    g = torch.Generator().manual_seed(11 + act)
+    x = _bf(torch.randn((n, c, h, w), generator=g) * 2 + 0.5)
+    gamma = torch.rand((c,), generator=g) + 0.5
+    beta = torch.randn((c,), generator=g) * 0.1
+    res = _bf(torch.randn((n, c, h, w), generator=g))
+    scale = (torch.rand((n,), generator=g) > 0.3).float()
+    rm, rv = torch.zeros(c), torch.ones(c)
+    xr = x.clone().requires_grad_(True)
+    gr, br, rr = gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True), res.clone().requires_grad_(True)
+    bn = F.batch_norm(xr, rm, rv, gr, br, training=True, momentum=0.1, eps=1e-5)
+    pre = bn * scale.view(-1, 1, 1, 1) + rr
+    ref = torch.relu(pre) if act == 1 else (torch.sigmoid(pre) if act == 2 else pre)
+    dy = _bf(torch.randn(ref.shape, generator=g))
+    ref.backward(dy)
+
+    xd = _to_nhwc(x)
+    flat = xd.float().reshape(-1, c)
+    stats = torch.stack([flat.sum(0), (flat * flat).sum(0)])
+    rmd, rvd = torch.zeros(c, device=DEV), torch.ones(c, device=DEV)
+    mi = ops.bn_finalize(stats, n * h * w, 1e-5, 0.1, rmd, rvd)
+    _close(rmd.cpu(), rm, 1e-4, "running_mean")
+    _close(rvd.cpu(), rv, 1e-4, "running_var")
+    resd = _to_nhwc(res)
+    y = ops.bn_act_fwd(xd, mi, gamma.to(DEV), beta.to(DEV), act, residual=resd, sample_scale=scale.to(DEV))
+    _close(_from_nhwc(y), ref.detach(), 6e-3, "bn_act_fwd")
+
+    dyd = _to_nhwc(dy)
+    sums = ops.bn_act_bwd_reduce(xd, y, dyd, mi, act, sample_scale=scale.to(DEV))
+    # dgamma / dbeta: the activation mask comes from the bf16 output, so allow bf16-level noise
+    _close(sums[0].cpu(), br.grad, 2e-2, "dbeta")
+    _close(sums[1].cpu(), gr.grad, 2e-2, "dgamma")
+    dres = ops.new_act(n, h, w, c, DEV)
+    dx = ops.bn_act_bwd_apply(xd, y, dyd, mi, gamma.to(DEV), act, sums, n * h * w, dres=dres,
+                              sample_scale=scale.to(DEV))
+    _close(_from_nhwc(dx), xr.grad, 2e-2, "bn dx")
+    _close(_from_nhwc(dres), rr.grad, 2e-2, "residual grad")
+
+
+def test_bn_zero_fill_strided_shortcut():
+    """ResNet shortcut: stride-2 sub-sampling + zero channel fill (classification/models.py:257-274)."""
+    ops = _ops()
+    g = torch.Generator().manual_seed(5)
+    n, h, w, c, rc = 2, 6, 6, 32, 16
+    x = _bf(torch.randn((n, c, h, w), generator=g))
+    res = _bf(torch.randn((n, rc, 2 * h, 2 * w), generator=g))
+    short = torch.cat([res[:, :, ::2, ::2], torch.zeros((n, c - rc, h, w))], 1)
+    ref = torch.relu(F.batch_norm(x, None, None, None, None, training=True) + short)
+    xd = _to_nhwc(x)
+    flat = xd.float().reshape(-1, c)
+    mi = ops.bn_finalize(torch.stack([flat.sum(0), (flat * flat).sum(0)]), n * h * w, 1e-5, 0.1)
+    y = ops.bn_act_fwd(xd, mi, None, None, 1, residual=_to_nhwc(res), r_stride=2)
+    _close(_from_nhwc(y), ref, 6e-3, "strided zero-fill shortcut")
+    dy = _bf(torch.randn(ref.shape, generator=g))
+    dyd = _to_nhwc(dy)
+    sums = ops.bn_act_bwd_reduce(xd, y, dyd, mi, 1)
+    dres = torch.zeros((n, 2 * h, 2 * w, rc), dtype=torch.bfloat16, device=DEV)
+    ops.bn_act_bwd_apply(xd, y, dyd, mi, None, 1, sums, n * h * w, dres=dres, r_stride=2)
+    gmask = dy * (ref > 0)
+    exp = torch.zeros((n, rc, 2 * h, 2 * w))
+    exp[:, :, ::2, ::2] = gmask[:, :rc]
+    _close(_from_nhwc(dres), exp, 1e-2, "strided shortcut grad")
+
+
+@pytest.mark.parametrize("k,s,p", [(3, 2, 1), (2, 2, 0)])
+def test_maxpool(k, s, p):
+    ops = _ops()
+    g = torch.Generator().manual_seed(9)
+    x = _bf(torch.randn((2, 16, 14, 14), generator=g)).requires_grad_(True)
+    ref = F.max_pool2d(x, k, s, p)
+    dy = _bf(torch.randn(ref.shape, generator=g))
+    ref.backward(dy)
+    xd = _to_nhwc(x.detach())
+    y, idx = ops.maxpool_fwd(xd, k, s, p)
+    assert torch.equal(_from_nhwc(y), ref.detach())
+    dx = ops.maxpool_bwd(idx, _to_nhwc(dy), tuple(xd.shape), k, s, p)
+    _close(_from_nhwc(dx), x.grad, 1e-2, "maxpool bwd")
+
+
+def test_upsample_avgpool_gate_elementwise():
+    ops = _ops()
+    g = torch.Generator().manual_seed(13)
+    x = _bf(torch.randn((2, 16, 6, 5), generator=g)).requires_grad_(True)
+    up = F.interpolate(x, scale_factor=2, mode="nearest")
+    dy = _bf(torch.randn(up.shape, generator=g))
+    up.backward(dy)
+    xd = _to_nhwc(x.detach())
+    assert torch.equal(_from_nhwc(ops.upsample2x_fwd(xd)), up.detach())
+    _close(_from_nhwc(ops.upsample2x_bwd(_to_nhwc(dy))), x.grad, 1e-2, "upsample bwd")
+
+    ap = ops.avgpool_fwd(xd)
+    _close(_from_nhwc(ap), x.detach().mean((2, 3), keepdim=True), 6e-3, "avgpool")
+    dap = _bf(torch.randn((2, 16, 1, 1), generator=g))
+    _close(_from_nhwc(ops.avgpool_bwd(_to_nhwc(dap), 6, 5)), (dap / 30).expand(2, 16, 6, 5), 1e-2, "avgpool bwd")
+
+    skip = _bf(torch.randn((2, 16, 12, 10), generator=g)).requires_grad_(True)
+    p = _bf(torch.rand((2, 16, 6, 5), generator=g)).requires_grad_(True)
+    out = skip * F.interpolate(p, scale_factor=2, mode="nearest")
+    out.backward(dy)
+    sd, pd = _to_nhwc(skip.detach()), _to_nhwc(p.detach())
+    _close(_from_nhwc(ops.gate_mul_fwd(sd, pd)), out.detach(), 6e-3, "gate fwd")
+    dskip, dp = ops.gate_mul_bwd(sd, pd, _to_nhwc(dy))
+    _close(_from_nhwc(dskip), skip.grad, 1e-2, "gate dskip")
+    _close(_from_nhwc(dp), p.grad, 1e-2, "gate dp")
+
+    a, b = _bf(torch.randn((2, 8, 3, 3), generator=g)), _bf(torch.randn((2, 8, 3, 3), generator=g))
+    ad, bd = _to_nhwc(a), _to_nhwc(b)
+    _close(_from_nhwc(ops.add_relu(ad, bd)), torch.relu(a + b), 6e-3, "add_relu")
+    _close(_from_nhwc(ops.add(ad, bd)), a + b, 6e-3, "add")
+    _close(_from_nhwc(ops.relu_bwd(ad, bd)), b * (a > 0), 1e-6, "relu_bwd")
+    _close(ops.channel_sum(ad).cpu(), a.sum((0, 2, 3)), 1e-3, "channel_sum")
+    buf = torch.zeros((2, 3, 3, 24), dtype=torch.bfloat16, device=DEV)
+    ops.copy_channels(ad, buf[..., 8:16])
+    assert torch.equal(buf[..., 8:16].float().cpu(), a.permute(0, 2, 3, 1))
+
+
+@pytest.mark.parametrize("k,act", [(1, "sigmoid"), (4, "softmax"), (5, "sigmoid"), (2, None)])
+@pytest.mark.parametrize("c", [16, 64])
+def test_final_conv_act(k, act, c):
+    ops = _ops()
+    g = torch.Generator().manual_seed(17 + k)
+    n, h, w = 2, 24, 20
+    x = _bf(torch.randn((n, c, h, w), generator=g)).requires_grad_(True)
+    wt = (torch.randn((k, c), generator=g) / math.sqrt(c)).requires_grad_(True)
+    b = torch.randn((k,), generator=g).requires_grad_(True)
+    logits = F.conv2d(x, wt.view(k, c, 1, 1), b)
+    ref = torch.sigmoid(logits) if act == "sigmoid" else (torch.softmax(logits, 1) if act == "softmax" else logits)
+    dp = torch.randn(ref.shape, generator=g)
+    ref.backward(dp)
+    xd = _to_nhwc(x.detach())
+    a = ops.HEAD_ACT[act]
+    prob, _ = ops.final_conv_act_fwd(xd, wt.detach().to(DEV), b.detach().to(DEV), a)
+    # fp32 math on identical bf16 inputs
+    _close(prob.cpu(), ref.detach(), 1e-5, "final conv prob")
+    dx, dw, db = ops.final_conv_act_bwd(xd, wt.detach().to(DEV), a, prob, dp.to(DEV))
+    _close(_from_nhwc(dx), x.grad, 6e-3, "final conv dx")
+    _close(dw.cpu(), wt.grad, 1e-4, "final conv dw")
+    _close(db.cpu(), b.grad, 1e-4, "final conv db")
