@@ -190,31 +190,38 @@ int msp_final_conv_act_bwd(const void* x, int N, int H, int W, int C, int x_cs, 
  * prob is NCHW fp32 [N][Cp][HW]; mask int64 [N][HW].  If two_class != 0 (requires Cp == 1) the classes
  * are [1-p, p] (losses.py:46-49); the `include_background=False`, one-channel branch (losses.py:50-52)
  * is Cp == 1, two_class = 0, label_offset = 1.
- * Outputs: sums fp64 [G][Ceff][3] (zeroed by the call), coef fp32 [G][Ceff][2] = the per-class gradient
- * coefficients consumed by msp_dice_bwd (dL/dp = a*y + b*p), loss fp32 [1]. */
-int msp_dice_fwd(const float* prob, const int64_t* mask, int N, int Cp, long long HW, int two_class,
-                 int label_offset, int batchwise, int class_start, float eps, double* sums,
-                 float* coef, float* loss, void* stream);
-/* dprob = gscale * dL/dprob (NCHW fp32, every element written). */
+ * msp_dice_sums -> sums fp64 [G][Ceff][3] (zeroed by the call); msp_dice_finalize -> coef fp32
+ * [G][Ceff][2] = the per-class gradient coefficients consumed by msp_dice_bwd (dL/dp = a*y + b*p)
+ * and loss fp32 [1]. */
+int msp_dice_sums(const float* prob, const int64_t* mask, int N, int Cp, long long HW, int two_class,
+                  int label_offset, int batchwise, double* sums, void* stream);
+/* (sums may have been all-reduced across ranks in between: batchwise Dice is a ratio of GLOBAL sums) */
+int msp_dice_finalize(const double* sums, int G, int Ceff, int class_start, float eps, float* coef,
+                      float* loss, void* stream);
+/* dprob = gscale * (*gscale_dev if non-NULL) * dL/dprob (NCHW fp32, every element written).  The
+ * device-side factor is autograd's incoming gradient (loss/loss.py:83-87), read without a host sync. */
 int msp_dice_bwd(const float* prob, const int64_t* mask, int N, int Cp, long long HW, int two_class,
-                 int label_offset, int batchwise, const float* coef, float gscale, float* dprob,
-                 void* stream);
+                 int label_offset, int batchwise, const float* coef, float gscale,
+                 const float* gscale_dev, float* dprob, void* stream);
 /* pixel-wise CE on probabilities (classification/losses.py:27-40, apply_softmax=False):
- * loss_sum (fp64 [1], zeroed by the call) = sum over pixels of -sum_c clamp(nan_to_num(log p_c),-100)*t_c
- * with t = one-hot(label) clamped to [smooth/C, 1-smooth/C] when smooth != 0; dprob (optional) =
- * gscale * d loss_sum / d prob.  label int64 [N][HW]. */
+ * loss_sum (fp64 [1], optional, zeroed by the call) = sum over pixels of
+ * -sum_c clamp(nan_to_num(log p_c),-100)*t_c with t = one-hot(label) clamped to [smooth/C, 1-smooth/C]
+ * when smooth != 0; dprob (optional) = gscale * (*gscale_dev) * d loss_sum / d prob.  label int64 [N][HW]. */
 int msp_ce_prob_fwd_bwd(const float* prob, const int64_t* label, int N, int C, long long HW,
-                        float smooth, float gscale, double* loss_sum, float* dprob, void* stream);
+                        float smooth, float gscale, const float* gscale_dev, double* loss_sum,
+                        float* dprob, void* stream);
 /* BCE sum: clamp_log = 0 -> classification/losses.py:4-11 (plain logs, autograd gradient);
  * clamp_log = 1 -> torch.nn.BCELoss (utils/default_dict.py:10; logs clamped at -100,
  * gradient (p-y)/max(p(1-p),1e-12)).  target fp32, same shape as prob. */
 int msp_bce_fwd_bwd(const float* prob, const float* target, long long numel, int clamp_log,
-                    float gscale, double* loss_sum, float* dprob, void* stream);
+                    float gscale, const float* gscale_dev, double* loss_sum, float* dprob,
+                    void* stream);
 /* classification head loss: F.cross_entropy(logits[N][C], label[N], label_smoothing)
  * (classification/losses.py:24-25): loss_sum fp64 [1] = sum of per-row losses; dlogits (optional) =
- * gscale * d loss_sum / d logits. */
+ * gscale * (*gscale_dev) * d loss_sum / d logits. */
 int msp_softmax_ce_fwd_bwd(const float* logits, const int64_t* label, int N, int C, float smooth,
-                           float gscale, double* loss_sum, float* dlogits, void* stream);
+                           float gscale, const float* gscale_dev, double* loss_sum, float* dlogits,
+                           void* stream);
 /* out[0] = (float)(in[0] * scale): turns a loss sum into the mean without a host round trip. */
 int msp_scale_to_float(const double* in, double scale, float* out, void* stream);
 

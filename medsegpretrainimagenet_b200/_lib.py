@@ -66,12 +66,13 @@ SIGNATURES = {
     "msp_gate_mul_bwd": [P, P, P, I, I, I, I, I, I, I, P, I, I, P, I, P],
     "msp_final_conv_act_fwd": [P, I, I, I, I, I, P, P, I, I, P, P, P],
     "msp_final_conv_act_bwd": [P, I, I, I, I, I, P, I, I, P, P, P, I, P, P, P],
-    "msp_dice_fwd": [P, P, I, I, LL, I, I, I, I, F, P, P, P, P],
-    "msp_dice_bwd": [P, P, I, I, LL, I, I, I, P, F, P, P],
+    "msp_dice_sums": [P, P, I, I, LL, I, I, I, P, P],
+    "msp_dice_finalize": [P, I, I, I, F, P, P, P],
+    "msp_dice_bwd": [P, P, I, I, LL, I, I, I, P, F, P, P, P],
     "msp_scale_to_float": [P, D, P, P],
-    "msp_ce_prob_fwd_bwd": [P, P, I, I, LL, F, F, P, P, P],
-    "msp_bce_fwd_bwd": [P, P, LL, I, F, P, P, P],
-    "msp_softmax_ce_fwd_bwd": [P, P, I, I, F, F, P, P, P],
+    "msp_ce_prob_fwd_bwd": [P, P, I, I, LL, F, F, P, P, P, P],
+    "msp_bce_fwd_bwd": [P, P, LL, I, F, P, P, P, P],
+    "msp_softmax_ce_fwd_bwd": [P, P, I, I, F, F, P, P, P, P],
     "msp_confusion_binary": [P, P, I, I, I, LL, F, I, P, P],
     "msp_confusion_multiclass": [P, P, I, I, I, LL, P, P],
     "msp_topk_hits": [P, P, I, I, LL, I, P, P],

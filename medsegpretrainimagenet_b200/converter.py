@@ -1,0 +1,364 @@
+"""Drop-in conversion of the reference's nn.Modules to the B200 path.
+
+`convert(model)` leaves the module tree, its Parameters / buffers and therefore `state_dict()`,
+`parameters()`, `.train()/.eval()`, `.requires_grad_()` and the optimizer untouched, and replaces only
+what happens inside `forward`: an interpreter walks the reference-structured module tree and issues the
+fused sm_100a kernels of libmsp_b200.so on bf16 NHWC activations.
+
+Recognised structures (by class name and attribute layout, so that the same code drives both the real
+reference modules and the oracle restatement in oracle/ref_models.py):
+  DeepResNet / ResBlock / BottleNeckBlock / BasicBlock / DropPath   classification/models.py:9-325
+  UNet / UNet_encoder / UNet_decoder                                 segmentation/models/unet_models.py:39-688
+  ConvBlock / UpConvBlock / AttentionBlock / ConcatBlock             segmentation/models/blocks.py:419-635
+  Model wrapper (`.model`)                                           model/model.py:18-75
+  nn.Conv2d / BatchNorm2d / ReLU / Sigmoid / MaxPool2d / Upsample(nearest, x2) / Sequential / Identity
+Anything else raises UnsupportedModule: there is no PyTorch fallback on this path.
+"""
+from __future__ import annotations
+
+import types
+from typing import List, Optional, Tuple
+
+import torch
+from torch import nn
+
+from . import functional as Fn
+from . import ops
+
+
+class UnsupportedModule(NotImplementedError):
+    pass
+
+
+class ExecContext:
+    """Per-model execution options: `group` = process group for SyncBN statistics (None = local)."""
+
+    def __init__(self, group=None):
+        self.group = group
+
+
+def _name(m) -> str:
+    return type(m).__name__
+
+
+def _unwrap(m):
+    """model.Model wrapper -> the wrapped module (model/model.py:62)."""
+    while _name(m) == "Model" and hasattr(m, "model"):
+        m = m.model
+    return m
+
+
+def _pad_of(conv: nn.Conv2d):
+    p = conv.padding
+    if isinstance(p, str):
+        if p == "same":
+            return "same"
+        if p == "valid":
+            return 0
+        raise UnsupportedModule(f"conv padding {p!r}")
+    if p[0] != p[1]:
+        return (int(p[0]), int(p[1]))
+    return int(p[0])
+
+
+def _check_conv(conv: nn.Conv2d):
+    if conv.groups != 1 or tuple(conv.dilation) != (1, 1) or conv.stride[0] != conv.stride[1] \
+            or conv.kernel_size[0] != conv.kernel_size[1] or conv.padding_mode != "zeros":
+        raise UnsupportedModule(f"convolution {conv} (groups/dilation/anisotropic) is outside the B200 path")
+    if conv.stride[0] not in (1, 2):
+        raise UnsupportedModule(f"convolution stride {conv.stride}")
+
+
+_ACT_OF = {"ReLU": ops.ACT_RELU, "Sigmoid": ops.ACT_SIGMOID, "Identity": ops.ACT_NONE}
+
+
+def _is_noop(m) -> bool:
+    n = _name(m)
+    if n == "Identity":
+        return True
+    if n in ("Dropout", "Dropout2d"):
+        if m.p == 0 or not m.training:
+            return True
+        raise UnsupportedModule("training-mode Dropout2d is not on the B200 path")
+    return False
+
+
+def conv_bn_act(ctx: ExecContext, x, conv: nn.Conv2d, bn: Optional[nn.BatchNorm2d] = None, act: int = 0,
+                residual=None, r_stride: int = 1, sample_scale=None):
+    """Conv2d [-> BatchNorm2d] [-> ReLU | Sigmoid], with optional fused residual / per-sample scale."""
+    _check_conv(conv)
+    stride, padding = conv.stride[0], _pad_of(conv)
+    if bn is None:
+        if residual is not None or sample_scale is not None or act == ops.ACT_SIGMOID:
+            raise UnsupportedModule("residual / sigmoid epilogue without BatchNorm")
+        y, _ = Fn.conv2d(x, conv.weight, conv.bias, stride, padding, relu=(act == ops.ACT_RELU))
+        return y
+    training = bn.training or bn.running_mean is None
+    # the conv adds its bias in the epilogue, but the bias *gradient* is produced by the BatchNorm node
+    bias = conv.bias.detach() if conv.bias is not None else None
+    y, stats = Fn.conv2d(x, conv.weight, bias, stride, padding, relu=False, want_stats=training)
+    return Fn.bn_act(y, stats, bn, act=act, residual=residual, r_stride=r_stride,
+                     sample_scale=sample_scale, group=ctx.group, conv_bias=conv.bias)
+
+
+def run_sequence(ctx: ExecContext, mods: List[nn.Module], x):
+    """Greedy fusion over a flat list of leaf modules."""
+    i, n = 0, len(mods)
+    while i < n:
+        m = _unwrap(mods[i])
+        nm = _name(m)
+        if _is_noop(m):
+            i += 1
+        elif nm == "Conv2d":
+            bn, act, j = None, ops.ACT_NONE, i + 1
+            if j < n and _name(_unwrap(mods[j])) == "BatchNorm2d":
+                bn = _unwrap(mods[j])
+                j += 1
+            if j < n and _name(_unwrap(mods[j])) in ("ReLU", "Sigmoid"):
+                act = _ACT_OF[_name(_unwrap(mods[j]))]
+                j += 1
+            x = conv_bn_act(ctx, x, m, bn, act)
+            i = j
+        elif nm == "MaxPool2d":
+            k = m.kernel_size if isinstance(m.kernel_size, int) else m.kernel_size[0]
+            s = m.stride if isinstance(m.stride, int) else m.stride[0]
+            p = m.padding if isinstance(m.padding, int) else m.padding[0]
+            if m.dilation not in (1, (1, 1)) or m.ceil_mode or m.return_indices:
+                raise UnsupportedModule(f"{m}")
+            x = Fn.maxpool2d(x, k, s or k, p)
+            i += 1
+        elif nm == "Upsample":
+            if m.mode != "nearest" or float(m.scale_factor if not isinstance(m.scale_factor, tuple)
+                                            else m.scale_factor[0]) != 2.0:
+                raise UnsupportedModule(f"{m}: only nearest x2 up-sampling is on the B200 path")
+            x = Fn.upsample2x(x)
+            i += 1
+        elif nm == "Sequential":
+            x = run_sequence(ctx, list(m.children()), x)
+            i += 1
+        else:
+            x = run_module(ctx, m, x)
+            i += 1
+    return x
+
+
+# ------------------------------------------------------------------------------------------------
+# classification/models.py
+# ------------------------------------------------------------------------------------------------
+def _drop_path_scale(block, n: int, device) -> Optional[torch.Tensor]:
+    dp = getattr(block, "drop_path", None)
+    if dp is None or _name(dp) == "Identity":
+        return None
+    if _name(dp) != "DropPath" or not hasattr(dp, "keep_prob"):
+        raise UnsupportedModule(f"drop path module {dp}")
+    if dp.training:
+        # same CPU-generator draw as classification/models.py:320-323 (no 1/keep rescale)
+        s = torch.bernoulli(dp.keep_prob * torch.ones((n, 1, 1, 1))).reshape(n)
+    else:
+        s = torch.full((n,), float(dp.keep_prob))
+    return s.to(device=device, dtype=torch.float32, non_blocking=True)
+
+
+def run_res_unit(ctx: ExecContext, blk, x):
+    """BottleNeckBlock.forward (models.py:277-290) / BasicBlock.forward (:203-212): the last BN, the
+    DropPath multiply, the strided zero-filled shortcut, the add and the ReLU are ONE kernel."""
+    bottleneck = hasattr(blk, "conv3")
+    convs = [blk.conv1, blk.conv2] + ([blk.conv3] if bottleneck else [])
+    bns = [blk.bn1, blk.bn2] + ([blk.bn3] if bottleneck else [])
+    r_stride = max(c.stride[0] for c in convs)
+    if convs[-1].out_channels < convs[0].in_channels:
+        raise UnsupportedModule("residual block that narrows its input")
+    scale = _drop_path_scale(blk, x.shape[0], x.device)
+    y = x
+    for conv, bn in zip(convs[:-1], bns[:-1]):
+        y = conv_bn_act(ctx, y, conv, bn, ops.ACT_RELU)
+    return conv_bn_act(ctx, y, convs[-1], bns[-1], ops.ACT_RELU, residual=x, r_stride=r_stride,
+                       sample_scale=scale)
+
+
+def run_deep_resnet(ctx: ExecContext, m, x, return_skip_vals: bool = False):
+    """DeepResNet.forward (models.py:89-103) on NHWC activations; returns NHWC tensors."""
+    if getattr(m, "version", "v1") != "v1":
+        raise UnsupportedModule("DeepResNet v2 (pre-activation) is not on the B200 path")
+    y = run_sequence(ctx, list(m.stem.children()), x)
+    skips = [y]
+    y = run_sequence(ctx, [m.max_pool], y)
+    for level in m.levels:
+        for blk in level:
+            if _name(blk) not in ("BottleNeckBlock", "BasicBlock"):
+                raise UnsupportedModule(f"residual unit {_name(blk)}")
+            y = run_res_unit(ctx, blk, y)
+        skips.append(y)
+    cls = m.classifier
+    if _name(cls) != "Identity":
+        mods = list(cls.children())
+        if [_name(c) for c in mods] != ["AdaptiveAvgPool2d", "Flatten", "Linear"]:
+            raise UnsupportedModule(f"classifier head {cls}")
+        lin = mods[2]
+        y = Fn.global_avgpool(y)
+        w4 = lin.weight.view(lin.out_features, lin.in_features, 1, 1)
+        y, _ = Fn.conv2d(y, w4, lin.bias, 1, 0)
+    return (y, skips[:-1]) if return_skip_vals else y
+
+
+# ------------------------------------------------------------------------------------------------
+# segmentation/models
+# ------------------------------------------------------------------------------------------------
+def run_conv_block(ctx, m, x):
+    return run_sequence(ctx, list(m.block.children()), x)
+
+
+def run_upconv_block(ctx, m, x):
+    return run_sequence(ctx, list(m.convup.children()), x)
+
+
+def run_attention_block(ctx, m, x, x_up, skip):
+    """AttentionBlock.forward (blocks.py:620-628)."""
+    g = run_module(ctx, _unwrap(m.gs_block), x)
+    wg_conv, wg_bn = list(m.W_g.children())
+    ws_conv, ws_bn = list(m.W_s.children())
+    psi = list(m.psi.children())
+    if [_name(c) for c in psi] != ["Conv2d", "BatchNorm2d", "Sigmoid"]:
+        raise UnsupportedModule(f"attention psi {m.psi}")
+    g1 = conv_bn_act(ctx, g, wg_conv, wg_bn, ops.ACT_NONE)
+    # relu(BN(W_s(skip)) + g1): the add + ReLU ride on the BN-apply kernel
+    p = conv_bn_act(ctx, skip, ws_conv, ws_bn, ops.ACT_RELU, residual=g1)
+    p = conv_bn_act(ctx, p, psi[0], psi[1], ops.ACT_SIGMOID)
+    return Fn.gate_concat(x_up, skip, p)
+
+
+def run_unet_encoder(ctx, m, x, return_skip_vals=False):
+    """UNet_encoder.forward (unet_models.py:200-236)."""
+    if getattr(m, "res_con", False) or getattr(m, "layer_scale", False):
+        raise UnsupportedModule("U-Net residual connections / layer scaling are not on the B200 path")
+    skips = []
+    x = run_sequence(ctx, [m.first_block], x)
+    for unit in m.down_layers:
+        for j in range(m.width):
+            x = run_module(ctx, _unwrap(unit[f"conv{j}"]), x)
+        skips.append(x)
+        if "downsampl" in unit:
+            x = run_sequence(ctx, [unit["downsampl"]], x)
+    for j in range(m.width):
+        x = run_module(ctx, _unwrap(m.bottom_block[f"conv{j}"]), x)
+    return (x, skips) if return_skip_vals else x
+
+
+def run_unet_decoder(ctx, m, x, skips: list, final_act=None):
+    """UNet_decoder.forward (unet_models.py:367-390) + the final activation of UNet.forward (:685-686).
+    Returns the fp32 NCHW prediction."""
+    if getattr(m, "res_con", False) or getattr(m, "layer_scale", False):
+        raise UnsupportedModule("U-Net residual connections / layer scaling are not on the B200 path")
+    skips = list(skips)
+    for i, unit in enumerate(m.up_layers):
+        x_up = run_module(ctx, _unwrap(unit["upsampl"]), x)
+        if i < m.skip_con_nr:
+            skip = skips.pop()
+            mix = _unwrap(unit["mixing"])
+            if _name(mix) == "ConcatBlock":
+                x = Fn.concat(x_up, skip)
+            elif _name(mix) == "AttentionBlock":
+                x = run_attention_block(ctx, mix, x, x_up, skip)
+            else:
+                raise UnsupportedModule(f"mixing block {_name(mix)}")
+        else:
+            x = x_up
+        for j in range(m.width):
+            x = run_module(ctx, _unwrap(unit[f"conv{j}"]), x)
+    fb = _unwrap(m.final_block)
+    act_name = "none" if final_act is None else _name(final_act)
+    if _name(fb) == "Conv2d" and fb.kernel_size == (1, 1) and fb.out_channels <= 8 and \
+            act_name in ("none", "Sigmoid", "Softmax", "Identity"):
+        if act_name == "Softmax" and final_act.dim != 1:
+            raise UnsupportedModule("softmax over a dimension other than 1")
+        act = {"none": 0, "Identity": 0, "Sigmoid": 1, "Softmax": 2}[act_name]
+        return Fn.final_conv_act(x, fb.weight, fb.bias, act)
+    raise UnsupportedModule(f"final block {fb} with activation {final_act}")
+
+
+def run_unet(ctx, m, x):
+    """UNet.forward (unet_models.py:681-688)."""
+    enc = _unwrap(m.encoder)
+    y, skips = run_module(ctx, enc, x, return_skip_vals=True)
+    return run_unet_decoder(ctx, m.decoder, y, skips, m.final_act)
+
+
+_RUNNERS = {
+    "DeepResNet": run_deep_resnet,
+    "UNet_encoder": run_unet_encoder,
+    "ConvBlock": run_conv_block,
+    "UpConvBlock": run_upconv_block,
+    "BottleNeckBlock": run_res_unit,
+    "BasicBlock": run_res_unit,
+    "UNet": run_unet,
+}
+
+
+def run_module(ctx, m, x, **kw):
+    m = _unwrap(m)
+    nm = _name(m)
+    if nm in _RUNNERS:
+        return _RUNNERS[nm](ctx, m, x, **kw)
+    if nm in ("Conv2d", "MaxPool2d", "Upsample", "Sequential", "Identity"):
+        return run_sequence(ctx, [m], x)
+    raise UnsupportedModule(f"module {nm} has no B200 implementation (no PyTorch fallback on this path)")
+
+
+# ------------------------------------------------------------------------------------------------
+# public entry point
+# ------------------------------------------------------------------------------------------------
+def _require_cuda(x):
+    if not x.is_cuda:
+        raise RuntimeError("medsegpretrainimagenet_b200: the converted model runs on CUDA (sm_100a) "
+                           "tensors only; there is no CPU fallback")
+
+
+def _forward_deep_resnet(self, x, return_skip_vals=False, *args, **kwargs):
+    _require_cuda(x)
+    ctx = self._msp_ctx
+    out = run_deep_resnet(ctx, self, Fn.to_nhwc(x), return_skip_vals=return_skip_vals)
+    y, skips = out if return_skip_vals else (out, None)
+    if _name(self.classifier) != "Identity":
+        y = Fn.to_nchw(y).flatten(1)
+    else:
+        y = Fn.to_nchw(y)
+    if return_skip_vals:
+        return y, [Fn.to_nchw(s) for s in skips]
+    return y
+
+
+def _forward_unet_encoder(self, x, return_skip_vals=False):
+    _require_cuda(x)
+    out = run_unet_encoder(self._msp_ctx, self, Fn.to_nhwc(x), return_skip_vals=return_skip_vals)
+    if return_skip_vals:
+        return Fn.to_nchw(out[0]), [Fn.to_nchw(s) for s in out[1]]
+    return Fn.to_nchw(out)
+
+
+def _forward_unet(self, x):
+    _require_cuda(x)
+    return run_unet(self._msp_ctx, self, Fn.to_nhwc(x))
+
+
+_TOP_LEVEL = {"DeepResNet": _forward_deep_resnet, "UNet_encoder": _forward_unet_encoder,
+              "UNet": _forward_unet}
+
+
+def convert(model: nn.Module, group=None) -> nn.Module:
+    """Route `model`'s forward through the B200 kernels (in place; returns `model`).
+
+    `model` may be the reference's `model.Model` wrapper or the bare network.  Parameters, buffers and
+    the module tree are shared, so state dicts, optimizers and checkpoints are unaffected.
+    `group`: torch.distributed process group whose ranks synchronise BatchNorm statistics."""
+    inner = _unwrap(model)
+    nm = _name(inner)
+    if nm not in _TOP_LEVEL:
+        raise UnsupportedModule(f"cannot convert top-level module {nm}")
+    inner._msp_ctx = ExecContext(group)
+    inner.forward = types.MethodType(_TOP_LEVEL[nm], inner)
+    inner._msp_converted = True
+    return model
+
+
+def is_converted(model: nn.Module) -> bool:
+    return bool(getattr(_unwrap(model), "_msp_converted", False))

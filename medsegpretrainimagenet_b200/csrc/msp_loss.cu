@@ -275,7 +275,8 @@ __global__ void dice_finalize_kernel(const double* __restrict__ sums, int G, int
 __global__ void dice_grad_kernel(const float* __restrict__ prob, const long long* __restrict__ mask,
                                  int Cp, long long HW, int two_class, int label_offset, int batchwise,
                                  const float* __restrict__ coef, float gscale,
-                                 float* __restrict__ dprob) {
+                                 const float* __restrict__ gdev, float* __restrict__ dprob) {
+  gscale *= gdev ? __ldg(gdev) : 1.f;
   const int n = blockIdx.y;
   const int Ceff = two_class ? 2 : Cp;
   const int g = batchwise ? 0 : n;
@@ -313,7 +314,7 @@ __device__ __forceinline__ void block_sum_to(double v, double* out) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (lane == 0) redd[warp] = v;
   __syncthreads();
-  if (threadIdx.x == 0) {
+  if (threadIdx.x == 0 && out != nullptr) {
     double a = 0.0;
     for (int w = 0; w < (int)(blockDim.x >> 5); ++w) a += redd[w];
     atomicAdd(out, a);
@@ -323,7 +324,9 @@ __device__ __forceinline__ void block_sum_to(double v, double* out) {
 // loss_sum (double) += sum_pix -sum_c clamp(nan_to_num(log p_c), -100) * t_c ; dprob = gscale * dL/dp
 __global__ void ce_prob_kernel(const float* __restrict__ prob, const long long* __restrict__ label,
                                int C, long long HW, float lo, float hi, int smooth_on, float gscale,
-                               double* __restrict__ loss_sum, float* __restrict__ dprob) {
+                               const float* __restrict__ gdev, double* __restrict__ loss_sum,
+                               float* __restrict__ dprob) {
+  gscale *= gdev ? __ldg(gdev) : 1.f;
   const int n = blockIdx.y;
   const float* pn = prob + (long long)n * C * HW;
   float* dn = dprob ? dprob + (long long)n * C * HW : nullptr;
@@ -342,7 +345,12 @@ __global__ void ce_prob_kernel(const float* __restrict__ prob, const long long* 
       else if (isinf(lp)) { lp = lp > 0 ? 3.4028234664e38f : -3.4028234664e38f; live = false; }
       if (lp < -100.f) { lp = -100.f; live = false; }
       acc = fmaf(-lp, t, acc);
-      if (dn) dn[(long long)c * HW + i] = live ? -t / p * gscale : 0.f;
+      if (dn) {
+        // autograd of log -> nan_to_num -> clamp: 0 * (1/p) where the chain is cut, i.e. NaN at p == 0 / NaN
+        float gr = live ? -t / p * gscale : 0.f;
+        if (p == 0.f || p != p) gr = __int_as_float(0x7fc00000);
+        dn[(long long)c * HW + i] = gr;
+      }
     }
   }
   block_sum_to((double)acc, loss_sum);
@@ -351,8 +359,9 @@ __global__ void ce_prob_kernel(const float* __restrict__ prob, const long long* 
 // mode 0: reference BCELoss (no clamp, autograd gradient); mode 1: torch.nn.BCELoss (log clamped at
 // -100, gradient (p - y) / max(p(1-p), 1e-12))
 __global__ void bce_kernel(const float* __restrict__ prob, const float* __restrict__ target,
-                           long long numel, int clamp_log, float gscale, double* __restrict__ loss_sum,
-                           float* __restrict__ dprob) {
+                           long long numel, int clamp_log, float gscale, const float* __restrict__ gdev,
+                           double* __restrict__ loss_sum, float* __restrict__ dprob) {
+  gscale *= gdev ? __ldg(gdev) : 1.f;
   float acc = 0.f;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < numel;
        i += (long long)gridDim.x * blockDim.x) {
@@ -374,8 +383,9 @@ __global__ void bce_kernel(const float* __restrict__ prob, const float* __restri
 
 // one block per row: F.cross_entropy(logits, label, label_smoothing) summed over rows
 __global__ void softmax_ce_kernel(const float* __restrict__ logits, const long long* __restrict__ label,
-                                  int C, float smooth, float gscale, double* __restrict__ loss_sum,
-                                  float* __restrict__ dlogits) {
+                                  int C, float smooth, float gscale, const float* __restrict__ gdev,
+                                  double* __restrict__ loss_sum, float* __restrict__ dlogits) {
+  gscale *= gdev ? __ldg(gdev) : 1.f;
   const int n = blockIdx.x;
   const float* z = logits + (long long)n * C;
   __shared__ float redf[8];
@@ -422,7 +432,7 @@ __global__ void softmax_ce_kernel(const float* __restrict__ logits, const long l
     // -(1-s) logp[y] - s/C sum_c logp[c]
     const float nll = (y >= 0 && y < C) ? lse - z[y] : 0.f;
     const float mean_nlp = lse - tz / (float)C;
-    atomicAdd(loss_sum, (double)((1.f - smooth) * nll + smooth * mean_nlp));
+    if (loss_sum) atomicAdd(loss_sum, (double)((1.f - smooth) * nll + smooth * mean_nlp));
   }
   if (dlogits) {
     float* d = dlogits + (long long)n * C;
@@ -503,60 +513,68 @@ extern "C" int msp_final_conv_act_bwd(const void* x, int N, int H, int W, int C,
   return MSP_OK;
 }
 
-extern "C" int msp_dice_fwd(const float* prob, const int64_t* mask, int N, int Cp, long long HW,
-                            int two_class, int label_offset, int batchwise, int class_start, float eps,
-                            double* sums, float* coef, float* loss, void* stream) {
-  MSP_REQUIRE(prob && mask && sums && loss, "dice_fwd: null pointer");
+extern "C" int msp_dice_sums(const float* prob, const int64_t* mask, int N, int Cp, long long HW,
+                             int two_class, int label_offset, int batchwise, double* sums, void* stream) {
+  MSP_REQUIRE(prob && mask && sums, "dice_sums: null pointer");
   const int Ceff = two_class ? 2 : Cp;
-  MSP_REQUIRE(Cp >= 1 && Ceff <= kMaxDiceC && (!two_class || Cp == 1), "dice_fwd: %d classes unsupported", Cp);
-  MSP_REQUIRE(class_start >= 0 && class_start < Ceff, "dice_fwd: class_start");
-  MSP_REQUIRE(N > 0 && HW > 0, "dice_fwd: empty prediction");
+  MSP_REQUIRE(Cp >= 1 && Ceff <= kMaxDiceC && (!two_class || Cp == 1), "dice_sums: %d classes unsupported", Cp);
+  MSP_REQUIRE(N > 0 && HW > 0, "dice_sums: empty prediction");
   const int G = batchwise ? 1 : N;
   MSP_CHECK_CUDA(cudaMemsetAsync(sums, 0, sizeof(double) * G * Ceff * 3, ST));
   dim3 grid(strip_grid(HW, 256, N), N);
   dice_sums_kernel<<<grid, 256, 0, ST>>>(prob, (const long long*)mask, Cp, HW, two_class, label_offset,
                                          batchwise, sums);
   MSP_CHECK_LAUNCH();
+  msp_count_launch(1);
+  return MSP_OK;
+}
+
+extern "C" int msp_dice_finalize(const double* sums, int G, int Ceff, int class_start, float eps,
+                                 float* coef, float* loss, void* stream) {
+  MSP_REQUIRE(sums && (coef || loss), "dice_finalize: null pointer");
+  MSP_REQUIRE(G >= 1 && Ceff >= 1 && Ceff <= kMaxDiceC && class_start >= 0 && class_start < Ceff,
+              "dice_finalize: bad class range");
   dice_finalize_kernel<<<1, 32, 0, ST>>>(sums, G, Ceff, class_start, eps, loss, coef);
   MSP_CHECK_LAUNCH();
-  msp_count_launch(2);
+  msp_count_launch(1);
   return MSP_OK;
 }
 
 extern "C" int msp_dice_bwd(const float* prob, const int64_t* mask, int N, int Cp, long long HW,
                             int two_class, int label_offset, int batchwise, const float* coef,
-                            float gscale, float* dprob, void* stream) {
+                            float gscale, const float* gscale_dev, float* dprob, void* stream) {
   MSP_REQUIRE(prob && mask && coef && dprob, "dice_bwd: null pointer");
   const int Ceff = two_class ? 2 : Cp;
   MSP_REQUIRE(Cp >= 1 && Ceff <= kMaxDiceC, "dice_bwd: %d classes unsupported", Cp);
   dim3 grid(strip_grid(HW, 256, N), N);
   dice_grad_kernel<<<grid, 256, 0, ST>>>(prob, (const long long*)mask, Cp, HW, two_class, label_offset,
-                                         batchwise, coef, gscale, dprob);
+                                         batchwise, coef, gscale, gscale_dev, dprob);
   MSP_CHECK_LAUNCH();
   msp_count_launch(1);
   return MSP_OK;
 }
 
 extern "C" int msp_ce_prob_fwd_bwd(const float* prob, const int64_t* label, int N, int C, long long HW,
-                                   float smooth, float gscale, double* loss_sum, float* dprob,
-                                   void* stream) {
-  MSP_REQUIRE(prob && label && loss_sum, "ce_prob: null pointer");
+                                   float smooth, float gscale, const float* gscale_dev,
+                                   double* loss_sum, float* dprob, void* stream) {
+  MSP_REQUIRE(prob && label && (loss_sum || dprob), "ce_prob: null pointer");
   MSP_REQUIRE(N > 0 && C > 0 && HW > 0, "ce_prob: empty prediction");
-  MSP_CHECK_CUDA(cudaMemsetAsync(loss_sum, 0, sizeof(double), ST));
+  if (loss_sum) MSP_CHECK_CUDA(cudaMemsetAsync(loss_sum, 0, sizeof(double), ST));
   dim3 grid(strip_grid(HW, 256, N), N);
   const float lo = smooth / (float)C, hi = 1.f - smooth / (float)C;
   ce_prob_kernel<<<grid, 256, 0, ST>>>(prob, (const long long*)label, C, HW, lo, hi, smooth != 0.f,
-                                       gscale, loss_sum, dprob);
+                                       gscale, gscale_dev, loss_sum, dprob);
   MSP_CHECK_LAUNCH();
   msp_count_launch(1);
   return MSP_OK;
 }
 
 extern "C" int msp_bce_fwd_bwd(const float* prob, const float* target, long long numel, int clamp_log,
-                               float gscale, double* loss_sum, float* dprob, void* stream) {
-  MSP_REQUIRE(prob && target && loss_sum && numel > 0, "bce: bad arguments");
-  MSP_CHECK_CUDA(cudaMemsetAsync(loss_sum, 0, sizeof(double), ST));
-  bce_kernel<<<strip_grid(numel, 256, 1), 256, 0, ST>>>(prob, target, numel, clamp_log, gscale, loss_sum,
+                               float gscale, const float* gscale_dev, double* loss_sum, float* dprob,
+                               void* stream) {
+  MSP_REQUIRE(prob && target && (loss_sum || dprob) && numel > 0, "bce: bad arguments");
+  if (loss_sum) MSP_CHECK_CUDA(cudaMemsetAsync(loss_sum, 0, sizeof(double), ST));
+  bce_kernel<<<strip_grid(numel, 256, 1), 256, 0, ST>>>(prob, target, numel, clamp_log, gscale, gscale_dev, loss_sum,
                                                         dprob);
   MSP_CHECK_LAUNCH();
   msp_count_launch(1);
@@ -564,11 +582,11 @@ extern "C" int msp_bce_fwd_bwd(const float* prob, const float* target, long long
 }
 
 extern "C" int msp_softmax_ce_fwd_bwd(const float* logits, const int64_t* label, int N, int C,
-                                      float smooth, float gscale, double* loss_sum, float* dlogits,
-                                      void* stream) {
-  MSP_REQUIRE(logits && label && loss_sum && N > 0 && C > 0, "softmax_ce: bad arguments");
-  MSP_CHECK_CUDA(cudaMemsetAsync(loss_sum, 0, sizeof(double), ST));
-  softmax_ce_kernel<<<N, 256, 0, ST>>>(logits, (const long long*)label, C, smooth, gscale, loss_sum,
+                                      float smooth, float gscale, const float* gscale_dev,
+                                      double* loss_sum, float* dlogits, void* stream) {
+  MSP_REQUIRE(logits && label && (loss_sum || dlogits) && N > 0 && C > 0, "softmax_ce: bad arguments");
+  if (loss_sum) MSP_CHECK_CUDA(cudaMemsetAsync(loss_sum, 0, sizeof(double), ST));
+  softmax_ce_kernel<<<N, 256, 0, ST>>>(logits, (const long long*)label, C, smooth, gscale, gscale_dev, loss_sum,
                                        dlogits);
   MSP_CHECK_LAUNCH();
   msp_count_launch(1);

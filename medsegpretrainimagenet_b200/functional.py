@@ -1,0 +1,313 @@
+"""torch.autograd.Function nodes over the C-ABI kernels.
+
+Every node consumes / produces bf16 NHWC activations (see ops.py) except the two boundary nodes
+(`to_nhwc`, `to_nchw`) and the segmentation head, which speak the reference's fp32 NCHW.  Parameters
+stay the reference's fp32 `nn.Parameter`s: gradients are produced in their native OIHW fp32 layout so
+`param.grad` is what `clip_grad_norm_` / the optimizer of train_model.py:93-107 expect.
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+import torch.distributed as dist
+
+from . import ops
+
+
+def _allreduce_sum(t: torch.Tensor, group) -> None:
+    """SyncBN / global-Dice exchange: a small NCCL all-reduce, only when a process group is active."""
+    if group is not None and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+
+
+# ------------------------------------------------------------------------------------------------
+# boundary
+# ------------------------------------------------------------------------------------------------
+class _ToNHWC(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        ctx.c = x.shape[1]
+        return ops.nchw_to_nhwc(x)
+
+    @staticmethod
+    def backward(ctx, dy):
+        return ops.nhwc_to_nchw(dy.contiguous() if dy.stride(3) != 1 else dy, ctx.c)
+
+
+class _ToNCHW(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, c):
+        ctx.cpad = x.shape[3]
+        return ops.nhwc_to_nchw(x, c)
+
+    @staticmethod
+    def backward(ctx, dy):
+        return ops.nchw_to_nhwc(dy, ctx.cpad), None
+
+
+def to_nhwc(x: torch.Tensor) -> torch.Tensor:
+    return _ToNHWC.apply(x)
+
+
+def to_nchw(x: torch.Tensor, c: Optional[int] = None) -> torch.Tensor:
+    return _ToNCHW.apply(x, x.shape[3] if c is None else c)
+
+
+# ------------------------------------------------------------------------------------------------
+# convolution
+# ------------------------------------------------------------------------------------------------
+class _Conv(torch.autograd.Function):
+    """y = conv2d(x, weight, bias) (+ReLU); optionally returns the fused per-channel (sum, sum of
+    squares) of y as a second, non-differentiable output."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, stride, padding, relu, want_stats, out):
+        k, c_true, kh, kw = weight.shape
+        n, h, w, c8 = x.shape
+        ho, wo, pt, pl = ops.conv_out_size(h, w, kh, kw, stride, padding)
+        need_dx = ctx.needs_input_grad[0]
+        wf, wd = ops.pack_weights(weight, need_dgrad=need_dx)
+        stats = torch.zeros((2, k), dtype=torch.float32, device=x.device) if want_stats else None
+        y = ops.conv_fprop(x, wf, bias.detach() if bias is not None else None, k, kh, kw, stride, pt, pl,
+                           ho, wo, relu=relu, out=out, stats=stats, c_true=c_true)
+        ctx.geom = (kh, kw, stride, pt, pl, c_true, relu, bias is not None)
+        ctx.x_shape = tuple(x.shape)
+        ctx.save_for_backward(x, wd, y if relu else None)
+        if want_stats:
+            ctx.mark_non_differentiable(stats)
+            return y, stats
+        return y, None
+
+    @staticmethod
+    def backward(ctx, dy, _dstats):
+        kh, kw, stride, pt, pl, c_true, relu, has_bias = ctx.geom
+        x, wd, y = ctx.saved_tensors
+        if dy.stride(3) != 1:
+            dy = dy.contiguous()
+        if relu:
+            dy = ops.relu_bwd(y, dy)
+        dx = dw = db = None
+        if ctx.needs_input_grad[0]:
+            dx = ops.conv_dgrad(dy, wd, ctx.x_shape, kh, kw, stride, pt, pl, c_true=c_true)
+        if ctx.needs_input_grad[1]:
+            dw = ops.conv_wgrad(x, dy, c_true, kh, kw, stride, pt, pl)
+        if has_bias and ctx.needs_input_grad[2]:
+            db = ops.channel_sum(dy)
+        return dx, dw, db, None, None, None, None, None
+
+
+def conv2d(x, weight, bias=None, stride=1, padding=0, relu=False, want_stats=False, out=None):
+    return _Conv.apply(x, weight, bias, stride, padding, relu, want_stats, out)
+
+
+# ------------------------------------------------------------------------------------------------
+# BatchNorm + activation + residual + per-sample scale
+# ------------------------------------------------------------------------------------------------
+class _BnAct(torch.autograd.Function):
+    """out = act( s[n] * BN(x) + residual ).  Train mode: batch statistics from `stats` (the conv
+    epilogue's sums), running buffers updated in place like nn.BatchNorm2d (momentum, unbiased
+    variance).  Eval mode: running statistics."""
+
+    @staticmethod
+    def forward(ctx, x, stats, gamma, beta, residual, sample_scale, running_mean, running_var, training,
+                momentum, eps, act, r_stride, group, conv_bias):
+        n, h, w, c = x.shape
+        count = n * h * w
+        if training:
+            if group is not None and dist.is_initialized() and dist.get_world_size(group) > 1:
+                # SyncBN: [2C] fp32 sums over NCCL; every rank holds the same per-GPU batch (weak scaling)
+                _allreduce_sum(stats, group)
+                count = count * dist.get_world_size(group)
+            mi = ops.bn_finalize(stats, count, eps, momentum, running_mean, running_var)
+        else:
+            mi = ops.bn_eval_stats(running_mean, running_var, eps)
+        y = ops.bn_act_fwd(x, mi, gamma.detach() if gamma is not None else None,
+                           beta.detach() if beta is not None else None, act, residual=residual,
+                           r_stride=r_stride, sample_scale=sample_scale)
+        ctx.cfg = (training, act, r_stride, count, group, residual is not None,
+                   tuple(residual.shape) if residual is not None else None)
+        ctx.save_for_backward(x, y, mi, gamma, sample_scale)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        training, act, r_stride, count, group, has_res, res_shape = ctx.cfg
+        x, y, mi, gamma, sscale = ctx.saved_tensors
+        n, h, w, c = x.shape
+        if dy.stride(3) != 1 or dy.stride(2) != y.stride(2):
+            full = torch.empty((n, h, w, y.stride(2)), dtype=dy.dtype, device=dy.device)[..., :c]
+            dy = ops.copy_channels(dy if dy.stride(3) == 1 else dy.contiguous(), full)
+        sums = ops.bn_act_bwd_reduce(x, y, dy, mi, act, sample_scale=sscale)
+        dbeta, dgamma = sums[0].clone(), sums[1].clone()
+        dbias = None
+        if ctx.needs_input_grad[14]:
+            # gradient of the producing conv's bias = sum over pixels of dx.  Train mode: BatchNorm
+            # removes the mean, so it is exactly zero; eval mode: gamma * invstd * sum(g).  Either way
+            # it comes from the fp32 sums instead of a second pass over the bf16 dx.
+            if training:
+                dbias = torch.zeros_like(dbeta)
+            else:
+                dbias = dbeta * mi[1] if gamma is None else dbeta * mi[1] * gamma.detach()
+        if training:
+            _allreduce_sum(sums, group)
+        else:
+            # frozen statistics: dx = gamma * invstd * s * g (no mean / projection terms)
+            sums = torch.zeros_like(sums)
+        dres = None
+        need_res = has_res and ctx.needs_input_grad[4]
+        if need_res:
+            rn, rh, rw, rc = res_shape
+            dres = ops.new_act(rn, rh, rw, rc, x.device, zero=(r_stride > 1 or rc > c))
+        dx = ops.bn_act_bwd_apply(x, y, dy, mi, gamma.detach() if gamma is not None else None, act, sums,
+                                  count, dres=dres, r_stride=r_stride, sample_scale=sscale)
+        if not ctx.needs_input_grad[0]:
+            dx = None
+        return (dx, None, dgamma if gamma is not None and ctx.needs_input_grad[2] else None,
+                dbeta if ctx.needs_input_grad[3] else None, dres, None, None, None, None, None, None, None,
+                None, None, dbias)
+
+
+def bn_act(x, stats, bn: torch.nn.BatchNorm2d, act=ops.ACT_NONE, residual=None, r_stride=1,
+           sample_scale=None, group=None, conv_bias=None):
+    training = bn.training or bn.running_mean is None
+    momentum = 0.1 if bn.momentum is None else bn.momentum
+    if training and bn.num_batches_tracked is not None:
+        bn.num_batches_tracked.add_(1)
+    return _BnAct.apply(x, stats, bn.weight, bn.bias, residual, sample_scale,
+                        bn.running_mean if bn.track_running_stats else None,
+                        bn.running_var if bn.track_running_stats else None, training, momentum, bn.eps,
+                        act, r_stride, group, conv_bias)
+
+
+# ------------------------------------------------------------------------------------------------
+# pooling / resampling / concat / gate
+# ------------------------------------------------------------------------------------------------
+class _MaxPool(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, k, stride, pad):
+        y, idx = ops.maxpool_fwd(x, k, stride, pad, want_idx=ctx.needs_input_grad[0])
+        ctx.cfg = (tuple(x.shape), k, stride, pad)
+        ctx.save_for_backward(idx)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x_shape, k, stride, pad = ctx.cfg
+        (idx,) = ctx.saved_tensors
+        if dy.stride(3) != 1:
+            dy = dy.contiguous()
+        return ops.maxpool_bwd(idx, dy, x_shape, k, stride, pad), None, None, None
+
+
+def maxpool2d(x, k, stride, pad):
+    return _MaxPool.apply(x, k, stride, pad)
+
+
+class _Upsample2x(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        return ops.upsample2x_fwd(x)
+
+    @staticmethod
+    def backward(ctx, dy):
+        if dy.stride(3) != 1:
+            dy = dy.contiguous()
+        return ops.upsample2x_bwd(dy)
+
+
+def upsample2x(x):
+    return _Upsample2x.apply(x)
+
+
+class _AvgPool(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        ctx.hw = (x.shape[1], x.shape[2])
+        return ops.avgpool_fwd(x)
+
+    @staticmethod
+    def backward(ctx, dy):
+        return ops.avgpool_bwd(dy, *ctx.hw)
+
+
+def global_avgpool(x):
+    return _AvgPool.apply(x)
+
+
+class _Concat(torch.autograd.Function):
+    """torch.cat along channels (blocks.py:628,635).  Backward hands out channel-slice views of dy."""
+
+    @staticmethod
+    def forward(ctx, a, b):
+        n, h, w, ca = a.shape
+        cb = b.shape[3]
+        out = ops.new_act(n, h, w, ca + cb, a.device)
+        ops.copy_channels(a, out[..., :ca])
+        ops.copy_channels(b, out[..., ca:])
+        ctx.ca = ca
+        return out
+
+    @staticmethod
+    def backward(ctx, dy):
+        return dy[..., : ctx.ca], dy[..., ctx.ca:]
+
+
+def concat(a, b):
+    return _Concat.apply(a, b)
+
+
+class _GateConcat(torch.autograd.Function):
+    """cat(x_up, skip * up2(p)) (blocks.py:625-628): the product is written straight into its slice."""
+
+    @staticmethod
+    def forward(ctx, x_up, skip, p):
+        n, h, w, ca = x_up.shape
+        cb = skip.shape[3]
+        out = ops.new_act(n, h, w, ca + cb, x_up.device)
+        ops.copy_channels(x_up, out[..., :ca])
+        ops.gate_mul_fwd(skip, p, out=out[..., ca:])
+        ctx.ca = ca
+        ctx.save_for_backward(skip, p)
+        return out
+
+    @staticmethod
+    def backward(ctx, dy):
+        skip, p = ctx.saved_tensors
+        dskip, dp = ops.gate_mul_bwd(skip, p, dy[..., ctx.ca:])
+        return dy[..., : ctx.ca], dskip, dp
+
+
+def gate_concat(x_up, skip, p):
+    return _GateConcat.apply(x_up, skip, p)
+
+
+# ------------------------------------------------------------------------------------------------
+# segmentation head: 1x1 conv (<= 8 classes) + sigmoid / softmax, fp32 NCHW out
+# ------------------------------------------------------------------------------------------------
+class _FinalConvAct(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, weight, bias, act):
+        k = weight.shape[0]
+        w2d = weight.detach().reshape(k, -1)
+        c_true = w2d.shape[1]
+        if c_true != x.shape[3]:  # input channels stored zero-padded to a multiple of 8
+            w2d = torch.nn.functional.pad(w2d, (0, x.shape[3] - c_true))
+        w2d = w2d.contiguous()
+        prob, _ = ops.final_conv_act_fwd(x, w2d, bias.detach() if bias is not None else None, act)
+        ctx.cfg = (act, c_true, tuple(weight.shape), bias is not None)
+        ctx.save_for_backward(x, w2d, prob)
+        return prob
+
+    @staticmethod
+    def backward(ctx, dprob):
+        act, c_true, wshape, has_bias = ctx.cfg
+        x, w2d, prob = ctx.saved_tensors
+        dx, dw, db = ops.final_conv_act_bwd(x, w2d, act, prob, dprob.contiguous(),
+                                            need_dx=ctx.needs_input_grad[0], has_bias=has_bias)
+        dw = dw[:, :c_true].reshape(wshape)
+        return dx, dw, db, None
+
+
+def final_conv_act(x, weight, bias, act: int):
+    return _FinalConvAct.apply(x, weight, bias, act)

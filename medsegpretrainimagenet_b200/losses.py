@@ -1,0 +1,162 @@
+"""Loss criteria with the reference's constructor signatures and call contract
+(`criterion(prediction, target) -> 0-dim tensor` carrying an autograd graph, wrapped by loss/loss.py:69-95
+which calls `.item()` and then `.backward()`), backed by the fused kernels of csrc/msp_loss.cu.
+
+Usable from YAML as `medsegpretrainimagenet_b200.losses.DiceLoss` etc., or swapped in for the
+reference's criteria by `patch.install()`.
+"""
+from __future__ import annotations
+
+import torch
+import torch.distributed as dist
+from torch import nn
+
+from . import ops
+
+
+def _world(group) -> int:
+    if group is not None and dist.is_initialized():
+        return dist.get_world_size(group)
+    return 1
+
+
+def _need_cuda(t, what):
+    if not t.is_cuda:
+        raise RuntimeError(f"{what}: CUDA tensors only (the B200 path has no CPU fallback)")
+
+
+class _Dice(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, prob, mask, two_class, label_offset, batchwise, class_start, eps, group):
+        sums = ops.dice_sums(prob, mask, two_class, label_offset, batchwise)
+        world = _world(group)
+        if batchwise and world > 1:
+            # a ratio of GLOBAL sums: 3*C doubles over NCCL
+            dist.all_reduce(sums, group=group)
+        loss, coef = ops.dice_finalize(sums, class_start, eps)
+        ctx.cfg = (two_class, label_offset, batchwise, world if batchwise else 1)
+        ctx.save_for_backward(prob, mask, coef)
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        two_class, label_offset, batchwise, world = ctx.cfg
+        prob, mask, coef = ctx.saved_tensors
+        # gradient averaging over ranks follows; the global-ratio gradient is a SUM over ranks
+        dprob = ops.dice_bwd(prob, mask, two_class, label_offset, batchwise, coef, gscale=float(world),
+                             gscale_dev=g.contiguous())
+        return dprob, None, None, None, None, None, None, None
+
+
+class DiceLoss(nn.Module):
+    """segmentation/losses/losses.py:11-58.  `prediction` (N, C, *spatial) fp32 probabilities, `mask`
+    (N, 1, *spatial) integer labels."""
+
+    def __init__(self, batchwise=True, include_background=True, smoothing_term=1e-5, apply_softmax=False,
+                 group=None, *args, **kwargs):
+        super().__init__()
+        if apply_softmax:
+            raise NotImplementedError("DiceLoss(apply_softmax=True): apply the softmax as the model's final "
+                                      "activation (fused into the head kernel) instead")
+        self.eps = smoothing_term
+        self.batchwise = bool(batchwise)
+        self.include_background = include_background
+        self.group = group
+
+    def forward(self, prediction, mask, *args, **kwargs):
+        _need_cuda(prediction, "DiceLoss")
+        prediction = prediction.contiguous()
+        if prediction.dtype != torch.float32:
+            prediction = prediction.float()
+        n_classes = prediction.shape[1]
+        two_class, label_offset, class_start = False, 0, int(not self.include_background)
+        if n_classes == 1:
+            if self.include_background:
+                two_class = True                      # [1 - p, p]            (losses.py:46-49)
+            else:
+                label_offset, class_start = 1, 0      # p against (mask == 1)  (losses.py:50-52)
+        mask = mask.reshape(prediction.shape[0], -1)
+        if mask.dtype != torch.int64:
+            mask = mask.long()
+        return _Dice.apply(prediction, mask.contiguous(), two_class, label_offset, self.batchwise,
+                           class_start, float(self.eps), self.group)
+
+
+class _SumLoss(torch.autograd.Function):
+    """Shared shape of the mean-reduced losses: forward = one reduction kernel, backward = the same
+    kernel emitting the gradient scaled by autograd's incoming (device-resident) factor."""
+
+    @staticmethod
+    def forward(ctx, pred, target, kind, arg, scale):
+        if kind == "ce_prob":
+            ls, _ = ops.ce_prob(pred, target, arg)
+        elif kind == "bce":
+            ls, _ = ops.bce(pred, target, arg)
+        else:
+            ls, _ = ops.softmax_ce(pred, target, arg)
+        ctx.cfg = (kind, arg, scale)
+        ctx.save_for_backward(pred, target)
+        return ops.sum_to_mean(ls, scale)
+
+    @staticmethod
+    def backward(ctx, g):
+        kind, arg, scale = ctx.cfg
+        pred, target = ctx.saved_tensors
+        g = g.contiguous()
+        if kind == "ce_prob":
+            _, d = ops.ce_prob(pred, target, arg, gscale=scale, gscale_dev=g, want_loss=False, want_grad=True)
+        elif kind == "bce":
+            _, d = ops.bce(pred, target, arg, gscale=scale, gscale_dev=g, want_loss=False, want_grad=True)
+        else:
+            _, d = ops.softmax_ce(pred, target, arg, gscale=scale, gscale_dev=g, want_loss=False,
+                                  want_grad=True)
+        return d, None, None, None, None
+
+
+def _f32c(t):
+    t = t.contiguous()
+    return t if t.dtype == torch.float32 else t.float()
+
+
+class CrossEntropyLoss(nn.Module):
+    """classification/losses.py:13-40: `apply_softmax=True` -> F.cross_entropy(logits (N, C),
+    label (N, 1), label_smoothing); `apply_softmax=False` -> pixel-wise CE on probabilities with the
+    log floor of -100 and the clamped one-hot target."""
+
+    def __init__(self, label_smoothing=0.0, apply_softmax=True, *args, **kwargs):
+        super().__init__()
+        if label_smoothing >= 0.5:
+            raise ValueError("Label smoothing value should be <0.5")
+        self.smooth = float(label_smoothing)
+        self.apply_softmax = apply_softmax
+
+    def forward(self, prediction, label, *args, **kwargs):
+        _need_cuda(prediction, "CrossEntropyLoss")
+        prediction = _f32c(prediction)
+        if self.apply_softmax:
+            if prediction.dim() != 2:
+                raise NotImplementedError("softmax cross entropy is implemented for (N, C) logits")
+            lab = label.squeeze(1).long().contiguous()
+            return _SumLoss.apply(prediction, lab, "softmax_ce", self.smooth, 1.0 / prediction.shape[0])
+        lab = label.flatten(1).long().contiguous()
+        n_pix = prediction.shape[0] * prediction[0, 0].numel()
+        return _SumLoss.apply(prediction, lab, "ce_prob", self.smooth, 1.0 / n_pix)
+
+
+class BCELoss(nn.Module):
+    """classification/losses.py:4-11 (`torch_semantics=False`: plain logs) or torch.nn.BCELoss
+    (`torch_semantics=True`, the framework default loss, utils/default_dict.py:10)."""
+
+    def __init__(self, reduction="mean", torch_semantics=False, *args, **kwargs):
+        super().__init__()
+        if reduction not in ("mean", "sum"):
+            raise NotImplementedError(f"BCELoss reduction {reduction!r}")
+        self.reduction = reduction
+        self.clamp = int(bool(torch_semantics))
+
+    def forward(self, prediction, label, *args, **kwargs):
+        _need_cuda(prediction, "BCELoss")
+        prediction = _f32c(prediction)
+        label = _f32c(label.reshape(prediction.shape))
+        scale = 1.0 / prediction.numel() if self.reduction == "mean" else 1.0
+        return _SumLoss.apply(prediction, label, "bce", self.clamp, scale)

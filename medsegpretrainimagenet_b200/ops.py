@@ -101,11 +101,41 @@ def conv_out_size(h: int, w: int, kh: int, kw: int, stride: int, padding) -> Tup
     return (h + 2 * ph - kh) // stride + 1, (w + 2 * pw - kw) // stride + 1, ph, pw
 
 
+# Optional per-call device timing of the convolution kernels (bench.py roofline): when a list is
+# installed, every conv call appends (kind, algorithmic_flops, start_event, end_event), the events being
+# recorded on the launching stream.
+_CONV_TIMELINE = None
+
+
+def set_conv_timeline(lst):
+    global _CONV_TIMELINE
+    _CONV_TIMELINE = lst
+
+
+class _timed:
+    def __init__(self, kind, flops):
+        self.kind, self.flops = kind, flops
+
+    def __enter__(self):
+        if _CONV_TIMELINE is not None:
+            self.e0 = torch.cuda.Event(enable_timing=True)
+            self.e1 = torch.cuda.Event(enable_timing=True)
+            self.e0.record()
+        return self
+
+    def __exit__(self, *exc):
+        if _CONV_TIMELINE is not None:
+            self.e1.record()
+            _CONV_TIMELINE.append((self.kind, self.flops, self.e0, self.e1))
+        return False
+
+
 def _conv_desc(n, h, w, c, x_cs, ho, wo, k, y_cs, kh, kw, stride, pad_t, pad_l, relu=0) -> ConvDesc:
     return ConvDesc(n, h, w, c, x_cs, ho, wo, k, y_cs, kh, kw, stride, pad_t, pad_l, relu)
 
 
-def conv_fprop(x, wf, bias, k, kh, kw, stride, pad_t, pad_l, ho, wo, relu=False, out=None, stats=None):
+def conv_fprop(x, wf, bias, k, kh, kw, stride, pad_t, pad_l, ho, wo, relu=False, out=None, stats=None,
+               c_true=None):
     """y = conv(x, w) [+ bias] [ReLU]; if `stats` (fp32 [2, K], zeroed by the caller) is given the
     per-channel sum / sum of squares of y are accumulated into it (BatchNorm batch statistics)."""
     n, h, w, c, x_cs = _chk_nhwc(x, "conv_fprop(x)")
@@ -117,11 +147,12 @@ def conv_fprop(x, wf, bias, k, kh, kw, stride, pad_t, pad_l, ho, wo, relu=False,
     s1 = s2 = None
     if stats is not None:
         s1, s2 = stats[0].data_ptr(), stats[1].data_ptr()
-    call("msp_conv_fprop", C.byref(d), _p(x), _p(wf), _p(bias), _p(out), s1, s2, _stream())
+    with _timed("fprop", 2.0 * n * ho * wo * k * (c_true or c) * kh * kw):
+        call("msp_conv_fprop", C.byref(d), _p(x), _p(wf), _p(bias), _p(out), s1, s2, _stream())
     return out
 
 
-def conv_dgrad(dy, wd, x_shape, kh, kw, stride, pad_t, pad_l, out=None, accumulate=False):
+def conv_dgrad(dy, wd, x_shape, kh, kw, stride, pad_t, pad_l, out=None, accumulate=False, c_true=None):
     """dx = conv_transpose(dy, w); x_shape = (N, H, W, C8)."""
     n, ho, wo, k, y_cs = _chk_nhwc(dy, "conv_dgrad(dy)")
     _, h, w, c = x_shape
@@ -130,7 +161,8 @@ def conv_dgrad(dy, wd, x_shape, kh, kw, stride, pad_t, pad_l, out=None, accumula
         accumulate = False
     _, _, _, _, x_cs = _chk_nhwc(out, "conv_dgrad(out)")
     d = _conv_desc(n, h, w, c, x_cs, ho, wo, k, y_cs, kh, kw, stride, pad_t, pad_l)
-    call("msp_conv_dgrad", C.byref(d), _p(dy), _p(wd), _p(out), int(accumulate), _stream())
+    with _timed("dgrad", 2.0 * n * ho * wo * k * (c_true or c) * kh * kw):
+        call("msp_conv_dgrad", C.byref(d), _p(dy), _p(wd), _p(out), int(accumulate), _stream())
     return out
 
 
@@ -140,7 +172,8 @@ def conv_wgrad(x, dy, c_true, kh, kw, stride, pad_t, pad_l) -> torch.Tensor:
     _, ho, wo, k, y_cs = _chk_nhwc(dy, "conv_wgrad(dy)")
     d = _conv_desc(n, h, w, c, x_cs, ho, wo, k, y_cs, kh, kw, stride, pad_t, pad_l)
     dwp = torch.empty((k, kh * kw, c), dtype=torch.float32, device=x.device)
-    call("msp_conv_wgrad", C.byref(d), _p(x), _p(dy), _p(dwp), _stream())
+    with _timed("wgrad", 2.0 * n * ho * wo * k * c_true * kh * kw):
+        call("msp_conv_wgrad", C.byref(d), _p(x), _p(dy), _p(dwp), _stream())
     dw = torch.empty((k, c_true, kh, kw), dtype=torch.float32, device=x.device)
     call("msp_unpack_wgrad", _p(dwp), k, c_true, kh, kw, c, _p(dw), _stream())
     return dw
@@ -342,58 +375,64 @@ def final_conv_act_bwd(x, w2d, act: int, prob, dprob, need_dx=True, has_bias=Tru
     return dx, dw, db
 
 
-def dice_fwd(prob, mask, two_class, label_offset, batchwise, class_start, eps):
+def dice_sums(prob, mask, two_class, label_offset, batchwise):
     n, cp = prob.shape[0], prob.shape[1]
     hw = prob[0, 0].numel()
     ceff = 2 if two_class else cp
     g = 1 if batchwise else n
     sums = torch.empty((g, ceff, 3), dtype=torch.float64, device=prob.device)
-    coef = torch.empty((g, ceff, 2), dtype=torch.float32, device=prob.device)
-    loss = torch.empty((), dtype=torch.float32, device=prob.device)
-    call("msp_dice_fwd", _p(prob), _p(mask), n, cp, hw, int(two_class), int(label_offset), int(batchwise),
-         int(class_start), float(eps), _p(sums), _p(coef), _p(loss), _stream())
-    return loss, coef, sums
+    call("msp_dice_sums", _p(prob), _p(mask), n, cp, hw, int(two_class), int(label_offset), int(batchwise),
+         _p(sums), _stream())
+    return sums
 
 
-def dice_bwd(prob, mask, two_class, label_offset, batchwise, coef, gscale):
+def dice_finalize(sums, class_start, eps):
+    g, ceff, _ = sums.shape
+    coef = torch.empty((g, ceff, 2), dtype=torch.float32, device=sums.device)
+    loss = torch.empty((), dtype=torch.float32, device=sums.device)
+    call("msp_dice_finalize", _p(sums), g, ceff, int(class_start), float(eps), _p(coef), _p(loss), _stream())
+    return loss, coef
+
+
+def dice_bwd(prob, mask, two_class, label_offset, batchwise, coef, gscale=1.0, gscale_dev=None):
     n, cp = prob.shape[0], prob.shape[1]
     hw = prob[0, 0].numel()
     dprob = torch.empty_like(prob)
     call("msp_dice_bwd", _p(prob), _p(mask), n, cp, hw, int(two_class), int(label_offset), int(batchwise),
-         _p(coef), float(gscale), _p(dprob), _stream())
+         _p(coef), float(gscale), _p(gscale_dev), _p(dprob), _stream())
     return dprob
 
 
-def _sum_to_mean(loss_sum, scale):
+def sum_to_mean(loss_sum, scale):
     out = torch.empty((), dtype=torch.float32, device=loss_sum.device)
     call("msp_scale_to_float", _p(loss_sum), float(scale), _p(out), _stream())
     return out
 
 
-def ce_prob(prob, label, smooth, gscale, want_grad=True):
+def ce_prob(prob, label, smooth, gscale=1.0, gscale_dev=None, want_loss=True, want_grad=False):
     n, c = prob.shape[0], prob.shape[1]
     hw = prob[0, 0].numel()
-    ls = torch.empty((1,), dtype=torch.float64, device=prob.device)
+    ls = torch.empty((1,), dtype=torch.float64, device=prob.device) if want_loss else None
     dprob = torch.empty_like(prob) if want_grad else None
-    call("msp_ce_prob_fwd_bwd", _p(prob), _p(label), n, c, hw, float(smooth), float(gscale), _p(ls),
-         _p(dprob), _stream())
+    call("msp_ce_prob_fwd_bwd", _p(prob), _p(label), n, c, hw, float(smooth), float(gscale), _p(gscale_dev),
+         _p(ls), _p(dprob), _stream())
     return ls, dprob
 
 
-def bce(prob, target, clamp_log, gscale, want_grad=True):
-    ls = torch.empty((1,), dtype=torch.float64, device=prob.device)
+def bce(prob, target, clamp_log, gscale=1.0, gscale_dev=None, want_loss=True, want_grad=False):
+    ls = torch.empty((1,), dtype=torch.float64, device=prob.device) if want_loss else None
     dprob = torch.empty_like(prob) if want_grad else None
-    call("msp_bce_fwd_bwd", _p(prob), _p(target), prob.numel(), int(clamp_log), float(gscale), _p(ls),
-         _p(dprob), _stream())
+    call("msp_bce_fwd_bwd", _p(prob), _p(target), prob.numel(), int(clamp_log), float(gscale),
+         _p(gscale_dev), _p(ls), _p(dprob), _stream())
     return ls, dprob
 
 
-def softmax_ce(logits, label, smooth, gscale, want_grad=True):
+def softmax_ce(logits, label, smooth, gscale=1.0, gscale_dev=None, want_loss=True, want_grad=False):
     n, c = logits.shape
-    ls = torch.empty((1,), dtype=torch.float64, device=logits.device)
+    ls = torch.empty((1,), dtype=torch.float64, device=logits.device) if want_loss else None
     dl = torch.empty_like(logits) if want_grad else None
-    call("msp_softmax_ce_fwd_bwd", _p(logits), _p(label), n, c, float(smooth), float(gscale), _p(ls),
-         _p(dl), _stream())
+    call("msp_softmax_ce_fwd_bwd", _p(logits), _p(label), n, c, float(smooth), float(gscale),
+         _p(gscale_dev), _p(ls), _p(dl), _stream())
     return ls, dl
 
 
