@@ -464,7 +464,7 @@ int make_act_map(CUtensorMap* m, const void* base, int C, int W, int H, int N, i
   uint64_t strides[3] = {(uint64_t)cs * 2, (uint64_t)W * cs * 2, (uint64_t)H * W * cs * 2};
   uint32_t box[4] = {64, (uint32_t)(b.bw * s), (uint32_t)(b.bh * s), (uint32_t)b.bn};
   uint32_t es[4] = {1, (uint32_t)s, (uint32_t)s, 1};
-  return msp_encode_tmap_bf16(m, base, 4, dims, strides, box, es, 1);
+  return msp_encode_tmap_bf16(m, base, 4, dims, strides, box, es, 128);
 }
 // B-operand map over packed weights [rows][taps][inner]: (inner, taps, rows), box (64, 1, box_rows).
 int make_w_map(CUtensorMap* m, const void* base, int inner, int taps, int rows, int box_rows) {
@@ -472,7 +472,7 @@ int make_w_map(CUtensorMap* m, const void* base, int inner, int taps, int rows, 
   uint64_t strides[2] = {(uint64_t)inner * 2, (uint64_t)taps * inner * 2};
   uint32_t box[3] = {64, 1, (uint32_t)box_rows};
   uint32_t es[3] = {1, 1, 1};
-  return msp_encode_tmap_bf16(m, base, 3, dims, strides, box, es, 1);
+  return msp_encode_tmap_bf16(m, base, 3, dims, strides, box, es, 128);
 }
 
 int check_desc(const msp_conv_desc* d) {

@@ -8,7 +8,7 @@ import numpy as np
 import pytest
 import torch
 
-from oracle import ref_losses, ref_metrics, ref_models, ref_robustness
+from oracle import bf16_emulation, ref_losses, ref_metrics, ref_models, ref_robustness
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda"
@@ -29,49 +29,38 @@ def _cos(a, b):
 
 
 def _run_pair(make, x, target_fn, seed=0, train=True, lossname="dice"):
-    """Build the oracle model, clone it to the GPU, convert the clone, run one fwd+loss+bwd on both."""
+    """Build the oracle model (weights made bf16-representable so that both sides hold IDENTICAL weights),
+    clone it to the GPU and convert the clone, run one fwd+loss+bwd on (a) the fp32 oracle, (b) the oracle
+    with the B200 path's storage precision emulated (oracle/bf16_emulation.py) and (c) the converted model."""
     b = _b200()
     torch.manual_seed(seed)
-    ref = ref_models.kaiming_init_(make())
+    ref = bf16_emulation.round_weights_(ref_models.kaiming_init_(make()))
+    x = x.to(torch.bfloat16).float()
     gpu = b.convert(copy.deepcopy(ref).to(DEV))
-    ref.train(train), gpu.train(train)
-    torch.manual_seed(100 + seed)          # DropPath masks come from the global CPU generator
-    y_ref = ref(x)
-    torch.manual_seed(100 + seed)
-    y = gpu(x.to(DEV))
-    assert y.shape == y_ref.shape and y.dtype == torch.float32
-    out = dict(y=y.detach().cpu(), y_ref=y_ref.detach())
-    # control: the fp32 oracle itself, fed weights and input rounded ONCE to bf16 — the sensitivity of
-    # this (randomly initialised, BatchNorm-heavy) network to a single 2^-9 perturbation.  The deep
-    # zero-fill-shortcut ResNet-50 amplifies it ~2.7x per level (15 % at level 4, tools/debug_parity.py).
-    ctl = copy.deepcopy(ref)
-    with torch.no_grad():
-        for (_, p), (_, q) in zip(ctl.named_parameters(), gpu.named_parameters()):
-            p.copy_(q.detach().cpu().to(torch.bfloat16).float())
-        for (_, p), (_, q) in zip(ctl.named_buffers(), ref.named_buffers()):
-            p.copy_(q)
-        # ref's buffers were already advanced by the forward above: rewind the control's by re-deriving
-        # them is unnecessary for the prediction; buffer drift is compared on the increment below
-        torch.manual_seed(100 + seed)
-        ctl.train(train)
-        y_ctl = ctl(x.to(torch.bfloat16).float())
-    out["ctl_err"] = _rms_rel(y_ctl, y_ref.detach())
+    emu = copy.deepcopy(ref)
+    bf16_emulation.emulate_bf16_storage(emu)
+    out = {}
+    models = {"ref": ref, "emu": emu, "gpu": gpu}
+    ys = {}
+    for k, m in models.items():
+        m.train(train)
+        torch.manual_seed(100 + seed)          # DropPath masks come from the global CPU generator
+        ys[k] = m(x.to(DEV) if k == "gpu" else x)
+    assert ys["gpu"].shape == ys["ref"].shape and ys["gpu"].dtype == torch.float32
+    out.update(y=ys["gpu"].detach().cpu(), y_ref=ys["ref"].detach(), y_emu=ys["emu"].detach())
     if train:
-        tgt = target_fn(y_ref)
-        if lossname == "dice":
-            l_ref = ref_losses.dice_loss(y_ref, tgt)
-            l = b.losses.DiceLoss()(y, tgt.to(DEV))
-        elif lossname == "ce":
-            l_ref = ref_losses.ce_with_softmax(y_ref, tgt, 0.1)
-            l = b.losses.CrossEntropyLoss(0.1)(y, tgt.to(DEV))
-        l_ref.backward()
-        l.backward()
-        out.update(loss=l.item(), loss_ref=l_ref.item(),
-                   grads=[p.grad.detach().cpu() for p in gpu.parameters()],
-                   grads_ref=[p.grad.detach() for p in ref.parameters()],
-                   names=[n for n, _ in ref.named_parameters()],
-                   buffers=[t.detach().cpu() for t in gpu.buffers()],
-                   buffers_ref=[t.detach() for t in ref.buffers()])
+        tgt = target_fn(ys["ref"])
+        for k, m in models.items():
+            t = tgt.to(DEV) if k == "gpu" else tgt
+            if lossname == "dice":
+                l = b.losses.DiceLoss()(ys[k], t) if k == "gpu" else ref_losses.dice_loss(ys[k], t)
+            else:
+                l = b.losses.CrossEntropyLoss(0.1)(ys[k], t) if k == "gpu" else ref_losses.ce_with_softmax(ys[k], t, 0.1)
+            l.backward()
+            out[f"loss_{k}"] = l.item()
+            out[f"grads_{k}"] = [p.grad.detach().cpu() for p in m.parameters()]
+            out[f"buffers_{k}"] = [t_.detach().cpu() for t_ in m.buffers()]
+        out["names"] = [n for n, _ in ref.named_parameters()]
     return out
 
 
@@ -80,38 +69,52 @@ def _rms_rel(got, ref):
     return (d.pow(2).mean().sqrt() / (ref.double().pow(2).mean().sqrt() + 1e-30)).item()
 
 
-def _check(out, y_rms_tol, loss_tol, min_cos, what):
-    """End-to-end: the per-layer bf16 rounding noise compounds over 50-80 layers (it grows by ~0.4 % rms per
-    ResNet level, tools/debug_parity.py), so the whole-network check is on the rms error, the loss
-    (BASELINE: within 1 %) and the direction of every parameter gradient; the per-layer bound
-    (BASELINE: rel <= 1e-2 per layer output) is enforced block by block in _blockwise_parity."""
-    r = _rms_rel(out["y"], out["y_ref"])
-    bound = max(y_rms_tol, 2.5 * out["ctl_err"])
-    assert r <= bound, f"{what}: prediction rms rel err {r:.4g} > {bound:.4g} (control {out['ctl_err']:.4g})"
-    if "loss" in out:
-        lr = abs(out["loss"] - out["loss_ref"]) / abs(out["loss_ref"])
-        assert lr <= loss_tol, f"{what}: loss {out['loss']} vs {out['loss_ref']}"
-        # Whole-network gradients at random initialisation: every ReLU layer between a parameter and the
-        # loss adds mask-flip noise (see _blockwise_parity), so the cosine decays with depth — the
-        # tensors next to the loss must agree closely, the ensemble must stay clearly aligned, and the
-        # gradient norms (what clip_grad_norm_ / the step size see) must match.  Convergence equivalence
-        # is asserted separately by test_loss_curve_200_steps.
-        live = [(g, gr, n) for g, gr, n in zip(out["grads"], out["grads_ref"], out["names"])
-                if gr.abs().max() > 1e-6]
-        cosines = [(_cos(g, gr), n) for g, gr, n in live]
-        worst = min(cosines)
-        mean_cos = sum(c for c, _ in cosines) / len(cosines)
-        head_cos = min(c for c, _ in cosines[-4:])
-        ratios = np.array([(g.norm() / gr.norm()).item() for g, gr, _ in live])
-        tot = (sum(g.double().pow(2).sum() for g, _, _ in live).sqrt() /
-               sum(gr.double().pow(2).sum() for _, gr, _ in live).sqrt()).item()
-        print(f"{what}: y rms rel {r:.4f} (control {out['ctl_err']:.4f}), loss rel {lr:.2e}, grad cosine head {head_cos:.4f} mean {mean_cos:.4f} "
-              f"worst {worst[0]:.4f} ({worst[1]}), norm ratio total {tot:.4f} median {np.median(ratios):.4f}")
-        assert head_cos >= 0.95 and mean_cos >= min_cos, f"{what}: gradient cosine head {head_cos:.4f}, mean {mean_cos:.4f}"
-        assert abs(tot - 1) <= 0.1 and abs(np.median(ratios) - 1) <= 0.1, f"{what}: gradient norm ratio {tot:.4f}"
-        for bg, br in zip(out["buffers"], out["buffers_ref"]):
-            assert _rel(bg.float(), br.float()) <= max(3e-2, 0.5 * out["ctl_err"]), \
-                f"{what}: BatchNorm running buffers differ by {_rel(bg.float(), br.float()):.4f}"
+def _grad_stats(ga, gb, names):
+    live = [(g, gr, n) for g, gr, n in zip(ga, gb, names) if gr.abs().max() > 1e-6]
+    cosines = [(_cos(g, gr), n) for g, gr, n in live]
+    tot = (sum(g.double().pow(2).sum() for g, _, _ in live).sqrt() /
+           sum(gr.double().pow(2).sum() for _, gr, _ in live).sqrt()).item()
+    return dict(worst=min(cosines), mean=sum(c for c, _ in cosines) / len(cosines),
+                head=min(c for c, _ in cosines[-4:]), norm_ratio=tot)
+
+
+def _check(out, what):
+    """Whole-network parity, two yardsticks (the per-layer bound of BASELINE.json, rel <= 1e-2 per layer
+    output, is enforced separately and tightly, block by block, in _blockwise_parity).
+
+    A randomly initialised 50-80 layer ReLU/BatchNorm network with zero-fill shortcuts amplifies ANY
+    perturbation (one bf16 ulp in one activation included) by ~2.7x per ResNet level, so two correct bf16
+    implementations decorrelate with depth.  How strongly is measured, not assumed: the control is the fp32
+    oracle with the B200 path's bf16 STORAGE emulated (oracle/bf16_emulation.py: same arithmetic, same
+    rounding points) compared with the plain fp32 oracle on the same weights and inputs.
+    (1) vs the emulated-storage oracle: the converted model must be closer to it than it is to fp32
+        (prediction rms, gradient direction), loss within 1e-3, gradient norm within 2 %.
+    (2) vs the plain fp32 oracle: loss within 1 % (BASELINE), prediction no further than 1.5x the control
+        (+1e-2), gradients at least as aligned as the control's (-0.1)."""
+    r_emu = _rms_rel(out["y"], out["y_emu"])
+    r_ref = _rms_rel(out["y"], out["y_ref"])
+    ctl = _rms_rel(out["y_emu"], out["y_ref"])
+    msg = f"{what}: y rms rel vs emulated-bf16 oracle {r_emu:.4f}, vs fp32 oracle {r_ref:.4f} (emulated vs fp32 {ctl:.4f})"
+    if "loss_gpu" in out:
+        l_emu = abs(out["loss_gpu"] - out["loss_emu"]) / abs(out["loss_emu"])
+        l_ref = abs(out["loss_gpu"] - out["loss_ref"]) / abs(out["loss_ref"])
+        ge = _grad_stats(out["grads_gpu"], out["grads_emu"], out["names"])
+        gr = _grad_stats(out["grads_gpu"], out["grads_ref"], out["names"])
+        gc = _grad_stats(out["grads_emu"], out["grads_ref"], out["names"])
+        msg += (f"; loss rel {l_emu:.2e} / {l_ref:.2e}; grad cosine vs emulated: head {ge['head']:.4f} mean {ge['mean']:.4f} worst "
+                f"{ge['worst'][0]:.4f} ({ge['worst'][1]}) norm ratio {ge['norm_ratio']:.4f}; vs fp32: mean "
+                f"{gr['mean']:.4f} (control, emulated vs fp32: mean {gc['mean']:.4f} worst {gc['worst'][0]:.4f})")
+    print(msg)
+    assert r_emu <= max(1e-2, 0.75 * ctl), msg
+    assert r_ref <= 1.5 * ctl + 1e-2, msg
+    if "loss_gpu" in out:
+        assert l_emu <= 1e-3 and l_ref <= 1e-2, msg
+        assert ge["head"] >= 0.99 and abs(ge["norm_ratio"] - 1) <= 2e-2, msg
+        assert ge["mean"] >= min(0.99, gc["mean"]) and ge["worst"][0] >= min(0.9, gc["worst"][0]), msg
+        assert gr["mean"] >= gc["mean"] - 0.1, msg
+        for bg, be in zip(out["buffers_gpu"], out["buffers_emu"]):
+            assert _rel(bg.float(), be.float()) <= max(1e-2, ctl), \
+                f"{what}: BatchNorm running buffers differ by {_rel(bg.float(), be.float()):.4f}"
 
 
 _BLOCKS = ("BottleNeckBlock", "BasicBlock", "ConvBlock", "UpConvBlock", "AttentionBlock")
@@ -191,7 +194,7 @@ def test_resnet18_attention_unet_cfg1():
     _blockwise_parity(lambda: ref_models.resnet18_attention_unet(), x)
     out = _run_pair(lambda: ref_models.resnet18_attention_unet(), x,
                     lambda y: (torch.rand(y.shape[0], 1, *y.shape[2:], generator=g) < 0.3).long())
-    _check(out, 0.1, 1e-2, 0.5, "R18 attention U-Net")
+    _check(out, "R18 attention U-Net")
 
 
 def test_resnet50_attention_unet_cfg3_4class():
@@ -200,7 +203,7 @@ def test_resnet50_attention_unet_cfg3_4class():
     make = lambda: ref_models.resnet50_attention_unet(out_ch=4, final_activation="softmax")
     _blockwise_parity(make, x)
     out = _run_pair(make, x, lambda y: torch.randint(0, 4, (y.shape[0], 1, *y.shape[2:]), generator=g))
-    _check(out, 0.1, 1e-2, 0.5, "R50 attention U-Net (4-class)")
+    _check(out, "R50 attention U-Net (4-class)")
 
 
 def test_basic_unet_cfg4_multilabel():
@@ -209,7 +212,7 @@ def test_basic_unet_cfg4_multilabel():
     make = lambda: ref_models.basic_unet(out_ch=5, final_activation="sigmoid")
     _blockwise_parity(make, x)
     out = _run_pair(make, x, None, train=False)
-    _check(out, 0.1, 0, 0, "basic U-Net eval")
+    _check(out, "basic U-Net eval")
 
 
 def test_resnet50_classifier_cfg2():
@@ -218,7 +221,7 @@ def test_resnet50_classifier_cfg2():
     _blockwise_parity(lambda: ref_models.resnet50_classifier(num_classes=1000), x)
     out = _run_pair(lambda: ref_models.resnet50_classifier(num_classes=1000), x,
                     lambda y: torch.randint(0, 1000, (y.shape[0], 1), generator=g), lossname="ce")
-    _check(out, 0.1, 1e-2, 0.5, "ResNet-50 classifier")
+    _check(out, "ResNet-50 classifier")
 
 
 def test_loss_curve_200_steps():
