@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define MSP_ABI_VERSION 1
+#define MSP_ABI_VERSION 2
 
 const char* msp_last_error(void);
 int msp_version(void);
@@ -51,12 +51,22 @@ typedef struct msp_conv_desc {
   int32_t stride;           /* 1 or 2                                                          */
   int32_t pad_t, pad_l;     /* top / left zero padding (bottom/right implied by Ho, Wo)        */
   int32_t relu;             /* fprop: apply ReLU in the epilogue (conv -> ReLU without BN)     */
+  /* Row-window mode for the tiny-channel first convolution (7x7/2 stem of DeepResNet,
+   * classification/models.py:43-46; 3x3 first_block of UNet_encoder, unet_models.py:440): win_px = 8 or 4
+   * pixels per window (0 = off).  x is then the W-padded tensor [N][H][Wp][C] written by
+   * msp_nchw_f32_to_rowwin_bf16 with C = 64 / win_px channels per pixel (image column w at column
+   * w + pad_l), and the weights come from msp_pack_weights_rowwin.  fprop and wgrad only.          */
+  int32_t win_px, Wp;
 } msp_conv_desc;
 
 /* OIHW fp32 master weights -> bf16 [K][KH*KW][Cpad] (fprop/wgrad operand) and, if w_dgrad != NULL,
  * bf16 [Cpad][KH*KW][Kpad] (dgrad operand).  Cpad/Kpad >= C/K, multiples of 8, padding zero-filled. */
 int msp_pack_weights(const float* w_oihw, int K, int C, int KH, int KW, int Cpad, int Kpad,
                      void* w_fprop, void* w_dgrad, void* stream);
+
+/* OIHW fp32 -> bf16 [K][KH][64] with element q*(64/win_px)+c of filter row r = w[k][c][r][q]. */
+int msp_pack_weights_rowwin(const float* w_oihw, int K, int C, int KH, int KW, int win_px,
+                            void* w_rowwin, void* stream);
 
 /* y = conv(x, w) (+ bias) (ReLU optional).  If ch_sum / ch_sqsum are non-NULL the per-output-channel
  * sum and sum of squares of the (bf16-rounded) outputs over N*Ho*Wo are ADDED to them (fp32, [K]) —
@@ -69,14 +79,16 @@ int msp_conv_fprop(const msp_conv_desc* d, const void* x, const void* w_fprop, c
 int msp_conv_dgrad(const msp_conv_desc* d, const void* dy, const void* w_dgrad, void* dx,
                    int accumulate /* dx += result (residual gradient already in dx) */, void* stream);
 
-/* dw[K][KH*KW][Cpad] (fp32, packed like w_fprop) = sum over pixels of dy^T * im2col(x).
- * The buffer is zeroed by the call; split-K partial sums are combined with fp32 atomics. */
-int msp_conv_wgrad(const msp_conv_desc* d, const void* x, const void* dy, float* dw_packed,
+/* Weight gradient, split-K over pixel tiles WITHOUT atomics (deterministic): split s writes its partial
+ * sum, packed like w_fprop ([K][KH*KW][C] fp32; [K][KH][64] in row-window mode), at
+ * dw_partials + s * K*taps*C.  msp_conv_wgrad_splits(d) >= 1 is the number of partials the caller must
+ * provide room for (it depends only on the descriptor and the SM count); every element is written. */
+int msp_conv_wgrad_splits(const msp_conv_desc* d);
+int msp_conv_wgrad(const msp_conv_desc* d, const void* x, const void* dy, float* dw_partials,
                    void* stream);
 
-/* packed fp32 [K][KH*KW][Cpad] -> OIHW fp32 [K][C][KH][KW] (the layout of nn.Conv2d.weight.grad);
- * also reduces bias grad if requested elsewhere. */
-int msp_unpack_wgrad(const float* dw_packed, int K, int C, int KH, int KW, int Cpad, float* dw_oihw,
+/* sum of the partials -> OIHW fp32 [K][C_true][KH][KW] (the layout of nn.Conv2d.weight.grad). */
+int msp_unpack_wgrad(const msp_conv_desc* d, const float* dw_partials, int C_true, float* dw_oihw,
                      void* stream);
 
 /* ------------------------------------------------------------------------------------------
@@ -86,6 +98,9 @@ int msp_nchw_f32_to_nhwc_bf16(const float* x, int N, int C, int H, int W, int Cp
                               void* stream);
 int msp_nhwc_bf16_to_nchw_f32(const void* x, int N, int C, int H, int W, int x_cs, float* y,
                               void* stream);
+/* NCHW fp32 -> W-padded [N][H][Wp][cpp] bf16 (cpp = 8 or 16 >= C) for row-window convolutions. */
+int msp_nchw_f32_to_rowwin_bf16(const float* x, int N, int C, int H, int W, int cpp, int pad_l, int Wp,
+                                void* y, void* stream);
 int msp_nchw_f32_grad_to_nhwc_bf16(const float* g, int N, int C, int H, int W, int g_cs_out,
                                    void* y, void* stream);
 

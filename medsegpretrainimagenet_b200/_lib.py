@@ -25,7 +25,7 @@ D = C.c_double
 class ConvDesc(C.Structure):
     _fields_ = [(n, C.c_int32) for n in (
         "N", "H", "W", "C", "x_cs", "Ho", "Wo", "K", "y_cs", "KH", "KW", "stride", "pad_t", "pad_l",
-        "relu")]
+        "relu", "win_px", "Wp")]
 
 
 class BnActDesc(C.Structure):
@@ -41,8 +41,11 @@ SIGNATURES = {
     "msp_pack_weights": [P, I, I, I, I, I, I, P, P, P],
     "msp_conv_fprop": [C.POINTER(ConvDesc), P, P, P, P, P, P, P],
     "msp_conv_dgrad": [C.POINTER(ConvDesc), P, P, P, I, P],
+    "msp_conv_wgrad_splits": [C.POINTER(ConvDesc)],
     "msp_conv_wgrad": [C.POINTER(ConvDesc), P, P, P, P],
-    "msp_unpack_wgrad": [P, I, I, I, I, I, P, P],
+    "msp_unpack_wgrad": [C.POINTER(ConvDesc), P, I, P, P],
+    "msp_pack_weights_rowwin": [P, I, I, I, I, I, P, P],
+    "msp_nchw_f32_to_rowwin_bf16": [P, I, I, I, I, I, I, I, P, P],
     "msp_nchw_f32_to_nhwc_bf16": [P, I, I, I, I, I, P, P],
     "msp_nhwc_bf16_to_nchw_f32": [P, I, I, I, I, I, P, P],
     "msp_nchw_f32_grad_to_nhwc_bf16": [P, I, I, I, I, I, P, P],

@@ -37,6 +37,18 @@ class ExecContext:
         self.group = group
 
 
+class RawInput:
+    """The network input as the reference hands it over (fp32 NCHW), not yet converted: the first
+    convolution consumes it directly through the row-window path (functional.input_conv2d)."""
+
+    def __init__(self, t: torch.Tensor):
+        self.t = t
+
+
+def _as_nhwc(x):
+    return Fn.to_nhwc(x.t) if isinstance(x, RawInput) else x
+
+
 def _name(m) -> str:
     return type(m).__name__
 
@@ -88,15 +100,19 @@ def conv_bn_act(ctx: ExecContext, x, conv: nn.Conv2d, bn: Optional[nn.BatchNorm2
     """Conv2d [-> BatchNorm2d] [-> ReLU | Sigmoid], with optional fused residual / per-sample scale."""
     _check_conv(conv)
     stride, padding = conv.stride[0], _pad_of(conv)
+    if isinstance(x, RawInput):
+        conv2d = lambda _x, *a, **k: Fn.input_conv2d(x.t, *a, **k)
+    else:
+        conv2d = Fn.conv2d
     if bn is None:
         if residual is not None or sample_scale is not None or act == ops.ACT_SIGMOID:
             raise UnsupportedModule("residual / sigmoid epilogue without BatchNorm")
-        y, _ = Fn.conv2d(x, conv.weight, conv.bias, stride, padding, relu=(act == ops.ACT_RELU))
+        y, _ = conv2d(x, conv.weight, conv.bias, stride, padding, relu=(act == ops.ACT_RELU))
         return y
     training = bn.training or bn.running_mean is None
     # the conv adds its bias in the epilogue, but the bias *gradient* is produced by the BatchNorm node
     bias = conv.bias.detach() if conv.bias is not None else None
-    y, stats = Fn.conv2d(x, conv.weight, bias, stride, padding, relu=False, want_stats=training)
+    y, stats = conv2d(x, conv.weight, bias, stride, padding, relu=False, want_stats=training)
     return Fn.bn_act(y, stats, bn, act=act, residual=residual, r_stride=r_stride,
                      sample_scale=sample_scale, group=ctx.group, conv_bias=conv.bias)
 
@@ -109,7 +125,10 @@ def run_sequence(ctx: ExecContext, mods: List[nn.Module], x):
         nm = _name(m)
         if _is_noop(m):
             i += 1
-        elif nm == "Conv2d":
+            continue
+        if nm not in ("Conv2d", "Sequential", "ConvBlock"):
+            x = _as_nhwc(x)
+        if nm == "Conv2d":
             bn, act, j = None, ops.ACT_NONE, i + 1
             if j < n and _name(_unwrap(mods[j])) == "BatchNorm2d":
                 bn = _unwrap(mods[j])
@@ -316,7 +335,7 @@ def _require_cuda(x):
 def _forward_deep_resnet(self, x, return_skip_vals=False, *args, **kwargs):
     _require_cuda(x)
     ctx = self._msp_ctx
-    out = run_deep_resnet(ctx, self, Fn.to_nhwc(x), return_skip_vals=return_skip_vals)
+    out = run_deep_resnet(ctx, self, RawInput(x), return_skip_vals=return_skip_vals)
     y, skips = out if return_skip_vals else (out, None)
     if _name(self.classifier) != "Identity":
         y = Fn.to_nchw(y).flatten(1)
@@ -329,7 +348,7 @@ def _forward_deep_resnet(self, x, return_skip_vals=False, *args, **kwargs):
 
 def _forward_unet_encoder(self, x, return_skip_vals=False):
     _require_cuda(x)
-    out = run_unet_encoder(self._msp_ctx, self, Fn.to_nhwc(x), return_skip_vals=return_skip_vals)
+    out = run_unet_encoder(self._msp_ctx, self, RawInput(x), return_skip_vals=return_skip_vals)
     if return_skip_vals:
         return Fn.to_nchw(out[0]), [Fn.to_nchw(s) for s in out[1]]
     return Fn.to_nchw(out)
@@ -337,7 +356,7 @@ def _forward_unet_encoder(self, x, return_skip_vals=False):
 
 def _forward_unet(self, x):
     _require_cuda(x)
-    return run_unet(self._msp_ctx, self, Fn.to_nhwc(x))
+    return run_unet(self._msp_ctx, self, RawInput(x))
 
 
 _TOP_LEVEL = {"DeepResNet": _forward_deep_resnet, "UNet_encoder": _forward_unet_encoder,

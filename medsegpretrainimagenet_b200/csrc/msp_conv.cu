@@ -7,15 +7,25 @@
 //    hardware zero fill for the padding halo and `elementStrides` for stride-2 convs.  The B operand
 //    is a [BN x 64] slab of the packed weights [K][tap][C] (3-D TMA).  Both land in shared memory
 //    in the 128-byte-swizzled K-major layout tcgen05.mma consumes directly.
-//  * warp-specialised CTA: warp 0 = TMA producer, warp 1 = MMA issuer (one elected lane,
-//    tcgen05.mma cta_group::1, M=128, fp32 accumulators in TMEM), warps 2-5 = epilogue
-//    (tcgen05.ld -> bias/ReLU -> bf16 -> global, plus per-channel sum / sum-of-squares for the
-//    following BatchNorm).  Two CTAs are co-resident per SM so one CTA's epilogue overlaps the
-//    other's main loop.
+//  * PERSISTENT, warp-specialised CTA, one per SM: warp 0 = TMA producer running up to kStages
+//    k-blocks (and therefore several tiles) ahead, warp 1 = MMA issuer (one elected lane,
+//    tcgen05.mma cta_group::1, M=128, N<=256, fp32 accumulators DOUBLE-BUFFERED in TMEM), warps 2-5 =
+//    epilogue: tcgen05.ld -> bias/ReLU -> bf16 -> 128B-swizzled staging tile in smem -> TMA tile store
+//    (hardware clips ragged tiles and channel tails; dgrad-on-top-of-a-gradient uses the TMA reduce-add),
+//    overlapped with the next tile's main loop.  The BatchNorm batch statistics (per-channel sum / sum
+//    of squares of the bf16-rounded outputs) are reduced from the staging tile and kept in REGISTERS across
+//    all the tiles a CTA owns (tiles are walked output-channel-block-major), so a launch issues
+//    ~2 x Cout x (#CTAs) atomics instead of 2 x Cout x (#tiles x 4).
 //  * dgrad = the same kernel on dy with transposed weights; stride-2 dgrad is decomposed into the
 //    four output-parity classes, each a small stride-1 tap-GEMM writing a strided sub-grid of dx.
-//  * wgrad contracts over pixels: A = dy tile, B = shifted x tile, both consumed MN-major straight
-//    from the same TMA boxes; split-K over pixel tiles, fp32 atomics into the packed dW.
+//  * wgrad contracts over pixels: A = dy tile (128 output channels), B = shifted x tile (up to 256 input
+//    channels), both consumed MN-major straight from the same TMA boxes; split-K over pixel tiles, each
+//    split writing its own fp32 partial (no atomics, deterministic), summed by msp_unpack_wgrad.
+//  * "row-window" mode for the tiny-channel first convolution (7x7/2 stem on 1-3 channels, 3x3 on 3
+//    channels): the input is stored zero-padded in W with 8 (or 16) channels per pixel, so the KW taps
+//    of one filter row are 64 CONTIGUOUS elements; an overlapping-stride tensor map (dim 1 = output
+//    column, stride = conv stride x pixel) turns each filter ROW into one 64-deep k-block: 7 TMA
+//    loads / 28 MMAs per tile for the 7x7 stem instead of 49 / 49.
 //
 // Replaces cuDNN conv fwd / bwd-data / bwd-filter behind nn.Conv2d
 // (reference classification/models.py:43-46,161-179,234-253; segmentation/models/blocks.py:458,518,590).
@@ -31,19 +41,20 @@ constexpr int kBM = 128;  // UMMA M (rows of the output tile)
 constexpr int kBK = 64;   // contraction elements per pipeline stage (= one 128-byte swizzle row)
 constexpr int kConvThreads = 192;
 constexpr int kATileBytes = kBM * kBK * 2;  // 16 KB
+constexpr int kEpiThreads = 128;
+constexpr int kEpiBarrier = 1;  // named barrier id of the 4 epilogue warps
 
 struct TapGemmParams {
   int bw, bh, bn, rows;
   int tiles_w, tiles_h, tiles_n;
+  int tiles_m, tiles_co, total_tiles;
   int OWs, OHs, N;  // output sub-grid extent
-  int sx;           // A coordinate multiplier (conv stride for fprop, 1 for dgrad)
+  int sxw, sxh;     // A coordinate multipliers (conv stride for fprop, 1 for dgrad / row-window W)
   int C;            // contraction channels per tap
   int ntaps;
   int Kout;         // valid output channels
   int relu;
-  int accumulate;  // epilogue adds into the existing output (dgrad on top of a residual grad)
-  long long y_off, y_n_stride, y_h_stride, y_w_stride;  // element strides of the output sub-grid
-  __nv_bfloat16* y;
+  int accumulate;  // the output tile is ADDED to memory (dgrad on top of a residual gradient)
   const float* bias;
   float* ch_sum;
   float* ch_sqsum;
@@ -56,34 +67,34 @@ template <int BN_>
 struct TapGemmCfg {
   static constexpr int kBTileBytes = BN_ * kBK * 2;
   static constexpr int kStageBytes = kATileBytes + kBTileBytes;
-  static constexpr int kStages = BN_ >= 256 ? 2 : (BN_ >= 128 ? 3 : 4);
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024;  // + alignment slack
-  static constexpr int kTmemCols = BN_ < 32 ? 32 : BN_;
-  static constexpr int kChunk = BN_ < 32 ? 16 : 32;  // epilogue column chunk
+  static constexpr int kStages = BN_ >= 256 ? 4 : (BN_ >= 128 ? 5 : 6);
+  static constexpr int kCH = BN_ < 64 ? BN_ : 64;  // epilogue column chunk (one TMA store box)
+  static constexpr int kNChunk = BN_ / kCH;
+  static constexpr int kStageBufs = BN_ >= 256 ? 1 : 2;  // 16 KB staging tiles for the TMA store
+  static constexpr int kScratchBytes = 4 * 64 * 2 * 4;   // per-row-quarter partial statistics
+  static constexpr int kSmemBytes =
+      kStages * kStageBytes + kStageBufs * kATileBytes + kScratchBytes + 1024;  // + alignment slack
+  static constexpr int kTmemCols = 2 * BN_ < 32 ? 32 : 2 * BN_;
 };
 
 template <int BN_>
-__global__ void __launch_bounds__(kConvThreads, 2)
+__global__ void __launch_bounds__(kConvThreads, 1)
 tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-               const TapGemmParams p) {
+               const __grid_constant__ CUtensorMap tmY, const TapGemmParams p) {
   using Cfg = TapGemmCfg<BN_>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~uintptr_t(1023));
+  uint8_t* staging = smem + Cfg::kStages * Cfg::kStageBytes;
+  float* scratch = reinterpret_cast<float*>(staging + Cfg::kStageBufs * kATileBytes);
   __shared__ uint64_t full_bar[Cfg::kStages];
   __shared__ uint64_t empty_bar[Cfg::kStages];
-  __shared__ uint64_t accum_bar;
+  __shared__ uint64_t tfull_bar[2];
+  __shared__ uint64_t tempty_bar[2];
   __shared__ uint32_t tmem_base_s;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-
-  const int tm = blockIdx.x;
-  const int tw = tm % p.tiles_w;
-  const int th = (tm / p.tiles_w) % p.tiles_h;
-  const int tn = tm / (p.tiles_w * p.tiles_h);
-  const int w0 = tw * p.bw, h0 = th * p.bh, n0 = tn * p.bn;
-  const int co0 = blockIdx.y * BN_;
   const int chunks = (p.C + kBK - 1) / kBK;
   const int kiters = p.ntaps * chunks;
 
@@ -92,7 +103,10 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
     }
-    mbar_init(&accum_bar, 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tfull_bar[s], 1);
+      mbar_init(&tempty_bar[s], kEpiThreads);
+    }
     mbar_fence_init();
   }
   if (warp == 1) tmem_alloc<Cfg::kTmemCols>(&tmem_base_s);
@@ -102,127 +116,193 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const uint32_t tmem_base = tmem_base_s;
 
   if (warp == 0) {
+    // ---------------- TMA producer ----------------
     if (lane == 0) {
       tma_prefetch_desc(&tmA);
       tma_prefetch_desc(&tmB);
       const uint32_t tx_bytes = (uint32_t)p.rows * 128u + (uint32_t)Cfg::kBTileBytes;
-      for (int it = 0; it < kiters; ++it) {
-        const int s = it % Cfg::kStages;
-        const uint32_t ph = (uint32_t)(it / Cfg::kStages) & 1u;
-        mbar_wait(&empty_bar[s], ph ^ 1u);
-        const int tap = it / chunks;
-        const int ch = it - tap * chunks;
-        uint8_t* a_s = smem + s * Cfg::kStageBytes;
-        uint8_t* b_s = a_s + kATileBytes;
-        mbar_expect_tx(&full_bar[s], tx_bytes);
-        tma_load_4d(a_s, &tmA, &full_bar[s], ch * kBK, w0 * p.sx + p.tap_dw[tap],
-                    h0 * p.sx + p.tap_dh[tap], n0);
-        tma_load_3d(b_s, &tmB, &full_bar[s], ch * kBK, (int)p.tap_w[tap], co0);
+      uint32_t it = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        const int tco = tile / p.tiles_m;
+        const int tm = tile - tco * p.tiles_m;
+        const int tw = tm % p.tiles_w;
+        const int th = (tm / p.tiles_w) % p.tiles_h;
+        const int tn = tm / (p.tiles_w * p.tiles_h);
+        const int w0 = tw * p.bw * p.sxw, h0 = th * p.bh * p.sxh, n0 = tn * p.bn;
+        const int co0 = tco * BN_;
+        for (int tap = 0; tap < p.ntaps; ++tap) {
+          const int cw = w0 + p.tap_dw[tap], chh = h0 + p.tap_dh[tap], wt = (int)p.tap_w[tap];
+          for (int ch = 0; ch < chunks; ++ch, ++it) {
+            const int s = it % Cfg::kStages;
+            const uint32_t ph = (it / Cfg::kStages) & 1u;
+            mbar_wait(&empty_bar[s], ph ^ 1u);
+            uint8_t* a_s = smem + s * Cfg::kStageBytes;
+            mbar_expect_tx(&full_bar[s], tx_bytes);
+            tma_load_4d(a_s, &tmA, &full_bar[s], ch * kBK, cw, chh, n0);
+            tma_load_3d(a_s + kATileBytes, &tmB, &full_bar[s], ch * kBK, wt, co0);
+          }
+        }
       }
     }
   } else if (warp == 1) {
+    // ---------------- MMA issuer ----------------
     if (lane == 0) {
       constexpr uint32_t idesc = umma_idesc_bf16(kBM, BN_, 0, 0);
-      for (int it = 0; it < kiters; ++it) {
-        const int s = it % Cfg::kStages;
-        const uint32_t ph = (uint32_t)(it / Cfg::kStages) & 1u;
-        mbar_wait(&full_bar[s], ph);
+      uint32_t it = 0, t = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++t) {
+        const uint32_t as = t & 1u;
+        mbar_wait(&tempty_bar[as], ((t >> 1) & 1u) ^ 1u);  // epilogue has drained this accumulator
         tc_fence_after();
-        const int ch = it % chunks;
-        int kvalid = p.C - ch * kBK;
-        kvalid = kvalid > kBK ? kBK : kvalid;
-        const int nk = (kvalid + 15) >> 4;
-        const uint32_t a_addr = smem_u32(smem + s * Cfg::kStageBytes);
-        const uint64_t adesc = umma_smem_desc_sw128(a_addr, 16, 1024);
-        const uint64_t bdesc = umma_smem_desc_sw128(a_addr + kATileBytes, 16, 1024);
-        for (int k = 0; k < nk; ++k)
-          umma_bf16(tmem_base, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc,
-                    (uint32_t)((it | k) != 0));
-        umma_commit(&empty_bar[s]);  // frees the smem slot once these MMAs have read it
+        const uint32_t tmem_d = tmem_base + as * BN_;
+        for (int ki = 0; ki < kiters; ++ki, ++it) {
+          const int s = it % Cfg::kStages;
+          const uint32_t ph = (it / Cfg::kStages) & 1u;
+          mbar_wait(&full_bar[s], ph);
+          tc_fence_after();
+          const int ch = ki % chunks;
+          int kvalid = p.C - ch * kBK;
+          kvalid = kvalid > kBK ? kBK : kvalid;
+          const int nk = (kvalid + 15) >> 4;
+          const uint32_t a_addr = smem_u32(smem + s * Cfg::kStageBytes);
+          const uint64_t adesc = umma_smem_desc_sw128(a_addr, 16, 1024);
+          const uint64_t bdesc = umma_smem_desc_sw128(a_addr + kATileBytes, 16, 1024);
+          for (int k = 0; k < nk; ++k)
+            umma_bf16(tmem_d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc,
+                      (uint32_t)((ki | k) != 0));
+          umma_commit(&empty_bar[s]);  // frees the smem slot once these MMAs have read it
+        }
+        umma_commit(&tfull_bar[as]);
       }
-      umma_commit(&accum_bar);
     }
     __syncwarp();
   } else {
-    // ---------------- epilogue: TMEM -> registers -> global ----------------
-    mbar_wait(&accum_bar, 0);
-    tc_fence_after();
-    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    // ---------------- epilogue: TMEM -> registers -> swizzled smem tile -> TMA store ----------------
+    const int et = threadIdx.x - 64;  // 0..127
+    const int q = warp & 3;           // TMEM lane quarter this warp may access
     const int row = q * 32 + lane;
     const int wi = row % p.bw;
     const int t2 = row / p.bw;
     const int hi = t2 % p.bh;
     const int ni = t2 / p.bh;
-    const bool valid = row < p.rows && (w0 + wi) < p.OWs && (h0 + hi) < p.OHs && (n0 + ni) < p.N;
-    __nv_bfloat16* yrow = p.y + p.y_off + (long long)(n0 + ni) * p.y_n_stride +
-                          (long long)(h0 + hi) * p.y_h_stride + (long long)(w0 + wi) * p.y_w_stride;
-    float* scratch = reinterpret_cast<float*>(smem) + q * (32 * 33);
     const bool do_stats = p.ch_sum != nullptr;
-    constexpr int CW = Cfg::kChunk;
-#pragma unroll 1
-    for (int c = 0; c < BN_; c += CW) {
-      const int cg = co0 + c;
-      if (cg >= p.Kout) break;
-      uint32_t v[CW];
-      if constexpr (CW == 32) tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + c, v);
-      else tmem_ld_32x16(tmem_base + ((uint32_t)(q * 32) << 16) + c, v);
-      tmem_ld_wait();
-      float f[CW];
+    const bool store_thread = (et == 0);
+    if (store_thread) tma_prefetch_desc(&tmY);
+    float run[Cfg::kNChunk];
 #pragma unroll
-      for (int j = 0; j < CW; ++j) {
-        float x = __uint_as_float(v[j]);
-        if (p.bias != nullptr && cg + j < p.Kout) x += __ldg(p.bias + cg + j);
-        if (p.relu) x = fmaxf(x, 0.f);
-        f[j] = x;
-      }
-      uint32_t pk[CW / 2];
+    for (int c = 0; c < Cfg::kNChunk; ++c) run[c] = 0.f;
+    constexpr int CH = Cfg::kCH;
+    uint32_t t = 0, sbuf = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++t) {
+      const int tco = tile / p.tiles_m;
+      const int tm = tile - tco * p.tiles_m;
+      const int tw = tm % p.tiles_w;
+      const int th = (tm / p.tiles_w) % p.tiles_h;
+      const int tn = tm / (p.tiles_w * p.tiles_h);
+      const int w0 = tw * p.bw, h0 = th * p.bh, n0 = tn * p.bn;
+      const int co0 = tco * BN_;
+      const bool valid = row < p.rows && (w0 + wi) < p.OWs && (h0 + hi) < p.OHs && (n0 + ni) < p.N;
+      const uint32_t as = t & 1u;
+      mbar_wait(&tfull_bar[as], (t >> 1) & 1u);
+      tc_fence_after();
+      const uint32_t tmem_row = tmem_base + ((uint32_t)(q * 32) << 16) + as * BN_;
 #pragma unroll
-      for (int j = 0; j < CW / 2; ++j) pk[j] = pack_bf16x2(f[2 * j], f[2 * j + 1]);
-      if (valid) {
+      for (int c = 0; c < Cfg::kNChunk; ++c) {
+        const int cg = co0 + c * CH;
+        uint8_t* stg = staging + (Cfg::kStageBufs == 2 ? sbuf * kATileBytes : 0);
+        // the staging tile must have been read by its previous TMA store (and by the statistics pass)
+        if (store_thread) {
+          if constexpr (Cfg::kStageBufs == 2) tma_store_wait_read<1>();
+          else tma_store_wait_read<0>();
+        }
+        named_bar_sync(kEpiBarrier, kEpiThreads);
+        uint32_t v[CH];
+        if constexpr (CH == 64) {
+          tmem_ld_32x32(tmem_row + c * CH, *reinterpret_cast<uint32_t(*)[32]>(&v[0]));
+          tmem_ld_32x32(tmem_row + c * CH + 32, *reinterpret_cast<uint32_t(*)[32]>(&v[32]));
+        } else if constexpr (CH == 32) {
+          tmem_ld_32x32(tmem_row + c * CH, *reinterpret_cast<uint32_t(*)[32]>(&v[0]));
+        } else {
+          tmem_ld_32x16(tmem_row + c * CH, *reinterpret_cast<uint32_t(*)[16]>(&v[0]));
+        }
+        tmem_ld_wait();
+        if (c == Cfg::kNChunk - 1) {  // accumulator fully read: hand it back to the MMA warp
+          tc_fence_before();
+          mbar_arrive(&tempty_bar[as]);
+        }
+        uint8_t* srow = stg + row * 128;
+        if (cg < p.Kout) {
 #pragma unroll
-        for (int g = 0; g < CW / 8; ++g) {
-          if (cg + g * 8 < p.Kout) {
-            uint4 o = make_uint4(pk[4 * g], pk[4 * g + 1], pk[4 * g + 2], pk[4 * g + 3]);
-            if (p.accumulate) {
-              const uint4 old = *reinterpret_cast<const uint4*>(yrow + cg + g * 8);
-              const uint32_t ov[4] = {old.x, old.y, old.z, old.w};
-              uint32_t nv[4];
+          for (int g = 0; g < CH / 8; ++g) {
+            uint32_t pk[4];
 #pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                const float2 a = unpack_bf16x2(ov[e]);
-                nv[e] = pack_bf16x2(a.x + f[g * 8 + 2 * e], a.y + f[g * 8 + 2 * e + 1]);
+            for (int e = 0; e < 4; ++e) {
+              float x0 = __uint_as_float(v[g * 8 + 2 * e]);
+              float x1 = __uint_as_float(v[g * 8 + 2 * e + 1]);
+              if (p.bias != nullptr) {
+                const int cc = cg + g * 8 + 2 * e;
+                if (cc < p.Kout) x0 += __ldg(p.bias + cc);
+                if (cc + 1 < p.Kout) x1 += __ldg(p.bias + cc + 1);
               }
-              o = make_uint4(nv[0], nv[1], nv[2], nv[3]);
+              if (p.relu) {
+                x0 = fmaxf(x0, 0.f);
+                x1 = fmaxf(x1, 0.f);
+              }
+              pk[e] = valid ? pack_bf16x2(x0, x1) : 0u;
             }
-            st_v4(yrow + cg + g * 8, o);
+            *reinterpret_cast<uint4*>(srow + ((g ^ (row & 7)) << 4)) =
+                make_uint4(pk[0], pk[1], pk[2], pk[3]);
           }
         }
-      }
-      if (do_stats) {
-        // per-channel sums over this warp's 32 rows via a padded smem transpose
-#pragma unroll
-        for (int j = 0; j < CW / 2; ++j) {
-          float2 r = unpack_bf16x2(pk[j]);
-          scratch[lane * 33 + 2 * j] = valid ? r.x : 0.f;
-          scratch[lane * 33 + 2 * j + 1] = valid ? r.y : 0.f;
-        }
-        __syncwarp();
-        if (lane < CW) {
-          float s1 = 0.f, s2 = 0.f;
+        fence_proxy_async_smem();
+        named_bar_sync(kEpiBarrier, kEpiThreads);
+        if (cg < p.Kout) {
+          if (store_thread) {
+            if (p.accumulate) tma_reduce_add_4d(&tmY, stg, cg, w0, h0, n0);
+            else tma_store_4d(&tmY, stg, cg, w0, h0, n0);
+            tma_store_commit();
+          }
+          if (do_stats) {
+            // column sums of the bf16 tile: thread -> (column pair, row quarter); conflict-free LDS.32
+            const int cp = et & 31, rq = et >> 5;
+            float s1a = 0.f, s2a = 0.f, s1b = 0.f, s2b = 0.f;
+            const uint8_t* base = stg + rq * 32 * 128 + (cp & 3) * 4;
 #pragma unroll 8
-          for (int i = 0; i < 32; ++i) {
-            const float x = scratch[i * 33 + lane];
-            s1 += x;
-            s2 = fmaf(x, x, s2);
-          }
-          if (cg + lane < p.Kout) {
-            atomicAdd(p.ch_sum + cg + lane, s1);
-            atomicAdd(p.ch_sqsum + cg + lane, s2);
+            for (int r = 0; r < 32; ++r) {
+              const uint32_t wv =
+                  *reinterpret_cast<const uint32_t*>(base + r * 128 + (((cp >> 2) ^ (r & 7)) << 4));
+              const float2 f = unpack_bf16x2(wv);
+              s1a += f.x;
+              s2a = fmaf(f.x, f.x, s2a);
+              s1b += f.y;
+              s2b = fmaf(f.y, f.y, s2b);
+            }
+            float* sc = scratch + rq * 128;  // [rq][which][64]
+            sc[2 * cp] = s1a;
+            sc[2 * cp + 1] = s1b;
+            sc[64 + 2 * cp] = s2a;
+            sc[64 + 2 * cp + 1] = s2b;
+            named_bar_sync(kEpiBarrier, kEpiThreads);
+            // thread et owns (which = et >> 6, column = et & 63) of every chunk of the tile
+            run[c] += scratch[et] + scratch[128 + et] + scratch[256 + et] + scratch[384 + et];
           }
         }
-        __syncwarp();
+        if constexpr (Cfg::kStageBufs == 2) sbuf ^= 1u;
+      }
+      // flush the running statistics when this CTA leaves the output-channel block (or finishes)
+      if (do_stats) {
+        const int next = tile + gridDim.x;
+        if (next >= p.total_tiles || next / p.tiles_m != tco) {
+          float* dst = (et >> 6) ? p.ch_sqsum : p.ch_sum;
+#pragma unroll
+          for (int c = 0; c < Cfg::kNChunk; ++c) {
+            const int col = co0 + c * CH + (et & 63);
+            if ((et & 63) < CH && col < p.Kout) atomicAdd(dst + col, run[c]);
+            run[c] = 0.f;
+          }
+        }
       }
     }
+    if (store_thread) tma_store_wait_all<0>();
   }
   tc_fence_before();
   __syncthreads();
@@ -235,19 +315,23 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 struct WgradParams {
   int bw, bh, bn, rows;
   int tiles_w, tiles_h, tiles_n, tiles_m;
-  int sx, pad_t, pad_l, KW;
-  int C, Cw;   // stored input channels, packed weight inner dim
+  int sxw, sxh, pad_t, pad_l, KW;
+  int Cw;      // packed weight inner dim (input channels, or 64 window elements in row-window mode)
   int Kout;    // output channels
-  int ntaps, chunks;
+  int ntaps, cchunks, nsub;  // nsub = 64-channel sub-tiles per CTA (1..4)
+  int rowwin;
   int splits;
+  long long split_stride;  // elements between the partial dW of consecutive splits
   float* dw;
 };
 
 constexpr int kWgStages = 2;
-constexpr int kWgStageBytes = 3 * kATileBytes;  // dY halves (2 x 16 KB) + X tile (16 KB)
+constexpr int kWgMaxSub = 4;
+constexpr int kWgStageBytes = (2 + kWgMaxSub) * kATileBytes;  // dY halves (2 x 16 KB) + X (<= 4 x 16 KB)
 constexpr int kWgSmemBytes = kWgStages * kWgStageBytes + 1024;
+constexpr int kWgTmemCols = 256;
 
-__global__ void __launch_bounds__(kConvThreads, 2)
+__global__ void __launch_bounds__(kConvThreads, 1)
 wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant__ CUtensorMap tmX,
              const WgradParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -260,10 +344,11 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant__ C
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int tap = blockIdx.x / p.chunks;
-  const int ci0 = (blockIdx.x - tap * p.chunks) * 64;
+  const int tap = blockIdx.x / p.cchunks;
+  const int ci0 = (blockIdx.x - tap * p.cchunks) * (64 * p.nsub);
   const int co0 = blockIdx.y * 128;
-  const int r = tap / p.KW, qx = tap - r * p.KW;
+  const int r = p.rowwin ? tap : tap / p.KW;
+  const int qx = p.rowwin ? 0 : tap - r * p.KW;
   const int split = blockIdx.z;
   const int my_tiles = (p.tiles_m - split + p.splits - 1) / p.splits;
 
@@ -282,7 +367,7 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant__ C
     mbar_init(&accum_bar, 1);
     mbar_fence_init();
   }
-  if (warp == 1) tmem_alloc<64>(&tmem_base_s);
+  if (warp == 1) tmem_alloc<kWgTmemCols>(&tmem_base_s);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -292,7 +377,7 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant__ C
     if (lane == 0) {
       tma_prefetch_desc(&tmDY);
       tma_prefetch_desc(&tmX);
-      const uint32_t tx_bytes = (uint32_t)p.rows * 128u * 3u;
+      const uint32_t tx_bytes = (uint32_t)p.rows * 128u * (uint32_t)(2 + p.nsub);
       for (int it = 0; it < my_tiles; ++it) {
         const int s = it % kWgStages;
         const uint32_t ph = (uint32_t)(it / kWgStages) & 1u;
@@ -306,13 +391,14 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant__ C
         mbar_expect_tx(&full_bar[s], tx_bytes);
         tma_load_4d(a_s, &tmDY, &full_bar[s], co0, w0, h0, n0);
         tma_load_4d(a_s + kATileBytes, &tmDY, &full_bar[s], co0 + 64, w0, h0, n0);
-        tma_load_4d(a_s + 2 * kATileBytes, &tmX, &full_bar[s], ci0, w0 * p.sx - p.pad_l + qx,
-                    h0 * p.sx - p.pad_t + r, n0);
+        const int xw = w0 * p.sxw - (p.rowwin ? 0 : p.pad_l) + qx, xh = h0 * p.sxh - p.pad_t + r;
+        for (int j = 0; j < p.nsub; ++j)
+          tma_load_4d(a_s + (2 + j) * kATileBytes, &tmX, &full_bar[s], ci0 + 64 * j, xw, xh, n0);
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(128, 64, 1, 1);
+      const uint32_t idesc = umma_idesc_bf16(128, 64 * p.nsub, 1, 1);
       const int nk = (p.rows + 15) >> 4;
       for (int it = 0; it < my_tiles; ++it) {
         const int s = it % kWgStages;
@@ -320,7 +406,7 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant__ C
         mbar_wait(&full_bar[s], ph);
         tc_fence_after();
         const uint32_t a_addr = smem_u32(smem + s * kWgStageBytes);
-        // MN-major: 8-row (K) groups 1024 B apart; the two 64-channel halves of dY are 16 KB apart
+        // MN-major: 8-row (K) groups 1024 B apart; consecutive 64-channel atoms are 16 KB apart
         const uint64_t adesc = umma_smem_desc_sw128(a_addr, kATileBytes, 1024);
         const uint64_t bdesc = umma_smem_desc_sw128(a_addr + 2 * kATileBytes, kATileBytes, 1024);
         for (int k = 0; k < nk; ++k)
@@ -332,28 +418,40 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant__ C
     }
     __syncwarp();
   } else {
+    const int q = warp & 3;
+    const int co = co0 + q * 32 + lane;
+    float* dst0 = p.dw + (long long)split * p.split_stride + ((long long)co * p.ntaps + tap) * p.Cw + ci0;
+    const int ncols = 64 * p.nsub;
     if (my_tiles > 0) {
       mbar_wait(&accum_bar, 0);
       tc_fence_after();
-      const int q = warp & 3;
-      const int co = co0 + q * 32 + lane;
 #pragma unroll 1
-      for (int c = 0; c < 64; c += 32) {
+      for (int c = 0; c < ncols; c += 32) {
         uint32_t v[32];
         tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + c, v);
         tmem_ld_wait();
         if (co < p.Kout) {
-          float* dst = p.dw + ((long long)co * p.ntaps + tap) * p.Cw + ci0 + c;
+          if (ci0 + c + 32 <= p.Cw) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (ci0 + c + j < p.Cw) atomicAdd(dst + j, __uint_as_float(v[j]));
+            for (int j = 0; j < 32; j += 4)
+              *reinterpret_cast<float4*>(dst0 + c + j) =
+                  make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]),
+                              __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (ci0 + c + j < p.Cw) dst0[c + j] = __uint_as_float(v[j]);
+          }
         }
       }
+    } else if (co < p.Kout) {
+      for (int c = 0; c < ncols; ++c)
+        if (ci0 + c < p.Cw) dst0[c] = 0.f;
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc<64>(tmem_base);
+  if (warp == 1) tmem_dealloc<kWgTmemCols>(tmem_base);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -385,8 +483,24 @@ __global__ void pack_w_dgrad_kernel(const float* __restrict__ w, int K, int C, i
     out[i] = __float2bfloat16_rn(v);
   }
 }
-__global__ void unpack_wgrad_kernel(const float* __restrict__ dwp, int K, int C, int taps, int Cpad,
-                                    float* __restrict__ out) {
+// row-window packing: out[k][r][q * cpp + c] = w[k][c][r][q]  (64 window elements per filter row)
+__global__ void pack_w_rowwin_kernel(const float* __restrict__ w, int K, int C, int KH, int KW, int cpp,
+                                     __nv_bfloat16* __restrict__ out) {
+  const long long total = (long long)K * KH * 64;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int e = (int)(i % 64);
+    const long long t = i / 64;
+    const int r = (int)(t % KH);
+    const int k = (int)(t / KH);
+    const int q = e / cpp, c = e - q * cpp;
+    const float v = (q < KW && c < C) ? w[(((long long)k * C + c) * KH + r) * KW + q] : 0.f;
+    out[i] = __float2bfloat16_rn(v);
+  }
+}
+// sum of `splits` packed partials [K][taps][Cpad] -> OIHW fp32
+__global__ void unpack_wgrad_kernel(const float* __restrict__ dwp, int splits, long long split_stride,
+                                    int K, int C, int taps, int Cpad, float* __restrict__ out) {
   const long long total = (long long)K * C * taps;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
@@ -394,7 +508,29 @@ __global__ void unpack_wgrad_kernel(const float* __restrict__ dwp, int K, int C,
     const long long t = i / taps;
     const int c = (int)(t % C);
     const int k = (int)(t / C);
-    out[i] = dwp[((long long)k * taps + tap) * Cpad + c];
+    const float* src = dwp + ((long long)k * taps + tap) * Cpad + c;
+    float acc = 0.f;
+    for (int s = 0; s < splits; ++s) acc += src[(long long)s * split_stride];
+    out[i] = acc;
+  }
+}
+// row-window partials [K][KH][64] -> OIHW
+__global__ void unpack_wgrad_rowwin_kernel(const float* __restrict__ dwp, int splits,
+                                           long long split_stride, int K, int C, int KH, int KW,
+                                           int cpp, float* __restrict__ out) {
+  const long long total = (long long)K * C * KH * KW;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int q = (int)(i % KW);
+    long long t = i / KW;
+    const int r = (int)(t % KH);
+    t /= KH;
+    const int c = (int)(t % C);
+    const int k = (int)(t / C);
+    const float* src = dwp + ((long long)k * KH + r) * 64 + q * cpp + c;
+    float acc = 0.f;
+    for (int s = 0; s < splits; ++s) acc += src[(long long)s * split_stride];
+    out[i] = acc;
   }
 }
 
@@ -432,8 +568,8 @@ Box pick_box(int OW, int OH, int N) {
 }
 
 template <int BN_>
-int launch_tapgemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const TapGemmParams& p,
-                   cudaStream_t st) {
+int launch_tapgemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmY,
+                   TapGemmParams& p, cudaStream_t st) {
   using Cfg = TapGemmCfg<BN_>;
   static bool attr_set = false;
   if (!attr_set) {
@@ -442,28 +578,64 @@ int launch_tapgemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const TapGemm
                                         Cfg::kSmemBytes));
     attr_set = true;
   }
-  dim3 grid(p.tiles_w * p.tiles_h * p.tiles_n, msp_cdiv(p.Kout, BN_), 1);
-  tapgemm_kernel<BN_><<<grid, kConvThreads, Cfg::kSmemBytes, st>>>(tmA, tmB, p);
+  p.tiles_m = p.tiles_w * p.tiles_h * p.tiles_n;
+  p.tiles_co = msp_cdiv(p.Kout, BN_);
+  const long long total = (long long)p.tiles_m * p.tiles_co;
+  MSP_REQUIRE(total < (1ll << 31), "conv: too many tiles");
+  p.total_tiles = (int)total;
+  const int sms = msp_num_sms();
+  const int grid = p.total_tiles < sms ? p.total_tiles : sms;
+  tapgemm_kernel<BN_><<<grid, kConvThreads, Cfg::kSmemBytes, st>>>(tmA, tmB, tmY, p);
   MSP_CHECK_LAUNCH();
   msp_count_launch(1);
   return MSP_OK;
 }
 
-int dispatch_tapgemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const TapGemmParams& p,
-                     cudaStream_t st) {
-  if (p.Kout <= 16) return launch_tapgemm<16>(tmA, tmB, p, st);
-  if (p.Kout <= 32) return launch_tapgemm<32>(tmA, tmB, p, st);
-  if (p.Kout <= 64) return launch_tapgemm<64>(tmA, tmB, p, st);
-  return launch_tapgemm<128>(tmA, tmB, p, st);
+inline int bn_tile_for(int K) {
+  return K <= 16 ? 16 : (K <= 32 ? 32 : (K <= 64 ? 64 : (K <= 128 ? 128 : 256)));
 }
 
-// A-operand tensor map over an NHWC bf16 tensor (C, W, H, N) with a (64, bw*s, bh*s, bn) box.
-int make_act_map(CUtensorMap* m, const void* base, int C, int W, int H, int N, int cs, Box b,
-                 int s) {
+int dispatch_tapgemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmY,
+                     TapGemmParams& p, cudaStream_t st) {
+  switch (bn_tile_for(p.Kout)) {
+    case 16: return launch_tapgemm<16>(tmA, tmB, tmY, p, st);
+    case 32: return launch_tapgemm<32>(tmA, tmB, tmY, p, st);
+    case 64: return launch_tapgemm<64>(tmA, tmB, tmY, p, st);
+    case 128: return launch_tapgemm<128>(tmA, tmB, tmY, p, st);
+    default: return launch_tapgemm<256>(tmA, tmB, tmY, p, st);
+  }
+}
+
+// Tensor map over an NHWC bf16 tensor (C, W, H, N) with a (64, bw*s, bh*s, bn) box (s = element stride).
+int make_act_map(CUtensorMap* m, const void* base, int C, int W, int H, int N, int cs, Box b, int s) {
   uint64_t dims[4] = {(uint64_t)C, (uint64_t)W, (uint64_t)H, (uint64_t)N};
   uint64_t strides[3] = {(uint64_t)cs * 2, (uint64_t)W * cs * 2, (uint64_t)H * W * cs * 2};
   uint32_t box[4] = {64, (uint32_t)(b.bw * s), (uint32_t)(b.bh * s), (uint32_t)b.bn};
   uint32_t es[4] = {1, (uint32_t)s, (uint32_t)s, 1};
+  return msp_encode_tmap_bf16(m, base, 4, dims, strides, box, es, 128);
+}
+// Output sub-grid map: dims (C, OWs, OHs, N) with explicit element strides (dgrad parity classes write
+// every s-th pixel of dx).  Box (64, bw, bh, bn).
+int make_out_map(CUtensorMap* m, const void* base, int C, int OWs, int OHs, int N, long long w_stride,
+                 long long h_stride, long long n_stride, Box b) {
+  uint64_t dims[4] = {(uint64_t)C, (uint64_t)OWs, (uint64_t)OHs, (uint64_t)N};
+  uint64_t strides[3] = {(uint64_t)w_stride * 2, (uint64_t)h_stride * 2, (uint64_t)n_stride * 2};
+  uint32_t box[4] = {64, (uint32_t)b.bw, (uint32_t)b.bh, (uint32_t)b.bn};
+  uint32_t es[4] = {1, 1, 1, 1};
+  // a size-1 dimension may carry any stride; keep it a positive multiple of 16 bytes
+  for (int i = 0; i < 3; ++i)
+    if (strides[i] == 0) strides[i] = 16;
+  return msp_encode_tmap_bf16(m, base, 4, dims, strides, box, es, 128);
+}
+// Row-window map over the W-padded input [N][H][Wp][cpp]: dim 0 = 64 contiguous elements (the KW taps of
+// one filter row), dim 1 = output column (stride = conv stride x pixel, OVERLAPPING windows), dim 2 = input
+// row (element stride = conv stride), dim 3 = image.
+int make_rowwin_map(CUtensorMap* m, const void* base, int cpp, int Wp, int H, int N, int OW, int s,
+                    Box b) {
+  uint64_t dims[4] = {64, (uint64_t)OW, (uint64_t)H, (uint64_t)N};
+  uint64_t strides[3] = {(uint64_t)s * cpp * 2, (uint64_t)Wp * cpp * 2, (uint64_t)H * Wp * cpp * 2};
+  uint32_t box[4] = {64, (uint32_t)b.bw, (uint32_t)(b.bh * s), (uint32_t)b.bn};
+  uint32_t es[4] = {1, 1, (uint32_t)s, 1};
   return msp_encode_tmap_bf16(m, base, 4, dims, strides, box, es, 128);
 }
 // B-operand map over packed weights [rows][taps][inner]: (inner, taps, rows), box (64, 1, box_rows).
@@ -488,10 +660,21 @@ int check_desc(const msp_conv_desc* d) {
               d->KH, d->KW);
   MSP_REQUIRE(d->stride == 1 || d->stride == 2, "conv: stride %d unsupported", d->stride);
   MSP_REQUIRE(d->pad_t >= 0 && d->pad_l >= 0 && d->pad_t < 64 && d->pad_l < 64, "conv: bad padding");
+  if (d->win_px != 0) {
+    MSP_REQUIRE(d->win_px == 4 || d->win_px == 8, "conv: row-window width must be 4 or 8 pixels");
+    MSP_REQUIRE(d->C * d->win_px == 64 && d->x_cs == d->C,
+                "conv: row-window mode needs C*win_px == 64 dense channels (C=%d)", d->C);
+    MSP_REQUIRE(d->KW <= d->win_px, "conv: filter width %d exceeds the %d-pixel window", d->KW, d->win_px);
+    MSP_REQUIRE(d->Wp >= d->stride * (d->Wo - 1) + d->win_px,
+                "conv: padded row pitch Wp=%d too small for the last window", d->Wp);
+  }
   return MSP_OK;
 }
 
-inline int bn_tile_for(int K) { return K <= 16 ? 16 : (K <= 32 ? 32 : (K <= 64 ? 64 : 128)); }
+inline bool is_flat(const msp_conv_desc* d) {
+  return d->win_px == 0 && d->KH * d->KW == 1 && d->stride == 1 && d->pad_t == 0 && d->pad_l == 0 &&
+         d->Ho == d->H && d->Wo == d->W;
+}
 
 }  // namespace
 
@@ -520,13 +703,15 @@ extern "C" int msp_pack_weights(const float* w, int K, int C, int KH, int KW, in
   return MSP_OK;
 }
 
-extern "C" int msp_unpack_wgrad(const float* dwp, int K, int C, int KH, int KW, int Cpad,
-                                float* dw_oihw, void* stream) {
-  MSP_REQUIRE(dwp && dw_oihw, "unpack_wgrad: null pointer");
-  const int taps = KH * KW;
-  const long long total = (long long)K * C * taps;
+extern "C" int msp_pack_weights_rowwin(const float* w, int K, int C, int KH, int KW, int win_px,
+                                       void* w_rowwin, void* stream) {
+  MSP_REQUIRE(w && w_rowwin, "pack_weights_rowwin: null pointer");
+  MSP_REQUIRE((win_px == 4 || win_px == 8) && KW <= win_px && C <= 64 / win_px,
+              "pack_weights_rowwin: C=%d KW=%d do not fit a %d-pixel window", C, KW, win_px);
+  const long long total = (long long)K * KH * 64;
   const int blocks = (int)((total + 255) / 256 < 4096 ? (total + 255) / 256 : 4096);
-  unpack_wgrad_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(dwp, K, C, taps, Cpad, dw_oihw);
+  pack_w_rowwin_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(w, K, C, KH, KW, 64 / win_px,
+                                                                 (__nv_bfloat16*)w_rowwin);
   MSP_CHECK_LAUNCH();
   msp_count_launch(1);
   return MSP_OK;
@@ -542,9 +727,8 @@ extern "C" int msp_conv_fprop(const msp_conv_desc* d, const void* x, const void*
   const int taps = d->KH * d->KW;
   TapGemmParams p;
   memset(&p, 0, sizeof(p));
-  const bool flat = (taps == 1 && d->stride == 1 && d->pad_t == 0 && d->pad_l == 0 &&
-                     d->Ho == d->H && d->Wo == d->W);
-  CUtensorMap tmA, tmB;
+  const bool flat = is_flat(d);
+  CUtensorMap tmA, tmB, tmY;
   Box b;
   if (flat) {
     // 1x1 stride-1: pixels form one long row -> perfectly filled 128-row tiles
@@ -552,33 +736,51 @@ extern "C" int msp_conv_fprop(const msp_conv_desc* d, const void* x, const void*
     MSP_REQUIRE(P < (1ll << 31), "conv_fprop: too many pixels");
     b = pick_box((int)P, 1, 1);
     rc = make_act_map(&tmA, x, d->C, (int)P, 1, 1, d->x_cs, b, 1);
+    if (rc) return rc;
+    rc = make_out_map(&tmY, y, d->K, (int)P, 1, 1, d->y_cs, 0, 0, b);
     p.OWs = (int)P; p.OHs = 1; p.N = 1;
-    p.y_n_stride = 0; p.y_h_stride = 0; p.y_w_stride = d->y_cs;
   } else {
     b = pick_box(d->Wo, d->Ho, d->N);
-    rc = make_act_map(&tmA, x, d->C, d->W, d->H, d->N, d->x_cs, b, d->stride);
+    if (d->win_px)
+      rc = make_rowwin_map(&tmA, x, d->C, d->Wp, d->H, d->N, d->Wo, d->stride, b);
+    else
+      rc = make_act_map(&tmA, x, d->C, d->W, d->H, d->N, d->x_cs, b, d->stride);
+    if (rc) return rc;
+    rc = make_out_map(&tmY, y, d->K, d->Wo, d->Ho, d->N, d->y_cs, (long long)d->Wo * d->y_cs,
+                      (long long)d->Ho * d->Wo * d->y_cs, b);
     p.OWs = d->Wo; p.OHs = d->Ho; p.N = d->N;
-    p.y_n_stride = (long long)d->Ho * d->Wo * d->y_cs;
-    p.y_h_stride = (long long)d->Wo * d->y_cs;
-    p.y_w_stride = d->y_cs;
   }
   if (rc) return rc;
-  rc = make_w_map(&tmB, w_fprop, d->C, taps, d->K, bn_tile_for(d->K));
+  const int bn_tile = bn_tile_for(d->K);
+  if (d->win_px)
+    rc = make_w_map(&tmB, w_fprop, 64, d->KH, d->K, bn_tile);
+  else
+    rc = make_w_map(&tmB, w_fprop, d->C, taps, d->K, bn_tile);
   if (rc) return rc;
   p.bw = b.bw; p.bh = b.bh; p.bn = b.bn; p.rows = b.bw * b.bh * b.bn;
   p.tiles_w = msp_cdiv(p.OWs, b.bw); p.tiles_h = msp_cdiv(p.OHs, b.bh); p.tiles_n = msp_cdiv(p.N, b.bn);
-  p.sx = flat ? 1 : d->stride;
-  p.C = d->C; p.ntaps = taps; p.Kout = d->K; p.relu = d->relu;
-  p.y = (__nv_bfloat16*)y; p.y_off = 0;
+  p.sxw = (flat || d->win_px) ? 1 : d->stride;
+  p.sxh = flat ? 1 : d->stride;
+  p.Kout = d->K; p.relu = d->relu;
   p.bias = bias; p.ch_sum = ch_sum; p.ch_sqsum = ch_sqsum;
-  for (int r = 0; r < d->KH; ++r)
-    for (int q = 0; q < d->KW; ++q) {
-      const int t = r * d->KW + q;
-      p.tap_dh[t] = (int8_t)(r - d->pad_t);
-      p.tap_dw[t] = (int8_t)(q - d->pad_l);
-      p.tap_w[t] = (uint8_t)t;
+  if (d->win_px) {
+    p.C = 64; p.ntaps = d->KH;
+    for (int r = 0; r < d->KH; ++r) {
+      p.tap_dh[r] = (int8_t)(r - d->pad_t);
+      p.tap_dw[r] = 0;
+      p.tap_w[r] = (uint8_t)r;
     }
-  return dispatch_tapgemm(tmA, tmB, p, (cudaStream_t)stream);
+  } else {
+    p.C = d->C; p.ntaps = taps;
+    for (int r = 0; r < d->KH; ++r)
+      for (int q = 0; q < d->KW; ++q) {
+        const int t = r * d->KW + q;
+        p.tap_dh[t] = (int8_t)(r - d->pad_t);
+        p.tap_dw[t] = (int8_t)(q - d->pad_l);
+        p.tap_w[t] = (uint8_t)t;
+      }
+  }
+  return dispatch_tapgemm(tmA, tmB, tmY, p, (cudaStream_t)stream);
 }
 
 extern "C" int msp_conv_dgrad(const msp_conv_desc* d, const void* dy, const void* w_dgrad, void* dx,
@@ -586,10 +788,11 @@ extern "C" int msp_conv_dgrad(const msp_conv_desc* d, const void* dy, const void
   int rc = check_desc(d);
   if (rc) return rc;
   MSP_REQUIRE(dy && w_dgrad && dx, "conv_dgrad: null pointer");
+  MSP_REQUIRE(d->win_px == 0, "conv_dgrad: not available in row-window mode (the network input needs no gradient)");
   const int taps = d->KH * d->KW;
   const int s = d->stride;
   cudaStream_t st = (cudaStream_t)stream;
-  CUtensorMap tmA, tmB;
+  CUtensorMap tmA, tmB, tmY;
   // weights [Cpad = d->C][taps][Kpad = d->K]: contraction over K (dy channels), outputs = C
   rc = make_w_map(&tmB, w_dgrad, d->K, taps, d->C, bn_tile_for(d->C));
   if (rc) return rc;
@@ -616,90 +819,149 @@ extern "C" int msp_conv_dgrad(const msp_conv_desc* d, const void* dy, const void
                       pw, d->KH, d->KW, s);
         return MSP_ERR_UNSUPPORTED;
       }
-      const bool flat = (taps == 1 && s == 1 && d->pad_t == 0 && d->pad_l == 0 && d->Ho == d->H &&
-                         d->Wo == d->W);
+      const bool flat = is_flat(d);
       Box b;
       if (flat) {
         const long long P = (long long)d->N * d->H * d->W;
         b = pick_box((int)P, 1, 1);
         rc = make_act_map(&tmA, dy, d->K, (int)P, 1, 1, d->y_cs, b, 1);
+        if (rc) return rc;
+        rc = make_out_map(&tmY, dx, d->C, (int)P, 1, 1, d->x_cs, 0, 0, b);
         p.OWs = (int)P; p.OHs = 1; p.N = 1;
-        p.y_w_stride = d->x_cs;
       } else {
         b = pick_box(OWs, OHs, d->N);
         rc = make_act_map(&tmA, dy, d->K, d->Wo, d->Ho, d->N, d->y_cs, b, 1);
+        if (rc) return rc;
+        const __nv_bfloat16* base = (const __nv_bfloat16*)dx + ((long long)ph * d->W + pw) * d->x_cs;
+        rc = make_out_map(&tmY, base, d->C, OWs, OHs, d->N, (long long)s * d->x_cs,
+                          (long long)s * d->W * d->x_cs, (long long)d->H * d->W * d->x_cs, b);
         p.OWs = OWs; p.OHs = OHs; p.N = d->N;
-        p.y_n_stride = (long long)d->H * d->W * d->x_cs;
-        p.y_h_stride = (long long)s * d->W * d->x_cs;
-        p.y_w_stride = (long long)s * d->x_cs;
-        p.y_off = ((long long)ph * d->W + pw) * d->x_cs;
       }
       if (rc) return rc;
       p.bw = b.bw; p.bh = b.bh; p.bn = b.bn; p.rows = b.bw * b.bh * b.bn;
       p.tiles_w = msp_cdiv(p.OWs, b.bw); p.tiles_h = msp_cdiv(p.OHs, b.bh);
       p.tiles_n = msp_cdiv(p.N, b.bn);
-      p.sx = 1; p.C = d->K; p.ntaps = nt; p.Kout = d->C; p.relu = 0; p.accumulate = accumulate;
-      p.y = (__nv_bfloat16*)dx;
-      rc = dispatch_tapgemm(tmA, tmB, p, st);
+      p.sxw = 1; p.sxh = 1; p.C = d->K; p.ntaps = nt; p.Kout = d->C; p.relu = 0; p.accumulate = accumulate;
+      rc = dispatch_tapgemm(tmA, tmB, tmY, p, st);
       if (rc) return rc;
     }
   return MSP_OK;
 }
 
-extern "C" int msp_conv_wgrad(const msp_conv_desc* d, const void* x, const void* dy,
-                              float* dw_packed, void* stream) {
+namespace {
+struct WgradPlan {
+  Box b;
+  int OW, OH, N, tiles_m, nsub, cchunks, gx, gy, splits, Cw, ntaps;
+};
+int plan_wgrad(const msp_conv_desc* d, WgradPlan* pl) {
+  const bool flat = is_flat(d);
+  if (flat) {
+    const long long P = (long long)d->N * d->H * d->W;
+    MSP_REQUIRE(P < (1ll << 31), "conv_wgrad: too many pixels");
+    pl->OW = (int)P; pl->OH = 1; pl->N = 1;
+  } else {
+    pl->OW = d->Wo; pl->OH = d->Ho; pl->N = d->N;
+  }
+  pl->b = pick_box(pl->OW, pl->OH, pl->N);
+  pl->tiles_m = msp_cdiv(pl->OW, pl->b.bw) * msp_cdiv(pl->OH, pl->b.bh) * msp_cdiv(pl->N, pl->b.bn);
+  pl->Cw = d->win_px ? 64 : d->C;
+  pl->ntaps = d->win_px ? d->KH : d->KH * d->KW;
+  const int c64 = msp_cdiv(pl->Cw, 64);
+  pl->nsub = c64 < kWgMaxSub ? c64 : kWgMaxSub;
+  pl->cchunks = msp_cdiv(c64, pl->nsub);
+  pl->gx = pl->ntaps * pl->cchunks;
+  pl->gy = msp_cdiv(d->K, 128);
+  const int base = pl->gx * pl->gy;
+  int splits = msp_num_sms() / base;
+  if (splits < 1) splits = 1;
+  if (splits > pl->tiles_m) splits = pl->tiles_m;
+  if (splits > 65535) splits = 65535;
+  pl->splits = splits;
+  return MSP_OK;
+}
+}  // namespace
+
+extern "C" int msp_conv_wgrad_splits(const msp_conv_desc* d) {
   int rc = check_desc(d);
   if (rc) return rc;
-  MSP_REQUIRE(x && dy && dw_packed, "conv_wgrad: null pointer");
+  WgradPlan pl;
+  rc = plan_wgrad(d, &pl);
+  if (rc) return rc;
+  return pl.splits;
+}
+
+extern "C" int msp_conv_wgrad(const msp_conv_desc* d, const void* x, const void* dy,
+                              float* dw_partials, void* stream) {
+  int rc = check_desc(d);
+  if (rc) return rc;
+  MSP_REQUIRE(x && dy && dw_partials, "conv_wgrad: null pointer");
   cudaStream_t st = (cudaStream_t)stream;
-  const int taps = d->KH * d->KW;
   static bool attr_set = false;
   if (!attr_set) {
     MSP_CHECK_CUDA(cudaFuncSetAttribute(wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         kWgSmemBytes));
     attr_set = true;
   }
-  MSP_CHECK_CUDA(cudaMemsetAsync(dw_packed, 0, sizeof(float) * (size_t)d->K * taps * d->C, st));
+  WgradPlan pl;
+  rc = plan_wgrad(d, &pl);
+  if (rc) return rc;
   WgradParams p;
   memset(&p, 0, sizeof(p));
-  const bool flat = (taps == 1 && d->stride == 1 && d->pad_t == 0 && d->pad_l == 0 &&
-                     d->Ho == d->H && d->Wo == d->W);
+  const bool flat = is_flat(d);
   CUtensorMap tmDY, tmX;
-  Box b;
-  int OW, OH, N;
+  const Box b = pl.b;
   if (flat) {
-    const long long P = (long long)d->N * d->H * d->W;
-    MSP_REQUIRE(P < (1ll << 31), "conv_wgrad: too many pixels");
-    OW = (int)P; OH = 1; N = 1;
-    b = pick_box(OW, OH, N);
-    rc = make_act_map(&tmDY, dy, d->K, OW, 1, 1, d->y_cs, b, 1);
+    rc = make_act_map(&tmDY, dy, d->K, pl.OW, 1, 1, d->y_cs, b, 1);
     if (rc) return rc;
-    rc = make_act_map(&tmX, x, d->C, OW, 1, 1, d->x_cs, b, 1);
+    rc = make_act_map(&tmX, x, d->C, pl.OW, 1, 1, d->x_cs, b, 1);
     if (rc) return rc;
-    p.sx = 1;
+    p.sxw = p.sxh = 1;
   } else {
-    OW = d->Wo; OH = d->Ho; N = d->N;
-    b = pick_box(OW, OH, N);
     rc = make_act_map(&tmDY, dy, d->K, d->Wo, d->Ho, d->N, d->y_cs, b, 1);
     if (rc) return rc;
-    rc = make_act_map(&tmX, x, d->C, d->W, d->H, d->N, d->x_cs, b, d->stride);
+    if (d->win_px) {
+      rc = make_rowwin_map(&tmX, x, d->C, d->Wp, d->H, d->N, d->Wo, d->stride, b);
+      p.sxw = 1;
+    } else {
+      rc = make_act_map(&tmX, x, d->C, d->W, d->H, d->N, d->x_cs, b, d->stride);
+      p.sxw = d->stride;
+    }
     if (rc) return rc;
-    p.sx = d->stride;
+    p.sxh = d->stride;
   }
   p.bw = b.bw; p.bh = b.bh; p.bn = b.bn; p.rows = b.bw * b.bh * b.bn;
-  p.tiles_w = msp_cdiv(OW, b.bw); p.tiles_h = msp_cdiv(OH, b.bh); p.tiles_n = msp_cdiv(N, b.bn);
-  p.tiles_m = p.tiles_w * p.tiles_h * p.tiles_n;
+  p.tiles_w = msp_cdiv(pl.OW, b.bw); p.tiles_h = msp_cdiv(pl.OH, b.bh); p.tiles_n = msp_cdiv(pl.N, b.bn);
+  p.tiles_m = pl.tiles_m;
   p.pad_t = d->pad_t; p.pad_l = d->pad_l; p.KW = d->KW;
-  p.C = d->C; p.Cw = d->C; p.Kout = d->K; p.ntaps = taps; p.chunks = msp_cdiv(d->C, 64);
-  p.dw = dw_packed;
-  const int gx = taps * p.chunks, gy = msp_cdiv(d->K, 128);
-  int splits = msp_cdiv(4 * msp_num_sms(), gx * gy);
-  if (splits > p.tiles_m) splits = p.tiles_m;
-  if (splits < 1) splits = 1;
-  if (splits > 65535) splits = 65535;
-  p.splits = splits;
-  dim3 grid(gx, gy, splits);
+  p.Cw = pl.Cw; p.Kout = d->K; p.ntaps = pl.ntaps; p.cchunks = pl.cchunks; p.nsub = pl.nsub;
+  p.rowwin = d->win_px != 0;
+  p.splits = pl.splits;
+  p.split_stride = (long long)d->K * pl.ntaps * pl.Cw;
+  p.dw = dw_partials;
+  dim3 grid(pl.gx, pl.gy, pl.splits);
   wgrad_kernel<<<grid, kConvThreads, kWgSmemBytes, st>>>(tmDY, tmX, p);
+  MSP_CHECK_LAUNCH();
+  msp_count_launch(1);
+  return MSP_OK;
+}
+
+extern "C" int msp_unpack_wgrad(const msp_conv_desc* d, const float* dw_partials, int C_true,
+                                float* dw_oihw, void* stream) {
+  int rc = check_desc(d);
+  if (rc) return rc;
+  MSP_REQUIRE(dw_partials && dw_oihw && C_true > 0 && C_true <= d->C, "unpack_wgrad: bad arguments");
+  WgradPlan pl;
+  rc = plan_wgrad(d, &pl);
+  if (rc) return rc;
+  const long long split_stride = (long long)d->K * pl.ntaps * pl.Cw;
+  const long long total = (long long)d->K * C_true * d->KH * d->KW;
+  const int blocks = (int)((total + 255) / 256 < 4096 ? (total + 255) / 256 : 4096);
+  if (d->win_px)
+    unpack_wgrad_rowwin_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(
+        dw_partials, pl.splits, split_stride, d->K, C_true, d->KH, d->KW, d->C, dw_oihw);
+  else
+    unpack_wgrad_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(
+        dw_partials, pl.splits, split_stride, d->K, C_true, d->KH * d->KW, d->C, dw_oihw);
   MSP_CHECK_LAUNCH();
   msp_count_launch(1);
   return MSP_OK;

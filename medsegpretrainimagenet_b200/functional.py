@@ -97,6 +97,59 @@ class _Conv(torch.autograd.Function):
         return dx, dw, db, None, None, None, None, None
 
 
+class _InputConv(torch.autograd.Function):
+    """First convolution of a network, straight from the reference's fp32 NCHW image: the layout
+    conversion writes the W-padded row-window tensor and every filter ROW becomes one 64-deep k-block
+    (msp_conv.cu).  The image receives no gradient."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, stride, padding, relu, want_stats, geom):
+        k, c_true, kh, kw = weight.shape
+        n, _, h, w = x.shape
+        win_px, cpp = geom
+        ho, wo, pt, pl = ops.conv_out_size(h, w, kh, kw, stride, padding)
+        wp = max(w + pl, stride * (wo - 1) + win_px)
+        wp += wp & 1
+        xw = ops.nchw_to_rowwin(x, cpp, pl, wp)
+        wr = ops.pack_weights_rowwin(weight, win_px)
+        stats = torch.zeros((2, k), dtype=torch.float32, device=x.device) if want_stats else None
+        y = ops.conv_fprop_rowwin(xw, w, wr, bias.detach() if bias is not None else None, k, kh, kw, stride,
+                                  pt, pl, ho, wo, win_px, relu=relu, stats=stats, c_true=c_true)
+        ctx.geom = (kh, kw, stride, pt, pl, c_true, relu, bias is not None, win_px, w)
+        ctx.save_for_backward(xw, y if relu else None)
+        if want_stats:
+            ctx.mark_non_differentiable(stats)
+            return y, stats
+        return y, None
+
+    @staticmethod
+    def backward(ctx, dy, _dstats):
+        kh, kw, stride, pt, pl, c_true, relu, has_bias, win_px, w_img = ctx.geom
+        xw, y = ctx.saved_tensors
+        if ctx.needs_input_grad[0]:
+            raise RuntimeError("medsegpretrainimagenet_b200: the input image of the first convolution "
+                               "cannot require a gradient on the B200 path")
+        if dy.stride(3) != 1:
+            dy = dy.contiguous()
+        if relu:
+            dy = ops.relu_bwd(y, dy)
+        dw = db = None
+        if ctx.needs_input_grad[1]:
+            dw = ops.conv_wgrad_rowwin(xw, w_img, dy, c_true, kh, kw, stride, pt, pl, win_px)
+        if has_bias and ctx.needs_input_grad[2]:
+            db = ops.channel_sum(dy)
+        return None, dw, db, None, None, None, None, None
+
+
+def input_conv2d(x_nchw, weight, bias=None, stride=1, padding=0, relu=False, want_stats=False):
+    """conv2d on the fp32 NCHW network input; falls back to to_nhwc + conv2d when the layer does not fit
+    the row-window scheme."""
+    geom = ops.rowwin_geometry(weight.shape[1], weight.shape[3], stride)
+    if geom is None or x_nchw.requires_grad:
+        return conv2d(to_nhwc(x_nchw), weight, bias, stride, padding, relu, want_stats)
+    return _InputConv.apply(x_nchw, weight, bias, stride, padding, relu, want_stats, geom)
+
+
 def conv2d(x, weight, bias=None, stride=1, padding=0, relu=False, want_stats=False, out=None):
     return _Conv.apply(x, weight, bias, stride, padding, relu, want_stats, out)
 

@@ -130,8 +130,9 @@ class _timed:
         return False
 
 
-def _conv_desc(n, h, w, c, x_cs, ho, wo, k, y_cs, kh, kw, stride, pad_t, pad_l, relu=0) -> ConvDesc:
-    return ConvDesc(n, h, w, c, x_cs, ho, wo, k, y_cs, kh, kw, stride, pad_t, pad_l, relu)
+def _conv_desc(n, h, w, c, x_cs, ho, wo, k, y_cs, kh, kw, stride, pad_t, pad_l, relu=0, win_px=0,
+               wp=0) -> ConvDesc:
+    return ConvDesc(n, h, w, c, x_cs, ho, wo, k, y_cs, kh, kw, stride, pad_t, pad_l, relu, win_px, wp)
 
 
 def conv_fprop(x, wf, bias, k, kh, kw, stride, pad_t, pad_l, ho, wo, relu=False, out=None, stats=None,
@@ -166,17 +167,87 @@ def conv_dgrad(dy, wd, x_shape, kh, kw, stride, pad_t, pad_l, out=None, accumula
     return out
 
 
+def _wgrad(d: ConvDesc, x, dy, c_true, flops) -> torch.Tensor:
+    splits = _lib.lib.msp_conv_wgrad_splits(C.byref(d))
+    _lib.check(0 if splits >= 1 else splits, "msp_conv_wgrad_splits")
+    taps = d.KH if d.win_px else d.KH * d.KW
+    cw = 64 if d.win_px else d.C
+    part = torch.empty((splits, d.K, taps, cw), dtype=torch.float32, device=x.device)
+    dw = torch.empty((d.K, c_true, d.KH, d.KW), dtype=torch.float32, device=x.device)
+    with _timed("wgrad", flops):
+        call("msp_conv_wgrad", C.byref(d), _p(x), _p(dy), _p(part), _stream())
+        call("msp_unpack_wgrad", C.byref(d), _p(part), c_true, _p(dw), _stream())
+    return dw
+
+
 def conv_wgrad(x, dy, c_true, kh, kw, stride, pad_t, pad_l) -> torch.Tensor:
-    """-> dW in the OIHW fp32 layout of nn.Conv2d.weight.grad."""
+    """-> dW in the OIHW fp32 layout of nn.Conv2d.weight.grad (deterministic split-K: per-split partials
+    summed in a fixed order by msp_unpack_wgrad)."""
     n, h, w, c, x_cs = _chk_nhwc(x, "conv_wgrad(x)")
     _, ho, wo, k, y_cs = _chk_nhwc(dy, "conv_wgrad(dy)")
     d = _conv_desc(n, h, w, c, x_cs, ho, wo, k, y_cs, kh, kw, stride, pad_t, pad_l)
-    dwp = torch.empty((k, kh * kw, c), dtype=torch.float32, device=x.device)
-    with _timed("wgrad", 2.0 * n * ho * wo * k * c_true * kh * kw):
-        call("msp_conv_wgrad", C.byref(d), _p(x), _p(dy), _p(dwp), _stream())
-    dw = torch.empty((k, c_true, kh, kw), dtype=torch.float32, device=x.device)
-    call("msp_unpack_wgrad", _p(dwp), k, c_true, kh, kw, c, _p(dw), _stream())
-    return dw
+    return _wgrad(d, x, dy, c_true, 2.0 * n * ho * wo * k * c_true * kh * kw)
+
+
+# ------------------------------------------------------------------------------------------------
+# row-window convolution: the tiny-channel first layer (7x7/2 stem, 3x3 first block)
+# ------------------------------------------------------------------------------------------------
+def rowwin_geometry(c_true: int, kw: int, stride: int):
+    """-> (win_px, cpp) or None when the layer does not qualify (see msp_conv.cu)."""
+    if stride not in (1, 2):
+        return None
+    if c_true <= 8 and kw <= 8:
+        return 8, 8          # 8 pixels x 8 channels per window
+    if c_true <= 16 and kw <= 4:
+        return 4, 16         # 4 pixels x 16 channels per window
+    return None
+
+
+def nchw_to_rowwin(x: torch.Tensor, cpp: int, pad_l: int, wp: int) -> torch.Tensor:
+    """fp32 NCHW -> bf16 [N, H, Wp, cpp], image column w at w + pad_l, zero elsewhere."""
+    x = x.contiguous()
+    if x.dtype != torch.float32:
+        x = x.float()
+    n, c, h, w = x.shape
+    y = torch.empty((n, h, wp, cpp), dtype=_BF16, device=x.device)
+    call("msp_nchw_f32_to_rowwin_bf16", _p(x), n, c, h, w, cpp, pad_l, wp, _p(y), _stream())
+    return y
+
+
+def pack_weights_rowwin(w: torch.Tensor, win_px: int) -> torch.Tensor:
+    w = w.detach()
+    if w.dtype != torch.float32 or not w.is_contiguous():
+        w = w.float().contiguous()
+    k, c, kh, kw = w.shape
+    out = torch.empty((k, kh, 64), dtype=_BF16, device=w.device)
+    call("msp_pack_weights_rowwin", _p(w), k, c, kh, kw, win_px, _p(out), _stream())
+    return out
+
+
+def _rowwin_desc(xw, w_img, k, kh, kw, stride, pad_t, pad_l, ho, wo, y_cs, win_px, relu=0):
+    n, h, wp, cpp = xw.shape
+    return _conv_desc(n, h, w_img, cpp, cpp, ho, wo, k, y_cs, kh, kw, stride, pad_t, pad_l, relu, win_px, wp)
+
+
+def conv_fprop_rowwin(xw, w_img, wr, bias, k, kh, kw, stride, pad_t, pad_l, ho, wo, win_px, relu=False,
+                      out=None, stats=None, c_true=None):
+    n = xw.shape[0]
+    if out is None:
+        out = new_act(n, ho, wo, k, xw.device)
+    _, _, _, _, y_cs = _chk_nhwc(out, "conv_fprop_rowwin(out)")
+    d = _rowwin_desc(xw, w_img, k, kh, kw, stride, pad_t, pad_l, ho, wo, y_cs, win_px, int(relu))
+    s1 = s2 = None
+    if stats is not None:
+        s1, s2 = stats[0].data_ptr(), stats[1].data_ptr()
+    with _timed("fprop", 2.0 * n * ho * wo * k * (c_true or xw.shape[3]) * kh * kw):
+        call("msp_conv_fprop", C.byref(d), _p(xw), _p(wr), _p(bias), _p(out), s1, s2, _stream())
+    return out
+
+
+def conv_wgrad_rowwin(xw, w_img, dy, c_true, kh, kw, stride, pad_t, pad_l, win_px) -> torch.Tensor:
+    n, ho, wo, k, y_cs = _chk_nhwc(dy, "conv_wgrad_rowwin(dy)")
+    d = _rowwin_desc(xw, w_img, k, kh, kw, stride, pad_t, pad_l, ho, wo, y_cs, win_px)
+    return _wgrad(d, xw, dy, c_true, 2.0 * n * ho * wo * k * c_true * kh * kw)
 
 
 def channel_sum(x: torch.Tensor) -> torch.Tensor:

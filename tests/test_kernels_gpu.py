@@ -115,8 +115,63 @@ def test_conv_fprop_dgrad_wgrad(case):
     _close(_from_nhwc(dx2, c), x.grad + base, 1e-2, "dgrad(accumulate)")
 
     dw = ops.conv_wgrad(xd, dyd, c, ks, ks, stride, pt, pl)
-    # fp32 accumulation over up to N*Ho*Wo pixels, fp32 atomics across split-K
+    # fp32 accumulation over up to N*Ho*Wo pixels, fixed-order fp32 sum of the split-K partials
     _close(dw.cpu(), wt.grad, 2e-3, "wgrad")
+
+
+ROWWIN_CASES = [
+    # N, H, W, C, K, k, stride, padding   (first convolutions: tiny channel counts)
+    (2, 64, 64, 3, 64, 7, 2, 3),       # DeepResNet stem (classification/models.py:43-46)
+    (3, 50, 46, 1, 64, 7, 2, 3),       # 1-channel stem (cfg1), ragged tiles
+    (2, 40, 36, 3, 64, 3, 1, 1),       # UNet_encoder first block (unet_models.py:440)
+    (1, 33, 130, 3, 32, 3, 1, 1),      # wide rows: several W tiles
+    (2, 16, 16, 12, 16, 3, 1, 1),      # 9..16 channels -> 4-pixel windows
+    (2, 18, 20, 5, 24, 2, 1, "same"),  # even kernel, right/bottom padding only
+]
+
+
+@pytest.mark.parametrize("case", ROWWIN_CASES, ids=lambda c: "x".join(map(str, c)))
+def test_conv_rowwin_fprop_wgrad(case):
+    """Row-window path of the first convolution: fp32 NCHW image in, same results as F.conv2d."""
+    ops = _ops()
+    n, h, w, c, k, ks, stride, padding = case
+    g = torch.Generator().manual_seed(300 + ROWWIN_CASES.index(case))
+    x = _bf(torch.randn((n, c, h, w), generator=g))
+    wt = _bf(torch.randn((k, c, ks, ks), generator=g) / math.sqrt(c * ks * ks))
+    bias = torch.randn((k,), generator=g)
+    wt.requires_grad_(True)
+    ref = _ref_conv(x, wt, bias, stride, padding)
+    dy = _bf(torch.randn(ref.shape, generator=g))
+    ref.backward(dy)
+    ho, wo, pt, pl = ops.conv_out_size(h, w, ks, ks, stride, padding)
+    win_px, cpp = ops.rowwin_geometry(c, ks, stride)
+    wp = max(w + pl, stride * (wo - 1) + win_px)
+    wp += wp & 1
+    xw = ops.nchw_to_rowwin(x.to(DEV), cpp, pl, wp)
+    # the padded layout itself (bit-exact: x is bf16-representable)
+    chk = torch.zeros((n, h, wp, cpp))
+    chk[:, :, pl:pl + w, :c] = x.permute(0, 2, 3, 1)
+    assert torch.equal(xw.float().cpu(), chk)
+    wr = ops.pack_weights_rowwin(wt.detach().to(DEV), win_px)
+    stats = torch.zeros((2, k), dtype=torch.float32, device=DEV)
+    y = ops.conv_fprop_rowwin(xw, w, wr, bias.to(DEV), k, ks, ks, stride, pt, pl, ho, wo, win_px, stats=stats)
+    _close(_from_nhwc(y), ref.detach(), 6e-3, "rowwin fprop")
+    yb = y.float().cpu().reshape(-1, k)
+    _close(stats[0].cpu(), yb.sum(0), 1e-3, "rowwin ch_sum")
+    _close(stats[1].cpu(), (yb * yb).sum(0), 1e-3, "rowwin ch_sqsum")
+    dw = ops.conv_wgrad_rowwin(xw, w, _to_nhwc(dy), c, ks, ks, stride, pt, pl, win_px)
+    _close(dw.cpu(), wt.grad, 2e-3, "rowwin wgrad")
+
+
+def test_conv_wgrad_deterministic():
+    """Split-K partials are summed in a fixed order: two runs are bit-identical."""
+    ops = _ops()
+    g = torch.Generator().manual_seed(9)
+    x = _to_nhwc(_bf(torch.randn((4, 64, 28, 28), generator=g)))
+    dy = _to_nhwc(_bf(torch.randn((4, 128, 28, 28), generator=g)))
+    a = ops.conv_wgrad(x, dy, 64, 3, 3, 1, 1, 1)
+    b = ops.conv_wgrad(x, dy, 64, 3, 3, 1, 1, 1)
+    assert torch.equal(a, b)
 
 
 def test_conv_concat_slices():

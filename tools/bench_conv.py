@@ -81,9 +81,18 @@ for name, hin, ci, co, k, s, pad in uniq:
     cnt = seen[(hin, ci, co, k, s, pad)][1]
     ho, wo, pt, pl = ops.conv_out_size(hin, hin, k, k, s, pad)
     M = B * ho * wo
-    x = torch.randn((B, hin, hin, ci), device=dev).to(torch.bfloat16)
-    w = torch.randn((co, ci, k, k), device=dev) * 0.05
-    wf, wd = ops.pack_weights(w)
+    rowwin = name == "stem"
+    if rowwin:
+        ci = 3
+        win_px, cpp = ops.rowwin_geometry(ci, k, s)
+        wp = max(hin + pl, s * (wo - 1) + win_px); wp += wp & 1
+        x = ops.nchw_to_rowwin(torch.randn((B, ci, hin, hin), device=dev), cpp, pl, wp)
+        w = torch.randn((co, ci, k, k), device=dev) * 0.05
+        wf, wd = ops.pack_weights_rowwin(w, win_px), None
+    else:
+        x = torch.randn((B, hin, hin, ci), device=dev).to(torch.bfloat16)
+        w = torch.randn((co, ci, k, k), device=dev) * 0.05
+        wf, wd = ops.pack_weights(w)
     dy = torch.randn((B, ho, wo, co), device=dev).to(torch.bfloat16)
     stats = torch.zeros((2, co), device=dev)
     fl = 2.0 * M * co * ci * k * k
@@ -99,7 +108,11 @@ for name, hin, ci, co, k, s, pad in uniq:
             flush.zero_()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-            if kind == "fprop":
+            if kind == "fprop" and rowwin:
+                ops.conv_fprop_rowwin(x, hin, wf, None, co, k, k, s, pt, pl, ho, wo, win_px, stats=stats)
+            elif kind == "wgrad" and rowwin:
+                ops.conv_wgrad_rowwin(x, hin, dy, ci, k, k, s, pt, pl, win_px)
+            elif kind == "fprop":
                 ops.conv_fprop(x, wf, None, co, k, k, s, pt, pl, ho, wo, stats=stats)
             elif kind == "dgrad":
                 ops.conv_dgrad(dy, wd, tuple(x.shape), k, k, s, pt, pl)
