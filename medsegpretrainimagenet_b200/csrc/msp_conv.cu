@@ -9,7 +9,7 @@
 //    in the 128-byte-swizzled K-major layout tcgen05.mma consumes directly.
 //  * PERSISTENT, warp-specialised CTA, one per SM: warp 0 = TMA producer running up to kStages
 //    k-blocks (and therefore several tiles) ahead, warp 1 = MMA issuer (one elected lane,
-//    tcgen05.mma cta_group::1, M=128, N<=256, fp32 accumulators DOUBLE-BUFFERED in TMEM), warps 2-5 =
+//    tcgen05.mma cta_group::1, M=128, N<=256, fp32 accumulators DOUBLE-BUFFERED in TMEM), warps 2-9 =
 //    epilogue: tcgen05.ld -> bias/ReLU -> bf16 -> 128B-swizzled staging tile in smem -> TMA tile store
 //    (hardware clips ragged tiles and channel tails; dgrad-on-top-of-a-gradient uses the TMA reduce-add),
 //    overlapped with the next tile's main loop.  The BatchNorm batch statistics (per-channel sum / sum
@@ -31,6 +31,7 @@
 // (reference classification/models.py:43-46,161-179,234-253; segmentation/models/blocks.py:458,518,590).
 #include "msp_common.cuh"
 #include "../../include/msp_b200.h"
+#include <stdlib.h>
 
 extern void msp_count_launch(int n);
 
@@ -39,10 +40,11 @@ namespace {
 constexpr int kMaxTaps = 49;
 constexpr int kBM = 128;  // UMMA M (rows of the output tile)
 constexpr int kBK = 64;   // contraction elements per pipeline stage (= one 128-byte swizzle row)
-constexpr int kConvThreads = 192;
+constexpr int kConvThreads = 192;  // wgrad: producer + MMA + 4 epilogue warps
+constexpr int kTapThreads = 320;   // tap-GEMM: producer + MMA + 8 epilogue warps
 constexpr int kATileBytes = kBM * kBK * 2;  // 16 KB
-constexpr int kEpiThreads = 128;
-constexpr int kEpiBarrier = 1;  // named barrier id of the 4 epilogue warps
+constexpr int kEpiThreads = 256;
+constexpr int kEpiBarrier = 1;  // named barrier id of the 8 epilogue warps
 
 struct TapGemmParams {
   int bw, bh, bn, rows;
@@ -55,6 +57,7 @@ struct TapGemmParams {
   int Kout;         // valid output channels
   int relu;
   int accumulate;  // the output tile is ADDED to memory (dgrad on top of a residual gradient)
+  int debug;       // MSP_CONV_DEBUG bit mask (profiling experiments only; 0 in production)
   const float* bias;
   float* ch_sum;
   float* ch_sqsum;
@@ -71,14 +74,14 @@ struct TapGemmCfg {
   static constexpr int kCH = BN_ < 64 ? BN_ : 64;  // epilogue column chunk (one TMA store box)
   static constexpr int kNChunk = BN_ / kCH;
   static constexpr int kStageBufs = BN_ >= 256 ? 1 : 2;  // 16 KB staging tiles for the TMA store
-  static constexpr int kScratchBytes = 4 * 64 * 2 * 4;   // per-row-quarter partial statistics
+  static constexpr int kScratchBytes = 8 * 128 * 4 + 4 * 128 * 4;  // per-slab partial + running statistics
   static constexpr int kSmemBytes =
       kStages * kStageBytes + kStageBufs * kATileBytes + kScratchBytes + 1024;  // + alignment slack
   static constexpr int kTmemCols = 2 * BN_ < 32 ? 32 : 2 * BN_;
 };
 
 template <int BN_>
-__global__ void __launch_bounds__(kConvThreads, 1)
+__global__ void __launch_bounds__(kTapThreads, 1)
 tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmY, const TapGemmParams p) {
   using Cfg = TapGemmCfg<BN_>;
@@ -177,20 +180,25 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     __syncwarp();
   } else {
     // ---------------- epilogue: TMEM -> registers -> swizzled smem tile -> TMA store ----------------
-    const int et = threadIdx.x - 64;  // 0..127
+    // 8 warps = 2 per scheduler: warps (w, w+4) share a TMEM lane quarter and split every 64-column
+    // chunk into two 32-column halves, so that dependent-issue latency of one hides behind the other.
+    const int et = threadIdx.x - 64;  // 0..255
     const int q = warp & 3;           // TMEM lane quarter this warp may access
+    const int half = (et >> 5) >> 2;  // column half of the chunk handled by this warp
     const int row = q * 32 + lane;
     const int wi = row % p.bw;
     const int t2 = row / p.bw;
     const int hi = t2 % p.bh;
     const int ni = t2 / p.bh;
-    const bool do_stats = p.ch_sum != nullptr;
+    const bool do_stats = p.ch_sum != nullptr && !(p.debug & 2);
+    const bool has_bias = p.bias != nullptr;
     const bool store_thread = (et == 0);
+    const uint32_t scratch_s = smem_u32(scratch);
+    const uint32_t run_s = scratch_s + 8 * 128 * 4;  // running statistics [chunk][which][64]
     if (store_thread) tma_prefetch_desc(&tmY);
-    float run[Cfg::kNChunk];
-#pragma unroll
-    for (int c = 0; c < Cfg::kNChunk; ++c) run[c] = 0.f;
+    for (int i = et; i < Cfg::kNChunk * 128; i += kEpiThreads) sts_f32(run_s + i * 4, 0.f);
     constexpr int CH = Cfg::kCH;
+    constexpr int CHH = CH / 2;  // columns per warp per chunk
     uint32_t t = 0, sbuf = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++t) {
       const int tco = tile / p.tiles_m;
@@ -204,42 +212,39 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const uint32_t as = t & 1u;
       mbar_wait(&tfull_bar[as], (t >> 1) & 1u);
       tc_fence_after();
-      const uint32_t tmem_row = tmem_base + ((uint32_t)(q * 32) << 16) + as * BN_;
-#pragma unroll
+      const uint32_t tmem_row = tmem_base + ((uint32_t)(q * 32) << 16) + as * BN_ + half * CHH;
+#pragma unroll 1
       for (int c = 0; c < Cfg::kNChunk; ++c) {
         const int cg = co0 + c * CH;
         uint8_t* stg = staging + (Cfg::kStageBufs == 2 ? sbuf * kATileBytes : 0);
+        const uint32_t stg_s = smem_u32(stg);
         // the staging tile must have been read by its previous TMA store (and by the statistics pass)
         if (store_thread) {
           if constexpr (Cfg::kStageBufs == 2) tma_store_wait_read<1>();
           else tma_store_wait_read<0>();
         }
         named_bar_sync(kEpiBarrier, kEpiThreads);
-        uint32_t v[CH];
-        if constexpr (CH == 64) {
-          tmem_ld_32x32(tmem_row + c * CH, *reinterpret_cast<uint32_t(*)[32]>(&v[0]));
-          tmem_ld_32x32(tmem_row + c * CH + 32, *reinterpret_cast<uint32_t(*)[32]>(&v[32]));
-        } else if constexpr (CH == 32) {
-          tmem_ld_32x32(tmem_row + c * CH, *reinterpret_cast<uint32_t(*)[32]>(&v[0]));
-        } else {
-          tmem_ld_32x16(tmem_row + c * CH, *reinterpret_cast<uint32_t(*)[16]>(&v[0]));
-        }
+        uint32_t v[CHH];
+        if constexpr (CHH == 32) tmem_ld_32x32(tmem_row + c * CH, v);
+        else if constexpr (CHH == 16) tmem_ld_32x16(tmem_row + c * CH, v);
+        else tmem_ld_32x8(tmem_row + c * CH, v);
         tmem_ld_wait();
         if (c == Cfg::kNChunk - 1) {  // accumulator fully read: hand it back to the MMA warp
           tc_fence_before();
           mbar_arrive(&tempty_bar[as]);
         }
-        uint8_t* srow = stg + row * 128;
         if (cg < p.Kout) {
+          const uint32_t srow = stg_s + row * 128;
+          const int cb = cg + half * CHH;  // first output channel of this warp's columns
 #pragma unroll
-          for (int g = 0; g < CH / 8; ++g) {
+          for (int g = 0; g < CHH / 8; ++g) {
             uint32_t pk[4];
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
               float x0 = __uint_as_float(v[g * 8 + 2 * e]);
               float x1 = __uint_as_float(v[g * 8 + 2 * e + 1]);
-              if (p.bias != nullptr) {
-                const int cc = cg + g * 8 + 2 * e;
+              if (has_bias) {
+                const int cc = cb + g * 8 + 2 * e;
                 if (cc < p.Kout) x0 += __ldg(p.bias + cc);
                 if (cc + 1 < p.Kout) x1 += __ldg(p.bias + cc + 1);
               }
@@ -249,55 +254,57 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               }
               pk[e] = valid ? pack_bf16x2(x0, x1) : 0u;
             }
-            *reinterpret_cast<uint4*>(srow + ((g ^ (row & 7)) << 4)) =
-                make_uint4(pk[0], pk[1], pk[2], pk[3]);
+            sts_v4(srow + (((half * (CHH / 8) + g) ^ (row & 7)) << 4), pk[0], pk[1], pk[2], pk[3]);
           }
         }
         fence_proxy_async_smem();
         named_bar_sync(kEpiBarrier, kEpiThreads);
         if (cg < p.Kout) {
-          if (store_thread) {
+          if (store_thread && !(p.debug & 1)) {
             if (p.accumulate) tma_reduce_add_4d(&tmY, stg, cg, w0, h0, n0);
             else tma_store_4d(&tmY, stg, cg, w0, h0, n0);
             tma_store_commit();
           }
           if (do_stats) {
-            // column sums of the bf16 tile: thread -> (column pair, row quarter); conflict-free LDS.32
-            const int cp = et & 31, rq = et >> 5;
+            // column sums of the bf16 tile: thread -> (column pair, 16-row slab); conflict-free LDS.32
+            const int cp = et & 31, re = et >> 5;
             float s1a = 0.f, s2a = 0.f, s1b = 0.f, s2b = 0.f;
-            const uint8_t* base = stg + rq * 32 * 128 + (cp & 3) * 4;
-#pragma unroll 8
-            for (int r = 0; r < 32; ++r) {
-              const uint32_t wv =
-                  *reinterpret_cast<const uint32_t*>(base + r * 128 + (((cp >> 2) ^ (r & 7)) << 4));
+            const uint32_t base = stg_s + re * 16 * 128 + (cp & 3) * 4;
+            const uint32_t sw = (uint32_t)(cp >> 2);
+#pragma unroll
+            for (int r = 0; r < 16; ++r) {
+              const uint32_t wv = lds_u32(base + r * 128 + ((sw ^ (uint32_t)(r & 7)) << 4));
               const float2 f = unpack_bf16x2(wv);
               s1a += f.x;
               s2a = fmaf(f.x, f.x, s2a);
               s1b += f.y;
               s2b = fmaf(f.y, f.y, s2b);
             }
-            float* sc = scratch + rq * 128;  // [rq][which][64]
-            sc[2 * cp] = s1a;
-            sc[2 * cp + 1] = s1b;
-            sc[64 + 2 * cp] = s2a;
-            sc[64 + 2 * cp + 1] = s2b;
+            const uint32_t sc = scratch_s + (re * 128 + 2 * cp) * 4;  // [re][which][64]
+            sts_f32(sc, s1a);
+            sts_f32(sc + 4, s1b);
+            sts_f32(sc + 256, s2a);
+            sts_f32(sc + 260, s2b);
             named_bar_sync(kEpiBarrier, kEpiThreads);
-            // thread et owns (which = et >> 6, column = et & 63) of every chunk of the tile
-            run[c] += scratch[et] + scratch[128 + et] + scratch[256 + et] + scratch[384 + et];
+            if (et < 128) {  // thread et owns (which = et >> 6, column = et & 63) of every chunk
+              float tot = lds_f32(run_s + (c * 128 + et) * 4);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) tot += lds_f32(scratch_s + (j * 128 + et) * 4);
+              sts_f32(run_s + (c * 128 + et) * 4, tot);
+            }
           }
         }
         if constexpr (Cfg::kStageBufs == 2) sbuf ^= 1u;
       }
       // flush the running statistics when this CTA leaves the output-channel block (or finishes)
-      if (do_stats) {
+      if (do_stats && et < 128) {
         const int next = tile + gridDim.x;
         if (next >= p.total_tiles || next / p.tiles_m != tco) {
           float* dst = (et >> 6) ? p.ch_sqsum : p.ch_sum;
-#pragma unroll
           for (int c = 0; c < Cfg::kNChunk; ++c) {
             const int col = co0 + c * CH + (et & 63);
-            if ((et & 63) < CH && col < p.Kout) atomicAdd(dst + col, run[c]);
-            run[c] = 0.f;
+            if ((et & 63) < CH && col < p.Kout) atomicAdd(dst + col, lds_f32(run_s + (c * 128 + et) * 4));
+            sts_f32(run_s + (c * 128 + et) * 4, 0.f);
           }
         }
       }
@@ -578,6 +585,11 @@ int launch_tapgemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtenso
                                         Cfg::kSmemBytes));
     attr_set = true;
   }
+  {
+    static int dbg = -1;
+    if (dbg < 0) { const char* e = getenv("MSP_CONV_DEBUG"); dbg = e ? atoi(e) : 0; }
+    p.debug = dbg;
+  }
   p.tiles_m = p.tiles_w * p.tiles_h * p.tiles_n;
   p.tiles_co = msp_cdiv(p.Kout, BN_);
   const long long total = (long long)p.tiles_m * p.tiles_co;
@@ -585,7 +597,7 @@ int launch_tapgemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtenso
   p.total_tiles = (int)total;
   const int sms = msp_num_sms();
   const int grid = p.total_tiles < sms ? p.total_tiles : sms;
-  tapgemm_kernel<BN_><<<grid, kConvThreads, Cfg::kSmemBytes, st>>>(tmA, tmB, tmY, p);
+  tapgemm_kernel<BN_><<<grid, kTapThreads, Cfg::kSmemBytes, st>>>(tmA, tmB, tmY, p);
   MSP_CHECK_LAUNCH();
   msp_count_launch(1);
   return MSP_OK;
