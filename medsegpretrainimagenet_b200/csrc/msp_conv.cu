@@ -58,6 +58,8 @@ struct TapGemmParams {
   int relu;
   int accumulate;  // the output tile is ADDED to memory (dgrad on top of a residual gradient)
   int debug;       // MSP_CONV_DEBUG bit mask (profiling experiments only; 0 in production)
+  long long y_off, y_n_stride, y_h_stride, y_w_stride;  // element strides of the output sub-grid
+  __nv_bfloat16* y;
   const float* bias;
   float* ch_sum;
   float* ch_sqsum;
@@ -83,7 +85,7 @@ struct TapGemmCfg {
 template <int BN_>
 __global__ void __launch_bounds__(kTapThreads, 1)
 tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-               const __grid_constant__ CUtensorMap tmY, const TapGemmParams p) {
+               const TapGemmParams p) {
   using Cfg = TapGemmCfg<BN_>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
@@ -179,26 +181,34 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     __syncwarp();
   } else {
-    // ---------------- epilogue: TMEM -> registers -> swizzled smem tile -> TMA store ----------------
+    // ---------------- epilogue: TMEM -> registers -> swizzled smem tile -> coalesced global stores -------
     // 8 warps = 2 per scheduler: warps (w, w+4) share a TMEM lane quarter and split every 64-column
-    // chunk into two 32-column halves, so that dependent-issue latency of one hides behind the other.
+    // chunk into two 32-column halves.  The bf16 tile is transposed through a 128B-swizzled staging tile
+    // so that every global store instruction writes four full 128-byte lines (thread = one 16-byte piece).
+    // No async-proxy hand-off: a TMA store here costs a MEMBAR + proxy fence per chunk, which at one
+    // k-block per tile (1x1 convolutions) made the epilogue the critical path (profiles/r01_*).
     const int et = threadIdx.x - 64;  // 0..255
     const int q = warp & 3;           // TMEM lane quarter this warp may access
     const int half = (et >> 5) >> 2;  // column half of the chunk handled by this warp
     const int row = q * 32 + lane;
-    const int wi = row % p.bw;
-    const int t2 = row / p.bw;
-    const int hi = t2 % p.bh;
-    const int ni = t2 / p.bh;
     const bool do_stats = p.ch_sum != nullptr && !(p.debug & 2);
     const bool has_bias = p.bias != nullptr;
-    const bool store_thread = (et == 0);
     const uint32_t scratch_s = smem_u32(scratch);
     const uint32_t run_s = scratch_s + 8 * 128 * 4;  // running statistics [chunk][which][64]
-    if (store_thread) tma_prefetch_desc(&tmY);
     for (int i = et; i < Cfg::kNChunk * 128; i += kEpiThreads) sts_f32(run_s + i * 4, 0.f);
     constexpr int CH = Cfg::kCH;
     constexpr int CHH = CH / 2;  // columns per warp per chunk
+    // tile-invariant decode of the rows this thread touches: its TMEM row, and the 4 rows it copies out
+    const int my_wi = row % p.bw, my_hi = (row / p.bw) % p.bh, my_ni = row / (p.bw * p.bh);
+    const int ck = et & 7;  // 16-byte piece (8 channels) of the staging row this thread copies out
+    int o_wi[4], o_hi[4], o_ni[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int r = j * 32 + (et >> 3);
+      o_wi[j] = r % p.bw;
+      o_hi[j] = (r / p.bw) % p.bh;
+      o_ni[j] = r / (p.bw * p.bh);
+    }
     uint32_t t = 0, sbuf = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++t) {
       const int tco = tile / p.tiles_m;
@@ -208,7 +218,16 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int tn = tm / (p.tiles_w * p.tiles_h);
       const int w0 = tw * p.bw, h0 = th * p.bh, n0 = tn * p.bn;
       const int co0 = tco * BN_;
-      const bool valid = row < p.rows && (w0 + wi) < p.OWs && (h0 + hi) < p.OHs && (n0 + ni) < p.N;
+      const bool valid = row < p.rows && (w0 + my_wi) < p.OWs && (h0 + my_hi) < p.OHs && (n0 + my_ni) < p.N;
+      long long o_off[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int r = j * 32 + (et >> 3);
+        const bool ok = r < p.rows && (w0 + o_wi[j]) < p.OWs && (h0 + o_hi[j]) < p.OHs && (n0 + o_ni[j]) < p.N;
+        o_off[j] = ok ? p.y_off + (long long)(n0 + o_ni[j]) * p.y_n_stride +
+                            (long long)(h0 + o_hi[j]) * p.y_h_stride + (long long)(w0 + o_wi[j]) * p.y_w_stride
+                      : -1;
+      }
       const uint32_t as = t & 1u;
       mbar_wait(&tfull_bar[as], (t >> 1) & 1u);
       tc_fence_after();
@@ -216,14 +235,9 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll 1
       for (int c = 0; c < Cfg::kNChunk; ++c) {
         const int cg = co0 + c * CH;
-        uint8_t* stg = staging + (Cfg::kStageBufs == 2 ? sbuf * kATileBytes : 0);
-        const uint32_t stg_s = smem_u32(stg);
-        // the staging tile must have been read by its previous TMA store (and by the statistics pass)
-        if (store_thread) {
-          if constexpr (Cfg::kStageBufs == 2) tma_store_wait_read<1>();
-          else tma_store_wait_read<0>();
-        }
-        named_bar_sync(kEpiBarrier, kEpiThreads);
+        const uint32_t stg_s = smem_u32(staging) + (Cfg::kStageBufs == 2 ? sbuf * kATileBytes : 0);
+        // single staging tile: everyone must have finished reading the previous chunk out of it
+        if constexpr (Cfg::kStageBufs == 1) named_bar_sync(kEpiBarrier, kEpiThreads);
         uint32_t v[CHH];
         if constexpr (CHH == 32) tmem_ld_32x32(tmem_row + c * CH, v);
         else if constexpr (CHH == 16) tmem_ld_32x16(tmem_row + c * CH, v);
@@ -236,34 +250,66 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (cg < p.Kout) {
           const uint32_t srow = stg_s + row * 128;
           const int cb = cg + half * CHH;  // first output channel of this warp's columns
+          float x[CHH];
 #pragma unroll
-          for (int g = 0; g < CHH / 8; ++g) {
-            uint32_t pk[4];
+          for (int j = 0; j < CHH; ++j) x[j] = __uint_as_float(v[j]);
+          // uniform branches around straight-line blocks (a per-element `if` costs a taken branch each)
+          if (has_bias) {
+            if (cb + CHH <= p.Kout && ((reinterpret_cast<uintptr_t>(p.bias) & 15) == 0)) {
+              const float4* b4 = reinterpret_cast<const float4*>(p.bias + cb);
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              float x0 = __uint_as_float(v[g * 8 + 2 * e]);
-              float x1 = __uint_as_float(v[g * 8 + 2 * e + 1]);
-              if (has_bias) {
-                const int cc = cb + g * 8 + 2 * e;
-                if (cc < p.Kout) x0 += __ldg(p.bias + cc);
-                if (cc + 1 < p.Kout) x1 += __ldg(p.bias + cc + 1);
+              for (int j = 0; j < CHH / 4; ++j) {
+                const float4 bb = __ldg(b4 + j);
+                x[4 * j] += bb.x;
+                x[4 * j + 1] += bb.y;
+                x[4 * j + 2] += bb.z;
+                x[4 * j + 3] += bb.w;
               }
-              if (p.relu) {
-                x0 = fmaxf(x0, 0.f);
-                x1 = fmaxf(x1, 0.f);
-              }
-              pk[e] = valid ? pack_bf16x2(x0, x1) : 0u;
+            } else {
+#pragma unroll
+              for (int j = 0; j < CHH; ++j)
+                if (cb + j < p.Kout) x[j] += __ldg(p.bias + cb + j);
             }
-            sts_v4(srow + (((half * (CHH / 8) + g) ^ (row & 7)) << 4), pk[0], pk[1], pk[2], pk[3]);
           }
+          if (p.relu) {
+#pragma unroll
+            for (int j = 0; j < CHH; ++j) x[j] = fmaxf(x[j], 0.f);
+          }
+          if (!valid) {
+#pragma unroll
+            for (int j = 0; j < CHH; ++j) x[j] = 0.f;
+          }
+#pragma unroll
+          for (int g = 0; g < CHH / 8; ++g)
+            sts_v4(srow + (((half * (CHH / 8) + g) ^ (row & 7)) << 4), pack_bf16x2(x[8 * g], x[8 * g + 1]),
+                   pack_bf16x2(x[8 * g + 2], x[8 * g + 3]), pack_bf16x2(x[8 * g + 4], x[8 * g + 5]),
+                   pack_bf16x2(x[8 * g + 6], x[8 * g + 7]));
         }
-        fence_proxy_async_smem();
         named_bar_sync(kEpiBarrier, kEpiThreads);
         if (cg < p.Kout) {
-          if (store_thread && !(p.debug & 1)) {
-            if (p.accumulate) tma_reduce_add_4d(&tmY, stg, cg, w0, h0, n0);
-            else tma_store_4d(&tmY, stg, cg, w0, h0, n0);
-            tma_store_commit();
+          // copy-out: thread = (row j*32 + et/8, 16-byte piece et%8); a warp stores 4 full 128-byte lines
+          if (ck < CH / 8 && cg + ck * 8 < p.Kout && !(p.debug & 1)) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              if (o_off[j] >= 0) {
+                const int r = j * 32 + (et >> 3);
+                uint4 o = lds_v4(stg_s + r * 128 + ((ck ^ (r & 7)) << 4));
+                __nv_bfloat16* dst = p.y + o_off[j] + cg + ck * 8;
+                if (p.accumulate) {
+                  const uint4 old = *reinterpret_cast<const uint4*>(dst);
+                  const uint32_t ov[4] = {old.x, old.y, old.z, old.w};
+                  const uint32_t nv[4] = {o.x, o.y, o.z, o.w};
+                  uint32_t rv[4];
+#pragma unroll
+                  for (int e = 0; e < 4; ++e) {
+                    const float2 a = unpack_bf16x2(ov[e]), b2 = unpack_bf16x2(nv[e]);
+                    rv[e] = pack_bf16x2(a.x + b2.x, a.y + b2.y);
+                  }
+                  o = make_uint4(rv[0], rv[1], rv[2], rv[3]);
+                }
+                st_v4(dst, o);
+              }
+            }
           }
           if (do_stats) {
             // column sums of the bf16 tile: thread -> (column pair, 16-row slab); conflict-free LDS.32
@@ -309,7 +355,6 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
       }
     }
-    if (store_thread) tma_store_wait_all<0>();
   }
   tc_fence_before();
   __syncthreads();
@@ -575,8 +620,7 @@ Box pick_box(int OW, int OH, int N) {
 }
 
 template <int BN_>
-int launch_tapgemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmY,
-                   TapGemmParams& p, cudaStream_t st) {
+int launch_tapgemm(const CUtensorMap& tmA, const CUtensorMap& tmB, TapGemmParams& p, cudaStream_t st) {
   using Cfg = TapGemmCfg<BN_>;
   static bool attr_set = false;
   if (!attr_set) {
@@ -597,7 +641,7 @@ int launch_tapgemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtenso
   p.total_tiles = (int)total;
   const int sms = msp_num_sms();
   const int grid = p.total_tiles < sms ? p.total_tiles : sms;
-  tapgemm_kernel<BN_><<<grid, kTapThreads, Cfg::kSmemBytes, st>>>(tmA, tmB, tmY, p);
+  tapgemm_kernel<BN_><<<grid, kTapThreads, Cfg::kSmemBytes, st>>>(tmA, tmB, p);
   MSP_CHECK_LAUNCH();
   msp_count_launch(1);
   return MSP_OK;
@@ -607,14 +651,13 @@ inline int bn_tile_for(int K) {
   return K <= 16 ? 16 : (K <= 32 ? 32 : (K <= 64 ? 64 : (K <= 128 ? 128 : 256)));
 }
 
-int dispatch_tapgemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmY,
-                     TapGemmParams& p, cudaStream_t st) {
+int dispatch_tapgemm(const CUtensorMap& tmA, const CUtensorMap& tmB, TapGemmParams& p, cudaStream_t st) {
   switch (bn_tile_for(p.Kout)) {
-    case 16: return launch_tapgemm<16>(tmA, tmB, tmY, p, st);
-    case 32: return launch_tapgemm<32>(tmA, tmB, tmY, p, st);
-    case 64: return launch_tapgemm<64>(tmA, tmB, tmY, p, st);
-    case 128: return launch_tapgemm<128>(tmA, tmB, tmY, p, st);
-    default: return launch_tapgemm<256>(tmA, tmB, tmY, p, st);
+    case 16: return launch_tapgemm<16>(tmA, tmB, p, st);
+    case 32: return launch_tapgemm<32>(tmA, tmB, p, st);
+    case 64: return launch_tapgemm<64>(tmA, tmB, p, st);
+    case 128: return launch_tapgemm<128>(tmA, tmB, p, st);
+    default: return launch_tapgemm<256>(tmA, tmB, p, st);
   }
 }
 
@@ -624,19 +667,6 @@ int make_act_map(CUtensorMap* m, const void* base, int C, int W, int H, int N, i
   uint64_t strides[3] = {(uint64_t)cs * 2, (uint64_t)W * cs * 2, (uint64_t)H * W * cs * 2};
   uint32_t box[4] = {64, (uint32_t)(b.bw * s), (uint32_t)(b.bh * s), (uint32_t)b.bn};
   uint32_t es[4] = {1, (uint32_t)s, (uint32_t)s, 1};
-  return msp_encode_tmap_bf16(m, base, 4, dims, strides, box, es, 128);
-}
-// Output sub-grid map: dims (C, OWs, OHs, N) with explicit element strides (dgrad parity classes write
-// every s-th pixel of dx).  Box (64, bw, bh, bn).
-int make_out_map(CUtensorMap* m, const void* base, int C, int OWs, int OHs, int N, long long w_stride,
-                 long long h_stride, long long n_stride, Box b) {
-  uint64_t dims[4] = {(uint64_t)C, (uint64_t)OWs, (uint64_t)OHs, (uint64_t)N};
-  uint64_t strides[3] = {(uint64_t)w_stride * 2, (uint64_t)h_stride * 2, (uint64_t)n_stride * 2};
-  uint32_t box[4] = {64, (uint32_t)b.bw, (uint32_t)b.bh, (uint32_t)b.bn};
-  uint32_t es[4] = {1, 1, 1, 1};
-  // a size-1 dimension may carry any stride; keep it a positive multiple of 16 bytes
-  for (int i = 0; i < 3; ++i)
-    if (strides[i] == 0) strides[i] = 16;
   return msp_encode_tmap_bf16(m, base, 4, dims, strides, box, es, 128);
 }
 // Row-window map over the W-padded input [N][H][Wp][cpp]: dim 0 = 64 contiguous elements (the KW taps of
@@ -740,7 +770,7 @@ extern "C" int msp_conv_fprop(const msp_conv_desc* d, const void* x, const void*
   TapGemmParams p;
   memset(&p, 0, sizeof(p));
   const bool flat = is_flat(d);
-  CUtensorMap tmA, tmB, tmY;
+  CUtensorMap tmA, tmB;
   Box b;
   if (flat) {
     // 1x1 stride-1: pixels form one long row -> perfectly filled 128-row tiles
@@ -748,19 +778,18 @@ extern "C" int msp_conv_fprop(const msp_conv_desc* d, const void* x, const void*
     MSP_REQUIRE(P < (1ll << 31), "conv_fprop: too many pixels");
     b = pick_box((int)P, 1, 1);
     rc = make_act_map(&tmA, x, d->C, (int)P, 1, 1, d->x_cs, b, 1);
-    if (rc) return rc;
-    rc = make_out_map(&tmY, y, d->K, (int)P, 1, 1, d->y_cs, 0, 0, b);
     p.OWs = (int)P; p.OHs = 1; p.N = 1;
+    p.y_n_stride = 0; p.y_h_stride = 0; p.y_w_stride = d->y_cs;
   } else {
     b = pick_box(d->Wo, d->Ho, d->N);
     if (d->win_px)
       rc = make_rowwin_map(&tmA, x, d->C, d->Wp, d->H, d->N, d->Wo, d->stride, b);
     else
       rc = make_act_map(&tmA, x, d->C, d->W, d->H, d->N, d->x_cs, b, d->stride);
-    if (rc) return rc;
-    rc = make_out_map(&tmY, y, d->K, d->Wo, d->Ho, d->N, d->y_cs, (long long)d->Wo * d->y_cs,
-                      (long long)d->Ho * d->Wo * d->y_cs, b);
     p.OWs = d->Wo; p.OHs = d->Ho; p.N = d->N;
+    p.y_n_stride = (long long)d->Ho * d->Wo * d->y_cs;
+    p.y_h_stride = (long long)d->Wo * d->y_cs;
+    p.y_w_stride = d->y_cs;
   }
   if (rc) return rc;
   const int bn_tile = bn_tile_for(d->K);
@@ -774,6 +803,7 @@ extern "C" int msp_conv_fprop(const msp_conv_desc* d, const void* x, const void*
   p.sxw = (flat || d->win_px) ? 1 : d->stride;
   p.sxh = flat ? 1 : d->stride;
   p.Kout = d->K; p.relu = d->relu;
+  p.y = (__nv_bfloat16*)y; p.y_off = 0;
   p.bias = bias; p.ch_sum = ch_sum; p.ch_sqsum = ch_sqsum;
   if (d->win_px) {
     p.C = 64; p.ntaps = d->KH;
@@ -792,7 +822,7 @@ extern "C" int msp_conv_fprop(const msp_conv_desc* d, const void* x, const void*
         p.tap_w[t] = (uint8_t)t;
       }
   }
-  return dispatch_tapgemm(tmA, tmB, tmY, p, (cudaStream_t)stream);
+  return dispatch_tapgemm(tmA, tmB, p, (cudaStream_t)stream);
 }
 
 extern "C" int msp_conv_dgrad(const msp_conv_desc* d, const void* dy, const void* w_dgrad, void* dx,
@@ -804,7 +834,7 @@ extern "C" int msp_conv_dgrad(const msp_conv_desc* d, const void* dy, const void
   const int taps = d->KH * d->KW;
   const int s = d->stride;
   cudaStream_t st = (cudaStream_t)stream;
-  CUtensorMap tmA, tmB, tmY;
+  CUtensorMap tmA, tmB;
   // weights [Cpad = d->C][taps][Kpad = d->K]: contraction over K (dy channels), outputs = C
   rc = make_w_map(&tmB, w_dgrad, d->K, taps, d->C, bn_tile_for(d->C));
   if (rc) return rc;
@@ -837,24 +867,24 @@ extern "C" int msp_conv_dgrad(const msp_conv_desc* d, const void* dy, const void
         const long long P = (long long)d->N * d->H * d->W;
         b = pick_box((int)P, 1, 1);
         rc = make_act_map(&tmA, dy, d->K, (int)P, 1, 1, d->y_cs, b, 1);
-        if (rc) return rc;
-        rc = make_out_map(&tmY, dx, d->C, (int)P, 1, 1, d->x_cs, 0, 0, b);
         p.OWs = (int)P; p.OHs = 1; p.N = 1;
+        p.y_w_stride = d->x_cs;
       } else {
         b = pick_box(OWs, OHs, d->N);
         rc = make_act_map(&tmA, dy, d->K, d->Wo, d->Ho, d->N, d->y_cs, b, 1);
-        if (rc) return rc;
-        const __nv_bfloat16* base = (const __nv_bfloat16*)dx + ((long long)ph * d->W + pw) * d->x_cs;
-        rc = make_out_map(&tmY, base, d->C, OWs, OHs, d->N, (long long)s * d->x_cs,
-                          (long long)s * d->W * d->x_cs, (long long)d->H * d->W * d->x_cs, b);
         p.OWs = OWs; p.OHs = OHs; p.N = d->N;
+        p.y_n_stride = (long long)d->H * d->W * d->x_cs;
+        p.y_h_stride = (long long)s * d->W * d->x_cs;
+        p.y_w_stride = (long long)s * d->x_cs;
+        p.y_off = ((long long)ph * d->W + pw) * d->x_cs;
       }
       if (rc) return rc;
       p.bw = b.bw; p.bh = b.bh; p.bn = b.bn; p.rows = b.bw * b.bh * b.bn;
       p.tiles_w = msp_cdiv(p.OWs, b.bw); p.tiles_h = msp_cdiv(p.OHs, b.bh);
       p.tiles_n = msp_cdiv(p.N, b.bn);
       p.sxw = 1; p.sxh = 1; p.C = d->K; p.ntaps = nt; p.Kout = d->C; p.relu = 0; p.accumulate = accumulate;
-      rc = dispatch_tapgemm(tmA, tmB, tmY, p, st);
+      p.y = (__nv_bfloat16*)dx;
+      rc = dispatch_tapgemm(tmA, tmB, p, st);
       if (rc) return rc;
     }
   return MSP_OK;
