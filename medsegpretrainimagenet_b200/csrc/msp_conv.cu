@@ -289,27 +289,32 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (cg < p.Kout) {
           // copy-out: thread = (row j*32 + et/8, 16-byte piece et%8); a warp stores 4 full 128-byte lines
           if (ck < CH / 8 && cg + ck * 8 < p.Kout && !(p.debug & 1)) {
+            uint4 o[4];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              if (o_off[j] >= 0) {
-                const int r = j * 32 + (et >> 3);
-                uint4 o = lds_v4(stg_s + r * 128 + ((ck ^ (r & 7)) << 4));
-                __nv_bfloat16* dst = p.y + o_off[j] + cg + ck * 8;
-                if (p.accumulate) {
-                  const uint4 old = *reinterpret_cast<const uint4*>(dst);
+            for (int j = 0; j < 4; ++j) {  // all four smem reads in flight before the first store
+              const int r = j * 32 + (et >> 3);
+              o[j] = lds_v4(stg_s + r * 128 + ((ck ^ (r & 7)) << 4));
+            }
+            if (p.accumulate) {
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                if (o_off[j] >= 0) {
+                  const uint4 old = *reinterpret_cast<const uint4*>(p.y + o_off[j] + cg + ck * 8);
                   const uint32_t ov[4] = {old.x, old.y, old.z, old.w};
-                  const uint32_t nv[4] = {o.x, o.y, o.z, o.w};
+                  const uint32_t nv[4] = {o[j].x, o[j].y, o[j].z, o[j].w};
                   uint32_t rv[4];
 #pragma unroll
                   for (int e = 0; e < 4; ++e) {
                     const float2 a = unpack_bf16x2(ov[e]), b2 = unpack_bf16x2(nv[e]);
                     rv[e] = pack_bf16x2(a.x + b2.x, a.y + b2.y);
                   }
-                  o = make_uint4(rv[0], rv[1], rv[2], rv[3]);
+                  o[j] = make_uint4(rv[0], rv[1], rv[2], rv[3]);
                 }
-                st_v4(dst, o);
               }
             }
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              if (o_off[j] >= 0) st_v4(p.y + o_off[j] + cg + ck * 8, o[j]);
           }
           if (do_stats) {
             // column sums of the bf16 tile: thread -> (column pair, 16-row slab); conflict-free LDS.32
