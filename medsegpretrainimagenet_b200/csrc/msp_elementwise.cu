@@ -47,6 +47,16 @@ inline int grid_for(long long work_items, int per_block, int max_waves = 8) {
   if (b < 1) b = 1;
   return (int)b;
 }
+// persistent grid-stride kernels: exactly as many blocks as are co-resident (a partial second wave idles the GPU)
+template <typename K>
+inline int resident_grid(K kernel, int threads, size_t smem, long long work_items, int per_block) {
+  int occ = 1;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, threads, smem) != cudaSuccess || occ < 1) occ = 1;
+  long long b = (work_items + per_block - 1) / per_block;
+  const long long cap = (long long)msp_num_sms() * occ;
+  if (b > cap) b = cap;
+  return (int)(b < 1 ? 1 : b);
+}
 // threads per block such that blockDim % V == 0 (V = 8-channel vectors per pixel)
 inline int threads_for_vecs(int V) {
   if (V >= 256) return 256;
@@ -161,12 +171,33 @@ __device__ __forceinline__ float act_bwd(float y, float dy, int act) {
   return dy;
 }
 
-__global__ void bn_act_fwd_kernel(const msp_bn_act_desc d, const __nv_bfloat16* __restrict__ x,
-                                  const float* __restrict__ mean, const float* __restrict__ invstd,
-                                  const float* __restrict__ gamma, const float* __restrict__ beta,
-                                  const float* __restrict__ sscale,
-                                  const __nv_bfloat16* __restrict__ res,
-                                  __nv_bfloat16* __restrict__ y) {
+__device__ __forceinline__ F8 unpack8(const uint4& u) {
+  F8 r;
+  float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), c = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
+  r.v[0] = a.x; r.v[1] = a.y; r.v[2] = b.x; r.v[3] = b.y;
+  r.v[4] = c.x; r.v[5] = c.y; r.v[6] = d.x; r.v[7] = d.y;
+  return r;
+}
+// pixel index of the (strided, sub-sampled) shortcut tensor that output pixel `pix` of image `n` reads
+__device__ __forceinline__ long long shortcut_pixel(const msp_bn_act_desc& d, uint32_t pix, uint32_t n, uint32_t HW) {
+  if (d.r_stride <= 1) return pix;
+  const uint32_t hw = pix - n * HW;
+  const uint32_t h = hw / (uint32_t)d.W, w = hw - h * (uint32_t)d.W;
+  return ((long long)n * d.H * d.r_stride + (long long)h * d.r_stride) * ((long long)d.W * d.r_stride) +
+         (long long)w * d.r_stride;
+}
+
+// The three BatchNorm kernels share one thread mapping: thread -> (8-channel vector cg, pixel lane pl); a block
+// sweeps pixels with stride gridDim*ppb and every thread keeps U independent 16-byte loads per tensor in flight
+// (read-once tensors: ld.global.nc.L1::no_allocate).  Pixel counts are < 2^31 (checked on the host): the per-image
+// index needed by DropPath / strided shortcuts is one 32-bit division, skipped entirely when unused.
+template <int U>
+__global__ void __launch_bounds__(256, 2)
+bn_act_fwd_kernel(const msp_bn_act_desc d, const __nv_bfloat16* __restrict__ x,
+                  const float* __restrict__ mean, const float* __restrict__ invstd,
+                  const float* __restrict__ gamma, const float* __restrict__ beta,
+                  const float* __restrict__ sscale, const __nv_bfloat16* __restrict__ res,
+                  __nv_bfloat16* __restrict__ y) {
   const int V = d.C >> 3;
   const int cg = threadIdx.x % V, pl = threadIdx.x / V, ppb = blockDim.x / V;
   const int c = cg * 8;
@@ -177,44 +208,56 @@ __global__ void bn_act_fwd_kernel(const msp_bn_act_desc d, const __nv_bfloat16* 
     sc[j] = g * invstd[c + j];
     sh[j] = b - mean[c + j] * sc[j];
   }
-  const long long HW = (long long)d.H * d.W;
-  const long long P = (long long)d.N * HW;
+  const uint32_t HW = (uint32_t)d.H * (uint32_t)d.W;
+  const uint32_t P = (uint32_t)d.N * HW;
   const bool has_res = res != nullptr && c < d.r_C;
-  for (long long pix = (long long)blockIdx.x * ppb + pl; pix < P; pix += (long long)gridDim.x * ppb) {
-    F8 a = load_bf16x8(x + pix * d.x_cs + c);
-    const int n = (int)(pix / HW);
-    const float s = sscale ? sscale[n] : 1.f;
-    F8 r;
-    if (has_res) {
-      long long rp = pix;
-      if (d.r_stride > 1) {
-        const long long hw = pix - (long long)n * HW;
-        const int h = (int)(hw / d.W), w = (int)(hw - (long long)h * d.W);
-        rp = ((long long)n * d.H * d.r_stride + (long long)h * d.r_stride) * ((long long)d.W * d.r_stride) +
-             (long long)w * d.r_stride;
-      }
-      r = load_bf16x8(res + rp * d.r_cs + c);
-    }
-    F8 o;
+  const bool need_n = sscale != nullptr || (has_res && d.r_stride > 1);
+  const uint32_t step = gridDim.x * (uint32_t)ppb;
+  for (uint32_t p0 = blockIdx.x * (uint32_t)ppb + pl; p0 < P; p0 += step * U) {
+    uint4 a[U], r[U];  // raw bf16x8 until the math (half the registers of unpacked floats)
+    float s[U];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      float t = fmaf(a.v[j], sc[j], sh[j]) * s;
-      if (has_res) t += r.v[j];
-      o.v[j] = act_fwd(t, d.act);
+    for (int u = 0; u < U; ++u) {
+      const uint32_t pix = p0 + u * step;
+      s[u] = 1.f;
+      if (pix < P) {
+        a[u] = ld_nc_v4(x + (long long)pix * d.x_cs + c);
+        uint32_t n = 0;
+        if (need_n) {
+          n = pix / HW;
+          if (sscale) s[u] = __ldg(sscale + n);
+        }
+        if (has_res) r[u] = ld_nc_v4(res + shortcut_pixel(d, pix, n, HW) * d.r_cs + c);
+      }
     }
-    store_bf16x8(y + pix * d.y_cs + c, o);
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const uint32_t pix = p0 + u * step;
+      if (pix < P) {
+        F8 o;
+        const F8 av = unpack8(a[u]);
+        F8 rv;
+        if (has_res) rv = unpack8(r[u]);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          float t = fmaf(av.v[j], sc[j], sh[j]) * s[u];
+          if (has_res) t += rv.v[j];
+          o.v[j] = act_fwd(t, d.act);
+        }
+        store_bf16x8(y + (long long)pix * d.y_cs + c, o);
+      }
+    }
   }
 }
 
 // pass 1 of the backward: per-channel sum(s*g) and sum(s*g*xhat)
-__global__ void bn_act_bwd_reduce_kernel(const msp_bn_act_desc d, const __nv_bfloat16* __restrict__ x,
-                                         const __nv_bfloat16* __restrict__ y,
-                                         const __nv_bfloat16* __restrict__ dy,
-                                         const float* __restrict__ mean,
-                                         const float* __restrict__ invstd,
-                                         const float* __restrict__ sscale, float* sum_g,
-                                         float* sum_gx) {
-  extern __shared__ float red[];  // [blockDim][16] would be too big; reduce by pixel-lane below
+template <int U>
+__global__ void __launch_bounds__(256, 2)
+bn_act_bwd_reduce_kernel(const msp_bn_act_desc d, const __nv_bfloat16* __restrict__ x,
+                         const __nv_bfloat16* __restrict__ y, const __nv_bfloat16* __restrict__ dy,
+                         const float* __restrict__ mean, const float* __restrict__ invstd,
+                         const float* __restrict__ sscale, float* sum_g, float* sum_gx) {
+  extern __shared__ float red[];
   const int V = d.C >> 3;
   const int cg = threadIdx.x % V, pl = threadIdx.x / V, ppb = blockDim.x / V;
   const int c = cg * 8;
@@ -226,18 +269,34 @@ __global__ void bn_act_bwd_reduce_kernel(const msp_bn_act_desc d, const __nv_bfl
     a1[j] = 0.f;
     a2[j] = 0.f;
   }
-  const long long HW = (long long)d.H * d.W;
-  const long long P = (long long)d.N * HW;
-  for (long long pix = (long long)blockIdx.x * ppb + pl; pix < P; pix += (long long)gridDim.x * ppb) {
-    F8 xv = load_bf16x8(x + pix * d.x_cs + c);
-    F8 yv = load_bf16x8(y + pix * d.y_cs + c);
-    F8 gv = load_bf16x8(dy + pix * d.y_cs + c);
-    const float s = sscale ? sscale[(int)(pix / HW)] : 1.f;
+  const uint32_t HW = (uint32_t)d.H * (uint32_t)d.W;
+  const uint32_t P = (uint32_t)d.N * HW;
+  const uint32_t step = gridDim.x * (uint32_t)ppb;
+  for (uint32_t p0 = blockIdx.x * (uint32_t)ppb + pl; p0 < P; p0 += step * U) {
+    uint4 xr[U], yr[U], gr[U];
+    float s[U];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const float g = act_bwd(yv.v[j], gv.v[j], d.act) * s;
-      a1[j] += g;
-      a2[j] = fmaf(g, (xv.v[j] - mu[j]) * is[j], a2[j]);
+    for (int u = 0; u < U; ++u) {
+      const uint32_t pix = p0 + u * step;
+      s[u] = 0.f;
+      if (pix < P) {
+        xr[u] = ld_nc_v4(x + (long long)pix * d.x_cs + c);
+        yr[u] = ld_nc_v4(y + (long long)pix * d.y_cs + c);
+        gr[u] = ld_nc_v4(dy + (long long)pix * d.y_cs + c);
+        s[u] = sscale ? __ldg(sscale + pix / HW) : 1.f;
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      if (p0 + u * step < P) {
+        const F8 xv = unpack8(xr[u]), yv = unpack8(yr[u]), gv = unpack8(gr[u]);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float g = act_bwd(yv.v[j], gv.v[j], d.act) * s[u];
+          a1[j] += g;
+          a2[j] = fmaf(g, (xv.v[j] - mu[j]) * is[j], a2[j]);
+        }
+      }
     }
   }
   // block reduction over pixel lanes: red[pl][cg*16 + j]
@@ -248,34 +307,23 @@ __global__ void bn_act_bwd_reduce_kernel(const msp_bn_act_desc d, const __nv_bfl
     mine[8 + j] = a2[j];
   }
   __syncthreads();
-  if (pl == 0) {
-    for (int l = 1; l < ppb; ++l) {
-      const float* o = red + ((long long)l * V + cg) * 16;
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        a1[j] += o[j];
-        a2[j] += o[8 + j];
-      }
-    }
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      atomicAdd(sum_g + c + j, a1[j]);
-      atomicAdd(sum_gx + c + j, a2[j]);
-    }
+  // thread t sums column t of the [ppb][V*16] table (coalesced, conflict-free), one atomic per column
+  for (int col = threadIdx.x; col < V * 16; col += blockDim.x) {
+    float acc = 0.f;
+    for (int l = 0; l < ppb; ++l) acc += red[(long long)l * V * 16 + col];
+    const int ch = (col >> 4) * 8 + (col & 7);
+    atomicAdd(((col & 8) ? sum_gx : sum_g) + ch, acc);
   }
 }
 
-__global__ void bn_act_bwd_apply_kernel(const msp_bn_act_desc d, const __nv_bfloat16* __restrict__ x,
-                                        const __nv_bfloat16* __restrict__ y,
-                                        const __nv_bfloat16* __restrict__ dy,
-                                        const float* __restrict__ mean,
-                                        const float* __restrict__ invstd,
-                                        const float* __restrict__ gamma,
-                                        const float* __restrict__ sscale,
-                                        const float* __restrict__ sum_g,
-                                        const float* __restrict__ sum_gx, float inv_count,
-                                        __nv_bfloat16* __restrict__ dx, __nv_bfloat16* dres,
-                                        int dres_acc) {
+template <int U>
+__global__ void __launch_bounds__(256, 2)
+bn_act_bwd_apply_kernel(const msp_bn_act_desc d, const __nv_bfloat16* __restrict__ x,
+                        const __nv_bfloat16* __restrict__ y, const __nv_bfloat16* __restrict__ dy,
+                        const float* __restrict__ mean, const float* __restrict__ invstd,
+                        const float* __restrict__ gamma, const float* __restrict__ sscale,
+                        const float* __restrict__ sum_g, const float* __restrict__ sum_gx, float inv_count,
+                        __nv_bfloat16* __restrict__ dx, __nv_bfloat16* dres, int dres_acc) {
   const int V = d.C >> 3;
   const int cg = threadIdx.x % V, pl = threadIdx.x / V, ppb = blockDim.x / V;
   const int c = cg * 8;
@@ -289,38 +337,51 @@ __global__ void bn_act_bwd_apply_kernel(const msp_bn_act_desc d, const __nv_bflo
     k1[j] = gi * sum_g[c + j] * inv_count;
     k2[j] = gi * sum_gx[c + j] * inv_count;
   }
-  const long long HW = (long long)d.H * d.W;
-  const long long P = (long long)d.N * HW;
+  const uint32_t HW = (uint32_t)d.H * (uint32_t)d.W;
+  const uint32_t P = (uint32_t)d.N * HW;
   const bool has_res = dres != nullptr && c < d.r_C;
-  for (long long pix = (long long)blockIdx.x * ppb + pl; pix < P; pix += (long long)gridDim.x * ppb) {
-    F8 xv = load_bf16x8(x + pix * d.x_cs + c);
-    F8 yv = load_bf16x8(y + pix * d.y_cs + c);
-    F8 gv = load_bf16x8(dy + pix * d.y_cs + c);
-    const int n = (int)(pix / HW);
-    const float s = sscale ? sscale[n] : 1.f;
-    F8 o, g;
+  const bool need_n = sscale != nullptr || (has_res && d.r_stride > 1);
+  const uint32_t step = gridDim.x * (uint32_t)ppb;
+  for (uint32_t p0 = blockIdx.x * (uint32_t)ppb + pl; p0 < P; p0 += step * U) {
+    uint4 xr[U], yr[U], gr[U];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      g.v[j] = act_bwd(yv.v[j], gv.v[j], d.act);
-      const float xh = (xv.v[j] - mu[j]) * is[j];
-      o.v[j] = k0[j] * s * g.v[j] - k1[j] - xh * k2[j];
+    for (int u = 0; u < U; ++u) {
+      const uint32_t pix = p0 + u * step;
+      if (pix < P) {
+        xr[u] = ld_nc_v4(x + (long long)pix * d.x_cs + c);
+        yr[u] = ld_nc_v4(y + (long long)pix * d.y_cs + c);
+        gr[u] = ld_nc_v4(dy + (long long)pix * d.y_cs + c);
+      }
     }
-    store_bf16x8(dx + pix * d.x_cs + c, o);
-    if (has_res) {
-      long long rp = pix;
-      if (d.r_stride > 1) {
-        const long long hw = pix - (long long)n * HW;
-        const int h = (int)(hw / d.W), w = (int)(hw - (long long)h * d.W);
-        rp = ((long long)n * d.H * d.r_stride + (long long)h * d.r_stride) * ((long long)d.W * d.r_stride) +
-             (long long)w * d.r_stride;
-      }
-      __nv_bfloat16* rpz = dres + rp * d.r_cs + c;
-      if (dres_acc) {
-        F8 old = load_bf16x8(rpz);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) g.v[j] += old.v[j];
+    for (int u = 0; u < U; ++u) {
+      const uint32_t pix = p0 + u * step;
+      if (pix < P) {
+        uint32_t n = 0;
+        float s = 1.f;
+        if (need_n) {
+          n = pix / HW;
+          if (sscale) s = __ldg(sscale + n);
+        }
+        F8 o, g;
+        const F8 xv = unpack8(xr[u]), yv = unpack8(yr[u]), gv = unpack8(gr[u]);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          g.v[j] = act_bwd(yv.v[j], gv.v[j], d.act);
+          const float xh = (xv.v[j] - mu[j]) * is[j];
+          o.v[j] = k0[j] * s * g.v[j] - k1[j] - xh * k2[j];
+        }
+        store_bf16x8(dx + (long long)pix * d.x_cs + c, o);
+        if (has_res) {
+          __nv_bfloat16* rpz = dres + shortcut_pixel(d, pix, n, HW) * d.r_cs + c;
+          if (dres_acc) {
+            F8 old = load_bf16x8(rpz);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) g.v[j] += old.v[j];
+          }
+          store_bf16x8(rpz, g);
+        }
       }
-      store_bf16x8(rpz, g);
     }
   }
 }
@@ -711,7 +772,8 @@ extern "C" int msp_bn_act_fwd(const msp_bn_act_desc* d, const void* x, const flo
   }
   const int V = d->C / 8, T = threads_for_vecs(V), ppb = T / V;
   const long long P = (long long)d->N * d->H * d->W;
-  bn_act_fwd_kernel<<<grid_for(P, ppb * 4), T, 0, ST>>>(
+  MSP_REQUIRE(P < (1ll << 31), "bn_act: too many pixels");
+  bn_act_fwd_kernel<4><<<resident_grid(bn_act_fwd_kernel<4>, T, 0, P, ppb * 4), T, 0, ST>>>(
       *d, (const __nv_bfloat16*)x, mean, invstd, gamma, beta, sample_scale,
       (const __nv_bfloat16*)residual, (__nv_bfloat16*)y);
   MSP_CHECK_LAUNCH();
@@ -731,7 +793,8 @@ extern "C" int msp_bn_act_bwd_reduce(const msp_bn_act_desc* d, const void* x, co
   MSP_CHECK_CUDA(cudaMemsetAsync(sum_g, 0, sizeof(float) * d->C, ST));
   MSP_CHECK_CUDA(cudaMemsetAsync(sum_gx, 0, sizeof(float) * d->C, ST));
   const size_t smem = (size_t)T * 16 * sizeof(float);
-  bn_act_bwd_reduce_kernel<<<grid_for(P, ppb * 8, 4), T, smem, ST>>>(
+  MSP_REQUIRE(P < (1ll << 31), "bn_act: too many pixels");
+  bn_act_bwd_reduce_kernel<2><<<resident_grid(bn_act_bwd_reduce_kernel<2>, T, smem, P, ppb * 2), T, smem, ST>>>(
       *d, (const __nv_bfloat16*)x, (const __nv_bfloat16*)y, (const __nv_bfloat16*)dy, mean, invstd,
       sample_scale, sum_g, sum_gx);
   MSP_CHECK_LAUNCH();
@@ -750,7 +813,8 @@ extern "C" int msp_bn_act_bwd_apply(const msp_bn_act_desc* d, const void* x, con
               "bn_act_bwd_apply: null pointer");
   const int V = d->C / 8, T = threads_for_vecs(V), ppb = T / V;
   const long long P = (long long)d->N * d->H * d->W;
-  bn_act_bwd_apply_kernel<<<grid_for(P, ppb * 4), T, 0, ST>>>(
+  MSP_REQUIRE(P < (1ll << 31), "bn_act: too many pixels");
+  bn_act_bwd_apply_kernel<2><<<resident_grid(bn_act_bwd_apply_kernel<2>, T, 0, P, ppb * 2), T, 0, ST>>>(
       *d, (const __nv_bfloat16*)x, (const __nv_bfloat16*)y, (const __nv_bfloat16*)dy, mean, invstd,
       gamma, sample_scale, sum_g, sum_gx, (float)(1.0 / count), (__nv_bfloat16*)dx,
       (__nv_bfloat16*)dres, dres_accumulate);

@@ -82,11 +82,19 @@ def test_robustness_vs_reference_goldens():
             assert (got - ref).abs().max().item() <= 1e-4, (name, margin)
 
 
+def _rms(a, r):
+    return ((a - r).double().pow(2).mean().sqrt() / (r.double().pow(2).mean().sqrt() + 1e-30)).item()
+
+
 @pytest.mark.parametrize("idx", range(3))
 def test_unets_vs_reference_goldens(idx):
-    """Converted U-Nets against the reference's own outputs on the same (seeded) weights and input.  Eval mode
-    (running statistics: no batch-statistics amplification) within the bf16 storage tolerance; train mode loss
-    within 1 % (BASELINE.json)."""
+    """Converted U-Nets against the reference's own outputs on the same (seeded) weights and input, in the order the
+    fixture was minted: one train-mode forward (updates the running statistics), Dice loss, then an eval-mode forward.
+    Loss within 1 % (BASELINE.json).  Predictions: bf16 storage noise compounds over the 50-80 layers of these randomly
+    weighted networks, so the yardstick is the fp32 oracle with that storage emulated (oracle/bf16_emulation.py) run
+    here on the same weights — the converted model may be at most 1.5x as far from the reference (+1e-2)."""
+    import copy
+    from oracle import bf16_emulation
     b = _b()
     case = load("models")[idx]
     name = case["name"]
@@ -96,15 +104,21 @@ def test_unets_vs_reference_goldens(idx):
         m = ref_models.resnet50_attention_unet(out_ch=4 if "4class" in name else 1,
                                                final_activation="softmax" if "4class" in name else "sigmoid")
     fill_state_(m, 100)
+    emu = copy.deepcopy(m)
+    bf16_emulation.emulate_bf16_storage(bf16_emulation.round_weights_(emu))
     gpu = b.convert(m.to(DEV))
-    gpu.eval()
-    with torch.no_grad():
-        y = gpu(case["x"].to(DEV)).cpu()
-    ref = case["y_eval"]
-    rms = ((y - ref).double().pow(2).mean().sqrt() / ref.double().pow(2).mean().sqrt()).item()
-    assert rms <= 2e-2, f"{name}: eval prediction rms rel {rms:.4f}"
-    gpu.train()
-    torch.manual_seed(3)
-    yt = gpu(case["x"].to(DEV))
-    loss = b.losses.DiceLoss()(yt, case["mask"].to(DEV))
+    outs = {}
+    for k, mod, x in (("emu", emu, case["x"]), ("gpu", gpu, case["x"].to(DEV))):
+        mod.train()
+        torch.manual_seed(3)
+        yt = mod(x)
+        if k == "gpu":
+            loss = b.losses.DiceLoss()(yt, case["mask"].to(DEV))
+        mod.eval()
+        with torch.no_grad():
+            outs[k] = (yt.detach().cpu(), mod(x).cpu())
     assert abs(loss.item() - case["loss"]) <= 1e-2 * abs(case["loss"]), f"{name}: loss {loss.item()} vs {case['loss']}"
+    for which, gold in ((0, case["y_train"]), (1, case["y_eval"])):
+        ctl, got = _rms(outs["emu"][which], gold), _rms(outs["gpu"][which], gold)
+        print(f"{name} {'train' if which == 0 else 'eval'}: rms rel vs reference golden {got:.4f} (emulated-storage oracle {ctl:.4f})")
+        assert got <= 1.5 * ctl + 1e-2, f"{name}: prediction rms rel {got:.4f} vs control {ctl:.4f}"
