@@ -210,6 +210,7 @@ def main():
     ap.add_argument("--batch", type=int, default=0, help="per-GPU batch (default: the workload's)")
     ap.add_argument("--ref-steps", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="enqueue every step from Python instead of replaying a CUDA graph")
     args = ap.parse_args()
     if args.impl == "reference":
         return reference_arm(args)
@@ -239,7 +240,8 @@ def main():
     if args.workload == "cfg2":
         model = models.resnet50_classifier(group=group)
         crit = b200.losses.CrossEntropyLoss(label_smoothing=0.1)
-        make_opt = lambda ps: torch.optim.AdamW(ps, lr=0.004, betas=(0.9, 0.999), weight_decay=0.05, fused=True)
+        make_opt = lambda ps: torch.optim.AdamW(ps, lr=0.004, betas=(0.9, 0.999), weight_decay=0.05, fused=True,
+                                                capturable=True)
     elif args.workload == "cfg3":
         model = models.resnet50_attention_unet(out_ch=4, final_activation="softmax", group=group)
         crit = b200.losses.DiceLoss(group=group)
@@ -270,7 +272,7 @@ def main():
         cm = b200.metrics.ConfusionMatrix(None, threshold=0.5)
         top5 = None
 
-    def step(x, y, read_loss=False):
+    def step_core(x, y):
         reducer.zero_grad()
         pred = model(x)
         loss = crit(pred, y)
@@ -282,12 +284,17 @@ def main():
             b200.metrics.multiclass_confusion_matrix(pred, y)
         else:
             b200.metrics.binary_confusion_counts(pred, y, 0.5)
-        val = loss.item() if read_loss else None     # loss/loss.py:85
         loss.backward()                              # loss/loss.py:87
         reducer.finish()
         torch.nn.utils.clip_grad_norm_(params, float("inf"), foreach=True)   # train_model.py:95-98
         opt.step()
-        return val
+        return loss.detach()
+
+    graphed = None
+
+    def step(x, y, read_loss=False):
+        out = graphed(x, y) if graphed is not None else step_core(x, y)
+        return out.item() if read_loss else None     # loss/loss.py:85 (the one host read of the step)
 
     def barrier():
         if world > 1:
@@ -297,6 +304,13 @@ def main():
     for _ in range(warm):
         step(x_dev, y_dev)
     barrier()
+    if not args.no_graph:
+        # the whole step as ONE CUDA graph (graphs.GraphedStep): same kernels, one launch from the host
+        graphed = b200.GraphedStep(step_core, (x_dev, y_dev), models=[model], warmup=1)
+        x_dev, y_dev = graphed.static_in          # resident inputs ARE the graph's static buffers (no extra copy)
+        for _ in range(2):
+            step(x_dev, y_dev)
+        barrier()
 
     # ---- timed region 1: inputs resident in HBM ------------------------------------------------
     sampler = ClockSampler(local)
@@ -305,12 +319,16 @@ def main():
     l0 = ops.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    t_host0 = time.perf_counter()
     e0.record()
     for _ in range(args.steps):
         step(x_dev, y_dev)
     e1.record()
+    host_ms = (time.perf_counter() - t_host0) * 1e3 / args.steps   # CPU time to ENQUEUE one step (no sync inside)
     barrier()
     launches = ops.launch_count() - l0
+    if graphed is not None:
+        launches = graphed.launches_per_replay * args.steps
     ms = e0.elapsed_time(e1)
     clocks = sampler.stop() if rank == 0 else None
 
@@ -320,9 +338,9 @@ def main():
     e2.record()
     last = None
     for _ in range(args.steps):
-        x_dev.copy_(x_host, non_blocking=True)
+        x_dev.copy_(x_host, non_blocking=True)      # pinned host batch -> HBM inside the timed region
         y_dev.copy_(y_host, non_blocking=True)
-        last = step(x_dev, y_dev, read_loss=True)
+        last = step(x_dev, y_dev, read_loss=True)   # + D2H read of the loss
     e3.record()
     barrier()
     ms_e2e = e2.elapsed_time(e3)
@@ -335,7 +353,7 @@ def main():
     # ---- instrumented step: device time of every convolution launch -----------------------------
     timeline = []
     ops.set_conv_timeline(timeline)
-    step(x_dev, y_dev)
+    step_core(x_dev, y_dev)
     torch.cuda.synchronize()
     ops.set_conv_timeline(None)
     conv_ms = sum(a.elapsed_time(b) for _, _, a, b in timeline)
@@ -358,12 +376,13 @@ def main():
             "config": {"workload": name, "per_gpu_batch": batch, "global_batch": batch * world,
                        "parallelism": f"dp{world}", "params": n_params,
                        "optimizer": type(opt).__name__, "l2": "inputs_larger_than_l2 (batch + activations >> 126 MB)",
-                       "step": "fwd+loss+bwd+allreduce+metrics+gradnorm+optimizer"},
+                       "step": "fwd+loss+bwd+allreduce+metrics+gradnorm+optimizer",
+                       "execution": "eager launches" if graphed is None else "one CUDA graph replay per step"},
             "e2e": {"value": total_images / (ms_e2e * 1e-3), "unit": "images/sec",
                     "h2d_bytes_per_step": (x_host.numel() * x_host.element_size()
                                            + y_host.numel() * y_host.element_size()) * world,
                     "d2h_bytes_per_step": 4 * world, "ms_per_step": ms_e2e / args.steps, "last_loss": last},
-            "gpu_launches": int(launches),
+            "gpu_launches": int(launches), "host_enqueue_ms_per_step": host_ms,
             "clocks": clocks,
             "roofline": {"bound": "tensor", "kernel": "tapgemm_kernel / wgrad_kernel (tcgen05 implicit-GEMM conv)",
                          "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",

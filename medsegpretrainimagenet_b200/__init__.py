@@ -8,7 +8,8 @@ include/msp_b200.h) and fails if it has not been built: there is no PyTorch / CP
 """
 from . import _lib  # noqa: F401  (raises ImportError when the library is missing)
 from .converter import ExecContext, UnsupportedModule, convert, is_converted
-from . import converter, functional, losses, metrics, ops, robustness
+from . import converter, functional, graphs, losses, metrics, ops, robustness
+from .graphs import GraphedStep
 
-__all__ = ["convert", "is_converted", "ExecContext", "UnsupportedModule", "functional", "losses", "metrics",
+__all__ = ["convert", "is_converted", "ExecContext", "UnsupportedModule", "GraphedStep", "functional", "graphs", "losses", "metrics",
            "ops", "robustness"]

@@ -31,10 +31,45 @@ class UnsupportedModule(NotImplementedError):
 
 
 class ExecContext:
-    """Per-model execution options: `group` = process group for SyncBN statistics (None = local)."""
+    """Per-model execution options: `group` = process group for SyncBN statistics (None = local).
+    During a CUDA-graph capture (graphs.GraphedStep) the DropPath per-sample scales live in static device buffers
+    that are refilled from the CPU generator before every replay."""
 
     def __init__(self, group=None):
         self.group = group
+        self._static = None      # list of (DropPath module, n, device tensor) in forward order while capturing
+        self._replay = []
+
+    def begin_static_droppath(self):
+        self._static = []
+
+    def end_static_droppath(self):
+        self._replay, self._static = self._static or [], None
+
+    def droppath_scale(self, dp, n, device):
+        """classification/models.py:320-325: Bernoulli(keep) per sample on the CPU generator in training (no 1/keep
+        rescale), keep_prob in eval."""
+        if dp.training:
+            s = torch.bernoulli(dp.keep_prob * torch.ones((n, 1, 1, 1))).reshape(n)
+        else:
+            s = torch.full((n,), float(dp.keep_prob))
+        if self._static is not None:
+            buf = torch.empty((n,), dtype=torch.float32, device=device)
+            self._static.append((dp, n, buf))
+            return buf                      # filled by refresh_droppath() before each replay
+        return s.to(device=device, dtype=torch.float32, non_blocking=True)
+
+    def refresh_droppath(self):
+        for dp, n, buf in self._replay:
+            if dp.training:
+                s = torch.bernoulli(dp.keep_prob * torch.ones((n, 1, 1, 1))).reshape(n)
+            else:
+                s = torch.full((n,), float(dp.keep_prob))
+            buf.copy_(s, non_blocking=True)
+
+
+def context_of(model):
+    return getattr(_unwrap(model), "_msp_ctx", None)
 
 
 class RawInput:
@@ -164,18 +199,13 @@ def run_sequence(ctx: ExecContext, mods: List[nn.Module], x):
 # ------------------------------------------------------------------------------------------------
 # classification/models.py
 # ------------------------------------------------------------------------------------------------
-def _drop_path_scale(block, n: int, device) -> Optional[torch.Tensor]:
+def _drop_path_scale(ctx, block, n: int, device) -> Optional[torch.Tensor]:
     dp = getattr(block, "drop_path", None)
     if dp is None or _name(dp) == "Identity":
         return None
     if _name(dp) != "DropPath" or not hasattr(dp, "keep_prob"):
         raise UnsupportedModule(f"drop path module {dp}")
-    if dp.training:
-        # same CPU-generator draw as classification/models.py:320-323 (no 1/keep rescale)
-        s = torch.bernoulli(dp.keep_prob * torch.ones((n, 1, 1, 1))).reshape(n)
-    else:
-        s = torch.full((n,), float(dp.keep_prob))
-    return s.to(device=device, dtype=torch.float32, non_blocking=True)
+    return ctx.droppath_scale(dp, n, device)
 
 
 def run_res_unit(ctx: ExecContext, blk, x):
@@ -187,7 +217,7 @@ def run_res_unit(ctx: ExecContext, blk, x):
     r_stride = max(c.stride[0] for c in convs)
     if convs[-1].out_channels < convs[0].in_channels:
         raise UnsupportedModule("residual block that narrows its input")
-    scale = _drop_path_scale(blk, x.shape[0], x.device)
+    scale = _drop_path_scale(ctx, blk, x.shape[0], x.device)
     y = x
     for conv, bn in zip(convs[:-1], bns[:-1]):
         y = conv_bn_act(ctx, y, conv, bn, ops.ACT_RELU)
