@@ -109,10 +109,12 @@ int msp_nchw_f32_grad_to_nhwc_bf16(const float* g, int N, int C, int H, int W, i
  * the zero-fill / stride-2 shortcut + DropPath multiply of the ResNet blocks
  * (classification/models.py:203-212, 277-290) and BN+ReLU of ConvBlock (blocks.py:458-488).
  * ------------------------------------------------------------------------------------------ */
-/* sums -> mean / invstd, running-stat update (momentum, unbiased var) like torch (eps 1e-5). */
-int msp_bn_finalize(const float* ch_sum, const float* ch_sqsum, int C, double count, float eps,
-                    float momentum, float* mean, float* invstd, float* running_mean,
-                    float* running_var, void* stream);
+/* sums -> mean / invstd, running-stat update (momentum, unbiased var) like torch (eps 1e-5).
+ * reset_sums != 0: the two accumulators are zeroed after they have been read (persistent per-layer
+ * accumulators need no memset launch per step). */
+int msp_bn_finalize(float* ch_sum, float* ch_sqsum, int C, double count, float eps, float momentum,
+                    float* mean, float* invstd, float* running_mean, float* running_var, int reset_sums,
+                    void* stream);
 
 #define MSP_ACT_NONE 0
 #define MSP_ACT_RELU 1

@@ -49,7 +49,7 @@ SIGNATURES = {
     "msp_nchw_f32_to_nhwc_bf16": [P, I, I, I, I, I, P, P],
     "msp_nhwc_bf16_to_nchw_f32": [P, I, I, I, I, I, P, P],
     "msp_nchw_f32_grad_to_nhwc_bf16": [P, I, I, I, I, I, P, P],
-    "msp_bn_finalize": [P, P, I, D, F, F, P, P, P, P, P],
+    "msp_bn_finalize": [P, P, I, D, F, F, P, P, P, P, I, P],
     "msp_bn_act_fwd": [C.POINTER(BnActDesc), P, P, P, P, P, P, P, P, P],
     "msp_bn_act_bwd_reduce": [C.POINTER(BnActDesc), P, P, P, P, P, P, P, P, P],
     "msp_bn_act_bwd_apply": [C.POINTER(BnActDesc), P, P, P, P, P, P, P, P, P, D, P, P, I, P],

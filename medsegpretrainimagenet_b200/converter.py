@@ -39,6 +39,22 @@ class ExecContext:
         self.group = group
         self._static = None      # list of (DropPath module, n, device tensor) in forward order while capturing
         self._replay = []
+        self.counters = []       # num_batches_tracked buffers touched by the running forward
+
+    def stats_for(self, bn):
+        """Persistent, self-cleaning [2, C] accumulator of the conv epilogue's BatchNorm sums (zeroed once here, then
+        by msp_bn_finalize after every use)."""
+        buf = getattr(bn, "_msp_stats", None)
+        dev = bn.weight.device if bn.weight is not None else bn.running_mean.device
+        if buf is None or buf.device != dev or buf.shape[1] != bn.num_features:
+            buf = torch.zeros((2, bn.num_features), dtype=torch.float32, device=dev)
+            bn._msp_stats = buf
+        return buf
+
+    def finish_forward(self):
+        if self.counters:
+            torch._foreach_add_(self.counters, 1)
+            self.counters = []
 
     def begin_static_droppath(self):
         self._static = []
@@ -147,9 +163,11 @@ def conv_bn_act(ctx: ExecContext, x, conv: nn.Conv2d, bn: Optional[nn.BatchNorm2
     training = bn.training or bn.running_mean is None
     # the conv adds its bias in the epilogue, but the bias *gradient* is produced by the BatchNorm node
     bias = conv.bias.detach() if conv.bias is not None else None
-    y, stats = conv2d(x, conv.weight, bias, stride, padding, relu=False, want_stats=training)
+    y, stats = conv2d(x, conv.weight, bias, stride, padding, relu=False,
+                      want_stats=ctx.stats_for(bn) if training else False)
     return Fn.bn_act(y, stats, bn, act=act, residual=residual, r_stride=r_stride,
-                     sample_scale=sample_scale, group=ctx.group, conv_bias=conv.bias)
+                     sample_scale=sample_scale, group=ctx.group, conv_bias=conv.bias, persistent_stats=True,
+                     counters=ctx.counters)
 
 
 def run_sequence(ctx: ExecContext, mods: List[nn.Module], x):
@@ -366,6 +384,7 @@ def _forward_deep_resnet(self, x, return_skip_vals=False, *args, **kwargs):
     _require_cuda(x)
     ctx = self._msp_ctx
     out = run_deep_resnet(ctx, self, RawInput(x), return_skip_vals=return_skip_vals)
+    ctx.finish_forward()
     y, skips = out if return_skip_vals else (out, None)
     if _name(self.classifier) != "Identity":
         y = Fn.to_nchw(y).flatten(1)
@@ -379,6 +398,7 @@ def _forward_deep_resnet(self, x, return_skip_vals=False, *args, **kwargs):
 def _forward_unet_encoder(self, x, return_skip_vals=False):
     _require_cuda(x)
     out = run_unet_encoder(self._msp_ctx, self, RawInput(x), return_skip_vals=return_skip_vals)
+    self._msp_ctx.finish_forward()
     if return_skip_vals:
         return Fn.to_nchw(out[0]), [Fn.to_nchw(s) for s in out[1]]
     return Fn.to_nchw(out)
@@ -386,7 +406,9 @@ def _forward_unet_encoder(self, x, return_skip_vals=False):
 
 def _forward_unet(self, x):
     _require_cuda(x)
-    return run_unet(self._msp_ctx, self, RawInput(x))
+    out = run_unet(self._msp_ctx, self, RawInput(x))
+    self._msp_ctx.finish_forward()
+    return out
 
 
 _TOP_LEVEL = {"DeepResNet": _forward_deep_resnet, "UNet_encoder": _forward_unet_encoder,

@@ -110,7 +110,7 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tfull_bar[s], 1);
-      mbar_init(&tempty_bar[s], kEpiThreads);
+      mbar_init(&tempty_bar[s], kEpiThreads / 32);
     }
     mbar_fence_init();
   }
@@ -198,38 +198,59 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     for (int i = et; i < Cfg::kNChunk * 128; i += kEpiThreads) sts_f32(run_s + i * 4, 0.f);
     constexpr int CH = Cfg::kCH;
     constexpr int CHH = CH / 2;  // columns per warp per chunk
-    // tile-invariant decode of the rows this thread touches: its TMEM row, and the 4 rows it copies out
+    // Tile-invariant per-thread state (the epilogue is instruction-issue bound: everything that does not depend
+    // on the tile is computed once): its TMEM row, the 4 rows it copies out, their smem and global offsets.
     const int my_wi = row % p.bw, my_hi = (row / p.bw) % p.bh, my_ni = row / (p.bw * p.bh);
     const int ck = et & 7;  // 16-byte piece (8 channels) of the staging row this thread copies out
     int o_wi[4], o_hi[4], o_ni[4];
+    uint32_t o_lds[4];      // staging offset of (row j, piece ck)
+    long long o_rel[4];     // element offset of row j relative to the tile origin (+ this thread's 8 channels)
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const int r = j * 32 + (et >> 3);
       o_wi[j] = r % p.bw;
       o_hi[j] = (r / p.bw) % p.bh;
       o_ni[j] = r / (p.bw * p.bh);
+      o_lds[j] = (uint32_t)(r * 128 + ((ck ^ (r & 7)) << 4));
+      o_rel[j] = r < p.rows ? (long long)o_ni[j] * p.y_n_stride + (long long)o_hi[j] * p.y_h_stride +
+                                  (long long)o_wi[j] * p.y_w_stride + ck * 8
+                            : -1;
     }
+    uint32_t sts_off[CHH / 8];  // swizzled staging offsets of this thread's 16-byte groups
+#pragma unroll
+    for (int g = 0; g < CHH / 8; ++g)
+      sts_off[g] = (uint32_t)(row * 128 + (((half * (CHH / 8) + g) ^ (row & 7)) << 4));
+    const bool flat_tiles = p.tiles_h == 1 && p.tiles_n == 1;  // 1x1 "flat" convolutions: tile = 128 pixels of one row
     uint32_t t = 0, sbuf = 0;
+    int tco = blockIdx.x / p.tiles_m, tm = blockIdx.x - tco * p.tiles_m;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++t) {
-      const int tco = tile / p.tiles_m;
-      const int tm = tile - tco * p.tiles_m;
-      const int tw = tm % p.tiles_w;
-      const int th = (tm / p.tiles_w) % p.tiles_h;
-      const int tn = tm / (p.tiles_w * p.tiles_h);
+      int tw = tm, th = 0, tn = 0;
+      if (!flat_tiles) {
+        tw = (int)((uint32_t)tm % (uint32_t)p.tiles_w);
+        const uint32_t rest = (uint32_t)tm / (uint32_t)p.tiles_w;
+        th = (int)(rest % (uint32_t)p.tiles_h);
+        tn = (int)(rest / (uint32_t)p.tiles_h);
+      }
       const int w0 = tw * p.bw, h0 = th * p.bh, n0 = tn * p.bn;
       const int co0 = tco * BN_;
       const bool valid = row < p.rows && (w0 + my_wi) < p.OWs && (h0 + my_hi) < p.OHs && (n0 + my_ni) < p.N;
-      long long o_off[4];
+      const long long tile_off = p.y_off + (long long)n0 * p.y_n_stride + (long long)h0 * p.y_h_stride +
+                                 (long long)w0 * p.y_w_stride + co0;
+      __nv_bfloat16* o_ptr[4];
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        const int r = j * 32 + (et >> 3);
-        const bool ok = r < p.rows && (w0 + o_wi[j]) < p.OWs && (h0 + o_hi[j]) < p.OHs && (n0 + o_ni[j]) < p.N;
-        o_off[j] = ok ? p.y_off + (long long)(n0 + o_ni[j]) * p.y_n_stride +
-                            (long long)(h0 + o_hi[j]) * p.y_h_stride + (long long)(w0 + o_wi[j]) * p.y_w_stride
-                      : -1;
+        const bool ok = o_rel[j] >= 0 && (w0 + o_wi[j]) < p.OWs && (h0 + o_hi[j]) < p.OHs && (n0 + o_ni[j]) < p.N;
+        o_ptr[j] = ok ? p.y + tile_off + o_rel[j] : nullptr;
+      }
+      // advance (tco, tm) to this CTA's next tile without a division
+      int tco_next = tco, tm_next = tm + (int)gridDim.x;
+      while (tm_next >= p.tiles_m) {
+        tm_next -= p.tiles_m;
+        ++tco_next;
       }
       const uint32_t as = t & 1u;
-      mbar_wait(&tfull_bar[as], (t >> 1) & 1u);
+      if (lane == 0) mbar_wait(&tfull_bar[as], (t >> 1) & 1u);  // one poller per warp, not 256 on one mbarrier
+      __syncwarp();
       tc_fence_after();
       const uint32_t tmem_row = tmem_base + ((uint32_t)(q * 32) << 16) + as * BN_ + half * CHH;
 #pragma unroll 1
@@ -243,12 +264,12 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         else if constexpr (CHH == 16) tmem_ld_32x16(tmem_row + c * CH, v);
         else tmem_ld_32x8(tmem_row + c * CH, v);
         tmem_ld_wait();
-        if (c == Cfg::kNChunk - 1) {  // accumulator fully read: hand it back to the MMA warp
+        if (c == Cfg::kNChunk - 1) {  // accumulator fully read: hand it back to the MMA warp (one arrive per warp)
           tc_fence_before();
-          mbar_arrive(&tempty_bar[as]);
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tempty_bar[as]);
         }
         if (cg < p.Kout) {
-          const uint32_t srow = stg_s + row * 128;
           const int cb = cg + half * CHH;  // first output channel of this warp's columns
           float x[CHH];
 #pragma unroll
@@ -281,7 +302,7 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           }
 #pragma unroll
           for (int g = 0; g < CHH / 8; ++g)
-            sts_v4(srow + (((half * (CHH / 8) + g) ^ (row & 7)) << 4), pack_bf16x2(x[8 * g], x[8 * g + 1]),
+            sts_v4(stg_s + sts_off[g], pack_bf16x2(x[8 * g], x[8 * g + 1]),
                    pack_bf16x2(x[8 * g + 2], x[8 * g + 3]), pack_bf16x2(x[8 * g + 4], x[8 * g + 5]),
                    pack_bf16x2(x[8 * g + 6], x[8 * g + 7]));
         }
@@ -291,15 +312,13 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           if (ck < CH / 8 && cg + ck * 8 < p.Kout && !(p.debug & 1)) {
             uint4 o[4];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {  // all four smem reads in flight before the first store
-              const int r = j * 32 + (et >> 3);
-              o[j] = lds_v4(stg_s + r * 128 + ((ck ^ (r & 7)) << 4));
-            }
+            for (int j = 0; j < 4; ++j) o[j] = lds_v4(stg_s + o_lds[j]);  // all four smem reads in flight first
+            const int coff = c * CH;
             if (p.accumulate) {
 #pragma unroll
               for (int j = 0; j < 4; ++j) {
-                if (o_off[j] >= 0) {
-                  const uint4 old = *reinterpret_cast<const uint4*>(p.y + o_off[j] + cg + ck * 8);
+                if (o_ptr[j] != nullptr) {
+                  const uint4 old = *reinterpret_cast<const uint4*>(o_ptr[j] + coff);
                   const uint32_t ov[4] = {old.x, old.y, old.z, old.w};
                   const uint32_t nv[4] = {o[j].x, o[j].y, o[j].z, o[j].w};
                   uint32_t rv[4];
@@ -314,7 +333,7 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
 #pragma unroll
             for (int j = 0; j < 4; ++j)
-              if (o_off[j] >= 0) st_v4(p.y + o_off[j] + cg + ck * 8, o[j]);
+              if (o_ptr[j] != nullptr) st_v4(o_ptr[j] + coff, o[j]);
           }
           if (do_stats) {
             // column sums of the bf16 tile: thread -> (column pair, 16-row slab); conflict-free LDS.32
@@ -349,8 +368,7 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
       // flush the running statistics when this CTA leaves the output-channel block (or finishes)
       if (do_stats && et < 128) {
-        const int next = tile + gridDim.x;
-        if (next >= p.total_tiles || next / p.tiles_m != tco) {
+        if (tile + (int)gridDim.x >= p.total_tiles || tco_next != tco) {
           float* dst = (et >> 6) ? p.ch_sqsum : p.ch_sum;
           for (int c = 0; c < Cfg::kNChunk; ++c) {
             const int col = co0 + c * CH + (et & 63);
@@ -359,6 +377,8 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           }
         }
       }
+      tco = tco_next;
+      tm = tm_next;
     }
   }
   tc_fence_before();
@@ -480,7 +500,8 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant__ C
     float* dst0 = p.dw + (long long)split * p.split_stride + ((long long)co * p.ntaps + tap) * p.Cw + ci0;
     const int ncols = 64 * p.nsub;
     if (my_tiles > 0) {
-      mbar_wait(&accum_bar, 0);
+      if (lane == 0) mbar_wait(&accum_bar, 0);
+      __syncwarp();
       tc_fence_after();
 #pragma unroll 1
       for (int c = 0; c < ncols; c += 32) {

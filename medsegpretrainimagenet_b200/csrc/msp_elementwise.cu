@@ -137,13 +137,16 @@ __global__ void nhwc_to_nchw_kernel(const __nv_bfloat16* __restrict__ x, int C, 
 // ---------------------------------------------------------------------------------------------
 // BatchNorm
 // ---------------------------------------------------------------------------------------------
-__global__ void bn_finalize_kernel(const float* __restrict__ s1, const float* __restrict__ s2, int C,
-                                   double count, float eps, float momentum, float* mean,
-                                   float* invstd, float* rmean, float* rvar) {
+__global__ void bn_finalize_kernel(float* s1, float* s2, int C, double count, float eps, float momentum,
+                                   float* mean, float* invstd, float* rmean, float* rvar, int reset) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
   const double m = (double)s1[c] / count;
   double var = (double)s2[c] / count - m * m;
+  if (reset) {  // self-cleaning accumulators: ready for the next forward without a memset launch
+    s1[c] = 0.f;
+    s2[c] = 0.f;
+  }
   if (var < 0) var = 0;
   mean[c] = (float)m;
   invstd[c] = (float)(1.0 / sqrt(var + (double)eps));
@@ -730,14 +733,14 @@ extern "C" int msp_nchw_f32_grad_to_nhwc_bf16(const float* g, int N, int C, int 
   return msp_nchw_f32_to_nhwc_bf16(g, N, C, H, W, g_cs_out, y, stream);
 }
 
-extern "C" int msp_bn_finalize(const float* ch_sum, const float* ch_sqsum, int C, double count,
-                               float eps, float momentum, float* mean, float* invstd,
-                               float* running_mean, float* running_var, void* stream) {
+extern "C" int msp_bn_finalize(float* ch_sum, float* ch_sqsum, int C, double count, float eps,
+                               float momentum, float* mean, float* invstd, float* running_mean,
+                               float* running_var, int reset_sums, void* stream) {
   MSP_REQUIRE(ch_sum && ch_sqsum && mean && invstd && C > 0 && count > 0, "bn_finalize: bad arguments");
   MSP_REQUIRE((running_mean == nullptr) == (running_var == nullptr),
               "bn_finalize: need both running buffers or none");
   bn_finalize_kernel<<<(C + 127) / 128, 128, 0, ST>>>(ch_sum, ch_sqsum, C, count, eps, momentum, mean,
-                                                      invstd, running_mean, running_var);
+                                                      invstd, running_mean, running_var, reset_sums);
   MSP_CHECK_LAUNCH();
   msp_count_launch(1);
   return MSP_OK;

@@ -57,6 +57,16 @@ def to_nchw(x: torch.Tensor, c: Optional[int] = None) -> torch.Tensor:
 # ------------------------------------------------------------------------------------------------
 # convolution
 # ------------------------------------------------------------------------------------------------
+def _stats_buffer(want_stats, k, device):
+    """`want_stats` is False, True (fresh zeroed [2, K] accumulator) or a persistent accumulator that
+    msp_bn_finalize(reset) leaves zeroed for the next step."""
+    if want_stats is False or want_stats is None:
+        return None
+    if want_stats is True:
+        return torch.zeros((2, k), dtype=torch.float32, device=device)
+    return want_stats
+
+
 class _Conv(torch.autograd.Function):
     """y = conv2d(x, weight, bias) (+ReLU); optionally returns the fused per-channel (sum, sum of
     squares) of y as a second, non-differentiable output."""
@@ -68,13 +78,13 @@ class _Conv(torch.autograd.Function):
         ho, wo, pt, pl = ops.conv_out_size(h, w, kh, kw, stride, padding)
         need_dx = ctx.needs_input_grad[0]
         wf, wd = ops.pack_weights(weight, need_dgrad=need_dx)
-        stats = torch.zeros((2, k), dtype=torch.float32, device=x.device) if want_stats else None
+        stats = _stats_buffer(want_stats, k, x.device)
         y = ops.conv_fprop(x, wf, bias.detach() if bias is not None else None, k, kh, kw, stride, pt, pl,
                            ho, wo, relu=relu, out=out, stats=stats, c_true=c_true)
         ctx.geom = (kh, kw, stride, pt, pl, c_true, relu, bias is not None)
         ctx.x_shape = tuple(x.shape)
         ctx.save_for_backward(x, wd, y if relu else None)
-        if want_stats:
+        if stats is not None:
             ctx.mark_non_differentiable(stats)
             return y, stats
         return y, None
@@ -112,12 +122,12 @@ class _InputConv(torch.autograd.Function):
         wp += wp & 1
         xw = ops.nchw_to_rowwin(x, cpp, pl, wp)
         wr = ops.pack_weights_rowwin(weight, win_px)
-        stats = torch.zeros((2, k), dtype=torch.float32, device=x.device) if want_stats else None
+        stats = _stats_buffer(want_stats, k, x.device)
         y = ops.conv_fprop_rowwin(xw, w, wr, bias.detach() if bias is not None else None, k, kh, kw, stride,
                                   pt, pl, ho, wo, win_px, relu=relu, stats=stats, c_true=c_true)
         ctx.geom = (kh, kw, stride, pt, pl, c_true, relu, bias is not None, win_px, w)
         ctx.save_for_backward(xw, y if relu else None)
-        if want_stats:
+        if stats is not None:
             ctx.mark_non_differentiable(stats)
             return y, stats
         return y, None
@@ -164,7 +174,7 @@ class _BnAct(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, stats, gamma, beta, residual, sample_scale, running_mean, running_var, training,
-                momentum, eps, act, r_stride, group, conv_bias):
+                momentum, eps, act, r_stride, group, conv_bias, persistent_stats):
         n, h, w, c = x.shape
         count = n * h * w
         if training:
@@ -172,7 +182,7 @@ class _BnAct(torch.autograd.Function):
                 # SyncBN: [2C] fp32 sums over NCCL; every rank holds the same per-GPU batch (weak scaling)
                 _allreduce_sum(stats, group)
                 count = count * dist.get_world_size(group)
-            mi = ops.bn_finalize(stats, count, eps, momentum, running_mean, running_var)
+            mi = ops.bn_finalize(stats, count, eps, momentum, running_mean, running_var, reset=persistent_stats)
         else:
             mi = ops.bn_eval_stats(running_mean, running_var, eps)
         y = ops.bn_act_fwd(x, mi, gamma.detach() if gamma is not None else None,
@@ -192,7 +202,10 @@ class _BnAct(torch.autograd.Function):
             full = torch.empty((n, h, w, y.stride(2)), dtype=dy.dtype, device=dy.device)[..., :c]
             dy = ops.copy_channels(dy if dy.stride(3) == 1 else dy.contiguous(), full)
         sums = ops.bn_act_bwd_reduce(x, y, dy, mi, act, sample_scale=sscale)
-        dbeta, dgamma = sums[0].clone(), sums[1].clone()
+        synced = training and group is not None and dist.is_initialized() and dist.get_world_size(group) > 1
+        # dgamma / dbeta are the LOCAL sums (the gradient reducer averages parameters' gradients); only the
+        # SyncBN all-reduce below overwrites `sums` in place, so a copy is needed in that case alone
+        dbeta, dgamma = (sums[0].clone(), sums[1].clone()) if synced else (sums[0], sums[1])
         dbias = None
         if ctx.needs_input_grad[14]:
             # gradient of the producing conv's bias = sum over pixels of dx.  Train mode: BatchNorm
@@ -202,9 +215,9 @@ class _BnAct(torch.autograd.Function):
                 dbias = torch.zeros_like(dbeta)
             else:
                 dbias = dbeta * mi[1] if gamma is None else dbeta * mi[1] * gamma.detach()
-        if training:
+        if synced:
             _allreduce_sum(sums, group)
-        else:
+        elif not training:
             # frozen statistics: dx = gamma * invstd * s * g (no mean / projection terms)
             sums = torch.zeros_like(sums)
         dres = None
@@ -218,19 +231,24 @@ class _BnAct(torch.autograd.Function):
             dx = None
         return (dx, None, dgamma if gamma is not None and ctx.needs_input_grad[2] else None,
                 dbeta if ctx.needs_input_grad[3] else None, dres, None, None, None, None, None, None, None,
-                None, None, dbias)
+                None, None, dbias, None)
 
 
 def bn_act(x, stats, bn: torch.nn.BatchNorm2d, act=ops.ACT_NONE, residual=None, r_stride=1,
-           sample_scale=None, group=None, conv_bias=None):
+           sample_scale=None, group=None, conv_bias=None, persistent_stats=False, counters=None):
+    """`counters`: list collecting the num_batches_tracked buffers to bump (one fused add at the end of the forward,
+    converter._finish_forward) instead of one tiny launch per layer; None = bump immediately."""
     training = bn.training or bn.running_mean is None
     momentum = 0.1 if bn.momentum is None else bn.momentum
     if training and bn.num_batches_tracked is not None:
-        bn.num_batches_tracked.add_(1)
+        if counters is None:
+            bn.num_batches_tracked.add_(1)
+        else:
+            counters.append(bn.num_batches_tracked)
     return _BnAct.apply(x, stats, bn.weight, bn.bias, residual, sample_scale,
                         bn.running_mean if bn.track_running_stats else None,
                         bn.running_var if bn.track_running_stats else None, training, momentum, bn.eps,
-                        act, r_stride, group, conv_bias)
+                        act, r_stride, group, conv_bias, persistent_stats)
 
 
 # ------------------------------------------------------------------------------------------------

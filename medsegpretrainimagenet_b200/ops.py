@@ -260,11 +260,12 @@ def channel_sum(x: torch.Tensor) -> torch.Tensor:
 # ------------------------------------------------------------------------------------------------
 # BatchNorm (+ activation + residual)
 # ------------------------------------------------------------------------------------------------
-def bn_finalize(stats, count, eps, momentum, running_mean=None, running_var=None):
+def bn_finalize(stats, count, eps, momentum, running_mean=None, running_var=None, reset=False):
     c = stats.shape[1]
     mi = torch.empty((2, c), dtype=torch.float32, device=stats.device)
     call("msp_bn_finalize", stats[0].data_ptr(), stats[1].data_ptr(), c, float(count), float(eps),
-         float(momentum), mi[0].data_ptr(), mi[1].data_ptr(), _p(running_mean), _p(running_var), _stream())
+         float(momentum), mi[0].data_ptr(), mi[1].data_ptr(), _p(running_mean), _p(running_var), int(reset),
+         _stream())
     return mi
 
 

@@ -38,11 +38,19 @@ class GradReducer:
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.average = average
         params = [p for p in params if p.requires_grad]
+        self.params = params
+        self.buckets: List[_Bucket] = []
+        self._bucket_of = {}
+        self._hooks = []
+        if self.world == 1:
+            # single process: nothing to exchange — gradients stay the tensors the backward kernels produced
+            # (`param.grad = None` before backward lets autograd adopt them without an accumulate kernel each)
+            self.zero_grad()
+            return
         # autograd produces gradients roughly in reverse parameter order: bucket in that order so the
         # first bucket to fill is the first whose all-reduce can start
         order = list(reversed(params))
         limit = int(bucket_mb * (1 << 20))
-        self.buckets: List[_Bucket] = []
         cur, cur_bytes = [], 0
         for p in order:
             nbytes = p.numel() * p.element_size()
@@ -53,8 +61,6 @@ class GradReducer:
             cur_bytes += nbytes
         if cur:
             self._close(cur)
-        self._bucket_of = {}
-        self._hooks = []
         for b in self.buckets:
             for p in b.params:
                 self._bucket_of[p] = b
@@ -76,6 +82,10 @@ class GradReducer:
 
     def zero_grad(self) -> None:
         """Replaces optimizer.zero_grad(): keeps `param.grad` aliased to the bucket storage."""
+        if self.world == 1:
+            for p in self.params:
+                p.grad = None
+            return
         for b in self.buckets:
             b.flat.zero_()
             b.pending = len(b.params)
