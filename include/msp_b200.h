@@ -59,6 +59,11 @@ typedef struct msp_conv_desc {
   int32_t win_px, Wp;
 } msp_conv_desc;
 
+/* Kernel-variant policy of fprop / dgrad (tuning and tests; -1 restores the default / environment):
+ * pair: 0 never use the cta_group::2 CTA-pair tap-GEMM, 1 for >= 128 output channels per tile, 2 also for 64;
+ * halo: 0 never use the halo-reuse kernel, 1 when the weights stay resident in shared memory, 2 whenever it applies. */
+int msp_conv_set_policy(int pair, int halo);
+
 /* OIHW fp32 master weights -> bf16 [K][KH*KW][Cpad] (fprop/wgrad operand) and, if w_dgrad != NULL,
  * bf16 [Cpad][KH*KW][Kpad] (dgrad operand).  Cpad/Kpad >= C/K, multiples of 8, padding zero-filled. */
 int msp_pack_weights(const float* w_oihw, int K, int C, int KH, int KW, int Cpad, int Kpad,

@@ -38,6 +38,7 @@ SIGNATURES = {
     "msp_last_error": [],
     "msp_version": [],
     "msp_launch_count": [],
+    "msp_conv_set_policy": [I, I],
     "msp_pack_weights": [P, I, I, I, I, I, I, P, P, P],
     "msp_conv_fprop": [C.POINTER(ConvDesc), P, P, P, P, P, P, P],
     "msp_conv_dgrad": [C.POINTER(ConvDesc), P, P, P, I, P],

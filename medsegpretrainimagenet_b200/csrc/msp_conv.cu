@@ -58,6 +58,10 @@ struct TapGemmParams {
   int relu;
   int accumulate;  // the output tile is ADDED to memory (dgrad on top of a residual gradient)
   int debug;       // MSP_CONV_DEBUG bit mask (profiling experiments only; 0 in production)
+  // halo mode (tapgemm_halo_kernel): the A tile is the whole input halo of the output tile, loaded once per
+  // 64-channel chunk; tap (r', q') reads it from row r'*bw + q' on (tap_dh / tap_dw are then halo-relative)
+  int halo, org_dh, org_dw, halo_box_h, a_stages, b_stages, b_resident;
+  int dbg_stages;  // profiling experiments: ring depth override for the single-CTA tap kernel (0 = kStages)
   long long y_off, y_n_stride, y_h_stride, y_w_stride;  // element strides of the output sub-grid
   __nv_bfloat16* y;
   const float* bias;
@@ -82,105 +86,18 @@ struct TapGemmCfg {
   static constexpr int kTmemCols = 2 * BN_ < 32 ? 32 : 2 * BN_;
 };
 
+// Epilogue warps of both tap-GEMM kernels (warps 2..9): drain TMEM accumulators tile by tile.
 template <int BN_>
-__global__ void __launch_bounds__(kTapThreads, 1)
-tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-               const TapGemmParams p) {
+// Work items are walked as it0, it0 + it_step, ... < it_total; item -> (output-channel block tco = item / m_per_co,
+// m index pm = item % m_per_co).  pair_rank < 0: one M tile per item (tm = pm).  pair_rank = 0/1: CTA pair
+// (cta_group::2), the item is two M tiles and this CTA owns tm = 2*pm + pair_rank (possibly past the end: masked);
+// the accumulator is handed back through the LEADER CTA's tempty barrier.
+__device__ __forceinline__ void tap_epilogue(const TapGemmParams& p, uint8_t* staging, float* scratch,
+                                             uint32_t tmem_base, uint64_t* tfull_bar, uint64_t* tempty_bar,
+                                             int warp, int lane, int it0, int it_step, int it_total,
+                                             int m_per_co, int pair_rank) {
   using Cfg = TapGemmCfg<BN_>;
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
-                                             ~uintptr_t(1023));
-  uint8_t* staging = smem + Cfg::kStages * Cfg::kStageBytes;
-  float* scratch = reinterpret_cast<float*>(staging + Cfg::kStageBufs * kATileBytes);
-  __shared__ uint64_t full_bar[Cfg::kStages];
-  __shared__ uint64_t empty_bar[Cfg::kStages];
-  __shared__ uint64_t tfull_bar[2];
-  __shared__ uint64_t tempty_bar[2];
-  __shared__ uint32_t tmem_base_s;
-
-  const int warp = threadIdx.x >> 5;
-  const int lane = threadIdx.x & 31;
-  const int chunks = (p.C + kBK - 1) / kBK;
-  const int kiters = p.ntaps * chunks;
-
-  if (threadIdx.x == 0) {
-    for (int s = 0; s < Cfg::kStages; ++s) {
-      mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], 1);
-    }
-    for (int s = 0; s < 2; ++s) {
-      mbar_init(&tfull_bar[s], 1);
-      mbar_init(&tempty_bar[s], kEpiThreads / 32);
-    }
-    mbar_fence_init();
-  }
-  if (warp == 1) tmem_alloc<Cfg::kTmemCols>(&tmem_base_s);
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = tmem_base_s;
-
-  if (warp == 0) {
-    // ---------------- TMA producer ----------------
-    if (lane == 0) {
-      tma_prefetch_desc(&tmA);
-      tma_prefetch_desc(&tmB);
-      const uint32_t tx_bytes = (uint32_t)p.rows * 128u + (uint32_t)Cfg::kBTileBytes;
-      uint32_t it = 0;
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-        const int tco = tile / p.tiles_m;
-        const int tm = tile - tco * p.tiles_m;
-        const int tw = tm % p.tiles_w;
-        const int th = (tm / p.tiles_w) % p.tiles_h;
-        const int tn = tm / (p.tiles_w * p.tiles_h);
-        const int w0 = tw * p.bw * p.sxw, h0 = th * p.bh * p.sxh, n0 = tn * p.bn;
-        const int co0 = tco * BN_;
-        for (int tap = 0; tap < p.ntaps; ++tap) {
-          const int cw = w0 + p.tap_dw[tap], chh = h0 + p.tap_dh[tap], wt = (int)p.tap_w[tap];
-          for (int ch = 0; ch < chunks; ++ch, ++it) {
-            const int s = it % Cfg::kStages;
-            const uint32_t ph = (it / Cfg::kStages) & 1u;
-            mbar_wait(&empty_bar[s], ph ^ 1u);
-            uint8_t* a_s = smem + s * Cfg::kStageBytes;
-            mbar_expect_tx(&full_bar[s], tx_bytes);
-            tma_load_4d(a_s, &tmA, &full_bar[s], ch * kBK, cw, chh, n0);
-            tma_load_3d(a_s + kATileBytes, &tmB, &full_bar[s], ch * kBK, wt, co0);
-          }
-        }
-      }
-    }
-  } else if (warp == 1) {
-    // ---------------- MMA issuer ----------------
-    if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(kBM, BN_, 0, 0);
-      uint32_t it = 0, t = 0;
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++t) {
-        const uint32_t as = t & 1u;
-        mbar_wait(&tempty_bar[as], ((t >> 1) & 1u) ^ 1u);  // epilogue has drained this accumulator
-        tc_fence_after();
-        const uint32_t tmem_d = tmem_base + as * BN_;
-        for (int ki = 0; ki < kiters; ++ki, ++it) {
-          const int s = it % Cfg::kStages;
-          const uint32_t ph = (it / Cfg::kStages) & 1u;
-          mbar_wait(&full_bar[s], ph);
-          tc_fence_after();
-          const int ch = ki % chunks;
-          int kvalid = p.C - ch * kBK;
-          kvalid = kvalid > kBK ? kBK : kvalid;
-          const int nk = (kvalid + 15) >> 4;
-          const uint32_t a_addr = smem_u32(smem + s * Cfg::kStageBytes);
-          const uint64_t adesc = umma_smem_desc_sw128(a_addr, 16, 1024);
-          const uint64_t bdesc = umma_smem_desc_sw128(a_addr + kATileBytes, 16, 1024);
-          for (int k = 0; k < nk; ++k)
-            umma_bf16(tmem_d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc,
-                      (uint32_t)((ki | k) != 0));
-          umma_commit(&empty_bar[s]);  // frees the smem slot once these MMAs have read it
-        }
-        umma_commit(&tfull_bar[as]);
-      }
-    }
-    __syncwarp();
-  } else {
+  {
     // ---------------- epilogue: TMEM -> registers -> swizzled smem tile -> coalesced global stores -------
     // 8 warps = 2 per scheduler: warps (w, w+4) share a TMEM lane quarter and split every 64-column
     // chunk into two 32-column halves.  The bf16 tile is transposed through a 128B-swizzled staging tile
@@ -222,8 +139,11 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       sts_off[g] = (uint32_t)(row * 128 + (((half * (CHH / 8) + g) ^ (row & 7)) << 4));
     const bool flat_tiles = p.tiles_h == 1 && p.tiles_n == 1;  // 1x1 "flat" convolutions: tile = 128 pixels of one row
     uint32_t t = 0, sbuf = 0;
-    int tco = blockIdx.x / p.tiles_m, tm = blockIdx.x - tco * p.tiles_m;
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++t) {
+    int tco = it0 / m_per_co, pm = it0 - tco * m_per_co;
+    for (int item = it0; item < it_total; item += it_step, ++t) {
+      int tm = pair_rank < 0 ? pm : 2 * pm + pair_rank;
+      const bool tile_ok = tm < p.tiles_m;  // odd tile counts: the pair's second CTA idles on a masked duplicate
+      if (!tile_ok) tm = p.tiles_m - 1;
       int tw = tm, th = 0, tn = 0;
       if (!flat_tiles) {
         tw = (int)((uint32_t)tm % (uint32_t)p.tiles_w);
@@ -233,19 +153,21 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
       const int w0 = tw * p.bw, h0 = th * p.bh, n0 = tn * p.bn;
       const int co0 = tco * BN_;
-      const bool valid = row < p.rows && (w0 + my_wi) < p.OWs && (h0 + my_hi) < p.OHs && (n0 + my_ni) < p.N;
+      const bool valid =
+          tile_ok && row < p.rows && (w0 + my_wi) < p.OWs && (h0 + my_hi) < p.OHs && (n0 + my_ni) < p.N;
       const long long tile_off = p.y_off + (long long)n0 * p.y_n_stride + (long long)h0 * p.y_h_stride +
                                  (long long)w0 * p.y_w_stride + co0;
       __nv_bfloat16* o_ptr[4];
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        const bool ok = o_rel[j] >= 0 && (w0 + o_wi[j]) < p.OWs && (h0 + o_hi[j]) < p.OHs && (n0 + o_ni[j]) < p.N;
+        const bool ok = tile_ok && o_rel[j] >= 0 && (w0 + o_wi[j]) < p.OWs && (h0 + o_hi[j]) < p.OHs &&
+                        (n0 + o_ni[j]) < p.N;
         o_ptr[j] = ok ? p.y + tile_off + o_rel[j] : nullptr;
       }
-      // advance (tco, tm) to this CTA's next tile without a division
-      int tco_next = tco, tm_next = tm + (int)gridDim.x;
-      while (tm_next >= p.tiles_m) {
-        tm_next -= p.tiles_m;
+      // advance (tco, pm) to this CTA's next item without a division
+      int tco_next = tco, pm_next = pm + it_step;
+      while (pm_next >= m_per_co) {
+        pm_next -= m_per_co;
         ++tco_next;
       }
       const uint32_t as = t & 1u;
@@ -267,7 +189,10 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (c == Cfg::kNChunk - 1) {  // accumulator fully read: hand it back to the MMA warp (one arrive per warp)
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(&tempty_bar[as]);
+          if (lane == 0) {
+            if (pair_rank < 0) mbar_arrive(&tempty_bar[as]);
+            else mbar_arrive_leader(&tempty_bar[as]);
+          }
         }
         if (cg < p.Kout) {
           const int cb = cg + half * CHH;  // first output channel of this warp's columns
@@ -368,7 +293,7 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
       // flush the running statistics when this CTA leaves the output-channel block (or finishes)
       if (do_stats && et < 128) {
-        if (tile + (int)gridDim.x >= p.total_tiles || tco_next != tco) {
+        if (item + it_step >= it_total || tco_next != tco) {
           float* dst = (et >> 6) ? p.ch_sqsum : p.ch_sum;
           for (int c = 0; c < Cfg::kNChunk; ++c) {
             const int col = co0 + c * CH + (et & 63);
@@ -378,8 +303,473 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
       }
       tco = tco_next;
-      tm = tm_next;
+      pm = pm_next;
     }
+  }
+}
+
+template <int BN_>
+__global__ void __launch_bounds__(kTapThreads, 1)
+tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               const TapGemmParams p) {
+  using Cfg = TapGemmCfg<BN_>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~uintptr_t(1023));
+  uint8_t* staging = smem + Cfg::kStages * Cfg::kStageBytes;
+  float* scratch = reinterpret_cast<float*>(staging + Cfg::kStageBufs * kATileBytes);
+  __shared__ uint64_t full_bar[Cfg::kStages];
+  __shared__ uint64_t empty_bar[Cfg::kStages];
+  __shared__ uint64_t tfull_bar[2];
+  __shared__ uint64_t tempty_bar[2];
+  __shared__ uint32_t tmem_base_s;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int chunks = (p.C + kBK - 1) / kBK;
+  const int kiters = p.ntaps * chunks;
+  (void)kiters;
+  long long dbg_c0 = 0;
+  unsigned long long dbg_t0 = 0;
+  if ((p.debug & 512) && blockIdx.x == 0 && threadIdx.x == 0) {  // profiling experiment: effective SM clock
+    dbg_c0 = clock64();
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(dbg_t0));
+  }
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < Cfg::kStages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tfull_bar[s], 1);
+      mbar_init(&tempty_bar[s], kEpiThreads / 32);
+    }
+    mbar_fence_init();
+  }
+  if (warp == 1) tmem_alloc<Cfg::kTmemCols>(&tmem_base_s);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_s;
+
+  if (warp == 0) {
+    // ---------------- TMA producer ----------------
+    if (lane == 0) {
+      tma_prefetch_desc(&tmA);
+      tma_prefetch_desc(&tmB);
+      const uint32_t tx_bytes = (uint32_t)p.rows * 128u + (uint32_t)Cfg::kBTileBytes;
+      uint32_t it = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        const int tco = tile / p.tiles_m;
+        const int tm = tile - tco * p.tiles_m;
+        const int tw = tm % p.tiles_w;
+        const int th = (tm / p.tiles_w) % p.tiles_h;
+        const int tn = tm / (p.tiles_w * p.tiles_h);
+        const int w0 = tw * p.bw * p.sxw, h0 = th * p.bh * p.sxh, n0 = tn * p.bn;
+        const int co0 = tco * BN_;
+        for (int tap = 0; tap < p.ntaps; ++tap) {
+          const int cw = w0 + p.tap_dw[tap], chh = h0 + p.tap_dh[tap], wt = (int)p.tap_w[tap];
+          for (int ch = 0; ch < chunks; ++ch, ++it) {
+            const uint32_t nst = p.dbg_stages ? (uint32_t)p.dbg_stages : (uint32_t)Cfg::kStages;
+            const int s = it % nst;
+            const uint32_t ph = (it / nst) & 1u;
+            mbar_wait(&empty_bar[s], ph ^ 1u);
+            uint8_t* a_s = smem + s * Cfg::kStageBytes;
+            if (p.debug & 128) {  // timing experiment: MMA side alone (no loads, garbage operands)
+              mbar_arrive(&full_bar[s]);
+              continue;
+            }
+            mbar_expect_tx(&full_bar[s], tx_bytes);
+            tma_load_4d(a_s, &tmA, &full_bar[s], ch * kBK, cw, chh, n0);
+            tma_load_3d(a_s + kATileBytes, &tmB, &full_bar[s], ch * kBK, wt, co0);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ---------------- MMA issuer ----------------
+    // One thread: keep its instruction stream short (descriptor halves, incremental stage / phase counters).
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(kBM, BN_, 0, 0);
+      const uint64_t d0 = umma_smem_desc_sw128(smem_u32(smem), 16, 1024);
+      const uint32_t desc_hi = (uint32_t)(d0 >> 32);
+      const uint32_t a_lo0 = (uint32_t)d0;
+      constexpr uint32_t kStageLo = Cfg::kStageBytes >> 4, kBLo = kATileBytes >> 4;
+      const int c_tail = p.C - (chunks - 1) * kBK;       // channels of the last chunk
+      const int nk_tail = (c_tail + 15) >> 4;
+      uint32_t s = 0, ph = 0, t = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++t) {
+        const uint32_t as = t & 1u;
+        mbar_wait(&tempty_bar[as], ((t >> 1) & 1u) ^ 1u);  // epilogue has drained this accumulator
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + as * BN_;
+        uint32_t acc = 0;
+        for (int tap = 0; tap < p.ntaps; ++tap) {
+          for (int ch = 0; ch < chunks; ++ch) {
+            mbar_wait(&full_bar[s], ph);
+            tc_fence_after();
+            const uint32_t a_lo = a_lo0 + s * kStageLo, b_lo = a_lo + kBLo;
+            if (p.debug & 256) {  // timing experiment: load side alone
+            } else if (ch + 1 < chunks || nk_tail == 4) {
+              umma_bf16_lohi(tmem_d, a_lo, desc_hi, b_lo, desc_hi, idesc, acc);
+              umma_bf16_lohi(tmem_d, a_lo + 2, desc_hi, b_lo + 2, desc_hi, idesc, 1u);
+              umma_bf16_lohi(tmem_d, a_lo + 4, desc_hi, b_lo + 4, desc_hi, idesc, 1u);
+              umma_bf16_lohi(tmem_d, a_lo + 6, desc_hi, b_lo + 6, desc_hi, idesc, 1u);
+            } else {
+              for (int k = 0; k < nk_tail; ++k)
+                umma_bf16_lohi(tmem_d, a_lo + 2 * k, desc_hi, b_lo + 2 * k, desc_hi, idesc, acc | (uint32_t)k);
+            }
+            acc = 1u;
+            umma_commit(&empty_bar[s]);  // frees the smem slot once these MMAs have read it
+            if (++s == (p.dbg_stages ? (uint32_t)p.dbg_stages : (uint32_t)Cfg::kStages)) {
+              s = 0;
+              ph ^= 1u;
+            }
+          }
+        }
+        umma_commit(&tfull_bar[as]);
+      }
+    }
+    __syncwarp();
+  } else {
+    tap_epilogue<BN_>(p, staging, scratch, tmem_base, tfull_bar, tempty_bar, warp, lane, (int)blockIdx.x,
+                      (int)gridDim.x, p.total_tiles, p.tiles_m, -1);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<Cfg::kTmemCols>(tmem_base);
+  if ((p.debug & 512) && blockIdx.x == 0 && threadIdx.x == 0) {
+    unsigned long long t1;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+    const long long c1 = clock64();
+    printf("msp clock probe: %lld cycles in %llu ns -> %.0f MHz\n", c1 - dbg_c0, t1 - dbg_t0,
+           1e3 * (double)(c1 - dbg_c0) / (double)(t1 - dbg_t0));
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// CTA-pair variant (tcgen05 cta_group::2): the two SMs of a TPC form a cluster and share one 256-row x BN tile.
+// Each CTA loads ITS 128-row A tile and HALF of the B tile (BN/2 weight rows); one thread of the leader CTA issues
+// M=256 MMAs that read both CTAs' shared memory and write each CTA's own TMEM; tcgen05.commit multicasts the
+// "slot free" / "accumulator ready" arrivals to both CTAs, both epilogues drain their 128 rows and hand the
+// accumulator back through the leader's barrier.  Per SM and k-block that is 16 KB + BN*64 B of operands instead
+// of 16 KB + BN*128 B, and twice the MMA issue width (a single-CTA MMA measured ~45 % of the tensor peak here).
+// ------------------------------------------------------------------------------------------------
+template <int BN_>
+struct TapGemm2Cfg {
+  static constexpr int kBHalfBytes = (BN_ / 2) * kBK * 2;
+  static constexpr int kStageBytes = kATileBytes + kBHalfBytes;
+  static constexpr int kStages = BN_ >= 256 ? 5 : 6;
+  static constexpr int kSmemBytes = kStages * kStageBytes + TapGemmCfg<BN_>::kStageBufs * kATileBytes +
+                                    TapGemmCfg<BN_>::kScratchBytes + 1024;
+};
+
+template <int BN_>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTapThreads, 1)
+tapgemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                const TapGemmParams p) {
+  using Cfg = TapGemmCfg<BN_>;
+  using Cfg2 = TapGemm2Cfg<BN_>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~uintptr_t(1023));
+  uint8_t* staging = smem + Cfg2::kStages * Cfg2::kStageBytes;
+  float* scratch = reinterpret_cast<float*>(staging + Cfg::kStageBufs * kATileBytes);
+  __shared__ uint64_t full_bar[Cfg2::kStages];
+  __shared__ uint64_t empty_bar[Cfg2::kStages];
+  __shared__ uint64_t tfull_bar[2];
+  __shared__ uint64_t tempty_bar[2];
+  __shared__ uint32_t tmem_base_s;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int rank = (int)cluster_ctarank();
+  const int chunks = (p.C + kBK - 1) / kBK;
+  const int npm = (p.tiles_m + 1) >> 1;            // M-tile pairs per output-channel block
+  const int items = npm * p.tiles_co;
+  const int it0 = (int)(blockIdx.x >> 1), it_step = (int)(gridDim.x >> 1);
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < Cfg2::kStages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tfull_bar[s], 1);
+      mbar_init(&tempty_bar[s], 2 * (kEpiThreads / 32));  // the epilogue warps of BOTH CTAs
+    }
+    mbar_fence_init();
+  }
+  cluster_sync_all();  // the peer's barriers exist before anything remote touches them
+  if (warp == 1) tmem_alloc2<Cfg::kTmemCols>(&tmem_base_s);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_s;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      tma_prefetch_desc(&tmA);
+      tma_prefetch_desc(&tmB);
+      const uint32_t tx_bytes = 2u * ((uint32_t)p.rows * 128u + (uint32_t)Cfg2::kBHalfBytes);  // both CTAs
+      uint32_t s = 0, ph = 0;
+      int tco = it0 / npm, pm = it0 - tco * npm;
+      for (int item = it0; item < items; item += it_step) {
+        int tm = 2 * pm + rank;
+        if (tm >= p.tiles_m) tm = p.tiles_m - 1;
+        const int tw = tm % p.tiles_w;
+        const int th = (tm / p.tiles_w) % p.tiles_h;
+        const int tn = tm / (p.tiles_w * p.tiles_h);
+        const int w0 = tw * p.bw * p.sxw, h0 = th * p.bh * p.sxh, n0 = tn * p.bn;
+        const int co0 = tco * BN_ + rank * (BN_ / 2);
+        for (int tap = 0; tap < p.ntaps; ++tap) {
+          const int cw = w0 + p.tap_dw[tap], chh = h0 + p.tap_dh[tap], wt = (int)p.tap_w[tap];
+          for (int ch = 0; ch < chunks; ++ch) {
+            mbar_wait(&empty_bar[s], ph ^ 1u);
+            uint8_t* a_s = smem + s * Cfg2::kStageBytes;
+            if (p.debug & 128) {  // timing experiment: MMA side alone
+              if (rank == 0) mbar_arrive(&full_bar[s]);
+            } else {
+              if (rank == 0) mbar_expect_tx(&full_bar[s], tx_bytes);
+              tma_load_4d_2sm(a_s, &tmA, &full_bar[s], ch * kBK, cw, chh, n0);
+              tma_load_3d_2sm(a_s + kATileBytes, &tmB, &full_bar[s], ch * kBK, wt, co0);
+            }
+            if (++s == (uint32_t)Cfg2::kStages) {
+              s = 0;
+              ph ^= 1u;
+            }
+          }
+        }
+        pm += it_step;
+        while (pm >= npm) {
+          pm -= npm;
+          ++tco;
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && rank == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(256, BN_, 0, 0);
+      const uint64_t d0 = umma_smem_desc_sw128(smem_u32(smem), 16, 1024);
+      const uint32_t desc_hi = (uint32_t)(d0 >> 32);
+      const uint32_t a_lo0 = (uint32_t)d0;
+      constexpr uint32_t kStageLo = Cfg2::kStageBytes >> 4, kBLo = kATileBytes >> 4;
+      const int c_tail = p.C - (chunks - 1) * kBK;
+      const int nk_tail = (c_tail + 15) >> 4;
+      uint32_t s = 0, ph = 0, t = 0;
+      for (int item = it0; item < items; item += it_step, ++t) {
+        const uint32_t as = t & 1u;
+        mbar_wait(&tempty_bar[as], ((t >> 1) & 1u) ^ 1u);  // both epilogues have drained this accumulator
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + as * BN_;
+        uint32_t acc = 0;
+        for (int tap = 0; tap < p.ntaps; ++tap) {
+          for (int ch = 0; ch < chunks; ++ch) {
+            mbar_wait(&full_bar[s], ph);
+            tc_fence_after();
+            const uint32_t a_lo = a_lo0 + s * kStageLo, b_lo = a_lo + kBLo;
+            const int nk = (ch + 1 < chunks) ? 4 : nk_tail;
+            for (int k = 0; k < nk; ++k)
+              umma_bf16_lohi_2sm(tmem_d, a_lo + 2 * k, desc_hi, b_lo + 2 * k, desc_hi, idesc, acc | (uint32_t)k);
+            acc = 1u;
+            umma_commit_mc(&empty_bar[s], 3u);  // frees the slot in BOTH CTAs once these MMAs have read it
+            if (++s == (uint32_t)Cfg2::kStages) {
+              s = 0;
+              ph ^= 1u;
+            }
+          }
+        }
+        umma_commit_mc(&tfull_bar[as], 3u);
+      }
+    }
+    __syncwarp();
+  } else {
+    tap_epilogue<BN_>(p, staging, scratch, tmem_base, tfull_bar, tempty_bar, warp, lane, it0, it_step, items, npm,
+                      rank);
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();  // no CTA of the pair frees TMEM / exits while the other may still read its shared memory
+  if (warp == 1) tmem_dealloc2<Cfg::kTmemCols>(tmem_base);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Halo variant of the tap-GEMM for stride-1 filters on feature maps up to 126 pixels wide.  The tap-GEMM above
+// fetches the A box once per tap (9x for a 3x3 filter) and is L2->SM bandwidth bound on those layers.  Here the
+// output tile is `bh` full-width rows stored with the HALO pitch bw = W + KW - 1, so that the input window of tap
+// (r', q') is the same shared-memory tile read from row r'*bw + q' on: ONE TMA load per 64-channel chunk, and the
+// tap offset goes into the UMMA descriptor's start address.  Output rows that fall on the
+// KW-1 pad columns of the pitch are computed and discarded (W/bw of the MMA rows are useful: 56/58, 28/30, 14/16).
+// When all the weights of the CTA's output-channel block fit (e.g. 64->64 3x3 = 72 KB) they are loaded once and
+// stay resident; otherwise B tiles stream through their own ring.
+// ------------------------------------------------------------------------------------------------
+constexpr int kHaloABytes = 32768;  // 256 rows x 128 B
+constexpr int kHaloMaxB = 12;
+
+template <int BN_>
+__global__ void __launch_bounds__(kTapThreads, 1)
+tapgemm_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                    const TapGemmParams p) {
+  using Cfg = TapGemmCfg<BN_>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~uintptr_t(1023));
+  uint8_t* a_ring = smem;
+  uint8_t* b_ring = a_ring + p.a_stages * kHaloABytes;
+  uint8_t* staging = b_ring + p.b_stages * Cfg::kBTileBytes;
+  float* scratch = reinterpret_cast<float*>(staging + Cfg::kStageBufs * kATileBytes);
+  __shared__ uint64_t a_full[3], a_empty[3];
+  __shared__ uint64_t b_full[kHaloMaxB], b_empty[kHaloMaxB];
+  __shared__ uint64_t bres_bar;
+  __shared__ uint64_t tfull_bar[2];
+  __shared__ uint64_t tempty_bar[2];
+  __shared__ uint32_t tmem_base_s;
+  __shared__ uint32_t tap_lo_s[kMaxTaps];  // descriptor start-address increment of every tap's window
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int chunks = (p.C + kBK - 1) / kBK;
+
+  if (threadIdx.x < p.ntaps) {
+    uint32_t rowoff = (uint32_t)(p.tap_dh[threadIdx.x] * p.bw + p.tap_dw[threadIdx.x]);
+    if (p.debug & 64) rowoff &= ~7u;  // timing experiment only: 1024-byte aligned windows (wrong results)
+    tap_lo_s[threadIdx.x] = rowoff * (128u >> 4);
+  }
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < 3; ++s) {
+      mbar_init(&a_full[s], 1);
+      mbar_init(&a_empty[s], 1);
+    }
+    for (int s = 0; s < kHaloMaxB; ++s) {
+      mbar_init(&b_full[s], 1);
+      mbar_init(&b_empty[s], 1);
+    }
+    mbar_init(&bres_bar, 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tfull_bar[s], 1);
+      mbar_init(&tempty_bar[s], kEpiThreads / 32);
+    }
+    mbar_fence_init();
+  }
+  if (warp == 1) tmem_alloc<Cfg::kTmemCols>(&tmem_base_s);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_s;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      tma_prefetch_desc(&tmA);
+      tma_prefetch_desc(&tmB);
+      const uint32_t a_bytes = (uint32_t)(p.bw * p.halo_box_h) * 128u;
+      if (p.b_resident) {  // all weights of the (single) output-channel block: once per CTA
+        mbar_expect_tx(&bres_bar, (uint32_t)(p.ntaps * chunks) * (uint32_t)Cfg::kBTileBytes);
+        for (int tap = 0; tap < p.ntaps; ++tap)
+          for (int ch = 0; ch < chunks; ++ch)
+            tma_load_3d(b_ring + (tap * chunks + ch) * Cfg::kBTileBytes, &tmB, &bres_bar, ch * kBK,
+                        (int)p.tap_w[tap], 0);
+      }
+      uint32_t sa = 0, pha = 0, sb = 0, phb = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        const int tco = tile / p.tiles_m;
+        const int tm = tile - tco * p.tiles_m;
+        const int th = tm % p.tiles_h;
+        const int tn = tm / p.tiles_h;
+        const int h0 = th * p.bh;
+        const int co0 = tco * BN_;
+        for (int ch = 0; ch < chunks; ++ch) {
+          mbar_wait(&a_empty[sa], pha ^ 1u);
+          mbar_expect_tx(&a_full[sa], a_bytes);
+          tma_load_4d(a_ring + sa * kHaloABytes, &tmA, &a_full[sa], ch * kBK, p.org_dw, h0 + p.org_dh, tn);
+          if (++sa == (uint32_t)p.a_stages) {
+            sa = 0;
+            pha ^= 1u;
+          }
+          if (!p.b_resident) {
+            for (int tap = 0; tap < p.ntaps; ++tap) {
+              mbar_wait(&b_empty[sb], phb ^ 1u);
+              mbar_expect_tx(&b_full[sb], (uint32_t)Cfg::kBTileBytes);
+              tma_load_3d(b_ring + sb * Cfg::kBTileBytes, &tmB, &b_full[sb], ch * kBK, (int)p.tap_w[tap], co0);
+              if (++sb == (uint32_t)p.b_stages) {
+                sb = 0;
+                phb ^= 1u;
+              }
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(kBM, BN_, 0, 0);
+      const uint64_t d0 = umma_smem_desc_sw128(smem_u32(a_ring), 16, 1024);
+      const uint32_t desc_hi = (uint32_t)(d0 >> 32);
+      const uint32_t a_lo0 = (uint32_t)d0;
+      const uint32_t b_lo0 = (uint32_t)umma_smem_desc_sw128(smem_u32(b_ring), 16, 1024);
+      constexpr uint32_t kALo = kHaloABytes >> 4, kBLo = Cfg::kBTileBytes >> 4;
+      const int c_tail = p.C - (chunks - 1) * kBK;
+      const int nk_tail = (c_tail + 15) >> 4;
+      if (p.b_resident) {
+        mbar_wait(&bres_bar, 0);
+        tc_fence_after();
+      }
+      uint32_t sa = 0, pha = 0, sb = 0, phb = 0, t = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++t) {
+        const uint32_t as = t & 1u;
+        mbar_wait(&tempty_bar[as], ((t >> 1) & 1u) ^ 1u);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + as * BN_;
+        uint32_t acc = 0;
+        for (int ch = 0; ch < chunks; ++ch) {
+          mbar_wait(&a_full[sa], pha);
+          tc_fence_after();
+          const uint32_t a_lo = a_lo0 + sa * kALo;
+          const int nk = (ch + 1 < chunks) ? 4 : nk_tail;
+          for (int tap = 0; tap < p.ntaps; ++tap) {
+            uint32_t b_lo;
+            if (p.b_resident) {
+              b_lo = b_lo0 + (uint32_t)(tap * chunks + ch) * kBLo;
+            } else {
+              mbar_wait(&b_full[sb], phb);
+              tc_fence_after();
+              b_lo = b_lo0 + sb * kBLo;
+            }
+            // The 128B swizzle of a UMMA operand is a function of the absolute shared-memory address bits (like
+            // the TMA write; measured on B200), so the window of tap (r', q') needs only the start address shifted
+            // by r'*bw + q' rows of 128 B — the descriptor's "matrix base offset" field stays 0.
+            const uint32_t ta_lo = a_lo + tap_lo_s[tap];
+            if (nk == 4) {
+              umma_bf16_lohi(tmem_d, ta_lo, desc_hi, b_lo, desc_hi, idesc, acc);
+              umma_bf16_lohi(tmem_d, ta_lo + 2, desc_hi, b_lo + 2, desc_hi, idesc, 1u);
+              umma_bf16_lohi(tmem_d, ta_lo + 4, desc_hi, b_lo + 4, desc_hi, idesc, 1u);
+              umma_bf16_lohi(tmem_d, ta_lo + 6, desc_hi, b_lo + 6, desc_hi, idesc, 1u);
+            } else {
+              for (int k = 0; k < nk; ++k)
+                umma_bf16_lohi(tmem_d, ta_lo + 2 * k, desc_hi, b_lo + 2 * k, desc_hi, idesc, acc | (uint32_t)k);
+            }
+            acc = 1u;
+            if (!p.b_resident) {
+              umma_commit(&b_empty[sb]);
+              if (++sb == (uint32_t)p.b_stages) {
+                sb = 0;
+                phb ^= 1u;
+              }
+            }
+          }
+          umma_commit(&a_empty[sa]);
+          if (++sa == (uint32_t)p.a_stages) {
+            sa = 0;
+            pha ^= 1u;
+          }
+        }
+        umma_commit(&tfull_bar[as]);
+      }
+    }
+    __syncwarp();
+  } else {
+    tap_epilogue<BN_>(p, staging, scratch, tmem_base, tfull_bar, tempty_bar, warp, lane, (int)blockIdx.x,
+                      (int)gridDim.x, p.total_tiles, p.tiles_m, -1);
   }
   tc_fence_before();
   __syncthreads();
@@ -477,18 +867,25 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant__ C
     if (lane == 0) {
       const uint32_t idesc = umma_idesc_bf16(128, 64 * p.nsub, 1, 1);
       const int nk = (p.rows + 15) >> 4;
+      // MN-major: 8-row (K) groups 1024 B apart; consecutive 64-channel atoms are 16 KB apart
+      const uint64_t d0 = umma_smem_desc_sw128(smem_u32(smem), kATileBytes, 1024);
+      const uint32_t desc_hi = (uint32_t)(d0 >> 32), lo0 = (uint32_t)d0;
+      constexpr uint32_t kStageLo = kWgStageBytes >> 4, kXLo = (2 * kATileBytes) >> 4;
+      uint32_t acc = 0;
       for (int it = 0; it < my_tiles; ++it) {
-        const int s = it % kWgStages;
-        const uint32_t ph = (uint32_t)(it / kWgStages) & 1u;
-        mbar_wait(&full_bar[s], ph);
+        const uint32_t s = (uint32_t)it & 1u;  // kWgStages == 2
+        mbar_wait(&full_bar[s], ((uint32_t)it >> 1) & 1u);
         tc_fence_after();
-        const uint32_t a_addr = smem_u32(smem + s * kWgStageBytes);
-        // MN-major: 8-row (K) groups 1024 B apart; consecutive 64-channel atoms are 16 KB apart
-        const uint64_t adesc = umma_smem_desc_sw128(a_addr, kATileBytes, 1024);
-        const uint64_t bdesc = umma_smem_desc_sw128(a_addr + 2 * kATileBytes, kATileBytes, 1024);
-        for (int k = 0; k < nk; ++k)
-          umma_bf16(tmem_base, adesc + (uint64_t)(128 * k), bdesc + (uint64_t)(128 * k), idesc,
-                    (uint32_t)((it | k) != 0));
+        const uint32_t a_lo = lo0 + s * kStageLo, b_lo = a_lo + kXLo;
+        if (nk == 8) {
+#pragma unroll
+          for (int k = 0; k < 8; ++k)
+            umma_bf16_lohi(tmem_base, a_lo + 128 * k, desc_hi, b_lo + 128 * k, desc_hi, idesc, k ? 1u : acc);
+        } else {
+          for (int k = 0; k < nk; ++k)
+            umma_bf16_lohi(tmem_base, a_lo + 128 * k, desc_hi, b_lo + 128 * k, desc_hi, idesc, acc | (uint32_t)k);
+        }
+        acc = 1u;
         umma_commit(&empty_bar[s]);
       }
       umma_commit(&accum_bar);
@@ -656,9 +1053,14 @@ int launch_tapgemm(const CUtensorMap& tmA, const CUtensorMap& tmB, TapGemmParams
     attr_set = true;
   }
   {
-    static int dbg = -1;
-    if (dbg < 0) { const char* e = getenv("MSP_CONV_DEBUG"); dbg = e ? atoi(e) : 0; }
+    static int dbg = -1, dst = 0;
+    if (dbg < 0) {
+      const char* e = getenv("MSP_CONV_DEBUG"); dbg = e ? atoi(e) : 0;
+      const char* f = getenv("MSP_CONV_STAGES"); dst = f ? atoi(f) : 0;
+      if (dst > TapGemmCfg<BN_>::kStages) dst = TapGemmCfg<BN_>::kStages;
+    }
     p.debug = dbg;
+    p.dbg_stages = dst;
   }
   p.tiles_m = p.tiles_w * p.tiles_h * p.tiles_n;
   p.tiles_co = msp_cdiv(p.Kout, BN_);
@@ -673,17 +1075,171 @@ int launch_tapgemm(const CUtensorMap& tmA, const CUtensorMap& tmB, TapGemmParams
   return MSP_OK;
 }
 
+template <int BN_>
+int launch_tapgemm2(const CUtensorMap& tmA, const CUtensorMap& tmB, TapGemmParams& p, cudaStream_t st) {
+  using Cfg2 = TapGemm2Cfg<BN_>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    MSP_CHECK_CUDA(cudaFuncSetAttribute(tapgemm2_kernel<BN_>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        Cfg2::kSmemBytes));
+    attr_set = true;
+  }
+  {
+    static int dbg = -1;
+    if (dbg < 0) { const char* e = getenv("MSP_CONV_DEBUG"); dbg = e ? atoi(e) : 0; }
+    p.debug = dbg;
+  }
+  p.tiles_m = p.tiles_w * p.tiles_h * p.tiles_n;
+  p.tiles_co = msp_cdiv(p.Kout, BN_);
+  const long long items = (long long)((p.tiles_m + 1) / 2) * p.tiles_co;
+  MSP_REQUIRE(items < (1ll << 30), "conv: too many tiles");
+  p.total_tiles = (int)((long long)p.tiles_m * p.tiles_co);
+  const int pairs = msp_num_sms() / 2;
+  const int grid = 2 * (int)(items < pairs ? items : pairs);
+  tapgemm2_kernel<BN_><<<grid, kTapThreads, Cfg2::kSmemBytes, st>>>(tmA, tmB, p);
+  MSP_CHECK_LAUNCH();
+  msp_count_launch(1);
+  return MSP_OK;
+}
+
 inline int bn_tile_for(int K) {
   return K <= 16 ? 16 : (K <= 32 ? 32 : (K <= 64 ? 64 : (K <= 128 ? 128 : 256)));
 }
 
-int dispatch_tapgemm(const CUtensorMap& tmA, const CUtensorMap& tmB, TapGemmParams& p, cudaStream_t st) {
-  switch (bn_tile_for(p.Kout)) {
+// Kernel-variant policy (msp_conv_set_policy / environment), measured on ResNet-50 B=256 (profiles/r01_conv_variants.txt):
+//  pair (cta_group::2 tap-GEMM): 0 never (default: not faster than the single-CTA kernel on these shapes),
+//                                1 for tiles of >= 128 output channels, 2 also for 64
+//  halo (A tile loaded once per chunk, taps via descriptor offsets): 0 never, 1 (default) when the weights of the
+//                                output-channel block stay resident in shared memory, 2 whenever it applies
+int g_pair_policy = -1, g_halo_policy = -1;
+int pair_policy() {
+  if (g_pair_policy < 0) { const char* e = getenv("MSP_CONV_2CTA"); g_pair_policy = e ? atoi(e) : 0; }
+  return g_pair_policy;
+}
+int halo_policy() {
+  if (g_halo_policy < 0) {
+    const char* e = getenv("MSP_CONV_NOHALO");
+    const char* f = getenv("MSP_CONV_HALO");
+    g_halo_policy = (e && atoi(e)) ? 0 : (f ? atoi(f) : 1);
+  }
+  return g_halo_policy;
+}
+
+struct WMapArgs {  // packed weights [rows][taps][inner] (make_w_map)
+  const void* base;
+  int inner, taps, rows;
+};
+int make_w_map(CUtensorMap* m, const void* base, int inner, int taps, int rows, int box_rows);
+
+int dispatch_tapgemm(const CUtensorMap& tmA, const WMapArgs& w, TapGemmParams& p, cudaStream_t st) {
+  const int bn = bn_tile_for(p.Kout);
+  const int pol = pair_policy();
+  CUtensorMap tmB;
+  if (p.tiles_w * p.tiles_h * p.tiles_n >= 2 && !p.halo && ((bn >= 128 && pol >= 1) || (bn == 64 && pol >= 2))) {
+    int rc = make_w_map(&tmB, w.base, w.inner, w.taps, w.rows, bn / 2);  // each CTA of the pair loads half of B
+    if (rc) return rc;
+    if (bn == 256) return launch_tapgemm2<256>(tmA, tmB, p, st);
+    if (bn == 128) return launch_tapgemm2<128>(tmA, tmB, p, st);
+    return launch_tapgemm2<64>(tmA, tmB, p, st);
+  }
+  int rc = make_w_map(&tmB, w.base, w.inner, w.taps, w.rows, bn);
+  if (rc) return rc;
+  switch (bn) {
     case 16: return launch_tapgemm<16>(tmA, tmB, p, st);
     case 32: return launch_tapgemm<32>(tmA, tmB, p, st);
     case 64: return launch_tapgemm<64>(tmA, tmB, p, st);
     case 128: return launch_tapgemm<128>(tmA, tmB, p, st);
     default: return launch_tapgemm<256>(tmA, tmB, p, st);
+  }
+}
+
+// Decide whether the halo kernel applies (taps already in p.tap_dh/dw as absolute offsets) and re-plan the tiling.
+// A tensor = (Ain_W, Ain_H) feature map read by the taps; output sub-grid OW x OH x N, stride 1.
+bool plan_halo(TapGemmParams& p, int OW, int OH, int N, int BN, Box* box, int* halo_w) {
+  const int policy = halo_policy();
+  if (policy == 0 || p.ntaps <= 1) return false;
+  int dh0 = 127, dh1 = -127, dw0 = 127, dw1 = -127;
+  for (int t = 0; t < p.ntaps; ++t) {
+    dh0 = p.tap_dh[t] < dh0 ? p.tap_dh[t] : dh0; dh1 = p.tap_dh[t] > dh1 ? p.tap_dh[t] : dh1;
+    dw0 = p.tap_dw[t] < dw0 ? p.tap_dw[t] : dw0; dw1 = p.tap_dw[t] > dw1 ? p.tap_dw[t] : dw1;
+  }
+  const int ext_h = dh1 - dh0 + 1, ext_w = dw1 - dw0 + 1;
+  const int bw = OW + ext_w - 1;
+  if (bw > 128) return false;
+  int bh = 128 / bw;
+  if (bh > OH) bh = OH;
+  // balance the row tiles of an image (e.g. 14 rows -> 7 + 7 instead of 8 + 6)
+  bh = msp_cdiv(OH, msp_cdiv(OH, bh));
+  if (bh < 1 || OW * bh < 72) return false;                         // < 56 % useful MMA rows: tap path
+  const int box_h = bh + ext_h - 1;
+  if (bw * box_h > 256 || box_h > 256) return false;                // halo tile must fit 32 KB
+  if ((ext_h - 1) * bw + (ext_w - 1) + 128 > 256) return false;     // the M=128 read window stays inside it
+  const int chunks = msp_cdiv(p.C, kBK);
+  const long long bt = (long long)BN * kBK * 2;
+  const long long fixed = (BN >= 256 ? 1 : 2) * (long long)kATileBytes + (8 * 128 * 4 + 4 * 128 * 4) + 1024 + 512;
+  const long long budget = 232448 - fixed;
+  const long long res_bytes = (long long)p.ntaps * chunks * bt;
+  p.b_resident = (msp_cdiv(p.Kout, BN) == 1 && res_bytes + 2 * kHaloABytes <= budget) ? 1 : 0;
+  if (!p.b_resident && policy < 2) return false;  // streaming-B halo is slower than the tap kernel (MMA-issue bound)
+  if (p.b_resident) {
+    p.b_stages = p.ntaps * chunks;
+    p.a_stages = (res_bytes + 3 * kHaloABytes <= budget) ? 3 : 2;
+  } else {
+    p.a_stages = BN >= 256 ? 2 : 3;
+    long long nb = (budget - (long long)p.a_stages * kHaloABytes) / bt;
+    if (nb > kHaloMaxB) nb = kHaloMaxB;
+    if (nb < 2) return false;
+    p.b_stages = (int)nb;
+  }
+  for (int t = 0; t < p.ntaps; ++t) {
+    p.tap_dh[t] = (int8_t)(p.tap_dh[t] - dh0);
+    p.tap_dw[t] = (int8_t)(p.tap_dw[t] - dw0);
+  }
+  p.halo = 1; p.org_dh = dh0; p.org_dw = dw0; p.halo_box_h = box_h;
+  p.bw = bw; p.bh = bh; p.bn = 1; p.rows = bw * bh;
+  p.tiles_w = 1; p.tiles_h = msp_cdiv(OH, bh); p.tiles_n = N;
+  p.OWs = OW; p.OHs = OH; p.N = N;
+  box->bw = bw; box->bh = box_h; box->bn = 1;
+  *halo_w = bw;
+  return true;
+}
+
+template <int BN_>
+int launch_halo(const CUtensorMap& tmA, const CUtensorMap& tmB, TapGemmParams& p, cudaStream_t st) {
+  using Cfg = TapGemmCfg<BN_>;
+  const int smem = p.a_stages * kHaloABytes + p.b_stages * Cfg::kBTileBytes + Cfg::kStageBufs * kATileBytes +
+                   Cfg::kScratchBytes + 1024;
+  static int attr_smem = 0;
+  if (smem > attr_smem) {
+    MSP_CHECK_CUDA(cudaFuncSetAttribute(tapgemm_halo_kernel<BN_>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        232448 - 1024));
+    attr_smem = 232448;
+  }
+  {
+    static int dbg = -1;
+    if (dbg < 0) { const char* e = getenv("MSP_CONV_DEBUG"); dbg = e ? atoi(e) : 0; }
+    p.debug = dbg;
+  }
+  p.tiles_m = p.tiles_w * p.tiles_h * p.tiles_n;
+  p.tiles_co = msp_cdiv(p.Kout, BN_);
+  const long long total = (long long)p.tiles_m * p.tiles_co;
+  MSP_REQUIRE(total < (1ll << 31), "conv: too many tiles");
+  p.total_tiles = (int)total;
+  const int sms = msp_num_sms();
+  const int grid = p.total_tiles < sms ? p.total_tiles : sms;
+  tapgemm_halo_kernel<BN_><<<grid, kTapThreads, smem, st>>>(tmA, tmB, p);
+  MSP_CHECK_LAUNCH();
+  msp_count_launch(1);
+  return MSP_OK;
+}
+
+int dispatch_halo(const CUtensorMap& tmA, const CUtensorMap& tmB, TapGemmParams& p, cudaStream_t st) {
+  switch (bn_tile_for(p.Kout)) {
+    case 16: return launch_halo<16>(tmA, tmB, p, st);
+    case 32: return launch_halo<32>(tmA, tmB, p, st);
+    case 64: return launch_halo<64>(tmA, tmB, p, st);
+    case 128: return launch_halo<128>(tmA, tmB, p, st);
+    default: return launch_halo<256>(tmA, tmB, p, st);
   }
 }
 
@@ -745,6 +1301,13 @@ inline bool is_flat(const msp_conv_desc* d) {
 }
 
 }  // namespace
+
+extern "C" int msp_conv_set_policy(int pair, int halo) {
+  MSP_REQUIRE(pair >= -1 && pair <= 2 && halo >= -1 && halo <= 2, "conv_set_policy: values are -1 (default) .. 2");
+  g_pair_policy = pair;
+  g_halo_policy = halo;
+  return MSP_OK;
+}
 
 extern "C" int msp_pack_weights(const float* w, int K, int C, int KH, int KW, int Cpad, int Kpad,
                                 void* w_fprop, void* w_dgrad, void* stream) {
@@ -819,11 +1382,7 @@ extern "C" int msp_conv_fprop(const msp_conv_desc* d, const void* x, const void*
   }
   if (rc) return rc;
   const int bn_tile = bn_tile_for(d->K);
-  if (d->win_px)
-    rc = make_w_map(&tmB, w_fprop, 64, d->KH, d->K, bn_tile);
-  else
-    rc = make_w_map(&tmB, w_fprop, d->C, taps, d->K, bn_tile);
-  if (rc) return rc;
+  const WMapArgs wm = d->win_px ? WMapArgs{w_fprop, 64, d->KH, d->K} : WMapArgs{w_fprop, d->C, taps, d->K};
   p.bw = b.bw; p.bh = b.bh; p.bn = b.bn; p.rows = b.bw * b.bh * b.bn;
   p.tiles_w = msp_cdiv(p.OWs, b.bw); p.tiles_h = msp_cdiv(p.OHs, b.bh); p.tiles_n = msp_cdiv(p.N, b.bn);
   p.sxw = (flat || d->win_px) ? 1 : d->stride;
@@ -848,7 +1407,18 @@ extern "C" int msp_conv_fprop(const msp_conv_desc* d, const void* x, const void*
         p.tap_w[t] = (uint8_t)t;
       }
   }
-  return dispatch_tapgemm(tmA, tmB, p, (cudaStream_t)stream);
+  if (!flat && !d->win_px && d->stride == 1) {
+    Box hb;
+    int hw = 0;
+    if (plan_halo(p, d->Wo, d->Ho, d->N, bn_tile, &hb, &hw)) {
+      rc = make_act_map(&tmA, x, d->C, d->W, d->H, d->N, d->x_cs, hb, 1);
+      if (rc) return rc;
+      rc = make_w_map(&tmB, wm.base, wm.inner, wm.taps, wm.rows, bn_tile);
+      if (rc) return rc;
+      return dispatch_halo(tmA, tmB, p, (cudaStream_t)stream);
+    }
+  }
+  return dispatch_tapgemm(tmA, wm, p, (cudaStream_t)stream);
 }
 
 extern "C" int msp_conv_dgrad(const msp_conv_desc* d, const void* dy, const void* w_dgrad, void* dx,
@@ -862,8 +1432,7 @@ extern "C" int msp_conv_dgrad(const msp_conv_desc* d, const void* dy, const void
   cudaStream_t st = (cudaStream_t)stream;
   CUtensorMap tmA, tmB;
   // weights [Cpad = d->C][taps][Kpad = d->K]: contraction over K (dy channels), outputs = C
-  rc = make_w_map(&tmB, w_dgrad, d->K, taps, d->C, bn_tile_for(d->C));
-  if (rc) return rc;
+  const WMapArgs wm{w_dgrad, d->K, taps, d->C};
   for (int ph = 0; ph < s; ++ph)
     for (int pw = 0; pw < s; ++pw) {
       TapGemmParams p;
@@ -910,7 +1479,20 @@ extern "C" int msp_conv_dgrad(const msp_conv_desc* d, const void* dy, const void
       p.tiles_n = msp_cdiv(p.N, b.bn);
       p.sxw = 1; p.sxh = 1; p.C = d->K; p.ntaps = nt; p.Kout = d->C; p.relu = 0; p.accumulate = accumulate;
       p.y = (__nv_bfloat16*)dx;
-      rc = dispatch_tapgemm(tmA, tmB, p, st);
+      if (!flat && s == 1) {
+        Box hb;
+        int hw = 0;
+        if (plan_halo(p, d->W, d->H, d->N, bn_tile_for(d->C), &hb, &hw)) {
+          rc = make_act_map(&tmA, dy, d->K, d->Wo, d->Ho, d->N, d->y_cs, hb, 1);
+          if (rc) return rc;
+          rc = make_w_map(&tmB, wm.base, wm.inner, wm.taps, wm.rows, bn_tile_for(d->C));
+          if (rc) return rc;
+          rc = dispatch_halo(tmA, tmB, p, st);
+          if (rc) return rc;
+          continue;
+        }
+      }
+      rc = dispatch_tapgemm(tmA, wm, p, st);
       if (rc) return rc;
     }
   return MSP_OK;

@@ -87,6 +87,11 @@ def pack_weights(w: torch.Tensor, need_dgrad: bool = True):
     return wf, wd
 
 
+def set_conv_policy(pair: int = -1, halo: int = -1) -> None:
+    """Kernel-variant policy of conv fprop / dgrad (see msp_conv_set_policy in include/msp_b200.h)."""
+    call("msp_conv_set_policy", int(pair), int(halo))
+
+
 def conv_out_size(h: int, w: int, kh: int, kw: int, stride: int, padding) -> Tuple[int, int, int, int]:
     """-> (Ho, Wo, pad_t, pad_l); padding is an int, (ph, pw) or 'same' (torch semantics: for even
     kernels the extra padding goes to the bottom/right, blocks.py:518 probe in SURVEY App. B)."""

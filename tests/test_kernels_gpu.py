@@ -174,6 +174,48 @@ def test_conv_wgrad_deterministic():
     assert torch.equal(a, b)
 
 
+VARIANT_CASES = [
+    # N, H, W, C, K, k, stride, padding
+    (3, 28, 28, 128, 128, 3, 1, 1),    # halo applies (streaming B); pair applies to the tap path
+    (2, 14, 14, 256, 256, 3, 1, 1),    # 256-wide tiles
+    (2, 30, 30, 64, 64, 3, 1, 1),      # resident weights in halo mode
+    (5, 14, 14, 512, 256, 1, 1, 0),    # flat 1x1, odd number of M tiles for the CTA pair
+    (3, 28, 28, 128, 128, 3, 2, 1),    # stride 2: tap / pair only
+]
+
+
+@pytest.mark.parametrize("policy", [(0, 0), (1, 0), (2, 0), (0, 2), (0, 1)], ids=lambda p: f"pair{p[0]}_halo{p[1]}")
+@pytest.mark.parametrize("case", VARIANT_CASES, ids=lambda c: "x".join(map(str, c)))
+def test_conv_kernel_variants(case, policy):
+    """Single-CTA tap-GEMM, cta_group::2 CTA-pair tap-GEMM and the halo-reuse kernel give the same results."""
+    ops = _ops()
+    n, h, w, c, k, ks, stride, padding = case
+    g = torch.Generator().manual_seed(500 + VARIANT_CASES.index(case))
+    x = _bf(torch.randn((n, c, h, w), generator=g))
+    wt = _bf(torch.randn((k, c, ks, ks), generator=g) / math.sqrt(c * ks * ks))
+    bias = torch.randn((k,), generator=g)
+    x.requires_grad_(True)
+    ref = _ref_conv(x, wt, bias, stride, padding)
+    dy = _bf(torch.randn(ref.shape, generator=g))
+    ref.backward(dy)
+    ho, wo, pt, pl = ops.conv_out_size(h, w, ks, ks, stride, padding)
+    xd, dyd = _to_nhwc(x.detach()), _to_nhwc(dy)
+    wf, wd = ops.pack_weights(wt.to(DEV))
+    ops.set_conv_policy(*policy)
+    try:
+        stats = torch.zeros((2, k), dtype=torch.float32, device=DEV)
+        y = ops.conv_fprop(xd, wf, bias.to(DEV), k, ks, ks, stride, pt, pl, ho, wo, stats=stats)
+        dx = ops.conv_dgrad(dyd, wd, tuple(xd.shape), ks, ks, stride, pt, pl)
+        torch.cuda.synchronize()
+    finally:
+        ops.set_conv_policy(-1, -1)
+    _close(_from_nhwc(y), ref.detach(), 6e-3, "fprop")
+    yb = y.float().cpu().reshape(-1, k)
+    _close(stats[0].cpu(), yb.sum(0), 1e-3, "ch_sum")
+    _close(stats[1].cpu(), (yb * yb).sum(0), 1e-3, "ch_sqsum")
+    _close(_from_nhwc(dx, c), x.grad, 6e-3, "dgrad")
+
+
 def test_conv_concat_slices():
     """Operands that are channel slices of wider buffers (zero-copy concat, blocks.py:628,635)."""
     ops = _ops()
