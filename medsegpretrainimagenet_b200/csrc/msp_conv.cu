@@ -785,7 +785,8 @@ struct WgradParams {
   int sxw, sxh, pad_t, pad_l, KW;
   int Cw;      // packed weight inner dim (input channels, or 64 window elements in row-window mode)
   int Kout;    // output channels
-  int ntaps, cchunks, nsub;  // nsub = 64-channel sub-tiles per CTA (1..4)
+  int ntaps, cchunks, nsub;  // nsub = csub * tsub 64-column sub-tiles of the accumulator per CTA (1..4)
+  int csub, tsub;            // ... = csub 64-channel chunks x tsub filter taps (narrow layers batch taps)
   int rowwin;
   int splits;
   long long split_stride;  // elements between the partial dW of consecutive splits
@@ -811,11 +812,12 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant__ C
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int tap = blockIdx.x / p.cchunks;
-  const int ci0 = (blockIdx.x - tap * p.cchunks) * (64 * p.nsub);
+  const int tgrp = blockIdx.x / p.cchunks;
+  const int tap0 = tgrp * p.tsub;
+  const int ci0 = (blockIdx.x - tgrp * p.cchunks) * (64 * p.csub);
   const int co0 = blockIdx.y * 128;
-  const int r = p.rowwin ? tap : tap / p.KW;
-  const int qx = p.rowwin ? 0 : tap - r * p.KW;
+  const int ntap_here = (p.ntaps - tap0) < p.tsub ? (p.ntaps - tap0) : p.tsub;
+  const int nsub = ntap_here * p.csub;  // accumulator sub-tiles of THIS block: (tap0 + j / csub, ci0 + 64 * (j % csub))
   const int split = blockIdx.z;
   const int my_tiles = (p.tiles_m - split + p.splits - 1) / p.splits;
 
@@ -844,7 +846,18 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant__ C
     if (lane == 0) {
       tma_prefetch_desc(&tmDY);
       tma_prefetch_desc(&tmX);
-      const uint32_t tx_bytes = (uint32_t)p.rows * 128u * (uint32_t)(2 + p.nsub);
+      const uint32_t tx_bytes = (uint32_t)p.rows * 128u * (uint32_t)(2 + nsub);
+      int sub_dw[kWgMaxSub], sub_dh[kWgMaxSub], sub_c[kWgMaxSub];  // per sub-tile: tap offset and first channel
+#pragma unroll
+      for (int j = 0; j < kWgMaxSub; ++j) {
+        const int tj = j / p.csub, cj = j - tj * p.csub;
+        const int tap = tap0 + tj;
+        const int r = p.rowwin ? tap : tap / p.KW;
+        const int qx = p.rowwin ? 0 : tap - r * p.KW;
+        sub_dw[j] = qx - (p.rowwin ? 0 : p.pad_l);
+        sub_dh[j] = r - p.pad_t;
+        sub_c[j] = ci0 + 64 * cj;
+      }
       for (int it = 0; it < my_tiles; ++it) {
         const int s = it % kWgStages;
         const uint32_t ph = (uint32_t)(it / kWgStages) & 1u;
@@ -858,14 +871,17 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant__ C
         mbar_expect_tx(&full_bar[s], tx_bytes);
         tma_load_4d(a_s, &tmDY, &full_bar[s], co0, w0, h0, n0);
         tma_load_4d(a_s + kATileBytes, &tmDY, &full_bar[s], co0 + 64, w0, h0, n0);
-        const int xw = w0 * p.sxw - (p.rowwin ? 0 : p.pad_l) + qx, xh = h0 * p.sxh - p.pad_t + r;
-        for (int j = 0; j < p.nsub; ++j)
-          tma_load_4d(a_s + (2 + j) * kATileBytes, &tmX, &full_bar[s], ci0 + 64 * j, xw, xh, n0);
+        const int xw0 = w0 * p.sxw, xh0 = h0 * p.sxh;
+#pragma unroll
+        for (int j = 0; j < kWgMaxSub; ++j)
+          if (j < nsub)
+            tma_load_4d(a_s + (2 + j) * kATileBytes, &tmX, &full_bar[s], sub_c[j], xw0 + sub_dw[j], xh0 + sub_dh[j],
+                        n0);
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      const uint32_t idesc = umma_idesc_bf16(128, 64 * p.nsub, 1, 1);
+      const uint32_t idesc = umma_idesc_bf16(128, 64 * nsub, 1, 1);
       const int nk = (p.rows + 15) >> 4;
       // MN-major: 8-row (K) groups 1024 B apart; consecutive 64-channel atoms are 16 KB apart
       const uint64_t d0 = umma_smem_desc_sw128(smem_u32(smem), kATileBytes, 1024);
@@ -894,8 +910,8 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant__ C
   } else {
     const int q = warp & 3;
     const int co = co0 + q * 32 + lane;
-    float* dst0 = p.dw + (long long)split * p.split_stride + ((long long)co * p.ntaps + tap) * p.Cw + ci0;
-    const int ncols = 64 * p.nsub;
+    float* dbase = p.dw + (long long)split * p.split_stride + (long long)co * p.ntaps * p.Cw;
+    const int ncols = 64 * nsub;
     if (my_tiles > 0) {
       if (lane == 0) mbar_wait(&accum_bar, 0);
       __syncwarp();
@@ -905,23 +921,29 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant__ C
         uint32_t v[32];
         tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + c, v);
         tmem_ld_wait();
+        const int j = c >> 6, tj = j / p.csub, cj = j - tj * p.csub;
+        const int ci = ci0 + 64 * cj + (c & 63);
+        float* dst = dbase + (long long)(tap0 + tj) * p.Cw + ci;
         if (co < p.Kout) {
-          if (ci0 + c + 32 <= p.Cw) {
+          if (ci + 32 <= p.Cw) {
 #pragma unroll
-            for (int j = 0; j < 32; j += 4)
-              *reinterpret_cast<float4*>(dst0 + c + j) =
-                  make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]),
-                              __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+            for (int jj = 0; jj < 32; jj += 4)
+              *reinterpret_cast<float4*>(dst + jj) =
+                  make_float4(__uint_as_float(v[jj]), __uint_as_float(v[jj + 1]),
+                              __uint_as_float(v[jj + 2]), __uint_as_float(v[jj + 3]));
           } else {
 #pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (ci0 + c + j < p.Cw) dst0[c + j] = __uint_as_float(v[j]);
+            for (int jj = 0; jj < 32; ++jj)
+              if (ci + jj < p.Cw) dst[jj] = __uint_as_float(v[jj]);
           }
         }
       }
     } else if (co < p.Kout) {
-      for (int c = 0; c < ncols; ++c)
-        if (ci0 + c < p.Cw) dst0[c] = 0.f;
+      for (int c = 0; c < ncols; ++c) {
+        const int j = c >> 6, tj = j / p.csub, cj = j - tj * p.csub;
+        const int ci = ci0 + 64 * cj + (c & 63);
+        if (ci < p.Cw) dbase[(long long)(tap0 + tj) * p.Cw + ci] = 0.f;
+      }
     }
   }
   tc_fence_before();
@@ -1501,7 +1523,7 @@ extern "C" int msp_conv_dgrad(const msp_conv_desc* d, const void* dy, const void
 namespace {
 struct WgradPlan {
   Box b;
-  int OW, OH, N, tiles_m, nsub, cchunks, gx, gy, splits, Cw, ntaps;
+  int OW, OH, N, tiles_m, nsub, csub, tsub, cchunks, gx, gy, splits, Cw, ntaps;
 };
 int plan_wgrad(const msp_conv_desc* d, WgradPlan* pl) {
   const bool flat = is_flat(d);
@@ -1516,10 +1538,15 @@ int plan_wgrad(const msp_conv_desc* d, WgradPlan* pl) {
   pl->tiles_m = msp_cdiv(pl->OW, pl->b.bw) * msp_cdiv(pl->OH, pl->b.bh) * msp_cdiv(pl->N, pl->b.bn);
   pl->Cw = d->win_px ? 64 : d->C;
   pl->ntaps = d->win_px ? d->KH : d->KH * d->KW;
+  // accumulator = 128 output channels x (csub 64-channel chunks x tsub taps) <= 256 columns: wide MMA instructions
+  // even for narrow layers (a 128x64x16 tcgen05.mma costs about as much as a 128x256x16 one)
   const int c64 = msp_cdiv(pl->Cw, 64);
-  pl->nsub = c64 < kWgMaxSub ? c64 : kWgMaxSub;
-  pl->cchunks = msp_cdiv(c64, pl->nsub);
-  pl->gx = pl->ntaps * pl->cchunks;
+  pl->csub = c64 < kWgMaxSub ? c64 : kWgMaxSub;
+  pl->tsub = kWgMaxSub / pl->csub;
+  if (pl->tsub > pl->ntaps) pl->tsub = pl->ntaps;
+  pl->nsub = pl->csub * pl->tsub;
+  pl->cchunks = msp_cdiv(c64, pl->csub);
+  pl->gx = msp_cdiv(pl->ntaps, pl->tsub) * pl->cchunks;
   pl->gy = msp_cdiv(d->K, 128);
   const int base = pl->gx * pl->gy;
   int splits = msp_num_sms() / base;
@@ -1583,7 +1610,7 @@ extern "C" int msp_conv_wgrad(const msp_conv_desc* d, const void* x, const void*
   p.tiles_w = msp_cdiv(pl.OW, b.bw); p.tiles_h = msp_cdiv(pl.OH, b.bh); p.tiles_n = msp_cdiv(pl.N, b.bn);
   p.tiles_m = pl.tiles_m;
   p.pad_t = d->pad_t; p.pad_l = d->pad_l; p.KW = d->KW;
-  p.Cw = pl.Cw; p.Kout = d->K; p.ntaps = pl.ntaps; p.cchunks = pl.cchunks; p.nsub = pl.nsub;
+  p.Cw = pl.Cw; p.Kout = d->K; p.ntaps = pl.ntaps; p.cchunks = pl.cchunks; p.nsub = pl.nsub; p.csub = pl.csub; p.tsub = pl.tsub;
   p.rowwin = d->win_px != 0;
   p.splits = pl.splits;
   p.split_stride = (long long)d->K * pl.ntaps * pl.Cw;
