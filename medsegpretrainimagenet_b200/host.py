@@ -1,0 +1,46 @@
+"""Host-side feeding of the hot path.
+
+The reference moves every batch with a synchronous pageable `.to(device)` inside the step (train_model.py:60).
+`BatchPrefetcher` keeps two sets of device buffers and a copy stream: the pinned host batch i+1 travels over PCIe while
+the step on batch i runs; the consumer stream only waits on the copy's event."""
+from __future__ import annotations
+
+from typing import Sequence
+
+import torch
+
+
+class BatchPrefetcher:
+    def __init__(self, example: Sequence[torch.Tensor], device):
+        self.device = torch.device(device)
+        self.bufs = [[torch.empty(t.shape, dtype=t.dtype, device=self.device) for t in example] for _ in range(2)]
+        self.copy_stream = torch.cuda.Stream(device=self.device)
+        self.ready = [torch.cuda.Event(), torch.cuda.Event()]
+        self.free = [None, None]      # recorded on the consumer stream once the buffer's step has been enqueued
+        self._put = 0                 # next buffer to fill
+        self._get = 0                 # next buffer to hand out
+        self._last = None
+
+    def put(self, *host: torch.Tensor) -> None:
+        """Enqueue the H2D copy of the next batch (pinned memory for a truly asynchronous copy)."""
+        k = self._put
+        if self.free[k] is not None:
+            self.copy_stream.wait_event(self.free[k])
+        with torch.cuda.stream(self.copy_stream):
+            for d, h in zip(self.bufs[k], host):
+                d.copy_(h, non_blocking=True)
+            self.ready[k].record(self.copy_stream)
+        self._put ^= 1
+
+    def get(self):
+        """Device tensors of the oldest pending batch; the current stream waits for its copy."""
+        cur = torch.cuda.current_stream(self.device)
+        if self._last is not None:   # everything enqueued so far has consumed the previous buffer
+            ev = torch.cuda.Event()
+            ev.record(cur)
+            self.free[self._last] = ev
+        k = self._get
+        cur.wait_event(self.ready[k])
+        self._last = k
+        self._get ^= 1
+        return self.bufs[k]
