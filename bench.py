@@ -27,8 +27,15 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
-# stdout carries exactly ONE JSON line: NCCL's banner / debug output goes to stderr
-os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+# stdout carries exactly ONE JSON line: everything any library prints to fd 1 (NCCL's banner, device printf) is
+# diverted to stderr for the whole run, and the result line goes to the saved descriptor.
+sys.stdout.flush()
+_RESULT_FD = os.dup(1)
+os.dup2(2, 1)
+
+
+def emit(obj) -> None:
+    os.write(_RESULT_FD, (json.dumps(obj) + "\n").encode())
 
 WORKLOADS = {
     # name: (description, per-GPU batch, input shape, cpu-sample batch)
@@ -155,14 +162,14 @@ def reference_arm(args):
     dt = time.perf_counter() - t0
     val = steps * cpu_batch / dt
     sample = f"{steps} steps x batch {cpu_batch} of the {name} training step (fp32, torch {torch.__version__} CPU)"
-    print(json.dumps({
+    emit({
         "impl": "reference", "metric": "train images/sec", "value": val, "unit": "images/sec",
         "n_gpus": args.gpus, "steps": steps, "warmup": warm, "ms_per_step": 1e3 * dt / steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
         "config": {"workload": name, "per_step_batch": cpu_batch},
         "cpu_baseline": {"value": val, "unit": "images/sec", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": "images/sec", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-    }))
+    })
 
 
 def cpu_baseline(workload, budget_s=25.0):
@@ -403,7 +410,7 @@ def main():
         }
         if world == 1 and not args.no_cpu_baseline:
             out["cpu_baseline"] = cpu_baseline(args.workload)
-        print(json.dumps(out), flush=True)
+        emit(out)
     if world > 1:
         # Tearing down a NCCL communicator whose collectives were captured in a live CUDA graph can block; the
         # measurement is complete and printed: synchronise, rendezvous once more and leave without the teardown.

@@ -980,6 +980,28 @@ __global__ void pack_w_dgrad_kernel(const float* __restrict__ w, int K, int C, i
     out[i] = __float2bfloat16_rn(v);
   }
 }
+// both packings in one launch (one per convolution per step)
+__global__ void pack_w_both_kernel(const float* __restrict__ w, int K, int C, int taps, int Cpad, int Kpad,
+                                   __nv_bfloat16* __restrict__ wf, __nv_bfloat16* __restrict__ wd) {
+  const long long nf = (long long)K * taps * Cpad, nd = (long long)Cpad * taps * Kpad;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nf + nd;
+       i += (long long)gridDim.x * blockDim.x) {
+    if (i < nf) {
+      const int c = (int)(i % Cpad);
+      const long long t = i / Cpad;
+      const int tap = (int)(t % taps);
+      const int k = (int)(t / taps);
+      wf[i] = __float2bfloat16_rn(c < C ? w[((long long)k * C + c) * taps + tap] : 0.f);
+    } else {
+      const long long i2 = i - nf;
+      const int k = (int)(i2 % Kpad);
+      const long long t = i2 / Kpad;
+      const int tap = (int)(t % taps);
+      const int c = (int)(t / taps);
+      wd[i2] = __float2bfloat16_rn((c < C && k < K) ? w[((long long)k * C + c) * taps + tap] : 0.f);
+    }
+  }
+}
 // row-window packing: out[k][r][q * cpp + c] = w[k][c][r][q]  (64 window elements per filter row)
 __global__ void pack_w_rowwin_kernel(const float* __restrict__ w, int K, int C, int KH, int KW, int cpp,
                                      __nv_bfloat16* __restrict__ out) {
@@ -1338,6 +1360,15 @@ extern "C" int msp_pack_weights(const float* w, int K, int C, int KH, int KW, in
               "pack_weights: padded sizes must be multiples of 8");
   cudaStream_t st = (cudaStream_t)stream;
   const int taps = KH * KW;
+  if (w_fprop && w_dgrad) {
+    const long long total = (long long)K * taps * Cpad + (long long)Cpad * taps * Kpad;
+    const int blocks = (int)((total + 255) / 256 < 4096 ? (total + 255) / 256 : 4096);
+    pack_w_both_kernel<<<blocks, 256, 0, st>>>(w, K, C, taps, Cpad, Kpad, (__nv_bfloat16*)w_fprop,
+                                               (__nv_bfloat16*)w_dgrad);
+    MSP_CHECK_LAUNCH();
+    msp_count_launch(1);
+    return MSP_OK;
+  }
   if (w_fprop) {
     const long long total = (long long)K * taps * Cpad;
     const int blocks = (int)((total + 255) / 256 < 4096 ? (total + 255) / 256 : 4096);

@@ -392,92 +392,102 @@ bn_act_bwd_apply_kernel(const msp_bn_act_desc d, const __nv_bfloat16* __restrict
 // ---------------------------------------------------------------------------------------------
 // pooling / resampling
 // ---------------------------------------------------------------------------------------------
-__global__ void maxpool_fwd_kernel(const __nv_bfloat16* __restrict__ x, int N, int H, int W, int C,
-                                   int x_cs, int k, int s, int pad, __nv_bfloat16* __restrict__ y,
-                                   uint8_t* __restrict__ idx, int Ho, int Wo, int y_cs) {
-  const int V = C >> 3;
-  const long long total = (long long)N * Ho * Wo * V;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
-    const int cg = (int)(i % V);
-    long long p = i / V;
-    const int wo = (int)(p % Wo); p /= Wo;
-    const int ho = (int)(p % Ho);
-    const int n = (int)(p / Ho);
-    float best[8];
-    int bi[8];
+// Max pooling, one block-iteration per OUTPUT ROW (n, ho): no 64-bit index arithmetic in the inner loop, 16-byte
+// vectors, the in-window arg-max (first maximum in scan order, like ATen; NaN propagates) as one byte per element.
+__global__ void __launch_bounds__(256)
+maxpool_fwd_kernel(const __nv_bfloat16* __restrict__ x, int N, int H, int W, int C, int x_cs, int k, int s,
+                   int pad, __nv_bfloat16* __restrict__ y, uint8_t* __restrict__ idx, int Ho, int Wo, int y_cs) {
+  const uint32_t V = (uint32_t)C >> 3;
+  const uint32_t per_row = (uint32_t)Wo * V;
+  const int rows = N * Ho;
+  for (int row = blockIdx.x; row < rows; row += gridDim.x) {
+    const int n = row / Ho, ho = row - n * Ho;
+    const int h_lo = ho * s - pad;
+    const __nv_bfloat16* xn = x + (long long)n * H * W * x_cs;
+    for (uint32_t t = threadIdx.x; t < per_row; t += blockDim.x) {
+      const uint32_t wo = t / V, cg = t - wo * V;
+      const int w_lo = (int)wo * s - pad;
+      float best[8];
+      uint32_t bi[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) { best[j] = -INFINITY; bi[j] = 0; }
-    for (int r = 0; r < k; ++r) {
-      const int h = ho * s - pad + r;
-      if (h < 0 || h >= H) continue;
-      for (int q = 0; q < k; ++q) {
-        const int w = wo * s - pad + q;
-        if (w < 0 || w >= W) continue;
-        F8 v = load_bf16x8(x + (((long long)n * H + h) * W + w) * x_cs + cg * 8);
+      for (int j = 0; j < 8; ++j) { best[j] = -INFINITY; bi[j] = 0; }
+      for (int r = 0; r < k; ++r) {
+        const int h = h_lo + r;
+        if (h < 0 || h >= H) continue;
+        for (int q = 0; q < k; ++q) {
+          const int w = w_lo + q;
+          if (w < 0 || w >= W) continue;
+          const F8 v = unpack8(ld_nc_v4(xn + ((long long)h * W + w) * x_cs + cg * 8));
+          const uint32_t me = (uint32_t)(r * k + q);
 #pragma unroll
-        for (int j = 0; j < 8; ++j)
-          if (v.v[j] > best[j] || v.v[j] != v.v[j]) { best[j] = v.v[j]; bi[j] = r * k + q; }
+          for (int j = 0; j < 8; ++j)
+            if (v.v[j] > best[j] || v.v[j] != v.v[j]) { best[j] = v.v[j]; bi[j] = me; }
+        }
       }
-    }
-    F8 o;
+      F8 o;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) o.v[j] = best[j];
-    const long long op = ((long long)n * Ho + ho) * Wo + wo;
-    store_bf16x8(y + op * y_cs + cg * 8, o);
-    if (idx) {
-      uint2 u;
-      u.x = (uint32_t)bi[0] | ((uint32_t)bi[1] << 8) | ((uint32_t)bi[2] << 16) | ((uint32_t)bi[3] << 24);
-      u.y = (uint32_t)bi[4] | ((uint32_t)bi[5] << 8) | ((uint32_t)bi[6] << 16) | ((uint32_t)bi[7] << 24);
-      *reinterpret_cast<uint2*>(idx + op * C + cg * 8) = u;
+      for (int j = 0; j < 8; ++j) o.v[j] = best[j];
+      const long long op = (long long)row * Wo + wo;
+      store_bf16x8(y + op * y_cs + cg * 8, o);
+      if (idx) {
+        uint2 u;
+        u.x = bi[0] | (bi[1] << 8) | (bi[2] << 16) | (bi[3] << 24);
+        u.y = bi[4] | (bi[5] << 8) | (bi[6] << 16) | (bi[7] << 24);
+        *reinterpret_cast<uint2*>(idx + op * C + cg * 8) = u;
+      }
     }
   }
 }
-// gather formulation: every input pixel sums dy of the windows whose arg-max it is
-__global__ void maxpool_bwd_kernel(const uint8_t* __restrict__ idx, const __nv_bfloat16* __restrict__ dy,
-                                   int N, int H, int W, int C, int k, int s, int pad, int Ho, int Wo,
-                                   int dy_cs, __nv_bfloat16* __restrict__ dx, int dx_cs, int acc) {
-  const int V = C >> 3;
-  const long long total = (long long)N * H * W * V;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
-    const int cg = (int)(i % V);
-    long long p = i / V;
-    const int w = (int)(p % W); p /= W;
-    const int h = (int)(p % H);
-    const int n = (int)(p / H);
-    float a[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) a[j] = 0.f;
-    // windows (ho, wo) with ho*s - pad <= h < ho*s - pad + k
+// gather formulation (no atomics): every INPUT pixel sums dy of the windows whose arg-max it is; one block-iteration
+// per input row (n, h)
+__global__ void __launch_bounds__(256)
+maxpool_bwd_kernel(const uint8_t* __restrict__ idx, const __nv_bfloat16* __restrict__ dy, int N, int H, int W, int C,
+                   int k, int s, int pad, int Ho, int Wo, int dy_cs, __nv_bfloat16* __restrict__ dx, int dx_cs,
+                   int acc) {
+  const uint32_t V = (uint32_t)C >> 3;
+  const uint32_t per_row = (uint32_t)W * V;
+  const int rows = N * H;
+  for (int row = blockIdx.x; row < rows; row += gridDim.x) {
+    const int n = row / H, h = row - n * H;
+    // windows ho with ho*s - pad <= h < ho*s - pad + k
     const int ho_lo = (h + pad - k + 1) <= 0 ? 0 : (h + pad - k + s) / s;
-    const int wo_lo = (w + pad - k + 1) <= 0 ? 0 : (w + pad - k + s) / s;
-    for (int ho = ho_lo; ho <= (h + pad) / s && ho < Ho; ++ho) {
-      const int r = h + pad - ho * s;
-      for (int wo = wo_lo; wo <= (w + pad) / s && wo < Wo; ++wo) {
-        const int q = w + pad - wo * s;
-        const int me = r * k + q;
-        const long long op = ((long long)n * Ho + ho) * Wo + wo;
-        const uint2 u = *reinterpret_cast<const uint2*>(idx + op * C + cg * 8);
-        F8 g = load_bf16x8(dy + op * dy_cs + cg * 8);
+    int ho_hi = (h + pad) / s;
+    if (ho_hi > Ho - 1) ho_hi = Ho - 1;
+    for (uint32_t t = threadIdx.x; t < per_row; t += blockDim.x) {
+      const uint32_t wu = t / V, cg = t - wu * V;
+      const int w = (int)wu;
+      const int wo_lo = (w + pad - k + 1) <= 0 ? 0 : (w + pad - k + s) / s;
+      int wo_hi = (w + pad) / s;
+      if (wo_hi > Wo - 1) wo_hi = Wo - 1;
+      float a[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const uint32_t b = ((j < 4 ? u.x : u.y) >> ((j & 3) * 8)) & 0xFFu;
-          if ((int)b == me) a[j] += g.v[j];
+      for (int j = 0; j < 8; ++j) a[j] = 0.f;
+      for (int ho = ho_lo; ho <= ho_hi; ++ho) {
+        const int r = h + pad - ho * s;
+        for (int wo = wo_lo; wo <= wo_hi; ++wo) {
+          const uint32_t me = (uint32_t)(r * k + (w + pad - wo * s));
+          const long long op = ((long long)n * Ho + ho) * Wo + wo;
+          const uint2 u = *reinterpret_cast<const uint2*>(idx + op * C + cg * 8);
+          const F8 g = unpack8(ld_nc_v4(dy + op * dy_cs + cg * 8));
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const uint32_t b = ((j < 4 ? u.x : u.y) >> ((j & 3) * 8)) & 0xFFu;
+            if (b == me) a[j] += g.v[j];
+          }
         }
       }
-    }
-    __nv_bfloat16* o = dx + (((long long)n * H + h) * W + w) * dx_cs + cg * 8;
-    F8 r8;
-    if (acc) {
-      F8 old = load_bf16x8(o);
+      __nv_bfloat16* o = dx + ((long long)row * W + w) * dx_cs + cg * 8;
+      F8 r8;
+      if (acc) {
+        const F8 old = load_bf16x8(o);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) r8.v[j] = old.v[j] + a[j];
-    } else {
+        for (int j = 0; j < 8; ++j) r8.v[j] = old.v[j] + a[j];
+      } else {
 #pragma unroll
-      for (int j = 0; j < 8; ++j) r8.v[j] = a[j];
+        for (int j = 0; j < 8; ++j) r8.v[j] = a[j];
+      }
+      store_bf16x8(o, r8);
     }
-    store_bf16x8(o, r8);
   }
 }
 
@@ -831,8 +841,7 @@ extern "C" int msp_maxpool_fwd(const void* x, int N, int H, int W, int C, int x_
   REQ_C8(C, x_cs, "maxpool_fwd(x)");
   REQ_C8(C, y_cs, "maxpool_fwd(y)");
   MSP_REQUIRE(x && y && k >= 1 && k <= 15 && stride >= 1 && pad >= 0, "maxpool_fwd: bad arguments");
-  const long long total = (long long)N * Ho * Wo * (C / 8);
-  maxpool_fwd_kernel<<<grid_for(total, 256), 256, 0, ST>>>((const __nv_bfloat16*)x, N, H, W, C, x_cs, k,
+  maxpool_fwd_kernel<<<resident_grid(maxpool_fwd_kernel, 256, 0, (long long)N * Ho, 1), 256, 0, ST>>>((const __nv_bfloat16*)x, N, H, W, C, x_cs, k,
                                                            stride, pad, (__nv_bfloat16*)y,
                                                            (uint8_t*)idx, Ho, Wo, y_cs);
   MSP_CHECK_LAUNCH();
@@ -845,8 +854,7 @@ extern "C" int msp_maxpool_bwd(const void* idx, const void* dy, int N, int H, in
   REQ_C8(C, dy_cs, "maxpool_bwd(dy)");
   REQ_C8(C, dx_cs, "maxpool_bwd(dx)");
   MSP_REQUIRE(idx && dy && dx, "maxpool_bwd: null pointer");
-  const long long total = (long long)N * H * W * (C / 8);
-  maxpool_bwd_kernel<<<grid_for(total, 256), 256, 0, ST>>>((const uint8_t*)idx, (const __nv_bfloat16*)dy,
+  maxpool_bwd_kernel<<<resident_grid(maxpool_bwd_kernel, 256, 0, (long long)N * H, 1), 256, 0, ST>>>((const uint8_t*)idx, (const __nv_bfloat16*)dy,
                                                            N, H, W, C, k, stride, pad, Ho, Wo, dy_cs,
                                                            (__nv_bfloat16*)dx, dx_cs, accumulate);
   MSP_CHECK_LAUNCH();
