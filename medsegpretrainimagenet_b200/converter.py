@@ -147,12 +147,14 @@ def _is_noop(m) -> bool:
 
 
 def conv_bn_act(ctx: ExecContext, x, conv: nn.Conv2d, bn: Optional[nn.BatchNorm2d] = None, act: int = 0,
-                residual=None, r_stride: int = 1, sample_scale=None):
+                residual=None, r_stride: int = 1, sample_scale=None, link_in=None, link_out=None):
     """Conv2d [-> BatchNorm2d] [-> ReLU | Sigmoid], with optional fused residual / per-sample scale."""
     _check_conv(conv)
     stride, padding = conv.stride[0], _pad_of(conv)
     if isinstance(x, RawInput):
         conv2d = lambda _x, *a, **k: Fn.input_conv2d(x.t, *a, **k)
+    elif link_in is not None:
+        conv2d = lambda *a, **k: Fn.conv2d(*a, link=link_in, **k)
     else:
         conv2d = Fn.conv2d
     if bn is None:
@@ -167,7 +169,7 @@ def conv_bn_act(ctx: ExecContext, x, conv: nn.Conv2d, bn: Optional[nn.BatchNorm2
                       want_stats=ctx.stats_for(bn) if training else False)
     return Fn.bn_act(y, stats, bn, act=act, residual=residual, r_stride=r_stride,
                      sample_scale=sample_scale, group=ctx.group, conv_bias=conv.bias, persistent_stats=True,
-                     counters=ctx.counters)
+                     counters=ctx.counters, link=link_out)
 
 
 def run_sequence(ctx: ExecContext, mods: List[nn.Module], x):
@@ -236,11 +238,13 @@ def run_res_unit(ctx: ExecContext, blk, x):
     if convs[-1].out_channels < convs[0].in_channels:
         raise UnsupportedModule("residual block that narrows its input")
     scale = _drop_path_scale(ctx, blk, x.shape[0], x.device)
+    # the shortcut gradient goes straight from the last BatchNorm's backward into the first conv's dgrad epilogue
+    link = Fn.ResidualLink() if torch.is_grad_enabled() and x.requires_grad else None
     y = x
-    for conv, bn in zip(convs[:-1], bns[:-1]):
-        y = conv_bn_act(ctx, y, conv, bn, ops.ACT_RELU)
+    for i, (conv, bn) in enumerate(zip(convs[:-1], bns[:-1])):
+        y = conv_bn_act(ctx, y, conv, bn, ops.ACT_RELU, link_in=link if i == 0 else None)
     return conv_bn_act(ctx, y, convs[-1], bns[-1], ops.ACT_RELU, residual=x, r_stride=r_stride,
-                       sample_scale=scale)
+                       sample_scale=scale, link_out=link)
 
 
 def run_deep_resnet(ctx: ExecContext, m, x, return_skip_vals: bool = False):

@@ -179,6 +179,15 @@ __device__ __forceinline__ void tap_epilogue(const TapGemmParams& p, uint8_t* st
       for (int c = 0; c < Cfg::kNChunk; ++c) {
         const int cg = co0 + c * CH;
         const uint32_t stg_s = smem_u32(staging) + (Cfg::kStageBufs == 2 ? sbuf * kATileBytes : 0);
+        // dgrad on top of an existing gradient: fetch the old values now, consume them after the transpose
+        uint4 old[4];
+        if (p.accumulate) {
+          const bool mine = ck < CH / 8 && cg + ck * 8 < p.Kout;
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            old[j] = (mine && o_ptr[j] != nullptr) ? __ldg(reinterpret_cast<const uint4*>(o_ptr[j] + c * CH))
+                                                   : make_uint4(0u, 0u, 0u, 0u);
+        }
         // single staging tile: everyone must have finished reading the previous chunk out of it
         if constexpr (Cfg::kStageBufs == 1) named_bar_sync(kEpiBarrier, kEpiThreads);
         uint32_t v[CHH];
@@ -242,18 +251,15 @@ __device__ __forceinline__ void tap_epilogue(const TapGemmParams& p, uint8_t* st
             if (p.accumulate) {
 #pragma unroll
               for (int j = 0; j < 4; ++j) {
-                if (o_ptr[j] != nullptr) {
-                  const uint4 old = *reinterpret_cast<const uint4*>(o_ptr[j] + coff);
-                  const uint32_t ov[4] = {old.x, old.y, old.z, old.w};
-                  const uint32_t nv[4] = {o[j].x, o[j].y, o[j].z, o[j].w};
-                  uint32_t rv[4];
+                const uint32_t ov[4] = {old[j].x, old[j].y, old[j].z, old[j].w};
+                const uint32_t nv[4] = {o[j].x, o[j].y, o[j].z, o[j].w};
+                uint32_t rv[4];
 #pragma unroll
-                  for (int e = 0; e < 4; ++e) {
-                    const float2 a = unpack_bf16x2(ov[e]), b2 = unpack_bf16x2(nv[e]);
-                    rv[e] = pack_bf16x2(a.x + b2.x, a.y + b2.y);
-                  }
-                  o[j] = make_uint4(rv[0], rv[1], rv[2], rv[3]);
+                for (int e = 0; e < 4; ++e) {
+                  const float2 a = unpack_bf16x2(ov[e]), b2 = unpack_bf16x2(nv[e]);
+                  rv[e] = pack_bf16x2(a.x + b2.x, a.y + b2.y);
                 }
+                o[j] = make_uint4(rv[0], rv[1], rv[2], rv[3]);
               }
             }
 #pragma unroll

@@ -417,7 +417,7 @@ maxpool_fwd_kernel(const __nv_bfloat16* __restrict__ x, int N, int H, int W, int
         for (int q = 0; q < k; ++q) {
           const int w = w_lo + q;
           if (w < 0 || w >= W) continue;
-          const F8 v = unpack8(ld_nc_v4(xn + ((long long)h * W + w) * x_cs + cg * 8));
+          const F8 v = load_bf16x8(xn + ((long long)h * W + w) * x_cs + cg * 8);  // windows overlap: keep in L1
           const uint32_t me = (uint32_t)(r * k + q);
 #pragma unroll
           for (int j = 0; j < 8; ++j)
@@ -468,11 +468,13 @@ maxpool_bwd_kernel(const uint8_t* __restrict__ idx, const __nv_bfloat16* __restr
           const uint32_t me = (uint32_t)(r * k + (w + pad - wo * s));
           const long long op = ((long long)n * Ho + ho) * Wo + wo;
           const uint2 u = *reinterpret_cast<const uint2*>(idx + op * C + cg * 8);
-          const F8 g = unpack8(ld_nc_v4(dy + op * dy_cs + cg * 8));
+          const F8 g = load_bf16x8(dy + op * dy_cs + cg * 8);                  // shared by neighbours: keep in L1
+          const uint32_t me4 = me * 0x01010101u;
+          const uint32_t m0 = __vcmpeq4(u.x, me4), m1 = __vcmpeq4(u.y, me4);  // 0xFF where this pixel won
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const uint32_t b = ((j < 4 ? u.x : u.y) >> ((j & 3) * 8)) & 0xFFu;
-            if (b == me) a[j] += g.v[j];
+          for (int j = 0; j < 4; ++j) {
+            if (m0 & (1u << (8 * j))) a[j] += g.v[j];
+            if (m1 & (1u << (8 * j))) a[4 + j] += g.v[4 + j];
           }
         }
       }
@@ -803,8 +805,12 @@ extern "C" int msp_bn_act_bwd_reduce(const msp_bn_act_desc* d, const void* x, co
   MSP_REQUIRE(x && y && dy && mean && invstd && sum_g && sum_gx, "bn_act_bwd_reduce: null pointer");
   const int V = d->C / 8, T = threads_for_vecs(V), ppb = T / V;
   const long long P = (long long)d->N * d->H * d->W;
-  MSP_CHECK_CUDA(cudaMemsetAsync(sum_g, 0, sizeof(float) * d->C, ST));
-  MSP_CHECK_CUDA(cudaMemsetAsync(sum_gx, 0, sizeof(float) * d->C, ST));
+  if (sum_gx == sum_g + d->C) {  // the usual [2][C] buffer: one memset node
+    MSP_CHECK_CUDA(cudaMemsetAsync(sum_g, 0, sizeof(float) * 2 * d->C, ST));
+  } else {
+    MSP_CHECK_CUDA(cudaMemsetAsync(sum_g, 0, sizeof(float) * d->C, ST));
+    MSP_CHECK_CUDA(cudaMemsetAsync(sum_gx, 0, sizeof(float) * d->C, ST));
+  }
   const size_t smem = (size_t)T * 16 * sizeof(float);
   MSP_REQUIRE(P < (1ll << 31), "bn_act: too many pixels");
   bn_act_bwd_reduce_kernel<2><<<resident_grid(bn_act_bwd_reduce_kernel<2>, T, smem, P, ppb * 2), T, smem, ST>>>(

@@ -57,6 +57,16 @@ def to_nchw(x: torch.Tensor, c: Optional[int] = None) -> torch.Tensor:
 # ------------------------------------------------------------------------------------------------
 # convolution
 # ------------------------------------------------------------------------------------------------
+class ResidualLink:
+    """Carries the shortcut gradient of a residual unit from its last BatchNorm's backward to its first
+    convolution's backward, which ADDS its dgrad into that buffer in the kernel epilogue — instead of autograd
+    summing two full-size gradient tensors with an extra elementwise kernel (and an extra bf16 rounding)."""
+    __slots__ = ("dres",)
+
+    def __init__(self):
+        self.dres = None
+
+
 def _stats_buffer(want_stats, k, device):
     """`want_stats` is False, True (fresh zeroed [2, K] accumulator) or a persistent accumulator that
     msp_bn_finalize(reset) leaves zeroed for the next step."""
@@ -72,7 +82,8 @@ class _Conv(torch.autograd.Function):
     squares) of y as a second, non-differentiable output."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias, stride, padding, relu, want_stats, out):
+    def forward(ctx, x, weight, bias, stride, padding, relu, want_stats, out, link):
+        ctx.link = link
         k, c_true, kh, kw = weight.shape
         n, h, w, c8 = x.shape
         ho, wo, pt, pl = ops.conv_out_size(h, w, kh, kw, stride, padding)
@@ -99,12 +110,19 @@ class _Conv(torch.autograd.Function):
             dy = ops.relu_bwd(y, dy)
         dx = dw = db = None
         if ctx.needs_input_grad[0]:
-            dx = ops.conv_dgrad(dy, wd, ctx.x_shape, kh, kw, stride, pt, pl, c_true=c_true)
+            link = ctx.link
+            if link is not None and link.dres is not None and tuple(link.dres.shape) == tuple(ctx.x_shape):
+                # residual unit: dx = shortcut gradient (already in the buffer) + dgrad, added in the epilogue
+                dx = ops.conv_dgrad(dy, wd, ctx.x_shape, kh, kw, stride, pt, pl, out=link.dres, accumulate=True,
+                                    c_true=c_true)
+                link.dres = None
+            else:
+                dx = ops.conv_dgrad(dy, wd, ctx.x_shape, kh, kw, stride, pt, pl, c_true=c_true)
         if ctx.needs_input_grad[1]:
             dw = ops.conv_wgrad(x, dy, c_true, kh, kw, stride, pt, pl)
         if has_bias and ctx.needs_input_grad[2]:
             db = ops.channel_sum(dy)
-        return dx, dw, db, None, None, None, None, None
+        return dx, dw, db, None, None, None, None, None, None
 
 
 class _InputConv(torch.autograd.Function):
@@ -160,8 +178,8 @@ def input_conv2d(x_nchw, weight, bias=None, stride=1, padding=0, relu=False, wan
     return _InputConv.apply(x_nchw, weight, bias, stride, padding, relu, want_stats, geom)
 
 
-def conv2d(x, weight, bias=None, stride=1, padding=0, relu=False, want_stats=False, out=None):
-    return _Conv.apply(x, weight, bias, stride, padding, relu, want_stats, out)
+def conv2d(x, weight, bias=None, stride=1, padding=0, relu=False, want_stats=False, out=None, link=None):
+    return _Conv.apply(x, weight, bias, stride, padding, relu, want_stats, out, link)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -174,7 +192,8 @@ class _BnAct(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, stats, gamma, beta, residual, sample_scale, running_mean, running_var, training,
-                momentum, eps, act, r_stride, group, conv_bias, persistent_stats):
+                momentum, eps, act, r_stride, group, conv_bias, persistent_stats, link):
+        ctx.link = link
         n, h, w, c = x.shape
         count = n * h * w
         if training:
@@ -229,13 +248,15 @@ class _BnAct(torch.autograd.Function):
                                   count, dres=dres, r_stride=r_stride, sample_scale=sscale)
         if not ctx.needs_input_grad[0]:
             dx = None
+        if dres is not None and ctx.link is not None:
+            ctx.link.dres, dres = dres, None    # consumed by the unit's first convolution (ResidualLink)
         return (dx, None, dgamma if gamma is not None and ctx.needs_input_grad[2] else None,
                 dbeta if ctx.needs_input_grad[3] else None, dres, None, None, None, None, None, None, None,
-                None, None, dbias, None)
+                None, None, dbias, None, None)
 
 
 def bn_act(x, stats, bn: torch.nn.BatchNorm2d, act=ops.ACT_NONE, residual=None, r_stride=1,
-           sample_scale=None, group=None, conv_bias=None, persistent_stats=False, counters=None):
+           sample_scale=None, group=None, conv_bias=None, persistent_stats=False, counters=None, link=None):
     """`counters`: list collecting the num_batches_tracked buffers to bump (one fused add at the end of the forward,
     converter._finish_forward) instead of one tiny launch per layer; None = bump immediately."""
     training = bn.training or bn.running_mean is None
@@ -248,7 +269,7 @@ def bn_act(x, stats, bn: torch.nn.BatchNorm2d, act=ops.ACT_NONE, residual=None, 
     return _BnAct.apply(x, stats, bn.weight, bn.bias, residual, sample_scale,
                         bn.running_mean if bn.track_running_stats else None,
                         bn.running_var if bn.track_running_stats else None, training, momentum, bn.eps,
-                        act, r_stride, group, conv_bias, persistent_stats)
+                        act, r_stride, group, conv_bias, persistent_stats, link)
 
 
 # ------------------------------------------------------------------------------------------------
