@@ -48,6 +48,7 @@ constexpr int kEpiBarrier = 1;  // named barrier id of the 8 epilogue warps
 
 struct TapGemmParams {
   int bw, bh, bn, rows;
+  int bw_valid;  // output columns per tile (= bw, except in halo mode where bw is the halo pitch)
   int tiles_w, tiles_h, tiles_n;
   int tiles_m, tiles_co, total_tiles;
   int OWs, OHs, N;  // output sub-grid extent
@@ -129,7 +130,7 @@ __device__ __forceinline__ void tap_epilogue(const TapGemmParams& p, uint8_t* st
       o_hi[j] = (r / p.bw) % p.bh;
       o_ni[j] = r / (p.bw * p.bh);
       o_lds[j] = (uint32_t)(r * 128 + ((ck ^ (r & 7)) << 4));
-      o_rel[j] = r < p.rows ? (long long)o_ni[j] * p.y_n_stride + (long long)o_hi[j] * p.y_h_stride +
+      o_rel[j] = (r < p.rows && o_wi[j] < p.bw_valid) ? (long long)o_ni[j] * p.y_n_stride + (long long)o_hi[j] * p.y_h_stride +
                                   (long long)o_wi[j] * p.y_w_stride + ck * 8
                             : -1;
     }
@@ -151,10 +152,10 @@ __device__ __forceinline__ void tap_epilogue(const TapGemmParams& p, uint8_t* st
         th = (int)(rest % (uint32_t)p.tiles_h);
         tn = (int)(rest / (uint32_t)p.tiles_h);
       }
-      const int w0 = tw * p.bw, h0 = th * p.bh, n0 = tn * p.bn;
+      const int w0 = tw * p.bw_valid, h0 = th * p.bh, n0 = tn * p.bn;
       const int co0 = tco * BN_;
       const bool valid =
-          tile_ok && row < p.rows && (w0 + my_wi) < p.OWs && (h0 + my_hi) < p.OHs && (n0 + my_ni) < p.N;
+          tile_ok && row < p.rows && my_wi < p.bw_valid && (w0 + my_wi) < p.OWs && (h0 + my_hi) < p.OHs && (n0 + my_ni) < p.N;
       const long long tile_off = p.y_off + (long long)n0 * p.y_n_stride + (long long)h0 * p.y_h_stride +
                                  (long long)w0 * p.y_w_stride + co0;
       __nv_bfloat16* o_ptr[4];
@@ -680,14 +681,15 @@ tapgemm_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
         const int tco = tile / p.tiles_m;
         const int tm = tile - tco * p.tiles_m;
-        const int th = tm % p.tiles_h;
-        const int tn = tm / p.tiles_h;
-        const int h0 = th * p.bh;
+        const int tw = tm % p.tiles_w;
+        const int th = (tm / p.tiles_w) % p.tiles_h;
+        const int tn = tm / (p.tiles_w * p.tiles_h);
+        const int h0 = th * p.bh, w0 = tw * p.bw_valid;
         const int co0 = tco * BN_;
         for (int ch = 0; ch < chunks; ++ch) {
           mbar_wait(&a_empty[sa], pha ^ 1u);
           mbar_expect_tx(&a_full[sa], a_bytes);
-          tma_load_4d(a_ring + sa * kHaloABytes, &tmA, &a_full[sa], ch * kBK, p.org_dw, h0 + p.org_dh, tn);
+          tma_load_4d(a_ring + sa * kHaloABytes, &tmA, &a_full[sa], ch * kBK, w0 + p.org_dw, h0 + p.org_dh, tn);
           if (++sa == (uint32_t)p.a_stages) {
             sa = 0;
             pha ^= 1u;
@@ -1112,6 +1114,7 @@ int launch_tapgemm(const CUtensorMap& tmA, const CUtensorMap& tmB, TapGemmParams
     p.debug = dbg;
     p.dbg_stages = dst;
   }
+  p.bw_valid = p.bw;
   p.tiles_m = p.tiles_w * p.tiles_h * p.tiles_n;
   p.tiles_co = msp_cdiv(p.Kout, BN_);
   const long long total = (long long)p.tiles_m * p.tiles_co;
@@ -1139,6 +1142,7 @@ int launch_tapgemm2(const CUtensorMap& tmA, const CUtensorMap& tmB, TapGemmParam
     if (dbg < 0) { const char* e = getenv("MSP_CONV_DEBUG"); dbg = e ? atoi(e) : 0; }
     p.debug = dbg;
   }
+  p.bw_valid = p.bw;
   p.tiles_m = p.tiles_w * p.tiles_h * p.tiles_n;
   p.tiles_co = msp_cdiv(p.Kout, BN_);
   const long long items = (long long)((p.tiles_m + 1) / 2) * p.tiles_co;
@@ -1214,16 +1218,24 @@ bool plan_halo(TapGemmParams& p, int OW, int OH, int N, int BN, Box* box, int* h
     dw0 = p.tap_dw[t] < dw0 ? p.tap_dw[t] : dw0; dw1 = p.tap_dw[t] > dw1 ? p.tap_dw[t] : dw1;
   }
   const int ext_h = dh1 - dh0 + 1, ext_w = dw1 - dw0 + 1;
-  const int bw = OW + ext_w - 1;
-  if (bw > 128) return false;
-  int bh = 128 / bw;
-  if (bh > OH) bh = OH;
-  // balance the row tiles of an image (e.g. 14 rows -> 7 + 7 instead of 8 + 6)
-  bh = msp_cdiv(OH, msp_cdiv(OH, bh));
-  if (bh < 1 || OW * bh < 72) return false;                         // < 56 % useful MMA rows: tap path
+  // tile = bh rows x bwv output columns stored with the halo pitch bw = bwv + ext_w - 1 (<= 128 MMA rows per tile);
+  // wide feature maps are cut into column strips.  Pick the pitch with the most useful MMA rows.
+  int bw = 0, bwv = 0, bh = 0;
+  double best = 0.0;
+  const int pmax = OW + ext_w - 1 < 128 ? OW + ext_w - 1 : 128;
+  for (int P = ext_w; P <= pmax; ++P) {
+    const int v = P - (ext_w - 1);
+    int h = 128 / P;
+    if (h < 1) continue;
+    if (h > OH) h = OH;
+    h = msp_cdiv(OH, msp_cdiv(OH, h));  // balance the row tiles of an image (14 rows -> 7 + 7, not 8 + 6)
+    if (P * (h + ext_h - 1) > 256) continue;                         // halo tile must fit 32 KB
+    if ((ext_h - 1) * P + (ext_w - 1) + 128 > 256) continue;         // the M=128 read window stays inside it
+    const double util = (double)OW * OH / ((double)msp_cdiv(OW, v) * msp_cdiv(OH, h) * 128.0);
+    if (util > best + 1e-9 || (util > best - 1e-9 && P > bw)) { best = util; bw = P; bwv = v; bh = h; }
+  }
+  if (bw == 0 || best < 0.55) return false;                          // too few useful MMA rows: tap path
   const int box_h = bh + ext_h - 1;
-  if (bw * box_h > 256 || box_h > 256) return false;                // halo tile must fit 32 KB
-  if ((ext_h - 1) * bw + (ext_w - 1) + 128 > 256) return false;     // the M=128 read window stays inside it
   const int chunks = msp_cdiv(p.C, kBK);
   const long long bt = (long long)BN * kBK * 2;
   const long long fixed = (BN >= 256 ? 1 : 2) * (long long)kATileBytes + (8 * 128 * 4 + 4 * 128 * 4) + 1024 + 512;
@@ -1246,8 +1258,8 @@ bool plan_halo(TapGemmParams& p, int OW, int OH, int N, int BN, Box* box, int* h
     p.tap_dw[t] = (int8_t)(p.tap_dw[t] - dw0);
   }
   p.halo = 1; p.org_dh = dh0; p.org_dw = dw0; p.halo_box_h = box_h;
-  p.bw = bw; p.bh = bh; p.bn = 1; p.rows = bw * bh;
-  p.tiles_w = 1; p.tiles_h = msp_cdiv(OH, bh); p.tiles_n = N;
+  p.bw = bw; p.bw_valid = bwv; p.bh = bh; p.bn = 1; p.rows = bw * bh;
+  p.tiles_w = msp_cdiv(OW, bwv); p.tiles_h = msp_cdiv(OH, bh); p.tiles_n = N;
   p.OWs = OW; p.OHs = OH; p.N = N;
   box->bw = bw; box->bh = box_h; box->bn = 1;
   *halo_w = bw;
