@@ -9,7 +9,7 @@
 //    in the 128-byte-swizzled K-major layout tcgen05.mma consumes directly.
 //  * PERSISTENT, warp-specialised CTA, one per SM: warp 0 = TMA producer running up to kStages
 //    k-blocks (and therefore several tiles) ahead, warp 1 = MMA issuer (one elected lane,
-//    tcgen05.mma cta_group::1, M=128, N<=256, fp32 accumulators DOUBLE-BUFFERED in TMEM), warps 2-9 =
+//    tcgen05.mma cta_group::1, M=128, N<=256, fp32 accumulators DOUBLE-BUFFERED in TMEM), warps 2-17 =
 //    epilogue: tcgen05.ld -> bias/ReLU -> bf16 -> 128B-swizzled staging tile in smem -> TMA tile store
 //    (hardware clips ragged tiles and channel tails; dgrad-on-top-of-a-gradient uses the TMA reduce-add),
 //    overlapped with the next tile's main loop.  The BatchNorm batch statistics (per-channel sum / sum
@@ -41,10 +41,16 @@ constexpr int kMaxTaps = 49;
 constexpr int kBM = 128;  // UMMA M (rows of the output tile)
 constexpr int kBK = 64;   // contraction elements per pipeline stage (= one 128-byte swizzle row)
 constexpr int kConvThreads = 192;  // wgrad: producer + MMA + 4 epilogue warps
-constexpr int kTapThreads = 320;   // tap-GEMM: producer + MMA + 8 epilogue warps
+constexpr int kEpiWarps = 8;       // tap-GEMM epilogue warps (2 per TMEM lane quarter / scheduler; 16 measured slower: barriers, registers)
+constexpr int kTapThreads = 64 + 32 * kEpiWarps;  // producer + MMA + epilogue
 constexpr int kATileBytes = kBM * kBK * 2;  // 16 KB
-constexpr int kEpiThreads = 256;
-constexpr int kEpiBarrier = 1;  // named barrier id of the 8 epilogue warps
+constexpr int kEpiThreads = 32 * kEpiWarps;
+constexpr int kEpiParts = kEpiWarps / 4;           // warps sharing one TMEM lane quarter
+constexpr int kEpiRowsPerPass = kEpiThreads / 8;   // copy-out: rows per pass (thread = one 16-byte piece)
+constexpr int kEpiPasses = 128 / kEpiRowsPerPass;
+constexpr int kEpiSlabs = kEpiThreads / 32;        // statistics: row slabs
+constexpr int kEpiSlabRows = 128 / kEpiSlabs;
+constexpr int kEpiBarrier = 1;  // named barrier id of the epilogue warps
 
 struct TapGemmParams {
   int bw, bh, bn, rows;
@@ -81,7 +87,7 @@ struct TapGemmCfg {
   static constexpr int kCH = BN_ < 64 ? BN_ : 64;  // epilogue column chunk (one TMA store box)
   static constexpr int kNChunk = BN_ / kCH;
   static constexpr int kStageBufs = BN_ >= 256 ? 1 : 2;  // 16 KB staging tiles for the TMA store
-  static constexpr int kScratchBytes = 8 * 128 * 4 + 4 * 128 * 4;  // per-slab partial + running statistics
+  static constexpr int kScratchBytes = kEpiSlabs * 128 * 4 + 4 * 128 * 4;  // per-slab partial + running statistics
   static constexpr int kSmemBytes =
       kStages * kStageBytes + kStageBufs * kATileBytes + kScratchBytes + 1024;  // + alignment slack
   static constexpr int kTmemCols = 2 * BN_ < 32 ? 32 : 2 * BN_;
@@ -100,32 +106,34 @@ __device__ __forceinline__ void tap_epilogue(const TapGemmParams& p, uint8_t* st
   using Cfg = TapGemmCfg<BN_>;
   {
     // ---------------- epilogue: TMEM -> registers -> swizzled smem tile -> coalesced global stores -------
-    // 8 warps = 2 per scheduler: warps (w, w+4) share a TMEM lane quarter and split every 64-column
-    // chunk into two 32-column halves.  The bf16 tile is transposed through a 128B-swizzled staging tile
+    // kEpiWarps warps (8 = 2 per scheduler; the epilogue is latency / issue bound, profiles/r01_epilogue_phases.txt): the
+    // warps of a TMEM lane quarter split every 64-column chunk into equal column parts.  The bf16 tile is transposed through a 128B-swizzled staging tile
     // so that every global store instruction writes four full 128-byte lines (thread = one 16-byte piece).
     // No async-proxy hand-off: a TMA store here costs a MEMBAR + proxy fence per chunk, which at one
     // k-block per tile (1x1 convolutions) made the epilogue the critical path (profiles/r01_*).
-    const int et = threadIdx.x - 64;  // 0..255
+    const int et = threadIdx.x - 64;  // 0..kEpiThreads-1
     const int q = warp & 3;           // TMEM lane quarter this warp may access
-    const int half = (et >> 5) >> 2;  // column half of the chunk handled by this warp
+    const int part = (et >> 5) >> 2;  // which column part of the chunk this warp handles
     const int row = q * 32 + lane;
     const bool do_stats = p.ch_sum != nullptr && !(p.debug & 2);
     const bool has_bias = p.bias != nullptr;
     const uint32_t scratch_s = smem_u32(scratch);
-    const uint32_t run_s = scratch_s + 8 * 128 * 4;  // running statistics [chunk][which][64]
+    const uint32_t run_s = scratch_s + kEpiSlabs * 128 * 4;  // running statistics [chunk][which][64]
     for (int i = et; i < Cfg::kNChunk * 128; i += kEpiThreads) sts_f32(run_s + i * 4, 0.f);
     constexpr int CH = Cfg::kCH;
-    constexpr int CHH = CH / 2;  // columns per warp per chunk
+    constexpr int CHH = (CH / kEpiParts) < 8 ? 8 : CH / kEpiParts;  // columns per warp per chunk
+    constexpr int kActiveParts = CH / CHH;                           // narrow tiles: the other warps only copy out
+    const bool active = part < kActiveParts;
     // Tile-invariant per-thread state (the epilogue is instruction-issue bound: everything that does not depend
-    // on the tile is computed once): its TMEM row, the 4 rows it copies out, their smem and global offsets.
+    // on the tile is computed once): its TMEM row, the rows it copies out, their smem and global offsets.
     const int my_wi = row % p.bw, my_hi = (row / p.bw) % p.bh, my_ni = row / (p.bw * p.bh);
     const int ck = et & 7;  // 16-byte piece (8 channels) of the staging row this thread copies out
-    int o_wi[4], o_hi[4], o_ni[4];
-    uint32_t o_lds[4];      // staging offset of (row j, piece ck)
-    long long o_rel[4];     // element offset of row j relative to the tile origin (+ this thread's 8 channels)
+    int o_wi[kEpiPasses], o_hi[kEpiPasses], o_ni[kEpiPasses];
+    uint32_t o_lds[kEpiPasses];      // staging offset of (row j, piece ck)
+    long long o_rel[kEpiPasses];     // element offset of row j relative to the tile origin (+ this thread's 8 channels)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int r = j * 32 + (et >> 3);
+    for (int j = 0; j < kEpiPasses; ++j) {
+      const int r = j * kEpiRowsPerPass + (et >> 3);
       o_wi[j] = r % p.bw;
       o_hi[j] = (r / p.bw) % p.bh;
       o_ni[j] = r / (p.bw * p.bh);
@@ -137,10 +145,23 @@ __device__ __forceinline__ void tap_epilogue(const TapGemmParams& p, uint8_t* st
     uint32_t sts_off[CHH / 8];  // swizzled staging offsets of this thread's 16-byte groups
 #pragma unroll
     for (int g = 0; g < CHH / 8; ++g)
-      sts_off[g] = (uint32_t)(row * 128 + (((half * (CHH / 8) + g) ^ (row & 7)) << 4));
+      sts_off[g] = (uint32_t)(row * 128 + ((((part % kActiveParts) * (CHH / 8) + g) ^ (row & 7)) << 4));
     const bool flat_tiles = p.tiles_h == 1 && p.tiles_n == 1;  // 1x1 "flat" convolutions: tile = 128 pixels of one row
     uint32_t t = 0, sbuf = 0;
     int tco = it0 / m_per_co, pm = it0 - tco * m_per_co;
+    // profiling build (-DMSP_EPI_PROFILE, MSP_CONV_DEBUG & 1024): cycles of epilogue thread 0 per phase
+#ifdef MSP_EPI_PROFILE
+    const bool prof = (p.debug & 1024) && blockIdx.x == 0 && et == 0;
+    long long pc[8] = {0, 0, 0, 0, 0, 0, 0, 0}, pt = prof ? clock64() : 0;
+#define MSP_PHASE(i)                     \
+  if (prof) {                            \
+    const long long now_ = clock64();    \
+    pc[i] += now_ - pt;                  \
+    pt = now_;                           \
+  }
+#else
+#define MSP_PHASE(i)
+#endif
     for (int item = it0; item < it_total; item += it_step, ++t) {
       int tm = pair_rank < 0 ? pm : 2 * pm + pair_rank;
       const bool tile_ok = tm < p.tiles_m;  // odd tile counts: the pair's second CTA idles on a masked duplicate
@@ -158,9 +179,9 @@ __device__ __forceinline__ void tap_epilogue(const TapGemmParams& p, uint8_t* st
           tile_ok && row < p.rows && my_wi < p.bw_valid && (w0 + my_wi) < p.OWs && (h0 + my_hi) < p.OHs && (n0 + my_ni) < p.N;
       const long long tile_off = p.y_off + (long long)n0 * p.y_n_stride + (long long)h0 * p.y_h_stride +
                                  (long long)w0 * p.y_w_stride + co0;
-      __nv_bfloat16* o_ptr[4];
+      __nv_bfloat16* o_ptr[kEpiPasses];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
+      for (int j = 0; j < kEpiPasses; ++j) {
         const bool ok = tile_ok && o_rel[j] >= 0 && (w0 + o_wi[j]) < p.OWs && (h0 + o_hi[j]) < p.OHs &&
                         (n0 + o_ni[j]) < p.N;
         o_ptr[j] = ok ? p.y + tile_off + o_rel[j] : nullptr;
@@ -172,30 +193,36 @@ __device__ __forceinline__ void tap_epilogue(const TapGemmParams& p, uint8_t* st
         ++tco_next;
       }
       const uint32_t as = t & 1u;
+      MSP_PHASE(0)  // tile preamble
       if (lane == 0) mbar_wait(&tfull_bar[as], (t >> 1) & 1u);  // one poller per warp, not 256 on one mbarrier
       __syncwarp();
       tc_fence_after();
-      const uint32_t tmem_row = tmem_base + ((uint32_t)(q * 32) << 16) + as * BN_ + half * CHH;
+      MSP_PHASE(1)  // wait for the accumulator
+      const uint32_t tmem_row = tmem_base + ((uint32_t)(q * 32) << 16) + as * BN_ + (part % kActiveParts) * CHH;
 #pragma unroll 1
       for (int c = 0; c < Cfg::kNChunk; ++c) {
         const int cg = co0 + c * CH;
         const uint32_t stg_s = smem_u32(staging) + (Cfg::kStageBufs == 2 ? sbuf * kATileBytes : 0);
         // dgrad on top of an existing gradient: fetch the old values now, consume them after the transpose
-        uint4 old[4];
+        uint4 old[kEpiPasses];
         if (p.accumulate) {
           const bool mine = ck < CH / 8 && cg + ck * 8 < p.Kout;
 #pragma unroll
-          for (int j = 0; j < 4; ++j)
+          for (int j = 0; j < kEpiPasses; ++j)
             old[j] = (mine && o_ptr[j] != nullptr) ? __ldg(reinterpret_cast<const uint4*>(o_ptr[j] + c * CH))
                                                    : make_uint4(0u, 0u, 0u, 0u);
         }
         // single staging tile: everyone must have finished reading the previous chunk out of it
         if constexpr (Cfg::kStageBufs == 1) named_bar_sync(kEpiBarrier, kEpiThreads);
+        MSP_PHASE(2)  // staging-free barrier (+ accumulate prefetch issue)
         uint32_t v[CHH];
-        if constexpr (CHH == 32) tmem_ld_32x32(tmem_row + c * CH, v);
-        else if constexpr (CHH == 16) tmem_ld_32x16(tmem_row + c * CH, v);
-        else tmem_ld_32x8(tmem_row + c * CH, v);
-        tmem_ld_wait();
+        if (active) {
+          if constexpr (CHH == 32) tmem_ld_32x32(tmem_row + c * CH, v);
+          else if constexpr (CHH == 16) tmem_ld_32x16(tmem_row + c * CH, v);
+          else tmem_ld_32x8(tmem_row + c * CH, v);
+          tmem_ld_wait();
+        }
+        MSP_PHASE(3)  // TMEM load
         if (c == Cfg::kNChunk - 1) {  // accumulator fully read: hand it back to the MMA warp (one arrive per warp)
           tc_fence_before();
           __syncwarp();
@@ -204,8 +231,8 @@ __device__ __forceinline__ void tap_epilogue(const TapGemmParams& p, uint8_t* st
             else mbar_arrive_leader(&tempty_bar[as]);
           }
         }
-        if (cg < p.Kout) {
-          const int cb = cg + half * CHH;  // first output channel of this warp's columns
+        if (cg < p.Kout && active) {
+          const int cb = cg + part * CHH;  // first output channel of this warp's columns
           float x[CHH];
 #pragma unroll
           for (int j = 0; j < CHH; ++j) x[j] = __uint_as_float(v[j]);
@@ -241,17 +268,19 @@ __device__ __forceinline__ void tap_epilogue(const TapGemmParams& p, uint8_t* st
                    pack_bf16x2(x[8 * g + 2], x[8 * g + 3]), pack_bf16x2(x[8 * g + 4], x[8 * g + 5]),
                    pack_bf16x2(x[8 * g + 6], x[8 * g + 7]));
         }
+        MSP_PHASE(4)  // bias / ReLU / pack / STS
         named_bar_sync(kEpiBarrier, kEpiThreads);
+        MSP_PHASE(5)  // staged barrier
         if (cg < p.Kout) {
           // copy-out: thread = (row j*32 + et/8, 16-byte piece et%8); a warp stores 4 full 128-byte lines
           if (ck < CH / 8 && cg + ck * 8 < p.Kout && !(p.debug & 1)) {
-            uint4 o[4];
+            uint4 o[kEpiPasses];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) o[j] = lds_v4(stg_s + o_lds[j]);  // all four smem reads in flight first
+            for (int j = 0; j < kEpiPasses; ++j) o[j] = lds_v4(stg_s + o_lds[j]);  // all smem reads in flight first
             const int coff = c * CH;
             if (p.accumulate) {
 #pragma unroll
-              for (int j = 0; j < 4; ++j) {
+              for (int j = 0; j < kEpiPasses; ++j) {
                 const uint32_t ov[4] = {old[j].x, old[j].y, old[j].z, old[j].w};
                 const uint32_t nv[4] = {o[j].x, o[j].y, o[j].z, o[j].w};
                 uint32_t rv[4];
@@ -264,18 +293,19 @@ __device__ __forceinline__ void tap_epilogue(const TapGemmParams& p, uint8_t* st
               }
             }
 #pragma unroll
-            for (int j = 0; j < 4; ++j)
+            for (int j = 0; j < kEpiPasses; ++j)
               if (o_ptr[j] != nullptr) st_v4(o_ptr[j] + coff, o[j]);
           }
+          MSP_PHASE(6)  // copy-out
           if (do_stats) {
-            // column sums of the bf16 tile: thread -> (column pair, 16-row slab); conflict-free LDS.32
+            // column sums of the bf16 tile: thread -> (column pair, row slab); conflict-free LDS.32
             const int cp = et & 31, re = et >> 5;
             float s1a = 0.f, s2a = 0.f, s1b = 0.f, s2b = 0.f;
-            const uint32_t base = stg_s + re * 16 * 128 + (cp & 3) * 4;
+            const uint32_t base = stg_s + re * kEpiSlabRows * 128 + (cp & 3) * 4;
             const uint32_t sw = (uint32_t)(cp >> 2);
 #pragma unroll
-            for (int r = 0; r < 16; ++r) {
-              const uint32_t wv = lds_u32(base + r * 128 + ((sw ^ (uint32_t)(r & 7)) << 4));
+            for (int r = 0; r < kEpiSlabRows; ++r) {
+              const uint32_t wv = lds_u32(base + r * 128 + ((sw ^ (uint32_t)((re * kEpiSlabRows + r) & 7)) << 4));
               const float2 f = unpack_bf16x2(wv);
               s1a += f.x;
               s2a = fmaf(f.x, f.x, s2a);
@@ -291,11 +321,12 @@ __device__ __forceinline__ void tap_epilogue(const TapGemmParams& p, uint8_t* st
             if (et < 128) {  // thread et owns (which = et >> 6, column = et & 63) of every chunk
               float tot = lds_f32(run_s + (c * 128 + et) * 4);
 #pragma unroll
-              for (int j = 0; j < 8; ++j) tot += lds_f32(scratch_s + (j * 128 + et) * 4);
+              for (int j = 0; j < kEpiSlabs; ++j) tot += lds_f32(scratch_s + (j * 128 + et) * 4);
               sts_f32(run_s + (c * 128 + et) * 4, tot);
             }
           }
         }
+        MSP_PHASE(7)  // statistics
         if constexpr (Cfg::kStageBufs == 2) sbuf ^= 1u;
       }
       // flush the running statistics when this CTA leaves the output-channel block (or finishes)
@@ -312,6 +343,13 @@ __device__ __forceinline__ void tap_epilogue(const TapGemmParams& p, uint8_t* st
       tco = tco_next;
       pm = pm_next;
     }
+#ifdef MSP_EPI_PROFILE
+    if (prof)
+      printf("msp epilogue phases (cycles, thread 0, %u tiles x %d chunks): preamble %lld wait-acc %lld bar-free %lld "
+             "tmem-ld %lld pack+sts %lld bar-staged %lld copy-out %lld stats %lld\n",
+             t, Cfg::kNChunk, pc[0], pc[1], pc[2], pc[3], pc[4], pc[5], pc[6], pc[7]);
+#endif
+#undef MSP_PHASE
   }
 }
 
@@ -1238,7 +1276,7 @@ bool plan_halo(TapGemmParams& p, int OW, int OH, int N, int BN, Box* box, int* h
   const int box_h = bh + ext_h - 1;
   const int chunks = msp_cdiv(p.C, kBK);
   const long long bt = (long long)BN * kBK * 2;
-  const long long fixed = (BN >= 256 ? 1 : 2) * (long long)kATileBytes + (8 * 128 * 4 + 4 * 128 * 4) + 1024 + 512;
+  const long long fixed = (BN >= 256 ? 1 : 2) * (long long)kATileBytes + (kEpiSlabs * 128 * 4 + 4 * 128 * 4) + 1024 + 512;
   const long long budget = 232448 - fixed;
   const long long res_bytes = (long long)p.ntaps * chunks * bt;
   p.b_resident = (msp_cdiv(p.Kout, BN) == 1 && res_bytes + 2 * kHaloABytes <= budget) ? 1 : 0;
