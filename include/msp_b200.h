@@ -140,17 +140,19 @@ int msp_bn_act_fwd(const msp_bn_act_desc* d, const void* x, const float* mean, c
                    const float* gamma, const float* beta, const float* sample_scale,
                    const void* residual, void* y, void* stream);
 
-/* Backward pass 1: with g = dy * act'(y) (ReLU mask recomputed from y; sigmoid from y),
+/* In both backward passes `y` may be NULL for BatchNorm -> ReLU without shortcut / sample scale: the ReLU mask is then
+ * recomputed from x with the forward's own expression (gamma, beta needed) and the stored activation is not read.
+ * Backward pass 1: with g = dy * act'(y) (ReLU mask recomputed from y; sigmoid from y),
  * accumulates sum_g[c] += sum s[n]*g, sum_gx[c] += sum s[n]*g*xhat (fp32 [C]); if dres != NULL also
  * writes the residual-branch gradient (g itself) — strided / channel-truncated like the forward. */
 int msp_bn_act_bwd_reduce(const msp_bn_act_desc* d, const void* x, const void* y, const void* dy,
-                          const float* mean, const float* invstd, const float* sample_scale,
-                          float* sum_g, float* sum_gx, void* stream);
+                          const float* mean, const float* invstd, const float* gamma, const float* beta,
+                          const float* sample_scale, float* sum_g, float* sum_gx, void* stream);
 /* Backward pass 2: dx = gamma*invstd*( s*g - sum_g/M - xhat*sum_gx/M ); M = N*H*W (x world size
  * when the sums were all-reduced: pass the global count).  dres (optional, same shape as the
  * residual tensor) receives g added into the sub-sampled positions (others untouched).          */
 int msp_bn_act_bwd_apply(const msp_bn_act_desc* d, const void* x, const void* y, const void* dy,
-                         const float* mean, const float* invstd, const float* gamma,
+                         const float* mean, const float* invstd, const float* gamma, const float* beta,
                          const float* sample_scale, const float* sum_g, const float* sum_gx,
                          double count, void* dx, void* dres, int dres_accumulate, void* stream);
 /* eval-mode BN uses running stats: same forward with mean=running_mean, invstd=rsqrt(var+eps):   */

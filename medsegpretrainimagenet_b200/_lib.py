@@ -52,8 +52,8 @@ SIGNATURES = {
     "msp_nchw_f32_grad_to_nhwc_bf16": [P, I, I, I, I, I, P, P],
     "msp_bn_finalize": [P, P, I, D, F, F, P, P, P, P, I, P],
     "msp_bn_act_fwd": [C.POINTER(BnActDesc), P, P, P, P, P, P, P, P, P],
-    "msp_bn_act_bwd_reduce": [C.POINTER(BnActDesc), P, P, P, P, P, P, P, P, P],
-    "msp_bn_act_bwd_apply": [C.POINTER(BnActDesc), P, P, P, P, P, P, P, P, P, D, P, P, I, P],
+    "msp_bn_act_bwd_reduce": [C.POINTER(BnActDesc), P, P, P, P, P, P, P, P, P, P, P],
+    "msp_bn_act_bwd_apply": [C.POINTER(BnActDesc), P, P, P, P, P, P, P, P, P, P, D, P, P, I, P],
     "msp_bn_eval_prepare": [P, I, F, P, P],
     "msp_maxpool_fwd": [P, I, I, I, I, I, I, I, I, P, P, I, I, I, P],
     "msp_maxpool_bwd": [P, P, I, I, I, I, I, I, I, I, I, I, P, I, I, P],

@@ -259,18 +259,24 @@ __global__ void __launch_bounds__(256, 2)
 bn_act_bwd_reduce_kernel(const msp_bn_act_desc d, const __nv_bfloat16* __restrict__ x,
                          const __nv_bfloat16* __restrict__ y, const __nv_bfloat16* __restrict__ dy,
                          const float* __restrict__ mean, const float* __restrict__ invstd,
-                         const float* __restrict__ sscale, float* sum_g, float* sum_gx) {
+                         const float* __restrict__ sscale, float* sum_g, float* sum_gx,
+                         const float* __restrict__ gamma, const float* __restrict__ beta) {
   extern __shared__ float red[];
   const int V = d.C >> 3;
   const int cg = threadIdx.x % V, pl = threadIdx.x / V, ppb = blockDim.x / V;
   const int c = cg * 8;
-  float mu[8], is[8], a1[8], a2[8];
+  // y == nullptr (BatchNorm -> ReLU without shortcut / sample scale): the ReLU mask is recomputed from x with the
+  // forward's own expression fmaf(x, sc, sh) > 0, and the stored activation is not read at all
+  const bool from_x = (y == nullptr);
+  float mu[8], is[8], a1[8], a2[8], sc[8], sh[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     mu[j] = mean[c + j];
     is[j] = invstd[c + j];
     a1[j] = 0.f;
     a2[j] = 0.f;
+    sc[j] = (gamma ? gamma[c + j] : 1.f) * is[j];
+    sh[j] = (beta ? beta[c + j] : 0.f) - mu[j] * sc[j];
   }
   const uint32_t HW = (uint32_t)d.H * (uint32_t)d.W;
   const uint32_t P = (uint32_t)d.N * HW;
@@ -284,7 +290,7 @@ bn_act_bwd_reduce_kernel(const msp_bn_act_desc d, const __nv_bfloat16* __restric
       s[u] = 0.f;
       if (pix < P) {
         xr[u] = ld_nc_v4(x + (long long)pix * d.x_cs + c);
-        yr[u] = ld_nc_v4(y + (long long)pix * d.y_cs + c);
+        if (!from_x) yr[u] = ld_nc_v4(y + (long long)pix * d.y_cs + c);
         gr[u] = ld_nc_v4(dy + (long long)pix * d.y_cs + c);
         s[u] = sscale ? __ldg(sscale + pix / HW) : 1.f;
       }
@@ -292,7 +298,14 @@ bn_act_bwd_reduce_kernel(const msp_bn_act_desc d, const __nv_bfloat16* __restric
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       if (p0 + u * step < P) {
-        const F8 xv = unpack8(xr[u]), yv = unpack8(yr[u]), gv = unpack8(gr[u]);
+        const F8 xv = unpack8(xr[u]), gv = unpack8(gr[u]);
+        F8 yv;
+        if (from_x) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) yv.v[j] = fmaf(xv.v[j], sc[j], sh[j]);  // only its sign is used (ReLU)
+        } else {
+          yv = unpack8(yr[u]);
+        }
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           const float g = act_bwd(yv.v[j], gv.v[j], d.act) * s[u];
@@ -326,16 +339,19 @@ bn_act_bwd_apply_kernel(const msp_bn_act_desc d, const __nv_bfloat16* __restrict
                         const float* __restrict__ mean, const float* __restrict__ invstd,
                         const float* __restrict__ gamma, const float* __restrict__ sscale,
                         const float* __restrict__ sum_g, const float* __restrict__ sum_gx, float inv_count,
-                        __nv_bfloat16* __restrict__ dx, __nv_bfloat16* dres, int dres_acc) {
+                        __nv_bfloat16* __restrict__ dx, __nv_bfloat16* dres, int dres_acc,
+                        const float* __restrict__ beta) {
   const int V = d.C >> 3;
   const int cg = threadIdx.x % V, pl = threadIdx.x / V, ppb = blockDim.x / V;
   const int c = cg * 8;
-  float mu[8], is[8], k0[8], k1[8], k2[8];
+  const bool from_x = (y == nullptr);  // see bn_act_bwd_reduce_kernel
+  float mu[8], is[8], k0[8], k1[8], k2[8], sh[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     mu[j] = mean[c + j];
     is[j] = invstd[c + j];
     const float gi = (gamma ? gamma[c + j] : 1.f) * is[j];
+    sh[j] = (beta ? beta[c + j] : 0.f) - mu[j] * gi;
     k0[j] = gi;
     k1[j] = gi * sum_g[c + j] * inv_count;
     k2[j] = gi * sum_gx[c + j] * inv_count;
@@ -352,7 +368,7 @@ bn_act_bwd_apply_kernel(const msp_bn_act_desc d, const __nv_bfloat16* __restrict
       const uint32_t pix = p0 + u * step;
       if (pix < P) {
         xr[u] = ld_nc_v4(x + (long long)pix * d.x_cs + c);
-        yr[u] = ld_nc_v4(y + (long long)pix * d.y_cs + c);
+        if (!from_x) yr[u] = ld_nc_v4(y + (long long)pix * d.y_cs + c);
         gr[u] = ld_nc_v4(dy + (long long)pix * d.y_cs + c);
       }
     }
@@ -367,7 +383,14 @@ bn_act_bwd_apply_kernel(const msp_bn_act_desc d, const __nv_bfloat16* __restrict
           if (sscale) s = __ldg(sscale + n);
         }
         F8 o, g;
-        const F8 xv = unpack8(xr[u]), yv = unpack8(yr[u]), gv = unpack8(gr[u]);
+        const F8 xv = unpack8(xr[u]), gv = unpack8(gr[u]);
+        F8 yv;
+        if (from_x) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) yv.v[j] = fmaf(xv.v[j], k0[j], sh[j]);
+        } else {
+          yv = unpack8(yr[u]);
+        }
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           g.v[j] = act_bwd(yv.v[j], gv.v[j], d.act);
@@ -796,13 +819,22 @@ extern "C" int msp_bn_act_fwd(const msp_bn_act_desc* d, const void* x, const flo
   return MSP_OK;
 }
 
+static int check_mask_from_x(const msp_bn_act_desc* d, const void* y, const float* sample_scale, const void* dres) {
+  if (y != nullptr) return MSP_OK;
+  MSP_REQUIRE(d->act == MSP_ACT_RELU && sample_scale == nullptr && dres == nullptr,
+              "bn_act_bwd: y may be omitted only for BatchNorm -> ReLU without shortcut / sample scale");
+  return MSP_OK;
+}
+
 extern "C" int msp_bn_act_bwd_reduce(const msp_bn_act_desc* d, const void* x, const void* y,
                                      const void* dy, const float* mean, const float* invstd,
-                                     const float* sample_scale, float* sum_g, float* sum_gx,
-                                     void* stream) {
+                                     const float* gamma, const float* beta, const float* sample_scale,
+                                     float* sum_g, float* sum_gx, void* stream) {
   int rc = check_bn_desc(d);
   if (rc) return rc;
-  MSP_REQUIRE(x && y && dy && mean && invstd && sum_g && sum_gx, "bn_act_bwd_reduce: null pointer");
+  MSP_REQUIRE(x && dy && mean && invstd && sum_g && sum_gx, "bn_act_bwd_reduce: null pointer");
+  rc = check_mask_from_x(d, y, sample_scale, nullptr);
+  if (rc) return rc;
   const int V = d->C / 8, T = threads_for_vecs(V), ppb = T / V;
   const long long P = (long long)d->N * d->H * d->W;
   if (sum_gx == sum_g + d->C) {  // the usual [2][C] buffer: one memset node
@@ -815,7 +847,7 @@ extern "C" int msp_bn_act_bwd_reduce(const msp_bn_act_desc* d, const void* x, co
   MSP_REQUIRE(P < (1ll << 31), "bn_act: too many pixels");
   bn_act_bwd_reduce_kernel<2><<<resident_grid(bn_act_bwd_reduce_kernel<2>, T, smem, P, ppb * 2), T, smem, ST>>>(
       *d, (const __nv_bfloat16*)x, (const __nv_bfloat16*)y, (const __nv_bfloat16*)dy, mean, invstd,
-      sample_scale, sum_g, sum_gx);
+      sample_scale, sum_g, sum_gx, gamma, beta);
   MSP_CHECK_LAUNCH();
   msp_count_launch(1);
   return MSP_OK;
@@ -823,20 +855,22 @@ extern "C" int msp_bn_act_bwd_reduce(const msp_bn_act_desc* d, const void* x, co
 
 extern "C" int msp_bn_act_bwd_apply(const msp_bn_act_desc* d, const void* x, const void* y,
                                     const void* dy, const float* mean, const float* invstd,
-                                    const float* gamma, const float* sample_scale, const float* sum_g,
-                                    const float* sum_gx, double count, void* dx, void* dres,
-                                    int dres_accumulate, void* stream) {
+                                    const float* gamma, const float* beta, const float* sample_scale,
+                                    const float* sum_g, const float* sum_gx, double count, void* dx,
+                                    void* dres, int dres_accumulate, void* stream) {
   int rc = check_bn_desc(d);
   if (rc) return rc;
-  MSP_REQUIRE(x && y && dy && mean && invstd && sum_g && sum_gx && dx && count > 0,
+  MSP_REQUIRE(x && dy && mean && invstd && sum_g && sum_gx && dx && count > 0,
               "bn_act_bwd_apply: null pointer");
+  rc = check_mask_from_x(d, y, sample_scale, dres);
+  if (rc) return rc;
   const int V = d->C / 8, T = threads_for_vecs(V), ppb = T / V;
   const long long P = (long long)d->N * d->H * d->W;
   MSP_REQUIRE(P < (1ll << 31), "bn_act: too many pixels");
   bn_act_bwd_apply_kernel<2><<<resident_grid(bn_act_bwd_apply_kernel<2>, T, 0, P, ppb * 2), T, 0, ST>>>(
       *d, (const __nv_bfloat16*)x, (const __nv_bfloat16*)y, (const __nv_bfloat16*)dy, mean, invstd,
       gamma, sample_scale, sum_g, sum_gx, (float)(1.0 / count), (__nv_bfloat16*)dx,
-      (__nv_bfloat16*)dres, dres_accumulate);
+      (__nv_bfloat16*)dres, dres_accumulate, beta);
   MSP_CHECK_LAUNCH();
   msp_count_launch(1);
   return MSP_OK;

@@ -209,18 +209,23 @@ class _BnAct(torch.autograd.Function):
                            r_stride=r_stride, sample_scale=sample_scale)
         ctx.cfg = (training, act, r_stride, count, group, residual is not None,
                    tuple(residual.shape) if residual is not None else None)
-        ctx.save_for_backward(x, y, mi, gamma, sample_scale)
+        # BatchNorm -> ReLU without shortcut / sample scale: the backward recomputes the mask from x and never reads y
+        mask_from_x = act == ops.ACT_RELU and residual is None and sample_scale is None
+        ctx.y_stride = y.stride(2)
+        ctx.save_for_backward(x, None if mask_from_x else y, mi, gamma, sample_scale, beta if mask_from_x else None)
         return y
 
     @staticmethod
     def backward(ctx, dy):
         training, act, r_stride, count, group, has_res, res_shape = ctx.cfg
-        x, y, mi, gamma, sscale = ctx.saved_tensors
+        x, y, mi, gamma, sscale, beta = ctx.saved_tensors
         n, h, w, c = x.shape
-        if dy.stride(3) != 1 or dy.stride(2) != y.stride(2):
-            full = torch.empty((n, h, w, y.stride(2)), dtype=dy.dtype, device=dy.device)[..., :c]
+        if dy.stride(3) != 1 or (y is not None and dy.stride(2) != y.stride(2)):
+            full = torch.empty((n, h, w, ctx.y_stride), dtype=dy.dtype, device=dy.device)[..., :c]
             dy = ops.copy_channels(dy if dy.stride(3) == 1 else dy.contiguous(), full)
-        sums = ops.bn_act_bwd_reduce(x, y, dy, mi, act, sample_scale=sscale)
+        gd = gamma.detach() if gamma is not None else None
+        bd = beta.detach() if beta is not None else None
+        sums = ops.bn_act_bwd_reduce(x, y, dy, mi, act, sample_scale=sscale, gamma=gd, beta=bd)
         synced = training and group is not None and dist.is_initialized() and dist.get_world_size(group) > 1
         # dgamma / dbeta are the LOCAL sums (the gradient reducer averages parameters' gradients); only the
         # SyncBN all-reduce below overwrites `sums` in place, so a copy is needed in that case alone
@@ -244,8 +249,8 @@ class _BnAct(torch.autograd.Function):
         if need_res:
             rn, rh, rw, rc = res_shape
             dres = ops.new_act(rn, rh, rw, rc, x.device, zero=(r_stride > 1 or rc > c))
-        dx = ops.bn_act_bwd_apply(x, y, dy, mi, gamma.detach() if gamma is not None else None, act, sums,
-                                  count, dres=dres, r_stride=r_stride, sample_scale=sscale)
+        dx = ops.bn_act_bwd_apply(x, y, dy, mi, gd, act, sums, count, dres=dres, r_stride=r_stride,
+                                  sample_scale=sscale, beta=bd)
         if not ctx.needs_input_grad[0]:
             dx = None
         if dres is not None and ctx.link is not None:

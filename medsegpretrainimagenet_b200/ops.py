@@ -301,26 +301,28 @@ def bn_act_fwd(x, mi, gamma, beta, act, residual=None, r_stride=1, sample_scale=
     return out
 
 
-def bn_act_bwd_reduce(x, y, dy, mi, act, sample_scale=None):
-    d = _bn_desc(x, y, act, None, 1)
+def bn_act_bwd_reduce(x, y, dy, mi, act, sample_scale=None, gamma=None, beta=None):
+    """`y` may be None for BatchNorm -> ReLU without shortcut / sample scale: the mask is recomputed from x."""
+    d = _bn_desc(x, dy if y is None else y, act, None, 1)
     _chk_nhwc(dy, "bn_act_bwd(dy)")
-    assert dy.stride(2) == y.stride(2), "dy must share the pixel stride of y"
+    if y is not None:
+        assert dy.stride(2) == y.stride(2), "dy must share the pixel stride of y"
     sums = torch.empty((2, x.shape[3]), dtype=torch.float32, device=x.device)
     call("msp_bn_act_bwd_reduce", C.byref(d), _p(x), _p(y), _p(dy), mi[0].data_ptr(), mi[1].data_ptr(),
-         _p(sample_scale), sums[0].data_ptr(), sums[1].data_ptr(), _stream())
+         _p(gamma), _p(beta), _p(sample_scale), sums[0].data_ptr(), sums[1].data_ptr(), _stream())
     return sums
 
 
 def bn_act_bwd_apply(x, y, dy, mi, gamma, act, sums, count, residual_like=None, r_stride=1,
-                     sample_scale=None, dres=None, dres_accumulate=False):
+                     sample_scale=None, dres=None, dres_accumulate=False, beta=None):
     n, h, w, c = x.shape
     if x.stride(2) == c:
         dx = new_act(n, h, w, c, x.device)
     else:  # x is a channel slice of a wider buffer: dx must share its pixel stride
         dx = torch.empty((n, h, w, x.stride(2)), dtype=_BF16, device=x.device)[..., :c]
-    d = _bn_desc(x, y, act, residual_like if dres is None else dres, r_stride)
+    d = _bn_desc(x, dy if y is None else y, act, residual_like if dres is None else dres, r_stride)
     call("msp_bn_act_bwd_apply", C.byref(d), _p(x), _p(y), _p(dy), mi[0].data_ptr(), mi[1].data_ptr(),
-         _p(gamma), _p(sample_scale), sums[0].data_ptr(), sums[1].data_ptr(), float(count), _p(dx),
+         _p(gamma), _p(beta), _p(sample_scale), sums[0].data_ptr(), sums[1].data_ptr(), float(count), _p(dx),
          _p(dres), int(dres_accumulate), _stream())
     return dx
 

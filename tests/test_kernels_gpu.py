@@ -288,6 +288,33 @@ def test_bn_act_fwd_bwd(shape, act):
     _close(_from_nhwc(dres), rr.grad, 2e-2, "residual grad")
 
 
+def test_bn_relu_backward_mask_from_x_is_identical():
+    """BatchNorm -> ReLU without shortcut: the backward may skip reading the stored activation and recompute the ReLU
+    mask from x with the forward's own expression — results must be BIT-identical to the stored-activation path."""
+    ops = _ops()
+    g = torch.Generator().manual_seed(6)
+    n, h, w, c = 3, 9, 7, 48
+    x = _to_nhwc(_bf(torch.randn((n, c, h, w), generator=g) * 2))
+    dy = _to_nhwc(_bf(torch.randn((n, c, h, w), generator=g)))
+    gamma = (torch.rand((c,), generator=g) + 0.5).to(DEV)
+    beta = (torch.randn((c,), generator=g) * 0.3).to(DEV)
+    flat = x.float().reshape(-1, c)
+    stats = torch.stack([flat.sum(0), (flat * flat).sum(0)])
+    mi = ops.bn_finalize(stats, n * h * w, 1e-5, 0.1)
+    y = ops.bn_act_fwd(x, mi, gamma, beta, ops.ACT_RELU)
+    s_ref = ops.bn_act_bwd_reduce(x, y, dy, mi, ops.ACT_RELU, gamma=gamma, beta=beta)
+    s_new = ops.bn_act_bwd_reduce(x, None, dy, mi, ops.ACT_RELU, gamma=gamma, beta=beta)
+    dx_ref = ops.bn_act_bwd_apply(x, y, dy, mi, gamma, ops.ACT_RELU, s_ref, n * h * w, beta=beta)
+    dx_new = ops.bn_act_bwd_apply(x, None, dy, mi, gamma, ops.ACT_RELU, s_ref, n * h * w, beta=beta)
+    assert torch.equal(dx_ref, dx_new)
+    # the per-channel sums are accumulated with atomics across blocks (order varies): compare within fp32 noise
+    _close(s_new.cpu(), s_ref.cpu(), 1e-5, "sums")
+    # omitting y is refused where the mask cannot be recomputed (shortcut / sigmoid)
+    import medsegpretrainimagenet_b200._lib as L
+    with pytest.raises(L.MspError):
+        ops.bn_act_bwd_reduce(x, None, dy, mi, ops.ACT_SIGMOID, gamma=gamma, beta=beta)
+
+
 def test_bn_zero_fill_strided_shortcut():
     """ResNet shortcut: stride-2 sub-sampling + zero channel fill (classification/models.py:257-274)."""
     ops = _ops()
