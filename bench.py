@@ -268,6 +268,8 @@ def main():
 
     gen = torch.Generator().manual_seed(1 + rank)
     x_host, y_host = synthetic_batch(args.workload, batch, gen, torch)
+    if args.workload == "cfg2":
+        x_host = x_host.to(torch.bfloat16)   # BASELINE configs[1]: "3x224x224 bf16" images (x ~ N(0,1) -> bf16)
     x_host, y_host = x_host.pin_memory(), y_host.pin_memory()
     x_dev, y_dev = x_host.to(dev), y_host.to(dev)
 
@@ -359,6 +361,17 @@ def main():
     barrier()
     ms_e2e = e2.elapsed_time(e3)
 
+    # the host -> device copy of one batch by itself (explains e2e when the PCIe link, not the step, is the limit)
+    h0, h1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    xb, yb = feeder.bufs[0]
+    h0.record()
+    for _ in range(3):
+        xb.copy_(x_host, non_blocking=True)
+        yb.copy_(y_host, non_blocking=True)
+    h1.record()
+    torch.cuda.synchronize()
+    h2d_ms = h0.elapsed_time(h1) / 3
+
     t = torch.tensor([ms, ms_e2e], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -395,7 +408,10 @@ def main():
             "e2e": {"value": total_images / (ms_e2e * 1e-3), "unit": "images/sec",
                     "h2d_bytes_per_step": (x_host.numel() * x_host.element_size()
                                            + y_host.numel() * y_host.element_size()) * world,
-                    "d2h_bytes_per_step": 4 * world, "ms_per_step": ms_e2e / args.steps, "last_loss": last},
+                    "d2h_bytes_per_step": 4 * world, "ms_per_step": ms_e2e / args.steps, "last_loss": last,
+                    "input_dtype": str(x_host.dtype).replace("torch.", ""), "h2d_ms_alone": h2d_ms,
+                    "h2d_gbs_alone": (x_host.numel() * x_host.element_size()
+                                      + y_host.numel() * y_host.element_size()) / (h2d_ms * 1e-3) / 1e9},
             "gpu_launches": int(launches), "host_enqueue_ms_per_step": host_ms,
             "clocks": clocks,
             "roofline": {"bound": "tensor", "kernel": "tapgemm_kernel / wgrad_kernel (tcgen05 implicit-GEMM conv)",

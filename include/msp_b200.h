@@ -106,6 +106,10 @@ int msp_nhwc_bf16_to_nchw_f32(const void* x, int N, int C, int H, int W, int x_c
 /* NCHW fp32 -> W-padded [N][H][Wp][cpp] bf16 (cpp = 8 or 16 >= C) for row-window convolutions. */
 int msp_nchw_f32_to_rowwin_bf16(const float* x, int N, int C, int H, int W, int cpp, int pad_l, int Wp,
                                 void* y, void* stream);
+/* same from a bf16 NCHW batch (BASELINE cfg2 feeds bf16 images: half the host -> device bytes of the
+ * reference's fp32 `.to(device)`, train_model.py:60). */
+int msp_nchw_bf16_to_rowwin_bf16(const void* x, int N, int C, int H, int W, int cpp, int pad_l, int Wp,
+                                 void* y, void* stream);
 int msp_nchw_f32_grad_to_nhwc_bf16(const float* g, int N, int C, int H, int W, int g_cs_out,
                                    void* y, void* stream);
 

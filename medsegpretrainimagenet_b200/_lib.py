@@ -47,6 +47,7 @@ SIGNATURES = {
     "msp_unpack_wgrad": [C.POINTER(ConvDesc), P, I, P, P],
     "msp_pack_weights_rowwin": [P, I, I, I, I, I, P, P],
     "msp_nchw_f32_to_rowwin_bf16": [P, I, I, I, I, I, I, I, P, P],
+    "msp_nchw_bf16_to_rowwin_bf16": [P, I, I, I, I, I, I, I, P, P],
     "msp_nchw_f32_to_nhwc_bf16": [P, I, I, I, I, I, P, P],
     "msp_nhwc_bf16_to_nchw_f32": [P, I, I, I, I, I, P, P],
     "msp_nchw_f32_grad_to_nhwc_bf16": [P, I, I, I, I, I, P, P],

@@ -109,6 +109,9 @@ __device__ __forceinline__ uint32_t lds_u32(uint32_t saddr) {
 __device__ __forceinline__ void sts_f32(uint32_t saddr, float v) {
   asm volatile("st.shared.f32 [%0], %1;" ::"r"(saddr), "f"(v) : "memory");
 }
+__device__ __forceinline__ void red_shared_add_f32(uint32_t saddr, float v) {
+  asm volatile("red.shared.add.f32 [%0], %1;" ::"r"(saddr), "f"(v) : "memory");
+}
 __device__ __forceinline__ float lds_f32(uint32_t saddr) {
   float v;
   asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(saddr) : "memory");

@@ -93,195 +93,197 @@ struct TapGemmCfg {
   static constexpr int kTmemCols = 2 * BN_ < 32 ? 32 : 2 * BN_;
 };
 
-// Epilogue warps of both tap-GEMM kernels (warps 2..9): drain TMEM accumulators tile by tile.
-template <int BN_>
+// Epilogue warps of the tap-GEMM kernels (warps 2..9): drain TMEM accumulators tile by tile.
 // Work items are walked as it0, it0 + it_step, ... < it_total; item -> (output-channel block tco = item / m_per_co,
 // m index pm = item % m_per_co).  pair_rank < 0: one M tile per item (tm = pm).  pair_rank = 0/1: CTA pair
 // (cta_group::2), the item is two M tiles and this CTA owns tm = 2*pm + pair_rank (possibly past the end: masked);
 // the accumulator is handed back through the LEADER CTA's tempty barrier.
-__device__ __forceinline__ void tap_epilogue(const TapGemmParams& p, uint8_t* staging, float* scratch,
+//
+// The warps are DECOUPLED: warp (q, part) owns TMEM lanes [32q, 32q+32) and a fixed set of column steps of every
+// tile, with a private staging slab — no CTA-wide barrier on the per-tile path (the barrier-per-chunk version spent
+// 2.8x the TMEM-read time per tile, profiles/r01_epilogue_phases.txt; the 1x1 convolutions are epilogue bound).
+// Per step (kCW columns): tcgen05.ld -> bias/ReLU -> bf16 -> swizzled slab (lane = row) -> __syncwarp -> the slab is
+// read back (a) piece-major for global stores that cover whole 16*P-byte row segments and (b) column-major for the
+// BatchNorm statistics, kept in registers per lane (its column pair) and flushed to global memory (2*Cout atomics
+// per CTA) only when the CTA leaves an output-channel block.
+template <int BN_>
+struct EpiCfg {
+  static constexpr int kCWraw = BN_ / kEpiParts;
+  static constexpr int kCW = kEpiParts == 2 ? (BN_ >= 128 ? 32 : BN_ / 2)
+                                            : (kCWraw > 32 ? 32 : (kCWraw < 8 ? 8 : kCWraw));  // columns per step
+  static constexpr int kP = kCW / 8;                                          // 16-byte pieces per slab row
+  static constexpr int kActiveParts = (BN_ / kCW) < kEpiParts ? (BN_ / kCW) : kEpiParts;
+  static constexpr int kSteps = BN_ / (kActiveParts * kCW);                   // steps per (active) warp and tile
+  static constexpr int kSlabBytes = 32 * kCW * 2 < 512 * kSteps ? 512 * kSteps : 32 * kCW * 2;
+  static constexpr int kBytes = kEpiWarps * kSlabBytes;
+  // first column (within the tile) of step s for column part `part`
+  __device__ static constexpr int col(int s, int part) { return (part * kSteps + s) * kCW; }
+};
+
+template <int BN_>
+__device__ __forceinline__ void tap_epilogue(const TapGemmParams& p, uint8_t* staging, float* /*scratch*/,
                                              uint32_t tmem_base, uint64_t* tfull_bar, uint64_t* tempty_bar,
                                              int warp, int lane, int it0, int it_step, int it_total,
                                              int m_per_co, int pair_rank) {
-  using Cfg = TapGemmCfg<BN_>;
-  {
-    // ---------------- epilogue: TMEM -> registers -> swizzled smem tile -> coalesced global stores -------
-    // kEpiWarps warps (8 = 2 per scheduler; the epilogue is latency / issue bound, profiles/r01_epilogue_phases.txt): the
-    // warps of a TMEM lane quarter split every 64-column chunk into equal column parts.  The bf16 tile is transposed through a 128B-swizzled staging tile
-    // so that every global store instruction writes four full 128-byte lines (thread = one 16-byte piece).
-    // No async-proxy hand-off: a TMA store here costs a MEMBAR + proxy fence per chunk, which at one
-    // k-block per tile (1x1 convolutions) made the epilogue the critical path (profiles/r01_*).
-    const int et = threadIdx.x - 64;  // 0..kEpiThreads-1
-    const int q = warp & 3;           // TMEM lane quarter this warp may access
-    const int part = (et >> 5) >> 2;  // which column part of the chunk this warp handles
-    const int row = q * 32 + lane;
-    const bool do_stats = p.ch_sum != nullptr && !(p.debug & 2);
-    const bool has_bias = p.bias != nullptr;
-    const uint32_t scratch_s = smem_u32(scratch);
-    const uint32_t run_s = scratch_s + kEpiSlabs * 128 * 4;  // running statistics [chunk][which][64]
-    for (int i = et; i < Cfg::kNChunk * 128; i += kEpiThreads) sts_f32(run_s + i * 4, 0.f);
-    constexpr int CH = Cfg::kCH;
-    constexpr int CHH = (CH / kEpiParts) < 8 ? 8 : CH / kEpiParts;  // columns per warp per chunk
-    constexpr int kActiveParts = CH / CHH;                           // narrow tiles: the other warps only copy out
-    const bool active = part < kActiveParts;
-    // Tile-invariant per-thread state (the epilogue is instruction-issue bound: everything that does not depend
-    // on the tile is computed once): its TMEM row, the rows it copies out, their smem and global offsets.
-    const int my_wi = row % p.bw, my_hi = (row / p.bw) % p.bh, my_ni = row / (p.bw * p.bh);
-    const int ck = et & 7;  // 16-byte piece (8 channels) of the staging row this thread copies out
-    int o_wi[kEpiPasses], o_hi[kEpiPasses], o_ni[kEpiPasses];
-    uint32_t o_lds[kEpiPasses];      // staging offset of (row j, piece ck)
-    long long o_rel[kEpiPasses];     // element offset of row j relative to the tile origin (+ this thread's 8 channels)
+  using E = EpiCfg<BN_>;
+  constexpr int CW = E::kCW, P = E::kP;
+  static_assert(E::kBytes <= TapGemmCfg<BN_>::kStageBufs * kATileBytes + TapGemmCfg<BN_>::kScratchBytes, "epilogue smem");
+  const int et = threadIdx.x - 64;  // 0..kEpiThreads-1
+  const int ew = et >> 5;           // epilogue warp 0..7
+  const int q = warp & 3;           // TMEM lane quarter this warp may access
+  const int part = ew >> 2;         // which column part of the tile this warp handles
+  const bool active = part < E::kActiveParts;  // very narrow tiles: the other warps only take part in the hand-offs
+  const int row = q * 32 + lane;    // this thread's accumulator row
+  const bool do_stats = p.ch_sum != nullptr && !(p.debug & 2);
+  const bool has_bias = p.bias != nullptr;
+  const uint32_t slab_s = smem_u32(staging) + ew * E::kSlabBytes;
+  float st_acc[E::kSteps][4];  // running (sum a, sum b, sumsq a, sumsq b) of this lane's column pair, per step
 #pragma unroll
-    for (int j = 0; j < kEpiPasses; ++j) {
-      const int r = j * kEpiRowsPerPass + (et >> 3);
-      o_wi[j] = r % p.bw;
-      o_hi[j] = (r / p.bw) % p.bh;
-      o_ni[j] = r / (p.bw * p.bh);
-      o_lds[j] = (uint32_t)(r * 128 + ((ck ^ (r & 7)) << 4));
-      o_rel[j] = (r < p.rows && o_wi[j] < p.bw_valid) ? (long long)o_ni[j] * p.y_n_stride + (long long)o_hi[j] * p.y_h_stride +
-                                  (long long)o_wi[j] * p.y_w_stride + ck * 8
-                            : -1;
-    }
-    uint32_t sts_off[CHH / 8];  // swizzled staging offsets of this thread's 16-byte groups
+  for (int i = 0; i < E::kSteps; ++i) st_acc[i][0] = st_acc[i][1] = st_acc[i][2] = st_acc[i][3] = 0.f;
+  // Tile-invariant per-thread state: its TMEM row, the row pieces it copies out, their slab and global offsets.
+  const int my_wi = row % p.bw, my_hi = (row / p.bw) % p.bh, my_ni = row / (p.bw * p.bh);
+  int o_wi[P], o_hi[P], o_ni[P], o_ch[P];
+  uint32_t o_lds[P];       // slab offset of (row, piece)
+  long long o_rel[P];      // element offset of the piece relative to the tile origin
 #pragma unroll
-    for (int g = 0; g < CHH / 8; ++g)
-      sts_off[g] = (uint32_t)(row * 128 + ((((part % kActiveParts) * (CHH / 8) + g) ^ (row & 7)) << 4));
-    const bool flat_tiles = p.tiles_h == 1 && p.tiles_n == 1;  // 1x1 "flat" convolutions: tile = 128 pixels of one row
-    uint32_t t = 0, sbuf = 0;
-    int tco = it0 / m_per_co, pm = it0 - tco * m_per_co;
-    // profiling build (-DMSP_EPI_PROFILE, MSP_CONV_DEBUG & 1024): cycles of epilogue thread 0 per phase
-#ifdef MSP_EPI_PROFILE
-    const bool prof = (p.debug & 1024) && blockIdx.x == 0 && et == 0;
-    long long pc[8] = {0, 0, 0, 0, 0, 0, 0, 0}, pt = prof ? clock64() : 0;
-#define MSP_PHASE(i)                     \
-  if (prof) {                            \
-    const long long now_ = clock64();    \
-    pc[i] += now_ - pt;                  \
-    pt = now_;                           \
+  for (int j = 0; j < P; ++j) {
+    const int u = j * 32 + lane, rl = u / P, g = u % P, r = q * 32 + rl;
+    o_wi[j] = r % p.bw;
+    o_hi[j] = (r / p.bw) % p.bh;
+    o_ni[j] = r / (p.bw * p.bh);
+    o_ch[j] = g * 8;
+    o_lds[j] = (uint32_t)((u >> 3) * 128 + (((u & 7) ^ ((u >> 3) & 7)) << 4));
+    o_rel[j] = (r < p.rows && o_wi[j] < p.bw_valid) ? (long long)o_ni[j] * p.y_n_stride + (long long)o_hi[j] * p.y_h_stride +
+                                                      (long long)o_wi[j] * p.y_w_stride + g * 8
+                                                    : -1;
   }
-#else
-#define MSP_PHASE(i)
-#endif
-    for (int item = it0; item < it_total; item += it_step, ++t) {
-      int tm = pair_rank < 0 ? pm : 2 * pm + pair_rank;
-      const bool tile_ok = tm < p.tiles_m;  // odd tile counts: the pair's second CTA idles on a masked duplicate
-      if (!tile_ok) tm = p.tiles_m - 1;
-      int tw = tm, th = 0, tn = 0;
-      if (!flat_tiles) {
-        tw = (int)((uint32_t)tm % (uint32_t)p.tiles_w);
-        const uint32_t rest = (uint32_t)tm / (uint32_t)p.tiles_w;
-        th = (int)(rest % (uint32_t)p.tiles_h);
-        tn = (int)(rest / (uint32_t)p.tiles_h);
+  uint32_t sts_off[P];  // swizzled slab offsets of this thread's (lane = row) 16-byte pieces
+#pragma unroll
+  for (int g = 0; g < P; ++g) {
+    const int u = lane * P + g;
+    sts_off[g] = (uint32_t)((u >> 3) * 128 + (((u & 7) ^ ((u >> 3) & 7)) << 4));
+  }
+  // statistics read: pass j, lane -> 32-bit word w = j*32 + lane of the slab (row w / (4P), column pair w % (4P))
+  const int st_cp = lane % (4 * P);
+  const uint32_t st_off0 = (uint32_t)((((lane >> 2) & 7) << 4) + (lane & 3) * 4);  // line j: pos16 = lane/4, xor (j & 7)
+  const bool flat_tiles = p.tiles_h == 1 && p.tiles_n == 1;  // 1x1 "flat" convolutions: tile = 128 pixels of one row
+  uint32_t t = 0;
+  int tco = it0 / m_per_co, pm = it0 - tco * m_per_co;
+  for (int item = it0; item < it_total; item += it_step, ++t) {
+    int tm = pair_rank < 0 ? pm : 2 * pm + pair_rank;
+    const bool tile_ok = tm < p.tiles_m;  // odd tile counts: the pair's second CTA idles on a masked duplicate
+    if (!tile_ok) tm = p.tiles_m - 1;
+    int tw = tm, th = 0, tn = 0;
+    if (!flat_tiles) {
+      tw = (int)((uint32_t)tm % (uint32_t)p.tiles_w);
+      const uint32_t rest = (uint32_t)tm / (uint32_t)p.tiles_w;
+      th = (int)(rest % (uint32_t)p.tiles_h);
+      tn = (int)(rest / (uint32_t)p.tiles_h);
+    }
+    const int w0 = tw * p.bw_valid, h0 = th * p.bh, n0 = tn * p.bn;
+    const int co0 = tco * BN_;
+    const bool valid =
+        tile_ok && row < p.rows && my_wi < p.bw_valid && (w0 + my_wi) < p.OWs && (h0 + my_hi) < p.OHs && (n0 + my_ni) < p.N;
+    const long long tile_off = p.y_off + (long long)n0 * p.y_n_stride + (long long)h0 * p.y_h_stride +
+                               (long long)w0 * p.y_w_stride + co0;
+    __nv_bfloat16* o_ptr[P];
+#pragma unroll
+    for (int j = 0; j < P; ++j) {
+      const bool ok = tile_ok && o_rel[j] >= 0 && (w0 + o_wi[j]) < p.OWs && (h0 + o_hi[j]) < p.OHs &&
+                      (n0 + o_ni[j]) < p.N;
+      o_ptr[j] = ok ? p.y + tile_off + o_rel[j] : nullptr;
+    }
+    // advance (tco, pm) to this CTA's next item without a division
+    int tco_next = tco, pm_next = pm + it_step;
+    while (pm_next >= m_per_co) {
+      pm_next -= m_per_co;
+      ++tco_next;
+    }
+    const uint32_t as = t & 1u;
+    if (lane == 0) mbar_wait(&tfull_bar[as], (t >> 1) & 1u);  // one poller per warp
+    __syncwarp();
+    tc_fence_after();
+    const uint32_t tmem_row = tmem_base + ((uint32_t)(q * 32) << 16) + as * BN_;
+    // TMEM loads run one step ahead of the arithmetic: step s+1 is in flight while step s is packed / stored / summed
+    uint32_t v[CW];
+    auto tm_issue = [&](int s_) {
+      const int c_ = E::col(s_, part);
+      if constexpr (CW == 64) {
+        tmem_ld_32x32(tmem_row + c_, *reinterpret_cast<uint32_t(*)[32]>(&v[0]));
+        tmem_ld_32x32(tmem_row + c_ + 32, *reinterpret_cast<uint32_t(*)[32]>(&v[32]));
+      } else if constexpr (CW == 32) {
+        tmem_ld_32x32(tmem_row + c_, v);
+      } else if constexpr (CW == 16) {
+        tmem_ld_32x16(tmem_row + c_, v);
+      } else {
+        tmem_ld_32x8(tmem_row + c_, v);
       }
-      const int w0 = tw * p.bw_valid, h0 = th * p.bh, n0 = tn * p.bn;
-      const int co0 = tco * BN_;
-      const bool valid =
-          tile_ok && row < p.rows && my_wi < p.bw_valid && (w0 + my_wi) < p.OWs && (h0 + my_hi) < p.OHs && (n0 + my_ni) < p.N;
-      const long long tile_off = p.y_off + (long long)n0 * p.y_n_stride + (long long)h0 * p.y_h_stride +
-                                 (long long)w0 * p.y_w_stride + co0;
-      __nv_bfloat16* o_ptr[kEpiPasses];
+    };
+    if (active) tm_issue(0);
 #pragma unroll
-      for (int j = 0; j < kEpiPasses; ++j) {
-        const bool ok = tile_ok && o_rel[j] >= 0 && (w0 + o_wi[j]) < p.OWs && (h0 + o_hi[j]) < p.OHs &&
-                        (n0 + o_ni[j]) < p.N;
-        o_ptr[j] = ok ? p.y + tile_off + o_rel[j] : nullptr;
+    for (int s = 0; s < E::kSteps; ++s) {
+      const int cl = E::col(s, part);  // first column of this step within the tile
+      const int cb = co0 + cl;         // first output channel
+      tmem_ld_wait();
+      float x[CW];
+#pragma unroll
+      for (int j = 0; j < CW; ++j) x[j] = __uint_as_float(v[j]);
+      if (s + 1 < E::kSteps) {
+        if (active) tm_issue(s + 1);
+      } else {  // accumulator fully read by this warp: hand it back to the MMA warp
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          if (pair_rank < 0) mbar_arrive(&tempty_bar[as]);
+          else mbar_arrive_leader(&tempty_bar[as]);
+        }
       }
-      // advance (tco, pm) to this CTA's next item without a division
-      int tco_next = tco, pm_next = pm + it_step;
-      while (pm_next >= m_per_co) {
-        pm_next -= m_per_co;
-        ++tco_next;
-      }
-      const uint32_t as = t & 1u;
-      MSP_PHASE(0)  // tile preamble
-      if (lane == 0) mbar_wait(&tfull_bar[as], (t >> 1) & 1u);  // one poller per warp, not 256 on one mbarrier
-      __syncwarp();
-      tc_fence_after();
-      MSP_PHASE(1)  // wait for the accumulator
-      const uint32_t tmem_row = tmem_base + ((uint32_t)(q * 32) << 16) + as * BN_ + (part % kActiveParts) * CHH;
-#pragma unroll 1
-      for (int c = 0; c < Cfg::kNChunk; ++c) {
-        const int cg = co0 + c * CH;
-        const uint32_t stg_s = smem_u32(staging) + (Cfg::kStageBufs == 2 ? sbuf * kATileBytes : 0);
-        // dgrad on top of an existing gradient: fetch the old values now, consume them after the transpose
-        uint4 old[kEpiPasses];
-        if (p.accumulate) {
-          const bool mine = ck < CH / 8 && cg + ck * 8 < p.Kout;
+      if (cb < p.Kout && active) {
+        // uniform branches around straight-line blocks (a per-element `if` costs a taken branch each)
+        if (has_bias) {
+          if (cb + CW <= p.Kout && ((reinterpret_cast<uintptr_t>(p.bias) & 15) == 0)) {
+            const float4* b4 = reinterpret_cast<const float4*>(p.bias + cb);
 #pragma unroll
-          for (int j = 0; j < kEpiPasses; ++j)
-            old[j] = (mine && o_ptr[j] != nullptr) ? __ldg(reinterpret_cast<const uint4*>(o_ptr[j] + c * CH))
-                                                   : make_uint4(0u, 0u, 0u, 0u);
-        }
-        // single staging tile: everyone must have finished reading the previous chunk out of it
-        if constexpr (Cfg::kStageBufs == 1) named_bar_sync(kEpiBarrier, kEpiThreads);
-        MSP_PHASE(2)  // staging-free barrier (+ accumulate prefetch issue)
-        uint32_t v[CHH];
-        if (active) {
-          if constexpr (CHH == 32) tmem_ld_32x32(tmem_row + c * CH, v);
-          else if constexpr (CHH == 16) tmem_ld_32x16(tmem_row + c * CH, v);
-          else tmem_ld_32x8(tmem_row + c * CH, v);
-          tmem_ld_wait();
-        }
-        MSP_PHASE(3)  // TMEM load
-        if (c == Cfg::kNChunk - 1) {  // accumulator fully read: hand it back to the MMA warp (one arrive per warp)
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) {
-            if (pair_rank < 0) mbar_arrive(&tempty_bar[as]);
-            else mbar_arrive_leader(&tempty_bar[as]);
-          }
-        }
-        if (cg < p.Kout && active) {
-          const int cb = cg + part * CHH;  // first output channel of this warp's columns
-          float x[CHH];
-#pragma unroll
-          for (int j = 0; j < CHH; ++j) x[j] = __uint_as_float(v[j]);
-          // uniform branches around straight-line blocks (a per-element `if` costs a taken branch each)
-          if (has_bias) {
-            if (cb + CHH <= p.Kout && ((reinterpret_cast<uintptr_t>(p.bias) & 15) == 0)) {
-              const float4* b4 = reinterpret_cast<const float4*>(p.bias + cb);
-#pragma unroll
-              for (int j = 0; j < CHH / 4; ++j) {
-                const float4 bb = __ldg(b4 + j);
-                x[4 * j] += bb.x;
-                x[4 * j + 1] += bb.y;
-                x[4 * j + 2] += bb.z;
-                x[4 * j + 3] += bb.w;
-              }
-            } else {
-#pragma unroll
-              for (int j = 0; j < CHH; ++j)
-                if (cb + j < p.Kout) x[j] += __ldg(p.bias + cb + j);
+            for (int j = 0; j < CW / 4; ++j) {
+              const float4 bb = __ldg(b4 + j);
+              x[4 * j] += bb.x;
+              x[4 * j + 1] += bb.y;
+              x[4 * j + 2] += bb.z;
+              x[4 * j + 3] += bb.w;
             }
-          }
-          if (p.relu) {
+          } else {
 #pragma unroll
-            for (int j = 0; j < CHH; ++j) x[j] = fmaxf(x[j], 0.f);
+            for (int j = 0; j < CW; ++j)
+              if (cb + j < p.Kout) x[j] += __ldg(p.bias + cb + j);
           }
-          if (!valid) {
-#pragma unroll
-            for (int j = 0; j < CHH; ++j) x[j] = 0.f;
-          }
-#pragma unroll
-          for (int g = 0; g < CHH / 8; ++g)
-            sts_v4(stg_s + sts_off[g], pack_bf16x2(x[8 * g], x[8 * g + 1]),
-                   pack_bf16x2(x[8 * g + 2], x[8 * g + 3]), pack_bf16x2(x[8 * g + 4], x[8 * g + 5]),
-                   pack_bf16x2(x[8 * g + 6], x[8 * g + 7]));
         }
-        MSP_PHASE(4)  // bias / ReLU / pack / STS
-        named_bar_sync(kEpiBarrier, kEpiThreads);
-        MSP_PHASE(5)  // staged barrier
-        if (cg < p.Kout) {
-          // copy-out: thread = (row j*32 + et/8, 16-byte piece et%8); a warp stores 4 full 128-byte lines
-          if (ck < CH / 8 && cg + ck * 8 < p.Kout && !(p.debug & 1)) {
-            uint4 o[kEpiPasses];
+        if (p.relu) {
 #pragma unroll
-            for (int j = 0; j < kEpiPasses; ++j) o[j] = lds_v4(stg_s + o_lds[j]);  // all smem reads in flight first
-            const int coff = c * CH;
-            if (p.accumulate) {
+          for (int j = 0; j < CW; ++j) x[j] = fmaxf(x[j], 0.f);
+        }
+        if (!valid) {
 #pragma unroll
-              for (int j = 0; j < kEpiPasses; ++j) {
-                const uint32_t ov[4] = {old[j].x, old[j].y, old[j].z, old[j].w};
+          for (int j = 0; j < CW; ++j) x[j] = 0.f;
+        }
+        __syncwarp();  // the previous step's slab reads are done
+#pragma unroll
+        for (int g = 0; g < P; ++g)
+          sts_v4(slab_s + sts_off[g], pack_bf16x2(x[8 * g], x[8 * g + 1]), pack_bf16x2(x[8 * g + 2], x[8 * g + 3]),
+                 pack_bf16x2(x[8 * g + 4], x[8 * g + 5]), pack_bf16x2(x[8 * g + 6], x[8 * g + 7]));
+        __syncwarp();
+        // (running the two slab consumers in opposite order on the two column parts measured slower)
+        auto copy_out = [&]() {
+          if (!(p.debug & 1)) {
+            // copy-out: lane -> (row, 16-byte piece); 32 lanes cover 32/P whole row segments of 16*P bytes
+            uint4 o[P];
+#pragma unroll
+            for (int j = 0; j < P; ++j) o[j] = lds_v4(slab_s + o_lds[j]);
+            if (p.accumulate) {  // dgrad on top of an existing gradient
+#pragma unroll
+              for (int j = 0; j < P; ++j) {
+                if (o_ptr[j] == nullptr || cb + o_ch[j] >= p.Kout) continue;
+                const uint4 old = __ldg(reinterpret_cast<const uint4*>(o_ptr[j] + cl));
+                const uint32_t ov[4] = {old.x, old.y, old.z, old.w};
                 const uint32_t nv[4] = {o[j].x, o[j].y, o[j].z, o[j].w};
                 uint32_t rv[4];
 #pragma unroll
@@ -293,63 +295,67 @@ __device__ __forceinline__ void tap_epilogue(const TapGemmParams& p, uint8_t* st
               }
             }
 #pragma unroll
-            for (int j = 0; j < kEpiPasses; ++j)
-              if (o_ptr[j] != nullptr) st_v4(o_ptr[j] + coff, o[j]);
+            for (int j = 0; j < P; ++j)
+              if (o_ptr[j] != nullptr && cb + o_ch[j] < p.Kout) st_v4(o_ptr[j] + cl, o[j]);
           }
-          MSP_PHASE(6)  // copy-out
+        };
+        auto col_stats = [&]() {
           if (do_stats) {
-            // column sums of the bf16 tile: thread -> (column pair, row slab); conflict-free LDS.32
-            const int cp = et & 31, re = et >> 5;
+            // column sums of the bf16 slab: lane -> column pair st_cp; 4P conflict-free LDS.32 (pass j = 128-byte line j)
             float s1a = 0.f, s2a = 0.f, s1b = 0.f, s2b = 0.f;
-            const uint32_t base = stg_s + re * kEpiSlabRows * 128 + (cp & 3) * 4;
-            const uint32_t sw = (uint32_t)(cp >> 2);
 #pragma unroll
-            for (int r = 0; r < kEpiSlabRows; ++r) {
-              const uint32_t wv = lds_u32(base + r * 128 + ((sw ^ (uint32_t)((re * kEpiSlabRows + r) & 7)) << 4));
-              const float2 f = unpack_bf16x2(wv);
+            for (int j = 0; j < 4 * P; ++j) {
+              const float2 f = unpack_bf16x2(lds_u32(slab_s + j * 128 + (st_off0 ^ (uint32_t)((j & 7) << 4))));
               s1a += f.x;
               s2a = fmaf(f.x, f.x, s2a);
               s1b += f.y;
               s2b = fmaf(f.y, f.y, s2b);
             }
-            const uint32_t sc = scratch_s + (re * 128 + 2 * cp) * 4;  // [re][which][64]
-            sts_f32(sc, s1a);
-            sts_f32(sc + 4, s1b);
-            sts_f32(sc + 256, s2a);
-            sts_f32(sc + 260, s2b);
-            named_bar_sync(kEpiBarrier, kEpiThreads);
-            if (et < 128) {  // thread et owns (which = et >> 6, column = et & 63) of every chunk
-              float tot = lds_f32(run_s + (c * 128 + et) * 4);
-#pragma unroll
-              for (int j = 0; j < kEpiSlabs; ++j) tot += lds_f32(scratch_s + (j * 128 + et) * 4);
-              sts_f32(run_s + (c * 128 + et) * 4, tot);
-            }
+            st_acc[s][0] += s1a;
+            st_acc[s][1] += s1b;
+            st_acc[s][2] += s2a;
+            st_acc[s][3] += s2b;
           }
-        }
-        MSP_PHASE(7)  // statistics
-        if constexpr (Cfg::kStageBufs == 2) sbuf ^= 1u;
+        };
+        copy_out();
+        col_stats();
       }
-      // flush the running statistics when this CTA leaves the output-channel block (or finishes)
-      if (do_stats && et < 128) {
-        if (item + it_step >= it_total || tco_next != tco) {
-          float* dst = (et >> 6) ? p.ch_sqsum : p.ch_sum;
-          for (int c = 0; c < Cfg::kNChunk; ++c) {
-            const int col = co0 + c * CH + (et & 63);
-            if ((et & 63) < CH && col < p.Kout) atomicAdd(dst + col, lds_f32(run_s + (c * 128 + et) * 4));
-            sts_f32(run_s + (c * 128 + et) * 4, 0.f);
-          }
-        }
-      }
-      tco = tco_next;
-      pm = pm_next;
     }
-#ifdef MSP_EPI_PROFILE
-    if (prof)
-      printf("msp epilogue phases (cycles, thread 0, %u tiles x %d chunks): preamble %lld wait-acc %lld bar-free %lld "
-             "tmem-ld %lld pack+sts %lld bar-staged %lld copy-out %lld stats %lld\n",
-             t, Cfg::kNChunk, pc[0], pc[1], pc[2], pc[3], pc[4], pc[5], pc[6], pc[7]);
-#endif
-#undef MSP_PHASE
+    // flush the CTA's statistics when it leaves the output-channel block (or finishes): the warps park their
+    // register sums in their (now idle) slabs, then 2*BN threads add the four lane quarters and issue one global
+    // atomic per (statistic, channel).  (Shared-memory float atomics compile to a CAS loop: not used.)
+    if (do_stats && (item + it_step >= it_total || tco_next != tco)) {
+#pragma unroll
+      for (int i = 0; i < E::kSteps; ++i) {
+#pragma unroll
+        for (int o = 16; o >= 4 * P; o >>= 1) {  // lanes that share a column pair (narrow steps)
+#pragma unroll
+          for (int e = 0; e < 4; ++e) st_acc[i][e] += __shfl_xor_sync(0xffffffffu, st_acc[i][e], o);
+        }
+      }
+      __syncwarp();
+#pragma unroll
+      for (int i = 0; i < E::kSteps; ++i) {
+        sts_v4(slab_s + (uint32_t)(i * 32 + lane) * 16, __float_as_uint(st_acc[i][0]), __float_as_uint(st_acc[i][1]),
+               __float_as_uint(st_acc[i][2]), __float_as_uint(st_acc[i][3]));
+        st_acc[i][0] = st_acc[i][1] = st_acc[i][2] = st_acc[i][3] = 0.f;
+      }
+      named_bar_sync(kEpiBarrier, kEpiThreads);
+      for (int i = et; i < 2 * BN_; i += kEpiThreads) {
+        const int which = i / BN_, cl = i - which * BN_, col = co0 + cl;
+        const int gs = cl / CW, prt = gs / E::kSteps, st = gs - prt * E::kSteps, cw = cl - gs * CW;
+        if (col < p.Kout) {
+          const uint32_t a = smem_u32(staging) + (uint32_t)(prt * 4) * E::kSlabBytes +
+                             (uint32_t)(st * 32 + (cw >> 1)) * 16 + (uint32_t)(which * 2 + (cw & 1)) * 4;
+          const float tot = lds_f32(a) + lds_f32(a + E::kSlabBytes) + lds_f32(a + 2 * E::kSlabBytes) +
+                            lds_f32(a + 3 * E::kSlabBytes);
+          atomicAdd((which ? p.ch_sqsum : p.ch_sum) + col, tot);
+        }
+      }
+      named_bar_sync(kEpiBarrier, kEpiThreads);
+    }
+    tco = tco_next;
+    pm = pm_next;
   }
 }
 
@@ -369,7 +375,7 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   __shared__ uint64_t tempty_bar[2];
   __shared__ uint32_t tmem_base_s;
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);  // warp-uniform
   const int lane = threadIdx.x & 31;
   const int chunks = (p.C + kBK - 1) / kBK;
   const int kiters = p.ntaps * chunks;
@@ -400,7 +406,7 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   if (warp == 0) {
     // ---------------- TMA producer ----------------
-    if (lane == 0) {
+    if (elect_one()) {  // elect.sync, not lane==0: ptxas then emits bare UTCHMMA / UTMALDG (no per-lane loop)
       tma_prefetch_desc(&tmA);
       tma_prefetch_desc(&tmB);
       const uint32_t tx_bytes = (uint32_t)p.rows * 128u + (uint32_t)Cfg::kBTileBytes;
@@ -435,7 +441,7 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   } else if (warp == 1) {
     // ---------------- MMA issuer ----------------
     // One thread: keep its instruction stream short (descriptor halves, incremental stage / phase counters).
-    if (lane == 0) {
+    if (elect_one()) {  // elect.sync, not lane==0: ptxas then emits bare UTCHMMA / UTMALDG (no per-lane loop)
       constexpr uint32_t idesc = umma_idesc_bf16(kBM, BN_, 0, 0);
       const uint64_t d0 = umma_smem_desc_sw128(smem_u32(smem), 16, 1024);
       const uint32_t desc_hi = (uint32_t)(d0 >> 32);
@@ -527,7 +533,7 @@ tapgemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   __shared__ uint64_t tempty_bar[2];
   __shared__ uint32_t tmem_base_s;
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);  // warp-uniform
   const int lane = threadIdx.x & 31;
   const int rank = (int)cluster_ctarank();
   const int chunks = (p.C + kBK - 1) / kBK;
@@ -554,7 +560,7 @@ tapgemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   const uint32_t tmem_base = tmem_base_s;
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (elect_one()) {  // elect.sync, not lane==0: ptxas then emits bare UTCHMMA / UTMALDG (no per-lane loop)
       tma_prefetch_desc(&tmA);
       tma_prefetch_desc(&tmB);
       const uint32_t tx_bytes = 2u * ((uint32_t)p.rows * 128u + (uint32_t)Cfg2::kBHalfBytes);  // both CTAs
@@ -594,7 +600,7 @@ tapgemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       }
     }
   } else if (warp == 1) {
-    if (lane == 0 && rank == 0) {
+    if (rank == 0 && elect_one()) {
       constexpr uint32_t idesc = umma_idesc_bf16(256, BN_, 0, 0);
       const uint64_t d0 = umma_smem_desc_sw128(smem_u32(smem), 16, 1024);
       const uint32_t desc_hi = (uint32_t)(d0 >> 32);
@@ -672,7 +678,7 @@ tapgemm_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   __shared__ uint32_t tmem_base_s;
   __shared__ uint32_t tap_lo_s[kMaxTaps];  // descriptor start-address increment of every tap's window
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);  // warp-uniform
   const int lane = threadIdx.x & 31;
   const int chunks = (p.C + kBK - 1) / kBK;
 
@@ -704,7 +710,7 @@ tapgemm_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   const uint32_t tmem_base = tmem_base_s;
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (elect_one()) {  // elect.sync, not lane==0: ptxas then emits bare UTCHMMA / UTMALDG (no per-lane loop)
       tma_prefetch_desc(&tmA);
       tma_prefetch_desc(&tmB);
       const uint32_t a_bytes = (uint32_t)(p.bw * p.halo_box_h) * 128u;
@@ -747,7 +753,7 @@ tapgemm_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    if (elect_one()) {  // elect.sync, not lane==0: ptxas then emits bare UTCHMMA / UTMALDG (no per-lane loop)
       constexpr uint32_t idesc = umma_idesc_bf16(kBM, BN_, 0, 0);
       const uint64_t d0 = umma_smem_desc_sw128(smem_u32(a_ring), 16, 1024);
       const uint32_t desc_hi = (uint32_t)(d0 >> 32);
@@ -856,7 +862,7 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant__ C
   __shared__ uint64_t accum_bar;
   __shared__ uint32_t tmem_base_s;
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);  // warp-uniform
   const int lane = threadIdx.x & 31;
   const int tgrp = blockIdx.x / p.cchunks;
   const int tap0 = tgrp * p.tsub;
@@ -889,7 +895,7 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant__ C
   const uint32_t tmem_base = tmem_base_s;
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (elect_one()) {  // elect.sync, not lane==0: ptxas then emits bare UTCHMMA / UTMALDG (no per-lane loop)
       tma_prefetch_desc(&tmDY);
       tma_prefetch_desc(&tmX);
       const uint32_t tx_bytes = (uint32_t)p.rows * 128u * (uint32_t)(2 + nsub);
@@ -926,7 +932,7 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant__ C
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    if (elect_one()) {  // elect.sync, not lane==0: ptxas then emits bare UTCHMMA / UTMALDG (no per-lane loop)
       const uint32_t idesc = umma_idesc_bf16(128, 64 * nsub, 1, 1);
       const int nk = (p.rows + 15) >> 4;
       // MN-major: 8-row (K) groups 1024 B apart; consecutive 64-channel atoms are 16 KB apart

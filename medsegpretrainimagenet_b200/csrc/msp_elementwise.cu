@@ -89,7 +89,10 @@ __global__ void nchw_to_nhwc_kernel(const float* __restrict__ x, int C, long lon
 }
 // NCHW fp32 -> W-padded NHWC bf16 [N][H][Wp][cpp] for the row-window convolution (msp_conv.cu): pixel w of
 // the image lands at column w + pad_l, everything else (pad columns, channels >= C) is zero.
-__global__ void nchw_to_rowwin_kernel(const float* __restrict__ x, int C, int H, int W, int cpp, int pad_l,
+__device__ __forceinline__ float src_to_f32(float v) { return v; }
+__device__ __forceinline__ float src_to_f32(__nv_bfloat16 v) { return __bfloat162float(v); }
+template <typename T>  // T = float (the reference's batches) or __nv_bfloat16 (half the host -> device bytes)
+__global__ void nchw_to_rowwin_kernel(const T* __restrict__ x, int C, int H, int W, int cpp, int pad_l,
                                       int Wp, long long total, __nv_bfloat16* __restrict__ y) {
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
@@ -99,12 +102,12 @@ __global__ void nchw_to_rowwin_kernel(const float* __restrict__ x, int C, int H,
     const long long n = t / H;
     const int w = wp - pad_l;
     const bool in = w >= 0 && w < W;
-    const float* src = x + (n * C * H + h) * (long long)W + w;
+    const T* src = x + (n * C * H + h) * (long long)W + w;
     uint32_t pk[8];
 #pragma unroll
     for (int c = 0; c < 16; c += 2) {
-      const float a = (in && c < C) ? src[(long long)c * H * W] : 0.f;
-      const float b = (in && c + 1 < C) ? src[(long long)(c + 1) * H * W] : 0.f;
+      const float a = (in && c < C) ? src_to_f32(src[(long long)c * H * W]) : 0.f;
+      const float b = (in && c + 1 < C) ? src_to_f32(src[(long long)(c + 1) * H * W]) : 0.f;
       pk[c >> 1] = pack_bf16x2(a, b);
     }
     uint4* dst = reinterpret_cast<uint4*>(y + i * cpp);
@@ -749,6 +752,18 @@ extern "C" int msp_nchw_f32_to_rowwin_bf16(const float* x, int N, int C, int H, 
   const long long total = (long long)N * H * Wp;
   const int blocks = (int)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
   nchw_to_rowwin_kernel<<<blocks, 256, 0, ST>>>(x, C, H, W, cpp, pad_l, Wp, total, (__nv_bfloat16*)y);
+  MSP_CHECK_LAUNCH();
+  msp_count_launch(1);
+  return MSP_OK;
+}
+extern "C" int msp_nchw_bf16_to_rowwin_bf16(const void* x, int N, int C, int H, int W, int cpp, int pad_l,
+                                           int Wp, void* y, void* stream) {
+  MSP_REQUIRE(x && y && N > 0 && C > 0 && (cpp == 8 || cpp == 16) && C <= cpp && pad_l >= 0 &&
+                  Wp >= W + pad_l,
+              "nchw_to_rowwin: bad arguments");
+  const long long total = (long long)N * H * Wp;
+  const int blocks = (int)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
+  nchw_to_rowwin_kernel<<<blocks, 256, 0, ST>>>((const __nv_bfloat16*)x, C, H, W, cpp, pad_l, Wp, total, (__nv_bfloat16*)y);
   MSP_CHECK_LAUNCH();
   msp_count_launch(1);
   return MSP_OK;

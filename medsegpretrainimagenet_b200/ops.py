@@ -209,13 +209,14 @@ def rowwin_geometry(c_true: int, kw: int, stride: int):
 
 
 def nchw_to_rowwin(x: torch.Tensor, cpp: int, pad_l: int, wp: int) -> torch.Tensor:
-    """fp32 NCHW -> bf16 [N, H, Wp, cpp], image column w at w + pad_l, zero elsewhere."""
+    """fp32 (or bf16) NCHW -> bf16 [N, H, Wp, cpp], image column w at w + pad_l, zero elsewhere."""
     x = x.contiguous()
-    if x.dtype != torch.float32:
+    if x.dtype not in (torch.float32, _BF16):
         x = x.float()
     n, c, h, w = x.shape
     y = torch.empty((n, h, wp, cpp), dtype=_BF16, device=x.device)
-    call("msp_nchw_f32_to_rowwin_bf16", _p(x), n, c, h, w, cpp, pad_l, wp, _p(y), _stream())
+    fn = "msp_nchw_bf16_to_rowwin_bf16" if x.dtype == _BF16 else "msp_nchw_f32_to_rowwin_bf16"
+    call(fn, _p(x), n, c, h, w, cpp, pad_l, wp, _p(y), _stream())
     return y
 
 

@@ -152,6 +152,8 @@ def test_conv_rowwin_fprop_wgrad(case):
     chk = torch.zeros((n, h, wp, cpp))
     chk[:, :, pl:pl + w, :c] = x.permute(0, 2, 3, 1)
     assert torch.equal(xw.float().cpu(), chk)
+    # a bf16 NCHW batch (BASELINE cfg2 feeds bf16 images) gives the identical row-window tensor
+    assert torch.equal(ops.nchw_to_rowwin(x.to(DEV).to(torch.bfloat16), cpp, pl, wp), xw)
     wr = ops.pack_weights_rowwin(wt.detach().to(DEV), win_px)
     stats = torch.zeros((2, k), dtype=torch.float32, device=DEV)
     y = ops.conv_fprop_rowwin(xw, w, wr, bias.to(DEV), k, ks, ks, stride, pt, pl, ho, wo, win_px, stats=stats)
