@@ -351,12 +351,16 @@ def main():
     # public host API: double-buffered prefetch — the pinned host batch i+1 crosses PCIe (inside the timed region)
     # while step i runs; every step still consumes a freshly copied batch and reads its loss back
     feeder = b200.BatchPrefetcher((x_host, y_host), dev)
+    reader = b200.ScalarReader(depth=1)             # every step's loss is read back; the host waits one step late
     feeder.put(x_host, y_host)
     for i in range(args.steps):
         xb, yb = feeder.get()
         if i + 1 < args.steps:
             feeder.put(x_host, y_host)
-        last = step(xb, yb, read_loss=True)         # + D2H read of the loss
+        out = graphed(xb, yb) if graphed is not None else step_core(xb, yb)
+        got = reader.push(out)                      # D2H copy of this step's loss (pinned, asynchronous)
+        last = got if got is not None else last
+    last = (reader.drain() or [last])[-1]
     e3.record()
     barrier()
     ms_e2e = e2.elapsed_time(e3)

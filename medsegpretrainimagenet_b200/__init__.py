@@ -10,7 +10,7 @@ from . import _lib  # noqa: F401  (raises ImportError when the library is missin
 from .converter import ExecContext, UnsupportedModule, convert, is_converted
 from . import converter, functional, graphs, losses, metrics, ops, robustness
 from .graphs import GraphedStep
-from .host import BatchPrefetcher
+from .host import BatchPrefetcher, ScalarReader
 
-__all__ = ["convert", "is_converted", "ExecContext", "UnsupportedModule", "GraphedStep", "BatchPrefetcher", "functional", "graphs", "losses", "metrics",
+__all__ = ["convert", "is_converted", "ExecContext", "UnsupportedModule", "GraphedStep", "BatchPrefetcher", "ScalarReader", "functional", "graphs", "losses", "metrics",
            "ops", "robustness"]

@@ -224,6 +224,15 @@ __device__ __forceinline__ void tap_epilogue(const TapGemmParams& p, uint8_t* st
     for (int s = 0; s < E::kSteps; ++s) {
       const int cl = E::col(s, part);  // first column of this step within the tile
       const int cb = co0 + cl;         // first output channel
+      // dgrad on top of an existing gradient: fetch the old values now, consume them after the transpose
+      uint4 old[P];
+      if (p.accumulate) {
+#pragma unroll
+        for (int j = 0; j < P; ++j)
+          old[j] = (active && o_ptr[j] != nullptr && cb + o_ch[j] < p.Kout)
+                       ? __ldg(reinterpret_cast<const uint4*>(o_ptr[j] + cl))
+                       : make_uint4(0u, 0u, 0u, 0u);
+      }
       tmem_ld_wait();
       float x[CW];
 #pragma unroll
@@ -281,9 +290,7 @@ __device__ __forceinline__ void tap_epilogue(const TapGemmParams& p, uint8_t* st
             if (p.accumulate) {  // dgrad on top of an existing gradient
 #pragma unroll
               for (int j = 0; j < P; ++j) {
-                if (o_ptr[j] == nullptr || cb + o_ch[j] >= p.Kout) continue;
-                const uint4 old = __ldg(reinterpret_cast<const uint4*>(o_ptr[j] + cl));
-                const uint32_t ov[4] = {old.x, old.y, old.z, old.w};
+                const uint32_t ov[4] = {old[j].x, old[j].y, old[j].z, old[j].w};
                 const uint32_t nv[4] = {o[j].x, o[j].y, o[j].z, o[j].w};
                 uint32_t rv[4];
 #pragma unroll

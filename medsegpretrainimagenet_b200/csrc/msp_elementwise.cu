@@ -464,6 +464,128 @@ maxpool_fwd_kernel(const __nv_bfloat16* __restrict__ x, int N, int H, int W, int
     }
   }
 }
+// Fixed-geometry variants (3x3/2 pad 1 of the ResNet stem, classification/models.py:49; 2x2/2 of the U-Net encoder,
+// unet_models.py:150): the window loops are compile-time, so all K*K (forward) / ceil(K/S)^2 (backward) 16-byte loads
+// of a thread are in flight before the first compare — the dynamic-bound kernels issue them one dependent load at a
+// time and ran at ~1/4 of the HBM roofline.
+template <int K, int S, int PAD>
+__global__ void __launch_bounds__(256)
+maxpool_fwd_fixed_kernel(const __nv_bfloat16* __restrict__ x, int N, int H, int W, int C, int x_cs,
+                         __nv_bfloat16* __restrict__ y, uint8_t* __restrict__ idx, int Ho, int Wo, int y_cs) {
+  const uint32_t V = (uint32_t)C >> 3;
+  const uint32_t per_row = (uint32_t)Wo * V;
+  const int rows = N * Ho;
+  for (int row = blockIdx.x; row < rows; row += gridDim.x) {
+    const int n = row / Ho, ho = row - n * Ho;
+    const int h_lo = ho * S - PAD;
+    const __nv_bfloat16* xn = x + (long long)n * H * W * x_cs;
+    for (uint32_t t = threadIdx.x; t < per_row; t += blockDim.x) {
+      const uint32_t wo = t / V, cg = t - wo * V;
+      const int w_lo = (int)wo * S - PAD;
+      uint4 raw[K * K];
+      bool ok[K * K];
+#pragma unroll
+      for (int r = 0; r < K; ++r) {
+#pragma unroll
+        for (int q = 0; q < K; ++q) {
+          const int h = h_lo + r, w = w_lo + q;
+          ok[r * K + q] = h >= 0 && h < H && w >= 0 && w < W;
+          raw[r * K + q] = ok[r * K + q]
+                               ? *reinterpret_cast<const uint4*>(xn + ((long long)h * W + w) * x_cs + cg * 8)
+                               : make_uint4(0u, 0u, 0u, 0u);
+        }
+      }
+      float best[8];
+      uint32_t bi[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { best[j] = -INFINITY; bi[j] = 0; }
+#pragma unroll
+      for (int e = 0; e < K * K; ++e) {
+        if (!ok[e]) continue;
+        const float2 a = unpack_bf16x2(raw[e].x), b = unpack_bf16x2(raw[e].y), c = unpack_bf16x2(raw[e].z),
+                     d = unpack_bf16x2(raw[e].w);
+        const float v[8] = {a.x, a.y, b.x, b.y, c.x, c.y, d.x, d.y};
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          if (v[j] > best[j] || v[j] != v[j]) { best[j] = v[j]; bi[j] = (uint32_t)e; }
+      }
+      F8 o;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o.v[j] = best[j];
+      const long long op = (long long)row * Wo + wo;
+      store_bf16x8(y + op * y_cs + cg * 8, o);
+      if (idx) {
+        uint2 u;
+        u.x = bi[0] | (bi[1] << 8) | (bi[2] << 16) | (bi[3] << 24);
+        u.y = bi[4] | (bi[5] << 8) | (bi[6] << 16) | (bi[7] << 24);
+        *reinterpret_cast<uint2*>(idx + op * C + cg * 8) = u;
+      }
+    }
+  }
+}
+template <int K, int S, int PAD>
+__global__ void __launch_bounds__(256)
+maxpool_bwd_fixed_kernel(const uint8_t* __restrict__ idx, const __nv_bfloat16* __restrict__ dy, int N, int H, int W,
+                         int C, int Ho, int Wo, int dy_cs, __nv_bfloat16* __restrict__ dx, int dx_cs, int acc) {
+  constexpr int D = (K + S - 1) / S;  // windows that can cover one pixel, per dimension
+  const uint32_t V = (uint32_t)C >> 3;
+  const uint32_t per_row = (uint32_t)W * V;
+  const int rows = N * H;
+  for (int row = blockIdx.x; row < rows; row += gridDim.x) {
+    const int n = row / H, h = row - n * H;
+    const int ho0 = (h + PAD) / S;  // last window row covering h; window ho0 - d sees it at filter row (h+PAD) - (ho0-d)*S
+    for (uint32_t t = threadIdx.x; t < per_row; t += blockDim.x) {
+      const uint32_t wu = t / V, cg = t - wu * V;
+      const int w = (int)wu;
+      const int wo0 = (w + PAD) / S;
+      uint2 iu[D * D];
+      uint4 gu[D * D];
+      uint32_t me[D * D];
+      bool ok[D * D];
+#pragma unroll
+      for (int a = 0; a < D; ++a) {
+#pragma unroll
+        for (int b = 0; b < D; ++b) {
+          const int ho = ho0 - a, wo = wo0 - b;
+          const int r = h + PAD - ho * S, q = w + PAD - wo * S;
+          const int e = a * D + b;
+          ok[e] = ho >= 0 && ho < Ho && wo >= 0 && wo < Wo && r < K && q < K;
+          me[e] = (uint32_t)(r * K + q) * 0x01010101u;
+          const long long op = ((long long)n * Ho + ho) * Wo + wo;
+          iu[e] = ok[e] ? *reinterpret_cast<const uint2*>(idx + op * C + cg * 8) : make_uint2(0u, 0u);
+          gu[e] = ok[e] ? *reinterpret_cast<const uint4*>(dy + op * dy_cs + cg * 8) : make_uint4(0u, 0u, 0u, 0u);
+        }
+      }
+      __nv_bfloat16* o = dx + ((long long)row * W + w) * dx_cs + cg * 8;
+      float s8[8];
+      if (acc) {
+        const F8 old = load_bf16x8(o);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) s8[j] = old.v[j];
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) s8[j] = 0.f;
+      }
+#pragma unroll
+      for (int e = 0; e < D * D; ++e) {
+        if (!ok[e]) continue;
+        const uint32_t m0 = __vcmpeq4(iu[e].x, me[e]), m1 = __vcmpeq4(iu[e].y, me[e]);  // 0xFF where this pixel won
+        const float2 a = unpack_bf16x2(gu[e].x), b = unpack_bf16x2(gu[e].y), c = unpack_bf16x2(gu[e].z),
+                     d = unpack_bf16x2(gu[e].w);
+        const float g[8] = {a.x, a.y, b.x, b.y, c.x, c.y, d.x, d.y};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          if (m0 & (1u << (8 * j))) s8[j] += g[j];
+          if (m1 & (1u << (8 * j))) s8[4 + j] += g[4 + j];
+        }
+      }
+      F8 r8;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) r8.v[j] = s8[j];
+      store_bf16x8(o, r8);
+    }
+  }
+}
 // gather formulation (no atomics): every INPUT pixel sums dy of the windows whose arg-max it is; one block-iteration
 // per input row (n, h)
 __global__ void __launch_bounds__(256)
@@ -896,9 +1018,15 @@ extern "C" int msp_maxpool_fwd(const void* x, int N, int H, int W, int C, int x_
   REQ_C8(C, x_cs, "maxpool_fwd(x)");
   REQ_C8(C, y_cs, "maxpool_fwd(y)");
   MSP_REQUIRE(x && y && k >= 1 && k <= 15 && stride >= 1 && pad >= 0, "maxpool_fwd: bad arguments");
-  maxpool_fwd_kernel<<<resident_grid(maxpool_fwd_kernel, 256, 0, (long long)N * Ho, 1), 256, 0, ST>>>((const __nv_bfloat16*)x, N, H, W, C, x_cs, k,
-                                                           stride, pad, (__nv_bfloat16*)y,
-                                                           (uint8_t*)idx, Ho, Wo, y_cs);
+  if (k == 3 && stride == 2 && pad == 1)
+    maxpool_fwd_fixed_kernel<3, 2, 1><<<resident_grid(maxpool_fwd_fixed_kernel<3, 2, 1>, 256, 0, (long long)N * Ho, 1), 256, 0, ST>>>(
+        (const __nv_bfloat16*)x, N, H, W, C, x_cs, (__nv_bfloat16*)y, (uint8_t*)idx, Ho, Wo, y_cs);
+  else if (k == 2 && stride == 2 && pad == 0)
+    maxpool_fwd_fixed_kernel<2, 2, 0><<<resident_grid(maxpool_fwd_fixed_kernel<2, 2, 0>, 256, 0, (long long)N * Ho, 1), 256, 0, ST>>>(
+        (const __nv_bfloat16*)x, N, H, W, C, x_cs, (__nv_bfloat16*)y, (uint8_t*)idx, Ho, Wo, y_cs);
+  else
+    maxpool_fwd_kernel<<<resident_grid(maxpool_fwd_kernel, 256, 0, (long long)N * Ho, 1), 256, 0, ST>>>(
+        (const __nv_bfloat16*)x, N, H, W, C, x_cs, k, stride, pad, (__nv_bfloat16*)y, (uint8_t*)idx, Ho, Wo, y_cs);
   MSP_CHECK_LAUNCH();
   msp_count_launch(1);
   return MSP_OK;
@@ -909,9 +1037,16 @@ extern "C" int msp_maxpool_bwd(const void* idx, const void* dy, int N, int H, in
   REQ_C8(C, dy_cs, "maxpool_bwd(dy)");
   REQ_C8(C, dx_cs, "maxpool_bwd(dx)");
   MSP_REQUIRE(idx && dy && dx, "maxpool_bwd: null pointer");
-  maxpool_bwd_kernel<<<resident_grid(maxpool_bwd_kernel, 256, 0, (long long)N * H, 1), 256, 0, ST>>>((const uint8_t*)idx, (const __nv_bfloat16*)dy,
-                                                           N, H, W, C, k, stride, pad, Ho, Wo, dy_cs,
-                                                           (__nv_bfloat16*)dx, dx_cs, accumulate);
+  if (k == 3 && stride == 2 && pad == 1)
+    maxpool_bwd_fixed_kernel<3, 2, 1><<<resident_grid(maxpool_bwd_fixed_kernel<3, 2, 1>, 256, 0, (long long)N * H, 1), 256, 0, ST>>>(
+        (const uint8_t*)idx, (const __nv_bfloat16*)dy, N, H, W, C, Ho, Wo, dy_cs, (__nv_bfloat16*)dx, dx_cs, accumulate);
+  else if (k == 2 && stride == 2 && pad == 0)
+    maxpool_bwd_fixed_kernel<2, 2, 0><<<resident_grid(maxpool_bwd_fixed_kernel<2, 2, 0>, 256, 0, (long long)N * H, 1), 256, 0, ST>>>(
+        (const uint8_t*)idx, (const __nv_bfloat16*)dy, N, H, W, C, Ho, Wo, dy_cs, (__nv_bfloat16*)dx, dx_cs, accumulate);
+  else
+    maxpool_bwd_kernel<<<resident_grid(maxpool_bwd_kernel, 256, 0, (long long)N * H, 1), 256, 0, ST>>>(
+        (const uint8_t*)idx, (const __nv_bfloat16*)dy, N, H, W, C, k, stride, pad, Ho, Wo, dy_cs, (__nv_bfloat16*)dx,
+        dx_cs, accumulate);
   MSP_CHECK_LAUNCH();
   msp_count_launch(1);
   return MSP_OK;

@@ -44,3 +44,37 @@ class BatchPrefetcher:
         self._last = k
         self._get ^= 1
         return self.bufs[k]
+
+
+class ScalarReader:
+    """Device -> host read of a per-step scalar (the loss) that does not stall the pipeline.
+
+    The reference reads the loss with a blocking `.item()` inside the step (loss/loss.py:85): the GPU then idles while
+    the host prepares the next step.  Here the value is copied into pinned host memory on the consumer stream and
+    handed out one step later (`depth` steps of slack), when its copy has long finished; `drain()` returns what is
+    still pending.  Every step's value is still read back — only the wait is deferred."""
+
+    def __init__(self, depth: int = 1, dtype=torch.float32):
+        self.depth = depth
+        self.slots = [torch.empty((), dtype=dtype).pin_memory() for _ in range(depth + 1)]
+        self.events = [torch.cuda.Event() for _ in range(depth + 1)]
+        self.pending = []          # slot indices in submission order
+        self._next = 0
+
+    def push(self, value: torch.Tensor):
+        """Enqueue the D2H copy of `value` (0-dim device tensor); returns the oldest value once more than `depth`
+        reads are pending, else None."""
+        k = self._next
+        self._next = (k + 1) % len(self.slots)
+        self.slots[k].copy_(value.detach().reshape(()), non_blocking=True)
+        self.events[k].record()
+        self.pending.append(k)
+        return self._pop() if len(self.pending) > self.depth else None
+
+    def _pop(self) -> float:
+        k = self.pending.pop(0)
+        self.events[k].synchronize()
+        return float(self.slots[k])
+
+    def drain(self):
+        return [self._pop() for _ in range(len(self.pending))]

@@ -342,11 +342,13 @@ def test_bn_zero_fill_strided_shortcut():
     _close(_from_nhwc(dres), exp, 1e-2, "strided shortcut grad")
 
 
-@pytest.mark.parametrize("k,s,p", [(3, 2, 1), (2, 2, 0)])
-def test_maxpool(k, s, p):
+@pytest.mark.parametrize("k,s,p,hw", [(3, 2, 1, (14, 14)), (2, 2, 0, (14, 14)), (3, 2, 1, (15, 13)), (2, 2, 0, (15, 13)),
+                                      (3, 1, 1, (9, 11)), (5, 3, 2, (17, 12))])
+def test_maxpool(k, s, p, hw):
+    """(3,2,1) and (2,2,0) run the fixed-geometry kernels (ResNet stem / U-Net encoder), the rest the generic ones."""
     ops = _ops()
     g = torch.Generator().manual_seed(9)
-    x = _bf(torch.randn((2, 16, 14, 14), generator=g)).requires_grad_(True)
+    x = _bf(torch.randn((2, 16, *hw), generator=g)).requires_grad_(True)
     ref = F.max_pool2d(x, k, s, p)
     dy = _bf(torch.randn(ref.shape, generator=g))
     ref.backward(dy)
