@@ -219,6 +219,8 @@ def main():
     ap.add_argument("--batch", type=int, default=0, help="per-GPU batch (default: the workload's)")
     ap.add_argument("--ref-steps", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--small-allreduce", default="p2p", choices=["p2p", "nccl"],
+                    help="SyncBN statistic exchange (N>1): one-kernel all-reduce over NVLink peer memory, or NCCL")
     ap.add_argument("--no-graph", action="store_true", help="enqueue every step from Python instead of replaying a CUDA graph")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -241,6 +243,10 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
         group = dist.group.WORLD
+        if args.small_allreduce == "p2p":
+            # SyncBN statistics through the peer-memory kernel (csrc/msp_p2p.cu) instead of ~100 tiny NCCL calls / step
+            from medsegpretrainimagenet_b200 import parallel as _par
+            _par.enable_peer_allreduce(group)
     warm = max(args.warmup, 3)
 
     name, batch, shape, _ = WORKLOADS[args.workload]
@@ -408,6 +414,7 @@ def main():
                        "parallelism": f"dp{world}", "params": n_params,
                        "optimizer": type(opt).__name__, "l2": "inputs_larger_than_l2 (batch + activations >> 126 MB)",
                        "step": "fwd+loss+bwd+allreduce+metrics+gradnorm+optimizer",
+                       "syncbn_exchange": None if world == 1 else ("peer-memory kernel" if args.small_allreduce == "p2p" else "nccl"),
                        "execution": "eager launches" if graphed is None else "one CUDA graph replay per step"},
             "e2e": {"value": total_images / (ms_e2e * 1e-3), "unit": "images/sec",
                     "h2d_bytes_per_step": (x_host.numel() * x_host.element_size()

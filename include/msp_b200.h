@@ -290,6 +290,24 @@ int msp_triplet_hinge(const float* dist, int N, const float* margins, int M, flo
  * framework in this round.
  * ------------------------------------------------------------------------------------------ */
 
+/* ------------------------------------------------------------------------------------------
+ * Small-vector all-reduce over NVLink peer memory (csrc/msp_p2p.cu): the SyncBN [2C] sums and the global Dice sums
+ * of a data-parallel step (replaces ~100 tiny NCCL all-reduces per step; the reference's
+ * nn.DataParallel, train_model.py:192-194, has no such exchange).  Set-up, once per process: allocate this rank's
+ * communication buffer (msp_p2p_buffer_bytes), exchange the 64-byte cudaIpc handles through any host channel, map the
+ * peers' buffers.  These four set-up calls are the only ones in the library that allocate or synchronise.
+ * msp_p2p_allreduce_sum_f32: data[0..n) <- sum over ranks, in place, one single-CTA kernel on `stream`, graph
+ * capturable; every rank must issue the same sequence of calls.  `bufs` = host array of `world` device pointers
+ * (entry `rank` = the local buffer), `seq` = one zero-initialised device uint32 owned by this communicator.
+ * ------------------------------------------------------------------------------------------ */
+long long msp_p2p_buffer_bytes(int world, int max_n);
+int msp_p2p_alloc(long long bytes, void** ptr, void* handle64);
+int msp_p2p_open(const void* handle64, void** ptr);
+int msp_p2p_close(void* ptr);
+int msp_p2p_free(void* ptr);
+int msp_p2p_allreduce_sum_f32(float* data, int n, int rank, int world, int max_n, void* const* bufs,
+                              unsigned* seq, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

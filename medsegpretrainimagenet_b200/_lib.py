@@ -83,8 +83,14 @@ SIGNATURES = {
     "msp_topk_hits": [P, P, I, I, LL, I, P, P],
     "msp_rowpair_distances": [P, P, I, LL, I, P, P],
     "msp_triplet_hinge": [P, I, P, I, P, P],
+    "msp_p2p_buffer_bytes": [I, I],
+    "msp_p2p_alloc": [LL, C.POINTER(C.c_void_p), P],
+    "msp_p2p_open": [P, C.POINTER(C.c_void_p)],
+    "msp_p2p_close": [P],
+    "msp_p2p_free": [P],
+    "msp_p2p_allreduce_sum_f32": [P, I, I, I, I, C.POINTER(C.c_void_p), P, P],
 }
-_RESTYPES = {"msp_last_error": C.c_char_p, "msp_launch_count": C.c_longlong}
+_RESTYPES = {"msp_last_error": C.c_char_p, "msp_launch_count": C.c_longlong, "msp_p2p_buffer_bytes": C.c_longlong}
 
 
 class MspError(RuntimeError):

@@ -17,8 +17,8 @@ from . import ops
 
 def _allreduce_sum(t: torch.Tensor, group) -> None:
     """SyncBN / global-Dice exchange: a small NCCL all-reduce, only when a process group is active."""
-    if group is not None and dist.is_initialized() and dist.get_world_size(group) > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+    from .parallel import allreduce_small_sum_
+    allreduce_small_sum_(t, group)
 
 
 # ------------------------------------------------------------------------------------------------

@@ -12,10 +12,13 @@ needed: autograd accumulates into the bucket, NCCL reduces it in place, the opti
 """
 from __future__ import annotations
 
+import ctypes as C
 from typing import List, Optional
 
 import torch
 import torch.distributed as dist
+
+from . import _lib
 
 
 class _Bucket:
@@ -127,3 +130,94 @@ def shard_rows(n_global: int, rank: int, world: int):
     """Rank-local row range [lo, hi) of a global batch (rank r gets rows [r*B, (r+1)*B))."""
     per = n_global // world
     return rank * per, (rank + 1) * per
+
+
+class PeerAllReduce:
+    """In-place sum of small fp32 vectors across the ranks of one node with ONE kernel over NVLink peer memory
+    (csrc/msp_p2p.cu) instead of a NCCL call: SyncBN statistics and global Dice sums.
+
+        par = PeerAllReduce(group)          # collective: every rank of `group`, once
+        par.allreduce_sum_(stats)           # fp32, contiguous, numel <= max_floats; current stream; graph capturable
+
+    Set-up allocates this rank's communication buffer with cudaMalloc, exchanges the cudaIpc handles with
+    `all_gather_object` and maps every peer's buffer.  Every rank must issue the same sequence of calls."""
+
+    def __init__(self, group=None, max_floats: int = 8192, device=None):
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.max_floats = int(max_floats)
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        nbytes = int(_lib.lib.msp_p2p_buffer_bytes(self.world, self.max_floats))
+        if nbytes <= 0:
+            raise ValueError(f"PeerAllReduce: unsupported world size {self.world}")
+        with torch.cuda.device(self.device):
+            local = C.c_void_p()
+            handle = C.create_string_buffer(64)
+            _lib.call("msp_p2p_alloc", nbytes, C.byref(local), handle)
+            self._local = local.value
+            handles = [None] * self.world
+            if self.world > 1:
+                dist.all_gather_object(handles, bytes(handle.raw), group=group)
+            self._ptrs = (C.c_void_p * self.world)()
+            self._opened = []
+            for r in range(self.world):
+                if r == self.rank:
+                    self._ptrs[r] = self._local
+                else:
+                    peer = C.c_void_p()
+                    _lib.call("msp_p2p_open", C.create_string_buffer(handles[r], 64), C.byref(peer))
+                    self._ptrs[r] = peer.value
+                    self._opened.append(peer.value)
+            self.seq = torch.zeros(1, dtype=torch.int32, device=self.device)
+            torch.cuda.synchronize()
+        if self.world > 1:
+            dist.barrier(group=group)       # every buffer is mapped everywhere before the first exchange
+
+    def allreduce_sum_(self, t: torch.Tensor) -> torch.Tensor:
+        if t.dtype != torch.float32 or not t.is_contiguous() or t.numel() > self.max_floats or t.numel() == 0:
+            raise ValueError("PeerAllReduce: needs a non-empty contiguous fp32 tensor of at most "
+                             f"{self.max_floats} elements (got {t.dtype}, {t.numel()})")
+        _lib.call("msp_p2p_allreduce_sum_f32", t.data_ptr(), t.numel(), self.rank, self.world, self.max_floats,
+                  self._ptrs, self.seq.data_ptr(), torch.cuda.current_stream(self.device).cuda_stream)
+        return t
+
+    def close(self) -> None:
+        torch.cuda.synchronize()
+        for p in self._opened:
+            _lib.call("msp_p2p_close", p)
+        self._opened = []
+        if self._local:
+            _lib.call("msp_p2p_free", self._local)
+            self._local = None
+
+
+_PEER = {}          # process group (None = default) -> PeerAllReduce
+
+
+def enable_peer_allreduce(group=None, max_floats: int = 8192) -> PeerAllReduce:
+    """Route the small exchanges of `group` (SyncBN sums, Dice sums) through the peer-memory kernel.  Collective."""
+    key = group if group is not None else "default"
+    if key not in _PEER:
+        _PEER[key] = PeerAllReduce(group, max_floats)
+    return _PEER[key]
+
+
+def peer_allreduce_for(group) -> Optional[PeerAllReduce]:
+    if not _PEER:
+        return None
+    par = _PEER.get(group if group is not None else "default")
+    if par is None and group is not None and dist.is_initialized() and group is dist.group.WORLD:
+        par = _PEER.get("default")
+    return par
+
+
+def allreduce_small_sum_(t: torch.Tensor, group) -> None:
+    """Sum `t` over the ranks of `group` in place: peer-memory kernel when enabled and applicable, NCCL/gloo otherwise."""
+    if group is None or not dist.is_initialized() or dist.get_world_size(group) <= 1:
+        return
+    par = peer_allreduce_for(group)
+    if par is not None and t.is_cuda and t.dtype == torch.float32 and t.is_contiguous() and 0 < t.numel() <= par.max_floats:
+        par.allreduce_sum_(t)
+    else:
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
