@@ -39,6 +39,34 @@ void msp_set_error(const char* fmt, ...);
     }                                                                                     \
   } while (0)
 
+// Programmatic dependent launch (PDL): a kernel launched through msp_launch_pdl may START while its predecessor in
+// the stream is still draining (its CTAs are scheduled as SMs free up, barrier init / TMEM allocation / descriptor
+// prefetch run early) and MUST call pdl_wait() before it touches global memory; pdl_trigger() at its top lets ITS
+// successor do the same.  Off unless MSP_PDL=1 (the device calls are then no-ops): replayed from the step's CUDA graph
+// the kernel-to-kernel gap is already ~1 us and the attribute measured no gain (profiles/r01_experiments.txt).
+bool msp_pdl_enabled();
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+template <typename... KArgs, typename... Args>
+inline cudaError_t msp_launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                                  Args... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute at;
+  memset(&at, 0, sizeof(at));
+  at.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at.val.programmaticStreamSerializationAllowed = msp_pdl_enabled() ? 1 : 0;
+  cfg.attrs = &at;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+#endif
+
 static inline int msp_cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
 
 int msp_num_sms();

@@ -372,6 +372,7 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                const TapGemmParams p) {
   using Cfg = TapGemmCfg<BN_>;
   extern __shared__ uint8_t smem_raw[];
+  pdl_trigger();
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~uintptr_t(1023));
   uint8_t* staging = smem + Cfg::kStages * Cfg::kStageBytes;
@@ -410,6 +411,7 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_s;
+  pdl_wait();  // everything above (barriers, TMEM, descriptors) may overlap the previous kernel's tail
 
   if (warp == 0) {
     // ---------------- TMA producer ----------------
@@ -530,6 +532,7 @@ tapgemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   using Cfg = TapGemmCfg<BN_>;
   using Cfg2 = TapGemm2Cfg<BN_>;
   extern __shared__ uint8_t smem_raw[];
+  pdl_trigger();
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~uintptr_t(1023));
   uint8_t* staging = smem + Cfg2::kStages * Cfg2::kStageBytes;
@@ -565,6 +568,7 @@ tapgemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_s;
+  pdl_wait();  // everything above (barriers, TMEM, descriptors) may overlap the previous kernel's tail
 
   if (warp == 0) {
     if (elect_one()) {  // elect.sync, not lane==0: ptxas then emits bare UTCHMMA / UTMALDG (no per-lane loop)
@@ -671,6 +675,7 @@ tapgemm_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                     const TapGemmParams p) {
   using Cfg = TapGemmCfg<BN_>;
   extern __shared__ uint8_t smem_raw[];
+  pdl_trigger();
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~uintptr_t(1023));
   uint8_t* a_ring = smem;
@@ -715,6 +720,7 @@ tapgemm_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_s;
+  pdl_wait();  // everything above (barriers, TMEM, descriptors) may overlap the previous kernel's tail
 
   if (warp == 0) {
     if (elect_one()) {  // elect.sync, not lane==0: ptxas then emits bare UTCHMMA / UTMALDG (no per-lane loop)
@@ -862,6 +868,7 @@ __global__ void __launch_bounds__(kConvThreads, 1)
 wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant__ CUtensorMap tmX,
              const WgradParams p) {
   extern __shared__ uint8_t smem_raw[];
+  pdl_trigger();
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~uintptr_t(1023));
   __shared__ uint64_t full_bar[kWgStages];
@@ -900,6 +907,7 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant__ C
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_s;
+  pdl_wait();  // everything above (barriers, TMEM, descriptors) may overlap the previous kernel's tail
 
   if (warp == 0) {
     if (elect_one()) {  // elect.sync, not lane==0: ptxas then emits bare UTCHMMA / UTMALDG (no per-lane loop)
@@ -1015,6 +1023,8 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant__ C
 // ------------------------------------------------------------------------------------------------
 __global__ void pack_w_fprop_kernel(const float* __restrict__ w, int K, int C, int taps, int Cpad,
                                     __nv_bfloat16* __restrict__ out) {
+  pdl_trigger();
+  pdl_wait();
   const long long total = (long long)K * taps * Cpad;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
@@ -1028,6 +1038,8 @@ __global__ void pack_w_fprop_kernel(const float* __restrict__ w, int K, int C, i
 }
 __global__ void pack_w_dgrad_kernel(const float* __restrict__ w, int K, int C, int taps, int Cpad,
                                     int Kpad, __nv_bfloat16* __restrict__ out) {
+  pdl_trigger();
+  pdl_wait();
   const long long total = (long long)Cpad * taps * Kpad;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
@@ -1042,6 +1054,8 @@ __global__ void pack_w_dgrad_kernel(const float* __restrict__ w, int K, int C, i
 // both packings in one launch (one per convolution per step)
 __global__ void pack_w_both_kernel(const float* __restrict__ w, int K, int C, int taps, int Cpad, int Kpad,
                                    __nv_bfloat16* __restrict__ wf, __nv_bfloat16* __restrict__ wd) {
+  pdl_trigger();
+  pdl_wait();
   const long long nf = (long long)K * taps * Cpad, nd = (long long)Cpad * taps * Kpad;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nf + nd;
        i += (long long)gridDim.x * blockDim.x) {
@@ -1079,6 +1093,8 @@ __global__ void pack_w_rowwin_kernel(const float* __restrict__ w, int K, int C, 
 // sum of `splits` packed partials [K][taps][Cpad] -> OIHW fp32
 __global__ void unpack_wgrad_kernel(const float* __restrict__ dwp, int splits, long long split_stride,
                                     int K, int C, int taps, int Cpad, float* __restrict__ out) {
+  pdl_trigger();
+  pdl_wait();
   const long long total = (long long)K * C * taps;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
@@ -1173,7 +1189,7 @@ int launch_tapgemm(const CUtensorMap& tmA, const CUtensorMap& tmB, TapGemmParams
   p.total_tiles = (int)total;
   const int sms = msp_num_sms();
   const int grid = p.total_tiles < sms ? p.total_tiles : sms;
-  tapgemm_kernel<BN_><<<grid, kTapThreads, Cfg::kSmemBytes, st>>>(tmA, tmB, p);
+  MSP_CHECK_CUDA(msp_launch_pdl(tapgemm_kernel<BN_>, dim3(grid), dim3(kTapThreads), Cfg::kSmemBytes, st, tmA, tmB, p));
   MSP_CHECK_LAUNCH();
   msp_count_launch(1);
   return MSP_OK;
@@ -1340,7 +1356,7 @@ int launch_halo(const CUtensorMap& tmA, const CUtensorMap& tmB, TapGemmParams& p
   p.total_tiles = (int)total;
   const int sms = msp_num_sms();
   const int grid = p.total_tiles < sms ? p.total_tiles : sms;
-  tapgemm_halo_kernel<BN_><<<grid, kTapThreads, smem, st>>>(tmA, tmB, p);
+  MSP_CHECK_CUDA(msp_launch_pdl(tapgemm_halo_kernel<BN_>, dim3(grid), dim3(kTapThreads), (size_t)smem, st, tmA, tmB, p));
   MSP_CHECK_LAUNCH();
   msp_count_launch(1);
   return MSP_OK;
@@ -1432,8 +1448,8 @@ extern "C" int msp_pack_weights(const float* w, int K, int C, int KH, int KW, in
   if (w_fprop && w_dgrad) {
     const long long total = (long long)K * taps * Cpad + (long long)Cpad * taps * Kpad;
     const int blocks = (int)((total + 255) / 256 < 4096 ? (total + 255) / 256 : 4096);
-    pack_w_both_kernel<<<blocks, 256, 0, st>>>(w, K, C, taps, Cpad, Kpad, (__nv_bfloat16*)w_fprop,
-                                               (__nv_bfloat16*)w_dgrad);
+    MSP_CHECK_CUDA(msp_launch_pdl(pack_w_both_kernel, dim3(blocks), dim3(256), 0, st, w, K, C, taps, Cpad, Kpad, (__nv_bfloat16*)w_fprop,
+                                               (__nv_bfloat16*)w_dgrad));
     MSP_CHECK_LAUNCH();
     msp_count_launch(1);
     return MSP_OK;
@@ -1716,7 +1732,7 @@ extern "C" int msp_conv_wgrad(const msp_conv_desc* d, const void* x, const void*
   p.split_stride = (long long)d->K * pl.ntaps * pl.Cw;
   p.dw = dw_partials;
   dim3 grid(pl.gx, pl.gy, pl.splits);
-  wgrad_kernel<<<grid, kConvThreads, kWgSmemBytes, st>>>(tmDY, tmX, p);
+  MSP_CHECK_CUDA(msp_launch_pdl(wgrad_kernel, dim3(grid), dim3(kConvThreads), (size_t)kWgSmemBytes, st, tmDY, tmX, p));
   MSP_CHECK_LAUNCH();
   msp_count_launch(1);
   return MSP_OK;
@@ -1737,8 +1753,8 @@ extern "C" int msp_unpack_wgrad(const msp_conv_desc* d, const float* dw_partials
     unpack_wgrad_rowwin_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(
         dw_partials, pl.splits, split_stride, d->K, C_true, d->KH, d->KW, d->C, dw_oihw);
   else
-    unpack_wgrad_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(
-        dw_partials, pl.splits, split_stride, d->K, C_true, d->KH * d->KW, d->C, dw_oihw);
+    MSP_CHECK_CUDA(msp_launch_pdl(unpack_wgrad_kernel, dim3(blocks), dim3(256), 0, (cudaStream_t)stream, dw_partials,
+                                  pl.splits, split_stride, d->K, C_true, d->KH * d->KW, d->C, dw_oihw));
   MSP_CHECK_LAUNCH();
   msp_count_launch(1);
   return MSP_OK;

@@ -142,6 +142,8 @@ __global__ void nhwc_to_nchw_kernel(const __nv_bfloat16* __restrict__ x, int C, 
 // ---------------------------------------------------------------------------------------------
 __global__ void bn_finalize_kernel(float* s1, float* s2, int C, double count, float eps, float momentum,
                                    float* mean, float* invstd, float* rmean, float* rvar, int reset) {
+  pdl_trigger();
+  pdl_wait();
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
   const double m = (double)s1[c] / count;
@@ -204,6 +206,8 @@ bn_act_fwd_kernel(const msp_bn_act_desc d, const __nv_bfloat16* __restrict__ x,
                   const float* __restrict__ gamma, const float* __restrict__ beta,
                   const float* __restrict__ sscale, const __nv_bfloat16* __restrict__ res,
                   __nv_bfloat16* __restrict__ y) {
+  pdl_trigger();
+  pdl_wait();
   const int V = d.C >> 3;
   const int cg = threadIdx.x % V, pl = threadIdx.x / V, ppb = blockDim.x / V;
   const int c = cg * 8;
@@ -264,6 +268,8 @@ bn_act_bwd_reduce_kernel(const msp_bn_act_desc d, const __nv_bfloat16* __restric
                          const float* __restrict__ mean, const float* __restrict__ invstd,
                          const float* __restrict__ sscale, float* sum_g, float* sum_gx,
                          const float* __restrict__ gamma, const float* __restrict__ beta) {
+  pdl_trigger();
+  pdl_wait();
   extern __shared__ float red[];
   const int V = d.C >> 3;
   const int cg = threadIdx.x % V, pl = threadIdx.x / V, ppb = blockDim.x / V;
@@ -344,6 +350,8 @@ bn_act_bwd_apply_kernel(const msp_bn_act_desc d, const __nv_bfloat16* __restrict
                         const float* __restrict__ sum_g, const float* __restrict__ sum_gx, float inv_count,
                         __nv_bfloat16* __restrict__ dx, __nv_bfloat16* dres, int dres_acc,
                         const float* __restrict__ beta) {
+  pdl_trigger();
+  pdl_wait();
   const int V = d.C >> 3;
   const int cg = threadIdx.x % V, pl = threadIdx.x / V, ppb = blockDim.x / V;
   const int c = cg * 8;
@@ -911,8 +919,8 @@ extern "C" int msp_bn_finalize(float* ch_sum, float* ch_sqsum, int C, double cou
   MSP_REQUIRE(ch_sum && ch_sqsum && mean && invstd && C > 0 && count > 0, "bn_finalize: bad arguments");
   MSP_REQUIRE((running_mean == nullptr) == (running_var == nullptr),
               "bn_finalize: need both running buffers or none");
-  bn_finalize_kernel<<<(C + 127) / 128, 128, 0, ST>>>(ch_sum, ch_sqsum, C, count, eps, momentum, mean,
-                                                      invstd, running_mean, running_var, reset_sums);
+  MSP_CHECK_CUDA(msp_launch_pdl(bn_finalize_kernel, dim3((C + 127) / 128), dim3(128), 0, ST, ch_sum, ch_sqsum, C, count,
+                                eps, momentum, mean, invstd, running_mean, running_var, reset_sums));
   MSP_CHECK_LAUNCH();
   msp_count_launch(1);
   return MSP_OK;
@@ -948,9 +956,9 @@ extern "C" int msp_bn_act_fwd(const msp_bn_act_desc* d, const void* x, const flo
   const int V = d->C / 8, T = threads_for_vecs(V), ppb = T / V;
   const long long P = (long long)d->N * d->H * d->W;
   MSP_REQUIRE(P < (1ll << 31), "bn_act: too many pixels");
-  bn_act_fwd_kernel<4><<<resident_grid(bn_act_fwd_kernel<4>, T, 0, P, ppb * 4), T, 0, ST>>>(
-      *d, (const __nv_bfloat16*)x, mean, invstd, gamma, beta, sample_scale,
-      (const __nv_bfloat16*)residual, (__nv_bfloat16*)y);
+  MSP_CHECK_CUDA(msp_launch_pdl(bn_act_fwd_kernel<4>, dim3(resident_grid(bn_act_fwd_kernel<4>, T, 0, P, ppb * 4)), dim3(T), 0,
+                                ST, *d, (const __nv_bfloat16*)x, mean, invstd, gamma, beta, sample_scale,
+                                (const __nv_bfloat16*)residual, (__nv_bfloat16*)y));
   MSP_CHECK_LAUNCH();
   msp_count_launch(1);
   return MSP_OK;
@@ -1004,10 +1012,10 @@ extern "C" int msp_bn_act_bwd_apply(const msp_bn_act_desc* d, const void* x, con
   const int V = d->C / 8, T = threads_for_vecs(V), ppb = T / V;
   const long long P = (long long)d->N * d->H * d->W;
   MSP_REQUIRE(P < (1ll << 31), "bn_act: too many pixels");
-  bn_act_bwd_apply_kernel<2><<<resident_grid(bn_act_bwd_apply_kernel<2>, T, 0, P, ppb * 2), T, 0, ST>>>(
-      *d, (const __nv_bfloat16*)x, (const __nv_bfloat16*)y, (const __nv_bfloat16*)dy, mean, invstd,
-      gamma, sample_scale, sum_g, sum_gx, (float)(1.0 / count), (__nv_bfloat16*)dx,
-      (__nv_bfloat16*)dres, dres_accumulate, beta);
+  MSP_CHECK_CUDA(msp_launch_pdl(bn_act_bwd_apply_kernel<2>, dim3(resident_grid(bn_act_bwd_apply_kernel<2>, T, 0, P, ppb * 2)),
+                                dim3(T), 0, ST, *d, (const __nv_bfloat16*)x, (const __nv_bfloat16*)y,
+                                (const __nv_bfloat16*)dy, mean, invstd, gamma, sample_scale, sum_g, sum_gx,
+                                (float)(1.0 / count), (__nv_bfloat16*)dx, (__nv_bfloat16*)dres, dres_accumulate, beta));
   MSP_CHECK_LAUNCH();
   msp_count_launch(1);
   return MSP_OK;

@@ -57,23 +57,27 @@ p2p_allreduce_kernel(float* __restrict__ data, int n, int rank, int world, int m
   //    of hanging the GPU)
   const uint2* mine = reinterpret_cast<const uint2*>(tbl.buf[rank]) + slot_off;
   for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    uint2 w[kP2PMaxWorld];
+#pragma unroll
+    for (int r = 0; r < kP2PMaxWorld; ++r)  // all peers' words in flight at once, then re-poll only the late ones
+      if (r < world && r != rank) w[r] = ld_word(mine + (size_t)r * max_n + i);
     float s = 0.f;
-    for (int r = 0; r < world; ++r) {
+#pragma unroll
+    for (int r = 0; r < kP2PMaxWorld; ++r) {
+      if (r >= world) continue;
       if (r == rank) {
         s += data[i];
         continue;
       }
-      const uint2* src = mine + (size_t)r * max_n + i;
-      uint2 w = ld_word(src);
       unsigned long long spins = 0;
-      while (w.y != seq) {
+      while (w[r].y != seq) {
         if (++spins > (1ull << 30)) {
           printf("msp p2p all-reduce: rank %d timed out waiting for rank %d (exchange %u, element %d)\n", rank, r, seq, i);
           __trap();
         }
-        w = ld_word(src);
+        w[r] = ld_word(mine + (size_t)r * max_n + i);
       }
-      s += __uint_as_float(w.x);
+      s += __uint_as_float(w[r].x);
     }
     data[i] = s;
   }

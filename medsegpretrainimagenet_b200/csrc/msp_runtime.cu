@@ -3,6 +3,7 @@
 #include "../../include/msp_b200.h"
 #include <atomic>
 #include <stdarg.h>
+#include <stdlib.h>
 
 namespace {
 thread_local char g_err[1024] = "";
@@ -20,6 +21,15 @@ void msp_count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed
 extern "C" const char* msp_last_error(void) { return g_err; }
 extern "C" int msp_version(void) { return MSP_ABI_VERSION; }
 extern "C" long long msp_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+bool msp_pdl_enabled() {
+  static int on = -1;
+  if (on < 0) {
+    const char* e = getenv("MSP_PDL");
+    on = (e && e[0] == '1') ? 1 : 0;  // opt-in: inside the step's CUDA graph it measured no gain (22.67 vs 22.43 ms / step)
+  }
+  return on != 0;
+}
 
 int msp_num_sms() {
   static int sms = 0;

@@ -1,11 +1,13 @@
 """One launch (after one warm-up launch) of every kernel family of the hot path at a BASELINE-config shape, for
 `ncu --set full` (GPU box):
 
-    ncu --set full --clock-control none --import-source on -k regex:'tapgemm|wgrad_kernel|bn_act|maxpool|dice|confusion|softmax_ce|final_conv|rowpair|bce|topk' \
-        -o gpurun_out/prof_kernels -f python tools/ncu_kernels.py
-    python tools/summarize_ncu.py gpurun_out/prof_kernels.ncu-rep > profiles/r01_ncu_kernels.txt
+    MSP_NCU_ONCE=1 ncu --section SpeedOfLight --section MemoryWorkloadAnalysis --section LaunchStats --section Occupancy \
+        --clock-control none -k regex:'tapgemm|wgrad_kernel|bn_act|maxpool|dice|confusion|softmax_ce|final_conv|rowpair|bce' \
+        -o /tmp/prof_kernels -f python tools/ncu_kernels.py
+    python tools/summarize_ncu.py /tmp/prof_kernels.ncu-rep > gpurun_out/ncu_kernels_summary.txt
 
-Every family is launched twice; the summary keeps the second launch of each kernel name + shape."""
+(`--set full` over all ~30 launches takes 9 GPU-minutes and a 100 MB report; the full-set captures of the dominant
+kernel are taken separately, one launch at a time.)"""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -17,7 +19,7 @@ B = int(os.environ.get("MSP_NCU_BATCH", "256"))
 
 
 def twice(fn):
-    for _ in range(2):
+    for _ in range(1 if os.environ.get("MSP_NCU_ONCE") == "1" else 2):   # ncu replays every launch itself
         fn()
     torch.cuda.synchronize()
 
