@@ -65,6 +65,66 @@ __global__ void confusion_binary_kernel(const float* __restrict__ pred, const TT
   }
 }
 
+// 4 elements per thread and iteration (16-byte loads); see confusion_binary_kernel for the semantics.  HW % 4 == 0 and
+// 16-byte aligned planes (the launcher checks and otherwise keeps the scalar kernel).
+template <typename TT>
+__global__ void __launch_bounds__(256)
+confusion_binary_vec4_kernel(const float* __restrict__ pred, const TT* __restrict__ target, int C, long long HW4,
+                             float thr, int per_channel, unsigned long long* __restrict__ out) {
+  const long long row = blockIdx.y;
+  const float4* p = reinterpret_cast<const float4*>(pred + row * HW4 * 4);
+  const TT* t = target + row * HW4 * 4;
+  unsigned tp = 0, tn = 0, fp = 0, fn = 0, nan = 0;
+#pragma unroll 2
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < HW4; i += (long long)gridDim.x * blockDim.x) {
+    const float4 pq = ld_nc_f4(p + i);
+    bool yp[4];
+    if constexpr (sizeof(TT) == 4) {
+      const float4 tq = ld_nc_f4(reinterpret_cast<const float4*>(t) + i);
+      const float tv[4] = {tq.x, tq.y, tq.z, tq.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        yp[e] = tv[e] == 1.f;
+        nan += (tv[e] != tv[e]);
+      }
+    } else {
+      const longlong2 a = reinterpret_cast<const longlong2*>(t)[2 * i], b = reinterpret_cast<const longlong2*>(t)[2 * i + 1];
+      yp[0] = a.x == 1; yp[1] = a.y == 1; yp[2] = b.x == 1; yp[3] = b.y == 1;
+    }
+    const float pv[4] = {pq.x, pq.y, pq.z, pq.w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const bool hp = pv[e] >= thr;  // NaN prediction -> negative, like torch
+      tp += (yp[e] && hp);
+      tn += (!yp[e] && !hp);
+      fp += (!yp[e] && hp);
+      fn += (yp[e] && !hp);
+    }
+  }
+  __shared__ unsigned red[5][8];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  tp = warp_sum_u32(tp); tn = warp_sum_u32(tn); fp = warp_sum_u32(fp); fn = warp_sum_u32(fn);
+  nan = warp_sum_u32(nan);
+  if (lane == 0) {
+    red[0][warp] = tp; red[1][warp] = tn; red[2][warp] = fp; red[3][warp] = fn; red[4][warp] = nan;
+  }
+  __syncthreads();
+  if (threadIdx.x < 5) {
+    unsigned long long a = 0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) a += red[threadIdx.x][w];
+    unsigned long long* o = out + (per_channel ? (row % C) * 6 : 0);
+    if (a) {
+      if (threadIdx.x < 4) atomicAdd(o + threadIdx.x, a);
+      else atomicAdd(o + 5, a);
+    }
+    if (threadIdx.x == 0) {
+      unsigned long long pos = 0;  // positives = TP + FN
+      for (int w = 0; w < (int)(blockDim.x >> 5); ++w) pos += (unsigned long long)red[0][w] + red[3][w];
+      if (pos) atomicAdd(o + 4, pos);
+    }
+  }
+}
+
 // argmax over the class dimension with torch semantics: first maximal index; a NaN is maximal
 // (first NaN wins).
 __device__ __forceinline__ void argmax_step(float v, int c, float& best, int& bi) {
@@ -105,6 +165,48 @@ __global__ void confusion_multiclass_pix_kernel(const float* __restrict__ pred,
       if (use_smem) atomicAdd(&hist[(int)t * C + bi], 1u);
       else atomicAdd(cm + t * C + bi, 1ull);
     }
+  }
+  if (use_smem) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < C * C; i += blockDim.x)
+      if (hist[i]) atomicAdd(cm + i, (unsigned long long)hist[i]);
+  }
+}
+
+// 4 pixels per thread and iteration for int64 label maps (HW % 4 == 0, 16-byte aligned planes): 16-byte loads of every
+// class plane, the shared-memory histogram as above.
+__global__ void __launch_bounds__(256)
+confusion_multiclass_pix4_kernel(const float* __restrict__ pred, const long long* __restrict__ target, int C,
+                                 long long HW4, long long P4, unsigned long long* __restrict__ cm) {
+  __shared__ unsigned hist[kCmSmemC * kCmSmemC];
+  const bool use_smem = C <= kCmSmemC;
+  if (use_smem) {
+    for (int i = threadIdx.x; i < C * C; i += blockDim.x) hist[i] = 0;
+    __syncthreads();
+  }
+#pragma unroll 2
+  for (long long g = blockIdx.x * (long long)blockDim.x + threadIdx.x; g < P4; g += (long long)gridDim.x * blockDim.x) {
+    const long long n = g / HW4, hw4 = g - n * HW4;
+    const float4* pp = reinterpret_cast<const float4*>(pred) + n * C * HW4 + hw4;
+    const longlong2 ta = reinterpret_cast<const longlong2*>(target)[2 * g], tb = reinterpret_cast<const longlong2*>(target)[2 * g + 1];
+    const float4 p0 = ld_nc_f4(pp);
+    float best[4] = {p0.x, p0.y, p0.z, p0.w};
+    int bi[4] = {0, 0, 0, 0};
+#pragma unroll 4
+    for (int c = 1; c < C; ++c) {
+      const float4 q = ld_nc_f4(pp + (long long)c * HW4);
+      argmax_step(q.x, c, best[0], bi[0]);
+      argmax_step(q.y, c, best[1], bi[1]);
+      argmax_step(q.z, c, best[2], bi[2]);
+      argmax_step(q.w, c, best[3], bi[3]);
+    }
+    const long long t[4] = {ta.x, ta.y, tb.x, tb.y};
+#pragma unroll
+    for (int e = 0; e < 4; ++e)
+      if (t[e] >= 0 && t[e] < C) {  // sklearn ignores labels outside `labels`
+        if (use_smem) atomicAdd(&hist[(int)t[e] * C + bi[e]], 1u);
+        else atomicAdd(cm + t[e] * C + bi[e], 1ull);
+      }
   }
   if (use_smem) {
     __syncthreads();
@@ -211,7 +313,20 @@ extern "C" int msp_confusion_binary(const float* pred, const void* target, int t
   if (chunks > cap) chunks = cap;
   if (chunks < 1) chunks = 1;
   dim3 grid((unsigned)chunks, (unsigned)rows);
-  if (target_is_float)
+  const bool vec = HW % 4 == 0 && ((reinterpret_cast<uintptr_t>(pred) | reinterpret_cast<uintptr_t>(target)) & 15) == 0;
+  if (vec) {
+    // one 16-byte group per thread and iteration, ~4 blocks per SM over all rows
+    long long vb = ((long long)msp_num_sms() * 4 + rows - 1) / rows, need = (HW / 4 + 255) / 256;
+    if (vb > need) vb = need;
+    if (vb < 1) vb = 1;
+    dim3 vgrid((unsigned)vb, (unsigned)rows);
+    if (target_is_float)
+      confusion_binary_vec4_kernel<float><<<vgrid, 256, 0, ST>>>(pred, (const float*)target, C, HW / 4, thr, per_channel,
+                                                                 (unsigned long long*)out);
+    else
+      confusion_binary_vec4_kernel<long long><<<vgrid, 256, 0, ST>>>(pred, (const long long*)target, C, HW / 4, thr,
+                                                                     per_channel, (unsigned long long*)out);
+  } else if (target_is_float)
     confusion_binary_kernel<float><<<grid, 256, 0, ST>>>(pred, (const float*)target, C, HW, thr,
                                                          per_channel, (unsigned long long*)out);
   else
@@ -233,6 +348,12 @@ extern "C" int msp_confusion_multiclass(const float* pred, const void* target, i
     const long long threads = P * 32;
     confusion_multiclass_row_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, ST>>>(
         pred, target, target_is_onehot, C, P, (unsigned long long*)cm);
+  } else if (!target_is_onehot && HW % 4 == 0 &&
+             ((reinterpret_cast<uintptr_t>(pred) | reinterpret_cast<uintptr_t>(target)) & 15) == 0) {
+    long long blocks = (P / 4 + 255) / 256;
+    if (blocks > (long long)msp_num_sms() * 4) blocks = (long long)msp_num_sms() * 4;
+    confusion_multiclass_pix4_kernel<<<(unsigned)blocks, 256, 0, ST>>>(pred, (const long long*)target, C, HW / 4, P / 4,
+                                                                       (unsigned long long*)cm);
   } else {
     long long blocks = (P + 255) / 256;
     if (blocks > (long long)msp_num_sms() * 8) blocks = (long long)msp_num_sms() * 8;

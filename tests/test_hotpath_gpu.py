@@ -304,12 +304,13 @@ def test_eval_mode_and_skip_values():
 @pytest.mark.parametrize("c,act", [(1, "sigmoid"), (4, "softmax"), (5, "sigmoid")])
 @pytest.mark.parametrize("batchwise", [True, False])
 @pytest.mark.parametrize("bg", [True, False])
-def test_dice_loss(c, act, batchwise, bg):
+@pytest.mark.parametrize("hw", [(40, 36), (19, 17)])          # 16-byte vectorised kernels / scalar kernels (odd planes)
+def test_dice_loss(c, act, batchwise, bg, hw):
     b = _b200()
     g = torch.Generator().manual_seed(10 + c)
-    logits = torch.randn((3, c, 40, 36), generator=g)
+    logits = torch.randn((3, c, *hw), generator=g)
     p = (torch.sigmoid(logits) if act == "sigmoid" else torch.softmax(logits, 1)).requires_grad_(True)
-    mask = torch.randint(0, max(c, 2), (3, 1, 40, 36), generator=g)
+    mask = torch.randint(0, max(c, 2), (3, 1, *hw), generator=g)
     l_ref = ref_losses.dice_loss(p, mask, batchwise=batchwise, include_background=bg) / 4.0
     l_ref.backward()
     pd = p.detach().to(DEV).requires_grad_(True)
@@ -350,17 +351,18 @@ def test_ce_and_bce_losses():
         nan_ref = torch.isnan(p4.grad)
         assert nan_ref.sum() == 1 and torch.equal(torch.isnan(pd.grad.cpu()), nan_ref)
         assert _rel(pd.grad.cpu().nan_to_num(), p4.grad.nan_to_num()) <= 1e-4
-    pr = torch.sigmoid(torch.randn((2, 5, 33, 31), generator=g)).requires_grad_(True)
-    t = (torch.rand((2, 5, 33, 31), generator=g) < 0.05).float()
-    for torch_sem, fn in ((False, ref_losses.bce_loss_plain), (True, ref_losses.bce_loss_torch)):
-        pr.grad = None
-        l_ref = fn(pr, t)
-        l_ref.backward()
-        pd = pr.detach().to(DEV).requires_grad_(True)
-        l = b.losses.BCELoss(torch_semantics=torch_sem)(pd, t.to(DEV))
-        l.backward()
-        assert abs(l.item() - l_ref.item()) <= 1e-5 * abs(l_ref.item())
-        assert _rel(pd.grad.cpu(), pr.grad) <= 1e-4
+    for shp in ((2, 5, 33, 31), (2, 5, 32, 48)):              # scalar kernel (odd element count) / 16-byte vectorised kernel
+        pr = torch.sigmoid(torch.randn(shp, generator=g)).requires_grad_(True)
+        t = (torch.rand(shp, generator=g) < 0.05).float()
+        for torch_sem, fn in ((False, ref_losses.bce_loss_plain), (True, ref_losses.bce_loss_torch)):
+            pr.grad = None
+            l_ref = fn(pr, t)
+            l_ref.backward()
+            pd = pr.detach().to(DEV).requires_grad_(True)
+            l = b.losses.BCELoss(torch_semantics=torch_sem)(pd, t.to(DEV))
+            l.backward()
+            assert abs(l.item() - l_ref.item()) <= 1e-5 * abs(l_ref.item())
+            assert _rel(pd.grad.cpu(), pr.grad) <= 1e-4
 
 
 # ------------------------------------------------------------------------------------------------
@@ -392,7 +394,7 @@ def test_confusion_binary_empty_input():
     assert all(int(v) == 0 for v in got.values())
 
 
-@pytest.mark.parametrize("n,c,hw", [(2, 4, (24, 20)), (3, 2, (5, 7)), (64, 1000, ()), (2, 20, (9, 9))])
+@pytest.mark.parametrize("n,c,hw", [(2, 4, (24, 20)), (3, 2, (5, 7)), (64, 1000, ()), (2, 20, (9, 9)), (2, 20, (8, 8))])
 def test_confusion_multiclass_and_topk_bit_exact(n, c, hw):
     b = _b200()
     g = torch.Generator().manual_seed(31)

@@ -10,6 +10,7 @@ METRICS = [
     "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
     "TPC.TriageCompute.sm__pipe_tensor_cycles_active_realtime.avg.pct_of_peak_sustained_elapsed",
     "sm__mem_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed",
+    "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed", "dram__bytes.sum.per_second",
     "sm__inst_executed_pipe_tensor.sum", "lts__t_bytes.sum", "sm__warps_active.avg.pct_of_peak_sustained_active",
     "launch__registers_per_thread", "launch__grid_size", "launch__block_size", "launch__shared_mem_per_block_dynamic",
     "sm__cycles_elapsed.max", "smsp__inst_executed.sum",
@@ -49,18 +50,22 @@ def main():
     for r in data:
         name = r[col["Kernel Name"]]
         short = name.replace("void ", "").replace("<unnamed>::", "").split("(")[0]
-        key = (short, r[col["launch__grid_size"]], r[col["launch__shared_mem_per_block_dynamic"]], round(val(r, "dram__bytes_read.sum", "bytes") / 4e6))
+        us = val(r, "gpu__time_duration.sum", "us")
+        rd, wr = val(r, "dram__bytes_read.sum", "bytes"), val(r, "dram__bytes_write.sum", "bytes")
+        if rd != rd:   # sections without the read / write split: total from the DRAM byte rate
+            i = col.get("dram__bytes.sum.per_second")
+            rate = float(r[i].replace(",", "")) * {"byte/s": 1, "kbyte/s": 1e3, "mbyte/s": 1e6, "gbyte/s": 1e9, "tbyte/s": 1e12}.get(units[i].lower().replace("second", "s"), 1)
+            rd, wr = rate * us * 1e-6, 0.0
+        key = (short, r[col["launch__grid_size"]], r[col["launch__shared_mem_per_block_dynamic"]], round(rd / 4e6))
         seen[key] = seen.get(key, 0) + 1
         if second_only and seen[key] != 2:
             continue
-        us = val(r, "gpu__time_duration.sum", "us")
-        rd, wr = val(r, "dram__bytes_read.sum", "bytes"), val(r, "dram__bytes_write.sum", "bytes")
         gbs = (rd + wr) / us / 1e3
         smem = val(r, "launch__shared_mem_per_block_dynamic", "bytes") / 1e3
         print(f"{short[:44]:44s} {int(val(r, 'launch__grid_size')):6d} {int(val(r, 'launch__registers_per_thread')):4d} {smem:7.1f} | "
               f"{us:8.1f} {rd / 1e6:8.1f} {wr / 1e6:8.1f} {gbs:6.0f} {gbs / hbm:6.2f} "
               f"{val(r, 'gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed'):6.1f} | "
-              f"{val(r, 'TPC.TriageCompute.sm__pipe_tensor_cycles_active_realtime.avg.pct_of_peak_sustained_elapsed'):7.1f} "
+              f"{max(val(r, 'TPC.TriageCompute.sm__pipe_tensor_cycles_active_realtime.avg.pct_of_peak_sustained_elapsed'), val(r, 'sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed')):7.1f} "
               f"{val(r, 'sm__mem_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed'):8.1f} "
               f"{val(r, 'sm__warps_active.avg.pct_of_peak_sustained_active'):6.1f}")
 
