@@ -858,9 +858,14 @@ struct WgradParams {
   float* dw;
 };
 
-constexpr int kWgStages = 2;
+// Pixel tiles of <= 64 rows in a 4-deep ring (192 KB in flight per SM; two 96 KB stages measured the same, 4.08 vs
+// 4.09 ms over the ResNet-50 layers: the kernel is bound by the operand re-reads through L2 — every x tile is fetched
+// once per output-channel block and tap group — not by the ring depth; profiles/r01_experiments.txt).
+constexpr int kWgRows = 64;
+constexpr int kWgAtomBytes = kWgRows * 128;  // one [pixels x 64 channels] MN-major atom
+constexpr int kWgStages = 4;
 constexpr int kWgMaxSub = 4;
-constexpr int kWgStageBytes = (2 + kWgMaxSub) * kATileBytes;  // dY halves (2 x 16 KB) + X (<= 4 x 16 KB)
+constexpr int kWgStageBytes = (2 + kWgMaxSub) * kWgAtomBytes;  // dY halves (2 atoms) + X (<= 4 atoms)
 constexpr int kWgSmemBytes = kWgStages * kWgStageBytes + 1024;
 constexpr int kWgTmemCols = 256;
 
@@ -937,12 +942,12 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant__ C
         uint8_t* a_s = smem + s * kWgStageBytes;
         mbar_expect_tx(&full_bar[s], tx_bytes);
         tma_load_4d(a_s, &tmDY, &full_bar[s], co0, w0, h0, n0);
-        tma_load_4d(a_s + kATileBytes, &tmDY, &full_bar[s], co0 + 64, w0, h0, n0);
+        tma_load_4d(a_s + kWgAtomBytes, &tmDY, &full_bar[s], co0 + 64, w0, h0, n0);
         const int xw0 = w0 * p.sxw, xh0 = h0 * p.sxh;
 #pragma unroll
         for (int j = 0; j < kWgMaxSub; ++j)
           if (j < nsub)
-            tma_load_4d(a_s + (2 + j) * kATileBytes, &tmX, &full_bar[s], sub_c[j], xw0 + sub_dw[j], xh0 + sub_dh[j],
+            tma_load_4d(a_s + (2 + j) * kWgAtomBytes, &tmX, &full_bar[s], sub_c[j], xw0 + sub_dw[j], xh0 + sub_dh[j],
                         n0);
       }
     }
@@ -950,19 +955,19 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant__ C
     if (elect_one()) {  // elect.sync, not lane==0: ptxas then emits bare UTCHMMA / UTMALDG (no per-lane loop)
       const uint32_t idesc = umma_idesc_bf16(128, 64 * nsub, 1, 1);
       const int nk = (p.rows + 15) >> 4;
-      // MN-major: 8-row (K) groups 1024 B apart; consecutive 64-channel atoms are 16 KB apart
-      const uint64_t d0 = umma_smem_desc_sw128(smem_u32(smem), kATileBytes, 1024);
+      // MN-major: 8-row (K) groups 1024 B apart; consecutive 64-channel atoms are one atom (8 KB) apart
+      const uint64_t d0 = umma_smem_desc_sw128(smem_u32(smem), kWgAtomBytes, 1024);
       const uint32_t desc_hi = (uint32_t)(d0 >> 32), lo0 = (uint32_t)d0;
-      constexpr uint32_t kStageLo = kWgStageBytes >> 4, kXLo = (2 * kATileBytes) >> 4;
+      constexpr uint32_t kStageLo = kWgStageBytes >> 4, kXLo = (2 * kWgAtomBytes) >> 4;
       uint32_t acc = 0;
       for (int it = 0; it < my_tiles; ++it) {
-        const uint32_t s = (uint32_t)it & 1u;  // kWgStages == 2
-        mbar_wait(&full_bar[s], ((uint32_t)it >> 1) & 1u);
+        const uint32_t s = (uint32_t)it % kWgStages;
+        mbar_wait(&full_bar[s], ((uint32_t)it / kWgStages) & 1u);
         tc_fence_after();
         const uint32_t a_lo = lo0 + s * kStageLo, b_lo = a_lo + kXLo;
-        if (nk == 8) {
+        if (nk == 4) {
 #pragma unroll
-          for (int k = 0; k < 8; ++k)
+          for (int k = 0; k < 4; ++k)
             umma_bf16_lohi(tmem_base, a_lo + 128 * k, desc_hi, b_lo + 128 * k, desc_hi, idesc, k ? 1u : acc);
         } else {
           for (int k = 0; k < nk; ++k)
@@ -1135,23 +1140,23 @@ struct Box {
   int bw, bh, bn;
 };
 
-// Largest-utilisation box of <= 128 output pixels: full rows first, then rows, then images.
-Box pick_box(int OW, int OH, int N) {
+// Largest-utilisation box of <= max_rows (128) output pixels: full rows first, then rows, then images.
+Box pick_box(int OW, int OH, int N, int max_rows = 128) {
   Box b{1, 1, 1};
-  if (OW >= 128) {
-    const int t = msp_cdiv(OW, 128);
+  if (OW >= max_rows) {
+    const int t = msp_cdiv(OW, max_rows);
     b.bw = msp_cdiv(OW, t);
     return b;
   }
   b.bw = OW;
-  const int maxh = 128 / OW;
+  const int maxh = max_rows / OW;
   if (OH > maxh) {
     const int t = msp_cdiv(OH, maxh);
     b.bh = msp_cdiv(OH, t);
     return b;
   }
   b.bh = OH;
-  const int maxn = 128 / (OW * OH);
+  const int maxn = max_rows / (OW * OH);
   if (N > maxn) {
     const int t = msp_cdiv(N, maxn);
     b.bn = msp_cdiv(N, t);
@@ -1650,7 +1655,7 @@ int plan_wgrad(const msp_conv_desc* d, WgradPlan* pl) {
   } else {
     pl->OW = d->Wo; pl->OH = d->Ho; pl->N = d->N;
   }
-  pl->b = pick_box(pl->OW, pl->OH, pl->N);
+  pl->b = pick_box(pl->OW, pl->OH, pl->N, kWgRows);
   pl->tiles_m = msp_cdiv(pl->OW, pl->b.bw) * msp_cdiv(pl->OH, pl->b.bh) * msp_cdiv(pl->N, pl->b.bn);
   pl->Cw = d->win_px ? 64 : d->C;
   pl->ntaps = d->win_px ? d->KH : d->KH * d->KW;

@@ -65,8 +65,10 @@ mma_rate_kernel(const uint8_t* __restrict__ src, int N, int mode, int kblocks, l
       }
     }
   } else if (warp == 1 && (kElect ? elect_one() : (lane == 0))) {
-    const uint32_t idesc = umma_idesc_bf16(M, N, 0, 0);
-    const uint64_t d0 = umma_smem_desc_sw128(smem_u32(smem), 16, 1024);
+    const int mn = (flags & 32) ? 1 : 0;  // 32 = both operands MN-major (the wgrad kernel's form)
+    const uint32_t idesc = umma_idesc_bf16(M, N, mn, mn);
+    const uint64_t d0 = umma_smem_desc_sw128(smem_u32(smem), mn ? 8192 : 16, 1024);
+    const uint32_t kstep = mn ? 128u : 2u;  // descriptor start-address advance per K=16 step (>>4)
     const uint32_t desc_hi = (uint32_t)(d0 >> 32), a_lo0 = (uint32_t)d0;
     uint32_t s = 0, ph = 0;
     const long long c0 = clock64();
@@ -80,14 +82,14 @@ mma_rate_kernel(const uint8_t* __restrict__ src, int N, int mode, int kblocks, l
       const uint32_t a_lo = a_lo0 + s * (kStageBytes >> 4), b_lo = a_lo + (16384 >> 4);
       const uint32_t tmem_d = tmem_base + (alt ? 0u : ((it / 36) & 1) * (uint32_t)N);
       umma_bf16_lohi(tmem_d, a_lo, desc_hi, b_lo, desc_hi, idesc, it > 0);
-      umma_bf16_lohi(tmem_d + alt, a_lo + 2, desc_hi, b_lo + 2, desc_hi, idesc, it > 0);
+      umma_bf16_lohi(tmem_d + alt, a_lo + kstep, desc_hi, b_lo + kstep, desc_hi, idesc, it > 0);
       if ((flags & 4) && mode >= 2 && it + 1 < kblocks) {   // overlap the next barrier wait with queued MMAs
         const uint32_t s1 = (s + 1 == kStages) ? 0 : s + 1, ph1 = (s + 1 == kStages) ? ph ^ 1u : ph;
         mbar_wait(&full_bar[s1], ph1);
         if (!(flags & 2)) tc_fence_after();
       }
-      umma_bf16_lohi(tmem_d, a_lo + 4, desc_hi, b_lo + 4, desc_hi, idesc, 1u);
-      umma_bf16_lohi(tmem_d + alt, a_lo + 6, desc_hi, b_lo + 6, desc_hi, idesc, 1u);
+      umma_bf16_lohi(tmem_d, a_lo + 2 * kstep, desc_hi, b_lo + 2 * kstep, desc_hi, idesc, 1u);
+      umma_bf16_lohi(tmem_d + alt, a_lo + 3 * kstep, desc_hi, b_lo + 3 * kstep, desc_hi, idesc, 1u);
       if (mode >= 1) umma_commit(&empty_bar[s]);
       if (++s == kStages) { s = 0; ph ^= 1u; }
       if (flags & 8) { const long long t0 = clock64(); while (clock64() - t0 < delay) {} }
@@ -135,13 +137,10 @@ int main() {
     const double n = 4.0 * kblocks;
     printf("%5d %4d %4d %5d %5d %5d | %12.1f %12.1f %10.1f\n", grid, mode, M, N, flags, delay, v[v.size() / 2] / n, mx / n, iss / n / grid);
   };
-  for (int f : {16, 0}) {
-    for (int N : {16, 64, 128, 256}) run(1, 0, 128, N, f, 0);
-    for (int N : {64, 128, 256}) run(1, 0, 64, N, f, 0);          // M=64
-    for (int d : {100, 400}) run(1, 0, 128, 256, f | 8, d);   // queue depth probe
-    for (int d : {100, 400}) run(1, 0, 128, 64, f | 8, d);
-    for (int N : {16, 64, 128, 256}) run(1, 2, 128, N, f, 0);
-    for (int N : {16, 64, 128, 256}) for (int m : {3, 4}) run(nsm, m, 128, N, f, 0);
+  for (int f : {0, 32}) {   // K-major vs MN-major operands
+    for (int N : {64, 128, 256}) run(1, 0, 128, N, f, 0);
+    for (int N : {64, 128, 256}) run(1, 2, 128, N, f, 0);
+    for (int N : {128, 256}) for (int m : {3, 4}) run(nsm, m, 128, N, f, 0);
   }
   return 0;
 }
