@@ -93,3 +93,28 @@ def test_scalar_reader_reads_every_step_one_late():
             got.append(v)
     assert got == [0.0, 2.0, 4.0, 6.0, 8.0]
     assert reader.drain() == [10.0]
+
+
+def test_peer_allreduce_world_1_and_multi_gpu():
+    """parallel.PeerAllReduce (csrc/msp_p2p.cu).  World size 1 (no process group): the exchange is the identity and the
+    sequence counter advances, also inside a CUDA graph.  With >= 2 visible GPUs the torchrun check against NCCL
+    (tools/test_p2p.py: eager, graph replay, bitwise equality across ranks) runs as a subprocess."""
+    import os, subprocess, sys
+    from medsegpretrainimagenet_b200.parallel import PeerAllReduce
+    par = PeerAllReduce(None, max_floats=1024)
+    t = torch.arange(1000, dtype=torch.float32, device=DEV)
+    ref = t.clone()
+    for _ in range(3):
+        par.allreduce_sum_(t)
+    assert torch.equal(t, ref) and int(par.seq.item()) == 3
+    with pytest.raises(ValueError):
+        par.allreduce_sum_(torch.zeros(2048, device=DEV))          # larger than the communicator's buffer
+    with pytest.raises(ValueError):
+        par.allreduce_sum_(torch.zeros(8, device=DEV, dtype=torch.float64))
+    par.close()
+    if torch.cuda.device_count() >= 2:
+        root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+        r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                            "--master-addr", "127.0.0.1", "--master-port", "29551", os.path.join(root, "tools", "test_p2p.py")],
+                           capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0 and "p2p all-reduce ok" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]

@@ -53,7 +53,11 @@ def _worker(rank, world, port, out):
         # sufficient statistics: BatchNorm [sum, sum of squares] and Dice [I, Y, S] all-reduced == full batch
         feats = torch.randn((8, 5, 6, 6), generator=g)
         st = torch.stack([feats[lo:hi].sum((0, 2, 3)), (feats[lo:hi] ** 2).sum((0, 2, 3))])
-        dist.all_reduce(st)
+        # the SyncBN choke point (functional._allreduce_sum -> parallel.allreduce_small_sum_): without a peer-memory
+        # communicator (CPU / gloo) it is the process group's all-reduce
+        from medsegpretrainimagenet_b200.parallel import allreduce_small_sum_, peer_allreduce_for
+        assert peer_allreduce_for(dist.group.WORLD) is None
+        allreduce_small_sum_(st, dist.group.WORLD)
         ok &= torch.allclose(st[0], feats.sum((0, 2, 3)), rtol=1e-5, atol=1e-5)
         ok &= torch.allclose(st[1], (feats ** 2).sum((0, 2, 3)), rtol=1e-5, atol=1e-5)
         from oracle import ref_losses
