@@ -70,6 +70,10 @@ int msp_pack_weights(const float* w_oihw, int K, int C, int KH, int KW, int Cpad
                      void* w_fprop, void* w_dgrad, void* stream);
 
 /* OIHW fp32 -> bf16 [K][KH][64] with element q*(64/win_px)+c of filter row r = w[k][c][r][q]. */
+/* All convolutions of a model in one launch: `items_dev` = device array of n_items x 10 int64
+ * {w_oihw ptr, w_fprop ptr, w_dgrad ptr (0 = not needed), K, C, KH*KW, Cpad, Kpad, first block, blocks} (layouts as in
+ * msp_pack_weights); item i owns blocks [first, first + blocks) of the `total_blocks` 256-thread blocks launched. */
+int msp_pack_weights_batched(const long long* items_dev, int n_items, int total_blocks, void* stream);
 int msp_pack_weights_rowwin(const float* w_oihw, int K, int C, int KH, int KW, int win_px,
                             void* w_rowwin, void* stream);
 

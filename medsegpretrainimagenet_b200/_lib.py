@@ -46,6 +46,7 @@ SIGNATURES = {
     "msp_conv_wgrad": [C.POINTER(ConvDesc), P, P, P, P],
     "msp_unpack_wgrad": [C.POINTER(ConvDesc), P, I, P, P],
     "msp_pack_weights_rowwin": [P, I, I, I, I, I, P, P],
+    "msp_pack_weights_batched": [P, I, I, P],
     "msp_nchw_f32_to_rowwin_bf16": [P, I, I, I, I, I, I, I, P, P],
     "msp_nchw_bf16_to_rowwin_bf16": [P, I, I, I, I, I, I, I, P, P],
     "msp_nchw_f32_to_nhwc_bf16": [P, I, I, I, I, I, P, P],

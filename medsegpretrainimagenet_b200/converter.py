@@ -40,6 +40,11 @@ class ExecContext:
         self._static = None      # list of (DropPath module, n, device tensor) in forward order while capturing
         self._replay = []
         self.counters = []       # num_batches_tracked buffers touched by the running forward
+        self.pack_cache = ops.WeightPackCache()   # bf16 operand copies of the conv weights, one repack kernel per step
+
+    def begin_forward(self):
+        self.pack_cache.begin_step()
+        ops.set_active_pack_cache(self.pack_cache)
 
     def stats_for(self, bn):
         """Persistent, self-cleaning [2, C] accumulator of the conv epilogue's BatchNorm sums (zeroed once here, then
@@ -52,6 +57,10 @@ class ExecContext:
         return buf
 
     def finish_forward(self):
+        ops.set_active_pack_cache(None)
+        self.pack_cache.end_step()
+        if not torch.cuda.is_current_stream_capturing():
+            self.pack_cache.build_table()
         if self.counters:
             torch._foreach_add_(self.counters, 1)
             self.counters = []
@@ -387,6 +396,7 @@ def _require_cuda(x):
 def _forward_deep_resnet(self, x, return_skip_vals=False, *args, **kwargs):
     _require_cuda(x)
     ctx = self._msp_ctx
+    ctx.begin_forward()
     out = run_deep_resnet(ctx, self, RawInput(x), return_skip_vals=return_skip_vals)
     ctx.finish_forward()
     y, skips = out if return_skip_vals else (out, None)
@@ -401,6 +411,7 @@ def _forward_deep_resnet(self, x, return_skip_vals=False, *args, **kwargs):
 
 def _forward_unet_encoder(self, x, return_skip_vals=False):
     _require_cuda(x)
+    self._msp_ctx.begin_forward()
     out = run_unet_encoder(self._msp_ctx, self, RawInput(x), return_skip_vals=return_skip_vals)
     self._msp_ctx.finish_forward()
     if return_skip_vals:
@@ -410,6 +421,7 @@ def _forward_unet_encoder(self, x, return_skip_vals=False):
 
 def _forward_unet(self, x):
     _require_cuda(x)
+    self._msp_ctx.begin_forward()
     out = run_unet(self._msp_ctx, self, RawInput(x))
     self._msp_ctx.finish_forward()
     return out

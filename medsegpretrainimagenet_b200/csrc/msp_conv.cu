@@ -1081,6 +1081,45 @@ __global__ void pack_w_both_kernel(const float* __restrict__ w, int K, int C, in
   }
 }
 // row-window packing: out[k][r][q * cpp + c] = w[k][c][r][q]  (64 window elements per filter row)
+// every convolution of a model in ONE launch: items[i] = {w, wf, wd (0 = none), K, C, taps, Cpad, Kpad, first block,
+// blocks} as int64; blocks are dealt out in proportion to the item's element count (a fixed share per item left the
+// largest layers of the U-Net with 1/128 of the parallelism they had and cost more than the launches saved).  Same
+// element mapping as pack_w_both_kernel.  The per-layer launches cost ~6.7 us each for microseconds of work: 49 of them
+// per ResNet-50 step, 79 per U-Net step.
+constexpr int kPackItemWords = 10;
+constexpr int kPackElemsPerBlock = 256 * 8;
+__global__ void __launch_bounds__(256)
+pack_w_batched_kernel(const long long* __restrict__ items, int n_items) {
+  int lo = 0, hi = n_items - 1;  // last item whose first block <= blockIdx.x
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (items[(long long)mid * kPackItemWords + 8] <= (long long)blockIdx.x) lo = mid;
+    else hi = mid - 1;
+  }
+  const long long* it = items + (long long)lo * kPackItemWords;
+  const float* __restrict__ w = reinterpret_cast<const float*>(it[0]);
+  __nv_bfloat16* __restrict__ wf = reinterpret_cast<__nv_bfloat16*>(it[1]);
+  __nv_bfloat16* __restrict__ wd = reinterpret_cast<__nv_bfloat16*>(it[2]);
+  const int K = (int)it[3], C = (int)it[4], taps = (int)it[5], Cpad = (int)it[6], Kpad = (int)it[7];
+  const long long blk = (long long)blockIdx.x - it[8], nblk = it[9];
+  const long long nf = (long long)K * taps * Cpad, nd = wd ? (long long)Cpad * taps * Kpad : 0;
+  for (long long i = blk * blockDim.x + threadIdx.x; i < nf + nd; i += nblk * blockDim.x) {
+    if (i < nf) {
+      const int c = (int)(i % Cpad);
+      const long long t = i / Cpad;
+      const int tap = (int)(t % taps);
+      const int k = (int)(t / taps);
+      wf[i] = __float2bfloat16_rn(c < C ? w[((long long)k * C + c) * taps + tap] : 0.f);
+    } else {
+      const long long i2 = i - nf;
+      const int k = (int)(i2 % Kpad);
+      const long long t = i2 / Kpad;
+      const int tap = (int)(t % taps);
+      const int c = (int)(t / taps);
+      wd[i2] = __float2bfloat16_rn((c < C && k < K) ? w[((long long)k * C + c) * taps + tap] : 0.f);
+    }
+  }
+}
 __global__ void pack_w_rowwin_kernel(const float* __restrict__ w, int K, int C, int KH, int KW, int cpp,
                                      __nv_bfloat16* __restrict__ out) {
   const long long total = (long long)K * KH * 64;
@@ -1474,6 +1513,14 @@ extern "C" int msp_pack_weights(const float* w, int K, int C, int KH, int KW, in
     MSP_CHECK_LAUNCH();
     msp_count_launch(1);
   }
+  return MSP_OK;
+}
+
+extern "C" int msp_pack_weights_batched(const long long* items_dev, int n_items, int total_blocks, void* stream) {
+  MSP_REQUIRE(items_dev && n_items >= 1 && total_blocks >= n_items, "pack_weights_batched: bad arguments");
+  pack_w_batched_kernel<<<(unsigned)total_blocks, 256, 0, (cudaStream_t)stream>>>(items_dev, n_items);
+  MSP_CHECK_LAUNCH();
+  msp_count_launch(1);
   return MSP_OK;
 }
 

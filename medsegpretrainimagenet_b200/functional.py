@@ -88,7 +88,7 @@ class _Conv(torch.autograd.Function):
         n, h, w, c8 = x.shape
         ho, wo, pt, pl = ops.conv_out_size(h, w, kh, kw, stride, padding)
         need_dx = ctx.needs_input_grad[0]
-        wf, wd = ops.pack_weights(weight, need_dgrad=need_dx)
+        wf, wd = ops.packed_weights(weight, need_dgrad=need_dx)
         stats = _stats_buffer(want_stats, k, x.device)
         y = ops.conv_fprop(x, wf, bias.detach() if bias is not None else None, k, kh, kw, stride, pt, pl,
                            ho, wo, relu=relu, out=out, stats=stats, c_true=c_true)

@@ -8,6 +8,7 @@ PyTorch is used only for device memory and the current stream.
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Optional, Tuple
 
 import torch
@@ -85,6 +86,87 @@ def pack_weights(w: torch.Tensor, need_dgrad: bool = True):
     wd = torch.empty((c8, kh * kw, k8), dtype=_BF16, device=w.device) if need_dgrad else None
     call("msp_pack_weights", _p(w), k, c, kh, kw, c8, k8, _p(wf), _p(wd), _stream())
     return wf, wd
+
+
+class WeightPackCache:
+    """bf16 operand copies of a model's convolution weights, repacked by ONE kernel per forward.
+
+    The weights stay the reference's fp32 OIHW Parameters; the tensor-core kernels read bf16 [K][tap][C] / [C][tap][K]
+    copies.  Packing them per layer inside every forward is ~50-80 launches of ~6.7 us for microseconds of work.  The
+    cache keeps one persistent pair of buffers per weight (keyed by its storage address); `begin_step()` — the top of
+    every forward of the converted model — repacks ALL of them with msp_pack_weights_batched, `lookup()` hands the
+    buffers to the convolutions.  The repack is unconditional: tensor version counters are not a safe "unchanged"
+    signal (fused optimizers and CUDA-graph replays update the parameters without moving them).  A weight seen for the
+    first time (or while the table is being rebuilt) is packed on the spot, as before."""
+
+    def __init__(self):
+        self.entries = {}       # data_ptr -> [weight alias, wf, wd]
+        self.table = None
+        self.total_blocks = 0
+        self.dirty = False
+        self.packed = False     # begin_step() of the running forward repacked every entry of the table
+        self.in_table = set()
+
+    def lookup(self, w: torch.Tensor, need_dgrad: bool):
+        if w.dtype != torch.float32 or not w.is_contiguous():
+            return pack_weights(w, need_dgrad)          # a temporary fp32 copy would be packed: not cacheable
+        key = w.data_ptr()
+        e = self.entries.get(key)
+        if e is not None and e[0].shape == w.shape and (e[2] is not None or not need_dgrad):
+            if not (self.packed and key in self.in_table):
+                k, c, kh, kw = w.shape
+                call("msp_pack_weights", _p(w.detach()), k, c, kh, kw, ceil8(c), ceil8(k), _p(e[1]), _p(e[2]), _stream())
+            return e[1], (e[2] if need_dgrad else None)
+        wf, wd = pack_weights(w, need_dgrad)
+        self.entries[key] = [w.detach(), wf, wd]
+        self.in_table.discard(key)                      # (a replaced entry's old buffers are what the table points to)
+        self.dirty = True
+        return wf, wd
+
+    def build_table(self) -> None:
+        """(Re)build the device table of the batched kernel at the end of a forward; never inside a graph capture."""
+        self.packed = False
+        if not self.dirty or not self.entries:
+            return
+        rows, first = [], 0
+        for w, wf, wd in self.entries.values():
+            k, c, kh, kw = w.shape
+            elems = k * kh * kw * ceil8(c) * (2 if wd is not None else 1)
+            nblk = max(1, min(1024, (elems + 2047) // 2048))       # ~8 elements per thread
+            rows.append([w.data_ptr(), wf.data_ptr(), wd.data_ptr() if wd is not None else 0, k, c, kh * kw,
+                         ceil8(c), ceil8(k), first, nblk])
+            first += nblk
+        self.total_blocks = first
+        dev = next(iter(self.entries.values()))[1].device
+        self.table = torch.tensor(rows, dtype=torch.int64).to(dev)
+        self.in_table = set(self.entries.keys())
+        self.dirty = False
+
+    def begin_step(self) -> None:
+        self.packed = False
+        if self.table is None:
+            return                                      # first forward: lookup() packs layer by layer
+        call("msp_pack_weights_batched", self.table.data_ptr(), self.table.shape[0], self.total_blocks, _stream())
+        self.packed = True
+
+    def end_step(self) -> None:
+        self.packed = False
+
+
+_PACK: Optional[WeightPackCache] = None     # the cache of the model whose forward is running (converter sets it)
+_PACK_ENABLED = os.environ.get("MSP_PACK_CACHE", "1") != "0"     # 0: pack layer by layer inside every forward
+
+
+def set_active_pack_cache(cache: Optional[WeightPackCache]) -> None:
+    global _PACK
+    _PACK = cache
+
+
+def packed_weights(w: torch.Tensor, need_dgrad: bool = True):
+    """Operand copies of `w` for conv_fprop / conv_dgrad: from the running model's cache, else packed now."""
+    if _PACK is not None and _PACK_ENABLED:
+        return _PACK.lookup(w, need_dgrad)
+    return pack_weights(w, need_dgrad)
 
 
 def set_conv_policy(pair: int = -1, halo: int = -1) -> None:

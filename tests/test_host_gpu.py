@@ -61,6 +61,24 @@ def test_graphed_step_matches_eager():
             torch.manual_seed(50 + i)              # DropPath masks come from the global CPU generator
             out.append(float(fn(xs[i], ms[i])))
         losses[mode] = out
+        if True:
+            # (both modes: the fused optimizer does not move the version counters either)
+            # the replayed optimizer steps changed the weights behind their version counters: an eager forward after
+            # the replays must see them (WeightPackCache repacks at the top of every forward), bit for bit like a
+            # freshly packed model
+            from medsegpretrainimagenet_b200 import converter as cv, ops
+            model.eval()
+            with torch.no_grad():
+                y_a = model(xs[0]).clone()
+            model.train()
+            fn(xs[1], ms[1])
+            model.eval()
+            with torch.no_grad():
+                y_b = model(xs[0]).clone()
+                cv.context_of(model).pack_cache = ops.WeightPackCache()
+                y_c = model(xs[0]).clone()
+            assert not torch.equal(y_a, y_b)
+            assert torch.equal(y_b, y_c)
     # step 0 runs on identical weights (2e-3); afterwards the two trajectories drift like any two runs of the same
     # bf16 training do (measured run to run: up to ~1 % after 4 SGD steps at lr 0.05)
     assert abs(losses["eager"][0] - losses["graph"][0]) <= 2e-3 * abs(losses["eager"][0]), losses
