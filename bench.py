@@ -246,7 +246,8 @@ def main():
         if args.small_allreduce == "p2p":
             # SyncBN statistics through the peer-memory kernel (csrc/msp_p2p.cu) instead of ~100 tiny NCCL calls / step
             from medsegpretrainimagenet_b200 import parallel as _par
-            _par.enable_peer_allreduce(group)
+            if _par.enable_peer_allreduce(group) is None:
+                args.small_allreduce = "nccl"        # CUDA IPC unavailable on this box: every rank fell back together
     warm = max(args.warmup, 3)
 
     name, batch, shape, _ = WORKLOADS[args.workload]

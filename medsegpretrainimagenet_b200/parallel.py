@@ -151,28 +151,45 @@ class PeerAllReduce:
         nbytes = int(_lib.lib.msp_p2p_buffer_bytes(self.world, self.max_floats))
         if nbytes <= 0:
             raise ValueError(f"PeerAllReduce: unsupported world size {self.world}")
+        # Every collective below is reached by every rank whatever failed locally, so that the ranks fail TOGETHER
+        # (a rank that raised early would leave the others blocked in the next collective).
+        self._local, self._opened, err = None, [], None
         with torch.cuda.device(self.device):
-            local = C.c_void_p()
-            handle = C.create_string_buffer(64)
-            _lib.call("msp_p2p_alloc", nbytes, C.byref(local), handle)
-            self._local = local.value
-            handles = [None] * self.world
+            handle = None
+            try:
+                local = C.c_void_p()
+                hbuf = C.create_string_buffer(64)
+                _lib.call("msp_p2p_alloc", nbytes, C.byref(local), hbuf)
+                self._local, handle = local.value, bytes(hbuf.raw)
+            except Exception as e:   # noqa: BLE001
+                err = e
+            handles = [handle]
             if self.world > 1:
-                dist.all_gather_object(handles, bytes(handle.raw), group=group)
+                handles = [None] * self.world
+                dist.all_gather_object(handles, handle, group=group)
             self._ptrs = (C.c_void_p * self.world)()
-            self._opened = []
-            for r in range(self.world):
-                if r == self.rank:
-                    self._ptrs[r] = self._local
-                else:
-                    peer = C.c_void_p()
-                    _lib.call("msp_p2p_open", C.create_string_buffer(handles[r], 64), C.byref(peer))
-                    self._ptrs[r] = peer.value
-                    self._opened.append(peer.value)
+            if err is None and all(h is not None for h in handles):
+                try:
+                    for r in range(self.world):
+                        if r == self.rank:
+                            self._ptrs[r] = self._local
+                        else:
+                            peer = C.c_void_p()
+                            _lib.call("msp_p2p_open", C.create_string_buffer(handles[r], 64), C.byref(peer))
+                            self._ptrs[r] = peer.value
+                            self._opened.append(peer.value)
+                except Exception as e:   # noqa: BLE001
+                    err = e
+            elif err is None:
+                err = RuntimeError("a peer rank could not allocate its communication buffer")
             self.seq = torch.zeros(1, dtype=torch.int32, device=self.device)
             torch.cuda.synchronize()
-        if self.world > 1:
-            dist.barrier(group=group)       # every buffer is mapped everywhere before the first exchange
+            ok = torch.tensor([0 if err is not None else 1], dtype=torch.int32, device=self.device)
+            if self.world > 1:
+                dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)   # also: every buffer is mapped everywhere
+            if int(ok.item()) == 0:
+                self.close()
+                raise RuntimeError(f"PeerAllReduce: CUDA IPC set-up failed on at least one rank ({err})")
 
     def allreduce_sum_(self, t: torch.Tensor) -> torch.Tensor:
         if t.dtype != torch.float32 or not t.is_contiguous() or t.numel() > self.max_floats or t.numel() == 0:
@@ -185,7 +202,10 @@ class PeerAllReduce:
     def close(self) -> None:
         torch.cuda.synchronize()
         for p in self._opened:
-            _lib.call("msp_p2p_close", p)
+            try:
+                _lib.call("msp_p2p_close", p)
+            except Exception:   # noqa: BLE001 - best effort on the failure path
+                pass
         self._opened = []
         if self._local:
             _lib.call("msp_p2p_free", self._local)
@@ -195,12 +215,25 @@ class PeerAllReduce:
 _PEER = {}          # process group (None = default) -> PeerAllReduce
 
 
-def enable_peer_allreduce(group=None, max_floats: int = 8192) -> PeerAllReduce:
-    """Route the small exchanges of `group` (SyncBN sums, Dice sums) through the peer-memory kernel.  Collective."""
+def enable_peer_allreduce(group=None, max_floats: int = 8192, strict: bool = False) -> Optional[PeerAllReduce]:
+    """Route the small exchanges of `group` (SyncBN sums) through the peer-memory kernel.  Collective.
+
+    The set-up needs CUDA IPC between the ranks' processes (one node, peer access).  Unless `strict`, a failure on ANY rank
+    makes EVERY rank keep the NCCL path (the decision is all-reduced, so the ranks cannot disagree) and returns None."""
     key = group if group is not None else "default"
-    if key not in _PEER:
-        _PEER[key] = PeerAllReduce(group, max_floats)
-    return _PEER[key]
+    if key in _PEER:
+        return _PEER[key]
+    try:
+        par = PeerAllReduce(group, max_floats)       # raises on EVERY rank if the set-up failed on any
+    except Exception as e:   # noqa: BLE001
+        if strict:
+            raise
+        import sys
+        print(f"[msp_b200] peer-memory all-reduce unavailable ({e}); SyncBN statistics stay on NCCL", file=sys.stderr,
+              flush=True)
+        return None
+    _PEER[key] = par
+    return par
 
 
 def peer_allreduce_for(group) -> Optional[PeerAllReduce]:
