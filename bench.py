@@ -42,6 +42,7 @@ WORKLOADS = {
     "cfg2": ("resnet50_imagenet_cls_3x224x224", 256, (3, 224, 224), 16),
     "cfg3": ("resnet50_attention_unet_acdc_4class_3x256x256", 24, (3, 256, 256), 2),
     "cfg1": ("resnet18_attention_unet_covidqu_binary_1x256x256", 8, (1, 256, 256), 8),
+    "cfg4": ("basic_unet_idrid_multilabel5_3x1024x1024", 4, (3, 1024, 1024), 1),
 }
 
 
@@ -111,6 +112,9 @@ def synthetic_batch(workload, batch, gen, torch):
     elif workload == "cfg3":
         x = torch.rand((batch, *shape), generator=gen)
         y = torch.randint(0, 4, (batch, 1, *shape[1:]), generator=gen)
+    elif workload == "cfg4":
+        x = torch.rand((batch, *shape), generator=gen)
+        y = (torch.rand((batch, 5, *shape[1:]), generator=gen) < 0.05).float()
     else:
         x = torch.rand((batch, *shape), generator=gen)
         y = (torch.rand((batch, 1, *shape[1:]), generator=gen) < 0.3).long()
@@ -136,6 +140,10 @@ def reference_arm(args):
         model = ref_models.resnet50_attention_unet(out_ch=4, final_activation="softmax")
         opt = torch.optim.SGD(model.parameters(), lr=0.05, momentum=0.9, weight_decay=1e-4)
         loss_fn = ref_losses.dice_loss
+    elif args.workload == "cfg4":
+        model = ref_models.basic_unet(out_ch=5, final_activation="sigmoid")
+        opt = torch.optim.SGD(model.parameters(), lr=0.05, momentum=0.9, weight_decay=1e-4)
+        loss_fn = ref_losses.bce_loss_torch
     else:
         model = ref_models.resnet18_attention_unet()
         opt = torch.optim.SGD(model.parameters(), lr=0.05, momentum=0.9, weight_decay=1e-4)
@@ -183,6 +191,8 @@ def cpu_baseline(workload, budget_s=25.0):
         model, loss_fn = ref_models.resnet50_classifier(), (lambda p, y: ref_losses.ce_with_softmax(p, y, 0.1))
     elif workload == "cfg3":
         model, loss_fn = ref_models.resnet50_attention_unet(out_ch=4, final_activation="softmax"), ref_losses.dice_loss
+    elif workload == "cfg4":
+        model, loss_fn = ref_models.basic_unet(out_ch=5, final_activation="sigmoid"), ref_losses.bce_loss_torch
     else:
         model, loss_fn = ref_models.resnet18_attention_unet(), ref_losses.dice_loss
     ref_models.kaiming_init_(model).train()
@@ -262,6 +272,10 @@ def main():
         model = models.resnet50_attention_unet(out_ch=4, final_activation="softmax", group=group)
         crit = b200.losses.DiceLoss(group=group)
         make_opt = lambda ps: torch.optim.SGD(ps, lr=0.05, momentum=0.9, weight_decay=1e-4, fused=True)
+    elif args.workload == "cfg4":
+        model = models.basic_unet(out_ch=5, final_activation="sigmoid", group=group)
+        crit = b200.losses.BCELoss(torch_semantics=True)            # torch.nn.BCELoss
+        make_opt = lambda ps: torch.optim.SGD(ps, lr=0.05, momentum=0.9, weight_decay=1e-4, fused=True)
     else:
         model = models.resnet18_attention_unet(group=group)
         crit = b200.losses.DiceLoss(group=group)
@@ -286,6 +300,9 @@ def main():
     elif args.workload == "cfg3":
         cm = b200.metrics.MultiClassConfusionMatrix(number_of_classes=4)
         top5 = None
+    elif args.workload == "cfg4":
+        cm = b200.metrics.ConfusionMatrix(None, threshold=0.5)
+        top5 = None
     else:
         cm = b200.metrics.ConfusionMatrix(None, threshold=0.5)
         top5 = None
@@ -300,6 +317,8 @@ def main():
             b200.metrics.topk_correct(pred, y, 5)
         elif args.workload == "cfg3":
             b200.metrics.multiclass_confusion_matrix(pred, y)
+        elif args.workload == "cfg4":
+            b200.metrics.binary_confusion_counts(pred, y, 0.5, per_channel=True)   # multilabel: 4 x (5,) counters
         else:
             b200.metrics.binary_confusion_counts(pred, y, 0.5)
         loss.backward()                              # loss/loss.py:87
