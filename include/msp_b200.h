@@ -312,6 +312,24 @@ int msp_p2p_free(void* ptr);
 int msp_p2p_allreduce_sum_f32(float* data, int n, int rank, int world, int max_n, void* const* bufs,
                               unsigned* seq, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Multi-tensor gradient norm / clip and optimizer step (csrc/msp_optim.cu).  Replaces
+ * torch.nn.utils.clip_grad_norm_ (train_model.py:93-98) and torch.optim.SGD / AdamW .step() (train_model.py:107 via
+ * optim/optimizer.py:41-48).  Each call takes 1..32 fp32 contiguous tensors as host arrays of device pointers + element
+ * counts (the pointer table travels in the kernel's parameter space); callers chunk longer lists.
+ * msp_optim_sqnorm ADDS sum(g^2) of its tensors to the device double `sq_accum` (zero it first);
+ * msp_optim_clip: g *= min(1, max_norm / (sqrt(*sq) + 1e-6)); msp_optim_sgd / msp_optim_adamw: torch's update formulas
+ * (`first_step`: momentum buffers are initialised to the gradient; `step_dev`: device float, the 1-based step count).
+ * ------------------------------------------------------------------------------------------ */
+int msp_optim_sqnorm(int n, void* const* grads, const long long* numel, double* sq_accum, void* stream);
+int msp_optim_clip(int n, void* const* grads, const long long* numel, const double* sq, float max_norm, void* stream);
+int msp_optim_sgd(int n, void* const* params, void* const* grads, void* const* momentum_bufs, const long long* numel,
+                  float lr, float momentum, float dampening, float weight_decay, int nesterov, int first_step,
+                  void* stream);
+int msp_optim_adamw(int n, void* const* params, void* const* grads, void* const* exp_avg, void* const* exp_avg_sq,
+                    const long long* numel, float lr, double beta1, double beta2, float eps, float weight_decay,
+                    const float* step_dev, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -84,6 +84,12 @@ SIGNATURES = {
     "msp_topk_hits": [P, P, I, I, LL, I, P, P],
     "msp_rowpair_distances": [P, P, I, LL, I, P, P],
     "msp_triplet_hinge": [P, I, P, I, P, P],
+    "msp_optim_sqnorm": [I, C.POINTER(C.c_void_p), C.POINTER(C.c_longlong), P, P],
+    "msp_optim_clip": [I, C.POINTER(C.c_void_p), C.POINTER(C.c_longlong), P, F, P],
+    "msp_optim_sgd": [I, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_longlong),
+                      F, F, F, F, I, I, P],
+    "msp_optim_adamw": [I, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
+                        C.POINTER(C.c_longlong), F, D, D, F, F, P, P],
     "msp_p2p_buffer_bytes": [I, I],
     "msp_p2p_alloc": [LL, C.POINTER(C.c_void_p), P],
     "msp_p2p_open": [P, C.POINTER(C.c_void_p)],
