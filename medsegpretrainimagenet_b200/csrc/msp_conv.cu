@@ -8,14 +8,17 @@
 //    is a [BN x 64] slab of the packed weights [K][tap][C] (3-D TMA).  Both land in shared memory
 //    in the 128-byte-swizzled K-major layout tcgen05.mma consumes directly.
 //  * PERSISTENT, warp-specialised CTA, one per SM: warp 0 = TMA producer running up to kStages
-//    k-blocks (and therefore several tiles) ahead, warp 1 = MMA issuer (one elected lane,
-//    tcgen05.mma cta_group::1, M=128, N<=256, fp32 accumulators DOUBLE-BUFFERED in TMEM), warps 2-17 =
-//    epilogue: tcgen05.ld -> bias/ReLU -> bf16 -> 128B-swizzled staging tile in smem -> TMA tile store
-//    (hardware clips ragged tiles and channel tails; dgrad-on-top-of-a-gradient uses the TMA reduce-add),
-//    overlapped with the next tile's main loop.  The BatchNorm batch statistics (per-channel sum / sum
-//    of squares of the bf16-rounded outputs) are reduced from the staging tile and kept in REGISTERS across
-//    all the tiles a CTA owns (tiles are walked output-channel-block-major), so a launch issues
-//    ~2 x Cout x (#CTAs) atomics instead of 2 x Cout x (#tiles x 4).
+//    k-blocks (and therefore several tiles) ahead, warp 1 = MMA issuer (tcgen05.mma cta_group::1, M=128,
+//    N<=256, fp32 accumulators DOUBLE-BUFFERED in TMEM).  Both roles are taken with elect.sync — under
+//    `if (lane == 0)` ptxas wraps every UTCHMMA / UTMALDG in a per-lane loop and one MMA costs ~120-170
+//    cycles of issue time whatever N is (tools/mma_rate.cu, profiles/r01_mma_issue_rate.txt).  Warps 2-9 =
+//    epilogue, DECOUPLED: warp (q, part) owns TMEM lanes [32q, 32q+32) and a fixed set of 32-column steps of
+//    every tile: tcgen05.ld (one step ahead) -> bias/ReLU -> bf16 -> private swizzled slab -> coalesced
+//    16-byte global stores (dgrad-on-top-of-a-gradient adds the old values here), overlapped with the next
+//    tile's main loop; no CTA-wide barrier on the per-tile path.  The BatchNorm batch statistics (per-channel
+//    sum / sum of squares of the bf16-rounded outputs) are read back column-wise from the slab and kept in
+//    REGISTERS across all the tiles a CTA owns (tiles are walked output-channel-block-major), so a launch
+//    issues ~2 x Cout x (#CTAs) atomics instead of 2 x Cout x (#tiles x 4).
 //  * dgrad = the same kernel on dy with transposed weights; stride-2 dgrad is decomposed into the
 //    four output-parity classes, each a small stride-1 tap-GEMM writing a strided sub-grid of dx.
 //  * wgrad contracts over pixels: A = dy tile (128 output channels), B = shifted x tile (up to 256 input
@@ -46,10 +49,7 @@ constexpr int kTapThreads = 64 + 32 * kEpiWarps;  // producer + MMA + epilogue
 constexpr int kATileBytes = kBM * kBK * 2;  // 16 KB
 constexpr int kEpiThreads = 32 * kEpiWarps;
 constexpr int kEpiParts = kEpiWarps / 4;           // warps sharing one TMEM lane quarter
-constexpr int kEpiRowsPerPass = kEpiThreads / 8;   // copy-out: rows per pass (thread = one 16-byte piece)
-constexpr int kEpiPasses = 128 / kEpiRowsPerPass;
-constexpr int kEpiSlabs = kEpiThreads / 32;        // statistics: row slabs
-constexpr int kEpiSlabRows = 128 / kEpiSlabs;
+constexpr int kEpiSlabs = kEpiThreads / 32;        // epilogue warps (shared-memory budget of their slabs / scratch)
 constexpr int kEpiBarrier = 1;  // named barrier id of the epilogue warps
 
 struct TapGemmParams {
@@ -84,10 +84,8 @@ struct TapGemmCfg {
   static constexpr int kBTileBytes = BN_ * kBK * 2;
   static constexpr int kStageBytes = kATileBytes + kBTileBytes;
   static constexpr int kStages = BN_ >= 256 ? 4 : (BN_ >= 128 ? 5 : 6);
-  static constexpr int kCH = BN_ < 64 ? BN_ : 64;  // epilogue column chunk (one TMA store box)
-  static constexpr int kNChunk = BN_ / kCH;
-  static constexpr int kStageBufs = BN_ >= 256 ? 1 : 2;  // 16 KB staging tiles for the TMA store
-  static constexpr int kScratchBytes = kEpiSlabs * 128 * 4 + 4 * 128 * 4;  // per-slab partial + running statistics
+  static constexpr int kStageBufs = BN_ >= 256 ? 1 : 2;  // 16 KB units of epilogue staging (the warps' slabs, EpiCfg)
+  static constexpr int kScratchBytes = kEpiSlabs * 128 * 4 + 4 * 128 * 4;  // + 6 KB (BN = 256 needs part of it)
   static constexpr int kSmemBytes =
       kStages * kStageBytes + kStageBufs * kATileBytes + kScratchBytes + 1024;  // + alignment slack
   static constexpr int kTmemCols = 2 * BN_ < 32 ? 32 : 2 * BN_;
