@@ -330,6 +330,24 @@ int msp_optim_adamw(int n, void* const* params, void* const* grads, void* const*
                     const long long* numel, float lr, double beta1, double beta2, float eps, float weight_decay,
                     const float* step_dev, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Input side of the step (csrc/msp_input.cu): what the reference does to a batch on the CPU.
+ * msp_u8_to_f32_nchw: uint8 [N][C][hw] -> fp32 [N][C*repeats][hw] = (float)((double)x / divisor) with every channel
+ *   repeated `repeats` times in place — `np.load(f) / 255` (classification/datasets.py:47), the float32 cast of
+ *   ConvertToType (transform/transforms.py:63-103) and RepeatChannels (transform/transforms.py:134-142).
+ * msp_color_jitter: torchvision.transforms.ColorJitter on a float [N][C][hw] batch in [0,1], C = 1 or 3, as
+ *   robustness/eval.py:61-66 applies it (one parameter draw for the whole batch).  `order_host` = 4 host ints, the
+ *   adjustments in application order (0 brightness, 1 contrast, 2 saturation, 3 hue, -1 none); `one_minus_host` = 3 host
+ *   floats (1 - factor) of brightness / contrast / saturation rounded as torch rounds its scalar operand; `gray_sums`
+ *   = [N] device doubles of workspace (needed when contrast is in the chain).  y may alias x only when contrast is not
+ *   in the chain.
+ * ------------------------------------------------------------------------------------------ */
+int msp_u8_to_f32_nchw(const void* x_u8, int n, int c, long long hw, int repeats, double divisor, float* y,
+                       void* stream);
+int msp_color_jitter(const float* x, int n, int c, long long hw, const int* order_host, float brightness,
+                     float contrast, float saturation, float hue, const float* one_minus_host, double* gray_sums,
+                     float* y, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

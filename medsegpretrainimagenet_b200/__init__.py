@@ -8,9 +8,9 @@ include/msp_b200.h) and fails if it has not been built: there is no PyTorch / CP
 """
 from . import _lib  # noqa: F401  (raises ImportError when the library is missing)
 from .converter import ExecContext, UnsupportedModule, convert, is_converted
-from . import converter, functional, graphs, losses, metrics, ops, optim, robustness
+from . import converter, functional, graphs, losses, metrics, ops, optim, robustness, transforms
 from .graphs import GraphedStep
 from .host import BatchPrefetcher, ScalarReader
 
 __all__ = ["convert", "is_converted", "ExecContext", "UnsupportedModule", "GraphedStep", "BatchPrefetcher", "ScalarReader", "functional", "graphs", "losses", "metrics",
-           "ops", "optim", "robustness"]
+           "ops", "optim", "robustness", "transforms"]

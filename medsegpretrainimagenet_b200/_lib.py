@@ -12,6 +12,8 @@ import os
 import sys
 from pathlib import Path
 
+import torch  # noqa: F401  (first: libmsp_b200.so links the CUDA runtime dynamically and must share torch's instance)
+
 _PKG = Path(__file__).resolve().parent
 LIB_PATH = _PKG / "libmsp_b200.so"
 
@@ -90,6 +92,8 @@ SIGNATURES = {
                       F, F, F, F, I, I, P],
     "msp_optim_adamw": [I, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
                         C.POINTER(C.c_longlong), F, D, D, F, F, P, P],
+    "msp_u8_to_f32_nchw": [P, I, I, LL, I, D, P, P],
+    "msp_color_jitter": [P, I, I, LL, C.POINTER(C.c_int), F, F, F, F, C.POINTER(C.c_float), P, P, P],
     "msp_p2p_buffer_bytes": [I, I],
     "msp_p2p_alloc": [LL, C.POINTER(C.c_void_p), P],
     "msp_p2p_open": [P, C.POINTER(C.c_void_p)],

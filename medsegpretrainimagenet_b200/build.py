@@ -39,7 +39,7 @@ def _digest(paths) -> str:
     for p in sorted(paths):
         h.update(p.name.encode())
         h.update(p.read_bytes())
-    h.update(" ".join(NVCC_FLAGS).encode())
+    h.update((" ".join(NVCC_FLAGS) + " cudart=shared").encode())
     return h.hexdigest()
 
 
@@ -70,9 +70,12 @@ def build_lib(force: bool = False, verbose: bool = False) -> Path:
 
     with ThreadPoolExecutor(max_workers=min(8, len(srcs))) as ex:
         objs = list(ex.map(compile_one, srcs))
-    # static cudart; libcuda is resolved lazily through cudaGetDriverEntryPoint and is NOT linked, so
-    # the library still loads (for symbol checks) on a box without a driver.
-    cmd = [nvcc, "-shared", "-o", str(LIB), *map(str, objs)]
+    # SHARED cudart (the process's one runtime: torch's libcudart.so.12 when torch is imported first, else the
+    # toolkit's through the rpath) - a statically linked runtime would carry every runtime entry point's name
+    # into the shipped .so whether or not anything calls it.  libcuda is resolved lazily through
+    # cudaGetDriverEntryPoint and is NOT linked, so the library still loads (symbol checks) without a driver.
+    cmd = [nvcc, "-shared", "--cudart", "shared", "-Xlinker", "-rpath,/usr/local/cuda/lib64",
+           "-o", str(LIB), *map(str, objs)]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")

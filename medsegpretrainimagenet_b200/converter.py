@@ -11,6 +11,7 @@ reference modules and the oracle restatement in oracle/ref_models.py):
   UNet / UNet_encoder / UNet_decoder                                 segmentation/models/unet_models.py:39-688
   ConvBlock / UpConvBlock / AttentionBlock / ConcatBlock             segmentation/models/blocks.py:419-635
   Model wrapper (`.model`)                                           model/model.py:18-75
+  FeedForwardModel (sequential `.layers`: encoder + pooled linear head)  config/pretraining/*/*.yaml
   nn.Conv2d / BatchNorm2d / ReLU / Sigmoid / MaxPool2d / Upsample(nearest, x2) / Sequential / Identity
 Anything else raises UnsupportedModule: there is no PyTorch fallback on this path.
 """
@@ -271,14 +272,45 @@ def run_deep_resnet(ctx: ExecContext, m, x, return_skip_vals: bool = False):
         skips.append(y)
     cls = m.classifier
     if _name(cls) != "Identity":
-        mods = list(cls.children())
-        if [_name(c) for c in mods] != ["AdaptiveAvgPool2d", "Flatten", "Linear"]:
-            raise UnsupportedModule(f"classifier head {cls}")
-        lin = mods[2]
-        y = Fn.global_avgpool(y)
-        w4 = lin.weight.view(lin.out_features, lin.in_features, 1, 1)
-        y, _ = Fn.conv2d(y, w4, lin.bias, 1, 0)
+        y = run_head(ctx, list(cls.children()), y)
     return (y, skips[:-1]) if return_skip_vals else y
+
+
+def run_head(ctx: ExecContext, mods: List[nn.Module], y):
+    """AdaptiveAvgPool2d(1) -> Flatten -> Linear (classification/models.py:73-77; the tail of the pretraining YAMLs'
+    layer list, config/pretraining/resnet50/simple.yaml:27-33) on an NHWC feature map: the pooled vector stays an
+    (N, 1, 1, C) activation and the Linear layer is a 1x1 convolution on the same tap-GEMM kernel."""
+    mods = [_unwrap(c) for c in mods]
+    if [_name(c) for c in mods] != ["AdaptiveAvgPool2d", "Flatten", "Linear"]:
+        raise UnsupportedModule(f"classifier head {[_name(c) for c in mods]}")
+    pool, flat, lin = mods
+    if pool.output_size not in (1, (1, 1)) or (flat.start_dim, flat.end_dim) != (1, -1):
+        raise UnsupportedModule(f"classifier head {pool} / {flat}")
+    if lin.out_features % 8 or lin.in_features != y.shape[3]:
+        raise UnsupportedModule(f"{lin}: the head's GEMM needs out_features % 8 == 0 and in_features == the "
+                                f"encoder's {y.shape[3]} channels on the B200 path")
+    y = Fn.global_avgpool(y)
+    w4 = lin.weight.view(lin.out_features, lin.in_features, 1, 1)
+    y, _ = Fn.conv2d(y, w4, lin.bias, 1, 0)
+    return y
+
+
+def run_feed_forward(ctx: ExecContext, m, x):
+    """The SEQUENTIAL compound model of the pretraining YAMLs (`model.FeedForwardModel: {layers: [...]}`,
+    config/pretraining/resnet50/simple.yaml:23-33; the class that produced the published `layers.0.` encoder
+    checkpoints, segmentation/models/unet_models.py:570-571, is not in the reference checkout — SURVEY.md App. C):
+    layers[0] = the encoder, the remaining layers = pooling / flatten / linear head."""
+    layers = [_unwrap(l) for l in m.layers]
+    if not layers or _name(layers[0]) != "DeepResNet":
+        raise UnsupportedModule(f"sequential model starting with {_name(layers[0]) if layers else None}")
+    y = run_deep_resnet(ctx, layers[0], x)
+    if _name(layers[0].classifier) != "Identity":
+        if len(layers) > 1:
+            raise UnsupportedModule("layers after an encoder that already carries a head")
+        return y
+    if len(layers) > 1:
+        y = run_head(ctx, layers[1:], y)
+    return y
 
 
 # ------------------------------------------------------------------------------------------------
@@ -427,8 +459,20 @@ def _forward_unet(self, x):
     return out
 
 
+def _forward_feed_forward(self, x, *args, **kwargs):
+    _require_cuda(x)
+    ctx = self._msp_ctx
+    ctx.begin_forward()
+    y = run_feed_forward(ctx, self, RawInput(x))
+    ctx.finish_forward()
+    y = Fn.to_nchw(y)
+    layers = [_unwrap(l) for l in self.layers]
+    has_head = len(layers) > 1 or _name(layers[0].classifier) != "Identity"
+    return y.flatten(1) if has_head else y
+
+
 _TOP_LEVEL = {"DeepResNet": _forward_deep_resnet, "UNet_encoder": _forward_unet_encoder,
-              "UNet": _forward_unet}
+              "UNet": _forward_unet, "FeedForwardModel": _forward_feed_forward}
 
 
 def convert(model: nn.Module, group=None) -> nn.Module:

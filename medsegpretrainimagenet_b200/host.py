@@ -20,10 +20,21 @@ class BatchPrefetcher:
         self._put = 0                 # next buffer to fill
         self._get = 0                 # next buffer to hand out
         self._last = None
+        self._outstanding = 0         # batches copied (or being copied) but not handed out yet
 
     def put(self, *host: torch.Tensor) -> None:
         """Enqueue the H2D copy of the next batch (pinned memory for a truly asynchronous copy)."""
         k = self._put
+        if self._outstanding >= 2:
+            raise RuntimeError("BatchPrefetcher: both buffers hold batches that were not handed out yet (call get())")
+        if self._last == k:
+            # the buffer about to be refilled is the one the consumer was handed LAST: whatever has been enqueued on
+            # the consumer stream so far may still read it, so the copy waits for that point (get() records the
+            # event itself for the usual get-then-put order; put, put, get, step, put lands here)
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream(self.device))
+            self.free[k] = ev
+            self._last = None
         if self.free[k] is not None:
             self.copy_stream.wait_event(self.free[k])
         with torch.cuda.stream(self.copy_stream):
@@ -31,6 +42,7 @@ class BatchPrefetcher:
                 d.copy_(h, non_blocking=True)
             self.ready[k].record(self.copy_stream)
         self._put ^= 1
+        self._outstanding += 1
 
     def get(self):
         """Device tensors of the oldest pending batch; the current stream waits for its copy."""
@@ -39,10 +51,13 @@ class BatchPrefetcher:
             ev = torch.cuda.Event()
             ev.record(cur)
             self.free[self._last] = ev
+        if self._outstanding == 0:
+            raise RuntimeError("BatchPrefetcher: get() without a pending put()")
         k = self._get
         cur.wait_event(self.ready[k])
         self._last = k
         self._get ^= 1
+        self._outstanding -= 1
         return self.bufs[k]
 
 

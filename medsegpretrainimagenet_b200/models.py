@@ -313,10 +313,67 @@ def kaiming_init_(model: nn.Module) -> nn.Module:
     return model
 
 
+class FeedForwardModel(nn.Module):
+    """The sequential compound model the pretraining YAMLs name (`model.FeedForwardModel: {layers: [...]}`,
+    config/pretraining/resnet50/simple.yaml:23-33): `.layers` is a ModuleList applied in order, so an encoder trained
+    as its first layer is checkpointed under the `layers.0.` prefix that `UNet.init_weights` strips
+    (segmentation/models/unet_models.py:570-571) and `eval_encoder` reads as `model.layers[0]` (robustness/eval.py:58).
+    The class shipped in the reference (model/model.py:313-333) takes `threads` and runs its sub-models in PARALLEL
+    (SURVEY.md App. C), so those YAMLs cannot be built from the checkout; `patch.install()` puts a class with this
+    behaviour in its place.  Each layer is wrapped in `Model` like the reference's CompoundModel does
+    (model/model.py:299-305); `state_dict()` keys carry no `.model.` segment (model/model.py:248-249).
+
+    Supported layer lists: [DeepResNet] or [DeepResNet, AdaptiveAvgPool2d(1), Flatten, Linear] — executed as ONE pass
+    of the B200 interpreter (the head is a pooled 1x1 convolution on the tap-GEMM kernel), never through torch.nn."""
+
+    def __init__(self, layers: Sequence[nn.Module], group=None, *args, **kwargs):
+        super().__init__()
+        if layers is None:
+            layers = []
+        if not isinstance(layers, (tuple, list)):
+            layers = [layers]
+        self.layers = nn.ModuleList([l if type(l).__name__ == "Model" else Model(l) for l in layers])
+        self.pass_all_inputs = [False] * len(self.layers)
+        self.PASS_ALL_INPUTS = False
+        _cv.convert(self, group=group)
+
+
+def encoder_state_dict(state_dict: dict, prefix: str = "layers.0") -> dict:
+    """unet_models.py:570-571: the entries of a pretraining checkpoint that belong to its first layer."""
+    n = len(prefix)
+    return {k[n + 1:]: v for k, v in state_dict.items() if k[:n] == prefix}
+
+
+def load_encoder_checkpoint(unet: nn.Module, checkpoint, strict: bool = True):
+    """`UNet.init_weights` (segmentation/models/unet_models.py:555-588) for models built without the reference:
+    load the `layers.0.` entries of a pretraining checkpoint (path or state dict) into `unet.encoder`, mapping keys
+    saved without the wrappers' `.model.` segments back onto them (:573-577).  Returns (missing, unexpected)."""
+    sd = torch.load(checkpoint, map_location="cpu") if isinstance(checkpoint, (str, bytes)) or hasattr(checkpoint, "__fspath__") \
+        else checkpoint
+    enc_sd = encoder_state_dict(sd)
+    encoder = unet.encoder
+    missing, _ = encoder.load_state_dict(enc_sd, strict=False)
+    for key in list(missing):
+        short = key.replace(".model.", ".")
+        if short in enc_sd:
+            enc_sd[key] = enc_sd.pop(short)
+    res = encoder.load_state_dict(enc_sd, strict=strict)
+    return list(res.missing_keys), list(res.unexpected_keys)
+
+
 # the BASELINE.json configurations -----------------------------------------------------------------
 def resnet50_classifier(num_classes=1000, in_channels=3, group=None):
     """cfg2 — config/pretraining/resnet50/simple.yaml:24-33."""
     return DeepResNet(bias=False, head=True, output_size=num_classes, in_channels=in_channels, group=group)
+
+
+def resnet50_pretraining_model(num_classes=1000, in_channels=3, stochastic_depth_rate=0, group=None):
+    """cfg2 exactly as its YAML lists it (config/pretraining/resnet50/simple.yaml:23-33): the sequential model
+    [DeepResNet(bias=False, v1), AdaptiveAvgPool2d(1), Flatten, Linear(2048, num_classes)]."""
+    enc = DeepResNet(bias=False, version="v1", in_channels=in_channels, stochastic_depth_rate=stochastic_depth_rate,
+                     group=group)
+    return FeedForwardModel([enc, nn.AdaptiveAvgPool2d(output_size=1), nn.Flatten(), nn.Linear(2048, num_classes)],
+                            group=group)
 
 
 def resnet50_attention_unet(out_ch=1, final_activation="sigmoid", in_channels=3, stochastic_depth_rate=0.1,

@@ -143,6 +143,28 @@ class AdamW(torch.optim.Optimizer):
         super().__init__(params, dict(lr=lr, betas=tuple(betas), eps=eps, weight_decay=weight_decay, amsgrad=False))
         self._host_steps = {}
 
+    def load_state_dict(self, state_dict):
+        """torch.optim.AdamW checkpoints load as they are: torch leaves a non-capturable optimizer's `step` on the
+        device it was saved on (the CPU for stock torch.optim.AdamW or a map_location='cpu' checkpoint), but the
+        kernel reads the counter on the GPU — so every `step` is moved to an fp32 scalar on its parameter's device,
+        and the host-side mirror of the step counts (one read per parameter, at load time only) is rebuilt."""
+        super().load_state_dict(state_dict)
+        self._host_steps = {}
+        for group in self.param_groups:
+            if group.get("amsgrad", False):
+                raise ValueError("medsegpretrainimagenet_b200.optim.AdamW: amsgrad state cannot be loaded")
+            for p in group["params"]:
+                st = self.state.get(p)
+                if not st or "step" not in st:
+                    continue
+                step = st["step"]
+                host = float(step.item()) if isinstance(step, torch.Tensor) else float(step)
+                st["step"] = torch.full((), host, dtype=torch.float32, device=p.device)
+                self._host_steps[id(p)] = int(round(host))
+                for k in ("exp_avg", "exp_avg_sq"):
+                    if k in st and (st[k].device != p.device or st[k].dtype != torch.float32 or not st[k].is_contiguous()):
+                        st[k] = st[k].to(device=p.device, dtype=torch.float32).contiguous()
+
     @torch.no_grad()
     def step(self, closure=None):
         loss = None

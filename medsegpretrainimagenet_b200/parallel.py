@@ -34,6 +34,13 @@ class GradReducer:
 
         reducer = GradReducer(model.parameters(), bucket_mb=32)
         loop:  reducer.zero_grad();  loss.backward();  reducer.finish();  optimizer.step()
+
+    Gradient accumulation (the reference's "virtual batch", train_model.py:53-55: `accumulation_scale` backward passes
+    per optimizer step): run every micro-batch but the last under `with reducer.no_sync():` — their gradients only
+    accumulate in the bucket storage — and call `finish()` after the last one, which is the only pass that exchanges.
+    A second backward outside `no_sync()` without a `finish()` in between, or a `param.grad` that no longer aliases
+    the bucket (e.g. after `optimizer.zero_grad(set_to_none=True)`; use `reducer.zero_grad()`), raises instead of
+    silently reducing stale or empty buckets.
     """
 
     def __init__(self, params, bucket_mb: float = 32.0, group=None, average: bool = True):
@@ -45,6 +52,8 @@ class GradReducer:
         self.buckets: List[_Bucket] = []
         self._bucket_of = {}
         self._hooks = []
+        self._sync = True
+        self._grad_ptr = {}
         if self.world == 1:
             # single process: nothing to exchange — gradients stay the tensors the backward kernels produced
             # (`param.grad = None` before backward lets autograd adopt them without an accumulate kernel each)
@@ -76,6 +85,7 @@ class GradReducer:
         off = 0
         for p in params:
             p.grad = flat[off:off + p.numel()].view_as(p)
+            self._grad_ptr[p] = p.grad.data_ptr()
             off += p.numel()
         self.buckets.append(_Bucket(flat, params))
 
@@ -94,31 +104,57 @@ class GradReducer:
             b.pending = len(b.params)
             b.work = None
 
+    def no_sync(self):
+        """Context manager for every micro-batch of an accumulated step except the last: backward passes inside it
+        add into the buckets without exchanging them."""
+        reducer = self
+
+        class _NoSync:
+            def __enter__(self_inner):
+                self_inner.prev, reducer._sync = reducer._sync, False
+                return reducer
+
+            def __exit__(self_inner, *exc):
+                reducer._sync = self_inner.prev
+                return False
+
+        return _NoSync()
+
+    def _launch(self, b) -> None:
+        # async_op: NCCL's own stream waits for the producer stream, then reduces while the remaining backward
+        # kernels keep running on the compute stream
+        op = dist.ReduceOp.AVG if (self.average and dist.get_backend(self.group) == "nccl") else dist.ReduceOp.SUM
+        b.work = dist.all_reduce(b.flat, op=op, group=self.group, async_op=True)
+
     def _on_grad(self, p) -> None:
+        if p.grad is None or p.grad.data_ptr() != self._grad_ptr[p]:
+            raise RuntimeError("GradReducer: param.grad no longer aliases the reduction bucket (was the gradient reset "
+                               "with optimizer.zero_grad(set_to_none=True)? use reducer.zero_grad())")
+        if not self._sync:
+            return                      # accumulating micro-batch: the exchange happens after the last one
         b = self._bucket_of[p]
+        if b.work is not None or b.pending <= 0:
+            raise RuntimeError("GradReducer: a second backward pass reached a bucket that was already exchanged; run "
+                               "all but the last micro-batch of an accumulated step under `with reducer.no_sync():` and "
+                               "call finish() after the last one")
         b.pending -= 1
         if b.pending == 0 and self.world > 1:
-            # async_op: NCCL's own stream waits for the producer stream, then reduces while the
-            # remaining backward kernels keep running on the compute stream
-            if self.average and dist.get_backend(self.group) == "nccl":
-                b.work = dist.all_reduce(b.flat, op=dist.ReduceOp.AVG, group=self.group, async_op=True)
-            else:
-                b.work = dist.all_reduce(b.flat, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+            self._launch(b)
 
     def finish(self) -> None:
-        """Call after backward: waits for the in-flight reductions (and launches any bucket whose
-        parameters received no gradient this step, e.g. frozen branches)."""
+        """Call after the (last) backward: launches every bucket that is not in flight yet (parameters without a
+        gradient this step, e.g. frozen branches), waits for all of them and re-arms the buckets."""
         if self.world == 1:
             return
         for b in self.buckets:
             if b.work is None:
-                op = dist.ReduceOp.AVG if (self.average and dist.get_backend(self.group) == "nccl") \
-                    else dist.ReduceOp.SUM
-                b.work = dist.all_reduce(b.flat, op=op, group=self.group, async_op=True)
+                self._launch(b)
         for b in self.buckets:
             b.work.wait()
             if self.average and dist.get_backend(self.group) != "nccl":
                 b.flat.div_(self.world)
+            b.work = None
+            b.pending = 0               # exchanged: a further backward before zero_grad() is an error (see _on_grad)
 
     def remove(self) -> None:
         for h in self._hooks:

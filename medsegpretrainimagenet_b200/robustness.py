@@ -103,3 +103,27 @@ def predict_w_model(model, imgs: torch.Tensor, batch_size: int = 32, device="cud
     if pool:
         return torch.mean(pred.flatten(2), dim=2)
     return pred
+
+
+def eval_encoder(model, imgs: torch.Tensor, scorer: Robustness, level: int, pool: bool, *args, **kwargs):
+    """robustness/eval.py:56-69: the encoder is the first layer of the sequential pretraining model
+    (`model.model.layers[0]`), two independent ColorJitter(0.1, 0.05, 0.1, 0.05) views of the image batch go through
+    it, the requested level's representations are scored.  The augmentation runs on the device
+    (transforms.ColorJitter, torchvision's parameter draw on the CPU generator) and the spatial mean of `pool=True`
+    is fused into the distance kernel instead of being materialised."""
+    from .transforms import ColorJitter
+    inner = getattr(model, "model", model)
+    encoder = inner.layers[0]
+    encoder.eval()
+    device = kwargs.pop("device", "cuda:0")
+    aug = ColorJitter(brightness=0.1, contrast=0.05, hue=0.05, saturation=0.1)
+    imgs = imgs.to(device)
+    imgs0, imgs1 = aug(imgs), aug(imgs)
+    preds0 = predict_w_model(encoder, imgs0, level=level, pool=False, device=device, *args, **kwargs)
+    preds1 = predict_w_model(encoder, imgs1, level=level, pool=False, device=device, *args, **kwargs)
+    if isinstance(scorer, Robustness):
+        return scorer(preds0, preds1, pool=pool)
+    # a reference-constructed scorer (robustness/eval.py:7-28, re-routed by patch.install)
+    if pool:
+        preds0, preds1 = torch.mean(preds0.flatten(2), dim=2), torch.mean(preds1.flatten(2), dim=2)
+    return scorer(preds0, preds1)

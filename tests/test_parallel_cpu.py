@@ -50,6 +50,30 @@ def _worker(rank, world, port, out):
         torch.nn.functional.mse_loss(ref_model(x), y).backward()
         ref = [p.grad for n, p in ref_model.named_parameters() if n != "2.bias"]
         ok = all(torch.allclose(a, b, rtol=1e-5, atol=1e-7) for a, b in zip(got, ref))
+        # gradient accumulation (train_model.py:53-55, loss/loss.py:83-84: loss / accumulation_scale per fragment):
+        # two micro-batches per rank, the first under no_sync(), one exchange after the second == full batch
+        reducer.zero_grad()
+        mid = (lo + hi) // 2
+        with reducer.no_sync():
+            (torch.nn.functional.mse_loss(model(x[lo:mid]), y[lo:mid]) / 2).backward()
+        (torch.nn.functional.mse_loss(model(x[mid:hi]), y[mid:hi]) / 2).backward()
+        reducer.finish()
+        ok &= all(torch.allclose(p.grad, b, rtol=1e-5, atol=1e-7) for p, b in zip(params, ref))
+        # the two silent failures of the first version now raise: a further backward after the exchange ...
+        try:
+            torch.nn.functional.mse_loss(model(x[lo:hi]), y[lo:hi]).backward()
+            ok = False
+        except RuntimeError as e:
+            ok &= "no_sync" in str(e)
+        # ... and gradients that were detached from the buckets by optimizer.zero_grad(set_to_none=True)
+        reducer.zero_grad()
+        torch.optim.SGD(params, lr=0.1).zero_grad(set_to_none=True)
+        try:
+            torch.nn.functional.mse_loss(model(x[lo:hi]), y[lo:hi]).backward()
+            ok = False
+        except RuntimeError as e:
+            ok &= "aliases" in str(e)
+        reducer.remove()
         # sufficient statistics: BatchNorm [sum, sum of squares] and Dice [I, Y, S] all-reduced == full batch
         feats = torch.randn((8, 5, 6, 6), generator=g)
         st = torch.stack([feats[lo:hi].sum((0, 2, 3)), (feats[lo:hi] ** 2).sum((0, 2, 3))])

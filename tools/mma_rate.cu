@@ -1,6 +1,6 @@
 // Microbenchmark: issue rate of tcgen05.mma (cta_group::1, kind::f16, bf16 -> fp32, M=128) on sm_100a under the
 // conv kernels' pipeline structure.  Build + run on the GPU box:
-//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -I medsegpretrainimagenet_b200/csrc \
+//   nvcc --cudart shared -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -I medsegpretrainimagenet_b200/csrc \
 //        tools/mma_rate.cu -o build/mma_rate && build/mma_rate
 // modes: 0 = back-to-back MMAs, one commit at the end
 //        1 = + tcgen05.commit after every k-block (4 MMAs)
