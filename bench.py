@@ -219,112 +219,146 @@ def cpu_baseline(workload, budget_s=25.0):
 
 
 # ------------------------------------------------------------------------------------------------
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
-    ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="cfg2", choices=list(WORKLOADS))
-    ap.add_argument("--batch", type=int, default=0, help="per-GPU batch (default: the workload's)")
-    ap.add_argument("--ref-steps", type=int, default=3)
-    ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--small-allreduce", default="p2p", choices=["p2p", "nccl"],
-                    help="SyncBN statistic exchange (N>1): one-kernel all-reduce over NVLink peer memory, or NCCL")
-    ap.add_argument("--no-graph", action="store_true", help="enqueue every step from Python instead of replaying a CUDA graph")
-    args = ap.parse_args()
-    if args.impl == "reference":
-        return reference_arm(args)
+def ncu_traffic(workload_name):
+    """Per-launch DRAM bytes of each kernel family from the committed ncu capture of this benchmark's step
+    (profiles/ncu_traffic.json, written by tools/ncu_traffic.py from `ncu --metrics dram__bytes_read.sum,
+    dram__bytes_write.sum`): the live run cannot measure DRAM traffic itself."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+            d = json.load(f)
+        return d.get(workload_name, {}), d.get("_source")
+    except Exception:
+        return {}, None
 
+
+def conv_roofline(timeline, ms_per_step, workload_name):
+    """`roofline` object: the dominant kernel (largest share of device time among the conv kernel variants, which are
+    60 % of the step) with its algorithmic FLOPs or bytes over its CUDA-event time, plus the per-kernel list."""
+    pk, pk_src = peaks()
+    peak_tf = pk.get("bf16_tflops_sustained", pk.get("bf16_tflops"))
+    hbm = pk.get("hbm_gbs")
+    traffic, traffic_src = ncu_traffic(workload_name)
+    fam = {}
+    by_kind = {}
+    for kind, f, a, b, nbytes, name in timeline:
+        t = a.elapsed_time(b)
+        d = fam.setdefault(name or "conv", {"launches": 0, "ms": 0.0, "gflop": 0.0, "gbyte": 0.0, "ideal_ms": 0.0})
+        d["launches"] += 1; d["ms"] += t; d["gflop"] += f / 1e9; d["gbyte"] += nbytes / 1e9
+        d["ideal_ms"] += max(f / (peak_tf * 1e12), nbytes / (hbm * 1e9)) * 1e3
+        k = by_kind.setdefault(kind, [0.0, 0.0, 0])
+        k[0] += f; k[1] += t; k[2] += 1
+    kernels = []
+    for name, d in sorted(fam.items(), key=lambda kv: -kv[1]["ms"]):
+        tensor_ms, hbm_ms = d["gflop"] / peak_tf, d["gbyte"] / hbm * 1e3      # GFLOP / (TFLOP/s) = ms; GB / (GB/s) = s
+        bound = "tensor" if tensor_ms >= hbm_ms else "hbm"
+        e = {"kernel": name, "launches": d["launches"], "ms": d["ms"], "share_of_step": d["ms"] / ms_per_step,
+             "algorithmic_gflop": d["gflop"], "algorithmic_gbyte": d["gbyte"],
+             "tflops": d["gflop"] / d["ms"] if d["ms"] > 0 else None,
+             "gbs": d["gbyte"] / d["ms"] * 1e3 if d["ms"] > 0 else None,
+             "bound": bound, "frac_of_tensor_peak": (d["gflop"] / d["ms"]) / peak_tf if d["ms"] > 0 else None,
+             "frac_of_hbm_peak": (d["gbyte"] / d["ms"] * 1e3) / hbm if d["ms"] > 0 else None,
+             "frac_of_per_launch_roofline": d["ideal_ms"] / d["ms"] if d["ms"] > 0 else None}
+        tr = traffic.get(name)
+        if tr:
+            e["dram_bytes_per_launch_ncu"] = tr.get("dram_bytes_per_launch")
+            e["algorithmic_bytes_per_launch"] = d["gbyte"] * 1e9 / d["launches"]
+        kernels.append(e)
+    conv_ms = sum(d["ms"] for d in fam.values())
+    conv_gflop = sum(d["gflop"] for d in fam.values())
+    dom = kernels[0] if kernels else None
+    out = {"bound": None, "kernel": None, "achieved": None, "peak": None, "unit": None, "frac": None, "traffic": None}
+    if dom:
+        if dom["bound"] == "tensor":
+            out.update(bound="tensor", achieved=dom["tflops"], peak=peak_tf, unit="TFLOP/s", frac=dom["frac_of_tensor_peak"])
+        else:
+            out.update(bound="hbm", achieved=dom["gbs"], peak=hbm, unit="GB/s", frac=dom["frac_of_hbm_peak"])
+        out["kernel"] = f"{dom['kernel']} (tcgen05 implicit-GEMM conv; dominant kernel: {dom['share_of_step']:.0%} of the step)"
+        out["traffic"] = dom.get("dram_bytes_per_launch_ncu")
+        out["traffic_source"] = traffic_src if out["traffic"] is not None else None
+        out["algorithmic_per_launch"] = {"gflop": dom["algorithmic_gflop"] / dom["launches"],
+                                         "bytes": dom["algorithmic_gbyte"] * 1e9 / dom["launches"]}
+        out["avg_launch_us"] = dom["ms"] * 1e3 / dom["launches"]
+    out["peak_source"] = f"{pk_src} (bf16 sustained {peak_tf} TFLOP/s, HBM copy {hbm} GB/s)"
+    all_tf = conv_gflop / conv_ms if conv_ms > 0 else 0.0
+    out["all_conv_kernels"] = {"achieved_tflops": all_tf, "frac_of_tensor_peak": all_tf / peak_tf if peak_tf else None,
+                               "frac_of_per_launch_roofline": (sum(d["ideal_ms"] for d in fam.values()) / conv_ms) if conv_ms else None,
+                               "conv_ms_per_step": conv_ms, "conv_share_of_step": conv_ms / ms_per_step,
+                               "algorithmic_gflop_per_step": conv_gflop}
+    out["by_kind"] = {k: {"gflop": v[0] / 1e9, "ms": v[1], "launches": v[2],
+                          "tflops": v[0] / (v[1] * 1e-3) / 1e12 if v[1] > 0 else None} for k, v in by_kind.items()}
+    out["kernels"] = kernels
+    return out
+
+
+def run_workload(args, workload, steps, warm, world, rank, local, dev, group, with_cpu_baseline, sample_clocks=True):
+    """One workload on this rank -> the JSON fields (rank 0) or None."""
     import torch
     import torch.distributed as dist
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py: no CUDA device (the B200 path has no CPU fallback)")
     import medsegpretrainimagenet_b200 as b200
-    from medsegpretrainimagenet_b200 import models, ops
+    from medsegpretrainimagenet_b200 import models, ops, optim as mopt
     from medsegpretrainimagenet_b200.parallel import GradReducer
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    group = None
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-        group = dist.group.WORLD
-        if args.small_allreduce == "p2p":
-            # SyncBN statistics through the peer-memory kernel (csrc/msp_p2p.cu) instead of ~100 tiny NCCL calls / step
-            from medsegpretrainimagenet_b200 import parallel as _par
-            if _par.enable_peer_allreduce(group) is None:
-                args.small_allreduce = "nccl"        # CUDA IPC unavailable on this box: every rank fell back together
-    warm = max(args.warmup, 3)
-
-    name, batch, shape, _ = WORKLOADS[args.workload]
-    batch = args.batch or batch
+    name, batch, shape, _ = WORKLOADS[workload]
+    batch = (args.batch or batch) if workload == args.workload else batch
     torch.manual_seed(0)
-    if args.workload == "cfg2":
-        model = models.resnet50_classifier(group=group)
+    torch_opt = args.optimizer == "torch"
+    if workload == "cfg2":
+        # the pretraining YAML's own model: the sequential [DeepResNet, AdaptiveAvgPool2d, Flatten, Linear]
+        # (config/pretraining/resnet50/simple.yaml:23-33), executed as one pass of the B200 interpreter
+        model = models.resnet50_pretraining_model(group=group)
         crit = b200.losses.CrossEntropyLoss(label_smoothing=0.1)
-        make_opt = lambda ps: torch.optim.AdamW(ps, lr=0.004, betas=(0.9, 0.999), weight_decay=0.05, fused=True,
-                                                capturable=True)
-    elif args.workload == "cfg3":
-        model = models.resnet50_attention_unet(out_ch=4, final_activation="softmax", group=group)
-        crit = b200.losses.DiceLoss(group=group)
-        make_opt = lambda ps: torch.optim.SGD(ps, lr=0.05, momentum=0.9, weight_decay=1e-4, fused=True)
-    elif args.workload == "cfg4":
-        model = models.basic_unet(out_ch=5, final_activation="sigmoid", group=group)
-        crit = b200.losses.BCELoss(torch_semantics=True)            # torch.nn.BCELoss
-        make_opt = lambda ps: torch.optim.SGD(ps, lr=0.05, momentum=0.9, weight_decay=1e-4, fused=True)
+        if torch_opt:
+            make_opt = lambda ps: torch.optim.AdamW(ps, lr=0.004, betas=(0.9, 0.999), weight_decay=0.05, fused=True, capturable=True)
+        else:
+            make_opt = lambda ps: mopt.AdamW(ps, lr=0.004, betas=(0.9, 0.999), weight_decay=0.05)
     else:
-        model = models.resnet18_attention_unet(group=group)
-        crit = b200.losses.DiceLoss(group=group)
-        make_opt = lambda ps: torch.optim.SGD(ps, lr=0.05, momentum=0.9, weight_decay=1e-4, fused=True)
+        if workload == "cfg3":
+            model = models.resnet50_attention_unet(out_ch=4, final_activation="softmax", group=group)
+            crit = b200.losses.DiceLoss(group=group)
+        elif workload == "cfg4":
+            model = models.basic_unet(out_ch=5, final_activation="sigmoid", group=group)
+            crit = b200.losses.BCELoss(torch_semantics=True)            # torch.nn.BCELoss (SURVEY 8d cfg4)
+        else:
+            model = models.resnet18_attention_unet(group=group)
+            crit = b200.losses.DiceLoss(group=group)
+        if torch_opt:
+            make_opt = lambda ps: torch.optim.SGD(ps, lr=0.05, momentum=0.9, weight_decay=1e-4, fused=True)
+        else:
+            make_opt = lambda ps: mopt.SGD(ps, lr=0.05, momentum=0.9, weight_decay=1e-4)
     models.kaiming_init_(model)
     model.to(dev).train()
     params = [p for p in model.parameters() if p.requires_grad]
     reducer = GradReducer(params, bucket_mb=32.0, group=group)
     opt = make_opt(params)
     n_params = sum(p.numel() for p in params)
+    clip = (lambda: torch.nn.utils.clip_grad_norm_(params, float("inf"), foreach=True)) if torch_opt \
+        else (lambda: mopt.clip_grad_norm_(params, float("inf")))
 
     gen = torch.Generator().manual_seed(1 + rank)
-    x_host, y_host = synthetic_batch(args.workload, batch, gen, torch)
-    if args.workload == "cfg2":
+    x_host, y_host = synthetic_batch(workload, batch, gen, torch)
+    if workload == "cfg2":
         x_host = x_host.to(torch.bfloat16)   # BASELINE configs[1]: "3x224x224 bf16" images (SURVEY 8d: x ~ N(0,1) -> bf16)
     x_host, y_host = x_host.pin_memory(), y_host.pin_memory()
     x_dev, y_dev = x_host.to(dev), y_host.to(dev)
-
-    if args.workload == "cfg2":
-        top5 = b200.metrics.Top5Accuracy()
-        cm = b200.metrics.MultiClassConfusionMatrix(number_of_classes=1000)
-    elif args.workload == "cfg3":
-        cm = b200.metrics.MultiClassConfusionMatrix(number_of_classes=4)
-        top5 = None
-    elif args.workload == "cfg4":
-        cm = b200.metrics.ConfusionMatrix(None, threshold=0.5)
-        top5 = None
-    else:
-        cm = b200.metrics.ConfusionMatrix(None, threshold=0.5)
-        top5 = None
 
     def step_core(x, y):
         reducer.zero_grad()
         pred = model(x)
         loss = crit(pred, y)
-        if args.workload == "cfg2":
+        if workload == "cfg2":
             # device-side counters (the .cpu() of the C x C matrix is deferred to evaluate_batch cadence)
             b200.metrics.multiclass_confusion_matrix(pred, y)
             b200.metrics.topk_correct(pred, y, 5)
-        elif args.workload == "cfg3":
+        elif workload == "cfg3":
             b200.metrics.multiclass_confusion_matrix(pred, y)
-        elif args.workload == "cfg4":
+        elif workload == "cfg4":
             b200.metrics.binary_confusion_counts(pred, y, 0.5, per_channel=True)   # multilabel: 4 x (5,) counters
         else:
             b200.metrics.binary_confusion_counts(pred, y, 0.5)
         loss.backward()                              # loss/loss.py:87
         reducer.finish()
-        torch.nn.utils.clip_grad_norm_(params, float("inf"), foreach=True)   # train_model.py:95-98
-        opt.step()
+        clip()                                       # train_model.py:95-98 (max_norm = inf: measured and logged)
+        opt.step()                                   # train_model.py:107
         return loss.detach()
 
     graphed = None
@@ -351,23 +385,23 @@ def main():
 
     # ---- timed region 1: inputs resident in HBM ------------------------------------------------
     sampler = ClockSampler(local)
-    if rank == 0:
+    if rank == 0 and sample_clocks:
         sampler.start()
     l0 = ops.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     t_host0 = time.perf_counter()
     e0.record()
-    for _ in range(args.steps):
+    for _ in range(steps):
         step(x_dev, y_dev)
     e1.record()
-    host_ms = (time.perf_counter() - t_host0) * 1e3 / args.steps   # CPU time to ENQUEUE one step (no sync inside)
+    host_ms = (time.perf_counter() - t_host0) * 1e3 / steps   # CPU time to ENQUEUE one step (no sync inside)
     barrier()
     launches = ops.launch_count() - l0
     if graphed is not None:
-        launches = graphed.launches_per_replay * args.steps
+        launches = graphed.launches_per_replay * steps
     ms = e0.elapsed_time(e1)
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop() if (rank == 0 and sample_clocks) else None
 
     # ---- timed region 2: end to end through the public API with host batches --------------------
     barrier()
@@ -379,9 +413,9 @@ def main():
     feeder = b200.BatchPrefetcher((x_host, y_host), dev)
     reader = b200.ScalarReader(depth=1)             # every step's loss is read back; the host waits one step late
     feeder.put(x_host, y_host)
-    for i in range(args.steps):
+    for i in range(steps):
         xb, yb = feeder.get()
-        if i + 1 < args.steps:
+        if i + 1 < steps:
             feeder.put(x_host, y_host)
         out = graphed(xb, yb) if graphed is not None else step_core(xb, yb)
         got = reader.push(out)                      # D2H copy of this step's loss (pinned, asynchronous)
@@ -413,59 +447,120 @@ def main():
     step_core(x_dev, y_dev)
     torch.cuda.synchronize()
     ops.set_conv_timeline(None)
-    conv_ms = sum(a.elapsed_time(b) for _, _, a, b in timeline)
-    conv_flops = sum(f for _, f, _, _ in timeline)
-    by_kind = {}
-    for kind, f, a, b in timeline:
-        d = by_kind.setdefault(kind, [0.0, 0.0, 0])
-        d[0] += f; d[1] += a.elapsed_time(b); d[2] += 1
-    pk, pk_src = peaks()
-    peak_tf = pk.get("bf16_tflops_sustained", pk.get("bf16_tflops"))
-    achieved_tf = conv_flops / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else 0.0
 
+    out = None
     if rank == 0:
-        total_images = args.steps * batch * world
+        total_images = steps * batch * world
+        h2d_bytes = x_host.numel() * x_host.element_size() + y_host.numel() * y_host.element_size()
         out = {
             "metric": "train images/sec", "value": total_images / (ms * 1e-3), "unit": "images/sec",
-            "n_gpus": world, "steps": args.steps, "warmup": warm, "ms_per_step": ms / args.steps,
+            "n_gpus": world, "steps": steps, "warmup": warm, "ms_per_step": ms / steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
             "data": "synthetic",
             "config": {"workload": name, "per_gpu_batch": batch, "global_batch": batch * world,
                        "parallelism": f"dp{world}", "params": n_params,
-                       "optimizer": type(opt).__name__, "l2": "inputs_larger_than_l2 (batch + activations >> 126 MB)",
+                       "optimizer": f"{type(opt).__module__}.{type(opt).__name__}",
+                       "l2": "inputs_larger_than_l2 (batch + activations >> 126 MB)",
                        "step": "fwd+loss+bwd+allreduce+metrics+gradnorm+optimizer",
                        "syncbn_exchange": None if world == 1 else ("peer-memory kernel" if args.small_allreduce == "p2p" else "nccl"),
                        "execution": "eager launches" if graphed is None else "one CUDA graph replay per step"},
             "e2e": {"value": total_images / (ms_e2e * 1e-3), "unit": "images/sec",
-                    "h2d_bytes_per_step": (x_host.numel() * x_host.element_size()
-                                           + y_host.numel() * y_host.element_size()) * world,
-                    "d2h_bytes_per_step": 4 * world, "ms_per_step": ms_e2e / args.steps, "last_loss": last,
+                    "h2d_bytes_per_step": h2d_bytes * world,
+                    "d2h_bytes_per_step": 4 * world, "ms_per_step": ms_e2e / steps, "last_loss": last,
                     "input_dtype": str(x_host.dtype).replace("torch.", ""), "h2d_ms_alone": h2d_ms,
-                    "h2d_gbs_alone": (x_host.numel() * x_host.element_size()
-                                      + y_host.numel() * y_host.element_size()) / (h2d_ms * 1e-3) / 1e9},
+                    "h2d_gbs_alone": h2d_bytes / (h2d_ms * 1e-3) / 1e9},
             "gpu_launches": int(launches), "host_enqueue_ms_per_step": host_ms,
             "clocks": clocks,
-            "roofline": {"bound": "tensor", "kernel": "tapgemm_kernel / wgrad_kernel (tcgen05 implicit-GEMM conv)",
-                         "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
-                         "frac": achieved_tf / peak_tf if peak_tf else None, "peak_source": f"{pk_src} (sustained)",
-                         "traffic": None,
-                         "conv_ms_per_step": conv_ms, "conv_share_of_step": conv_ms / (ms / args.steps),
-                         "algorithmic_gflop_per_step": conv_flops / 1e9,
-                         "by_kind": {k: {"gflop": v[0] / 1e9, "ms": v[1], "launches": v[2],
-                                         "tflops": v[0] / (v[1] * 1e-3) / 1e12 if v[1] > 0 else None}
-                                     for k, v in by_kind.items()}},
+            "roofline": conv_roofline(timeline, ms / steps, name),
         }
-        if world == 1 and not args.no_cpu_baseline:
-            out["cpu_baseline"] = cpu_baseline(args.workload)
+        if with_cpu_baseline:
+            out["cpu_baseline"] = cpu_baseline(workload)
+    # release this workload's graph, pools and model before the next one
+    del graphed, feeder, reader, timeline, opt, reducer, model, params
+    import gc
+    gc.collect()
+    torch.cuda.empty_cache()
+    return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="cfg2", choices=list(WORKLOADS))
+    ap.add_argument("--secondary", default="auto", choices=["auto", "none", *WORKLOADS],
+                    help="second workload measured in the same run and reported under `secondary` (auto: cfg3, the R50 "
+                         "attention U-Net the north-star targets are stated on, when the primary is cfg2)")
+    ap.add_argument("--batch", type=int, default=0, help="per-GPU batch (default: the workload's)")
+    ap.add_argument("--ref-steps", type=int, default=3)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--small-allreduce", default="p2p", choices=["p2p", "nccl"],
+                    help="SyncBN statistic exchange (N>1): one-kernel all-reduce over NVLink peer memory, or NCCL")
+    ap.add_argument("--optimizer", default="b200", choices=["b200", "torch"],
+                    help="gradient norm + optimizer step: this repo's multi-tensor kernels (default) or torch.optim")
+    ap.add_argument("--no-graph", action="store_true", help="enqueue every step from Python instead of replaying a CUDA graph")
+    ap.add_argument("--no-parity-check", action="store_true", help="skip the N-rank == 1-rank pre-check (N > 1)")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return reference_arm(args)
+
+    import torch
+    import torch.distributed as dist
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the B200 path has no CPU fallback)")
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    group = None
+    parity = None
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+        group = dist.group.WORLD
+        if args.small_allreduce == "p2p":
+            # SyncBN statistics through the peer-memory kernel (csrc/msp_p2p.cu) instead of ~100 tiny NCCL calls / step
+            from medsegpretrainimagenet_b200 import parallel as _par
+            if _par.enable_peer_allreduce(group) is None:
+                args.small_allreduce = "nccl"        # CUDA IPC unavailable on this box: every rank fell back together
+        if not args.no_parity_check:
+            # SURVEY.md §4 tier 6: the N-rank step (SyncBN, global Dice, averaged gradients) == the single-device
+            # step on the concatenated batch, checked on these very GPUs before anything is timed
+            from medsegpretrainimagenet_b200.selfcheck import n_rank_parity
+            parity = n_rank_parity(group, dev)
+    warm = max(args.warmup, 3)
+
+    out = run_workload(args, args.workload, args.steps, warm, world, rank, local, dev, group,
+                       with_cpu_baseline=(world == 1 and not args.no_cpu_baseline))
+    sec = args.secondary
+    if sec == "auto":
+        sec = "cfg3" if args.workload == "cfg2" else "none"
+    if sec != "none" and sec != args.workload:
+        s = run_workload(args, sec, args.steps, warm, world, rank, local, dev, group, with_cpu_baseline=False,
+                         sample_clocks=False)
+        if rank == 0:
+            out["secondary"] = {k: s[k] for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step",
+                                                  "config", "e2e", "gpu_launches", "host_enqueue_ms_per_step", "roofline")}
+    if rank == 0:
+        if parity is not None:
+            out["parity_n"] = "ok" if parity["ok"] else "FAILED"
+            out["parity_n_detail"] = parity
         emit(out)
     if world > 1:
-        # Tearing down a NCCL communicator whose collectives were captured in a live CUDA graph can block; the
-        # measurement is complete and printed: synchronise, rendezvous once more and leave without the teardown.
+        # every CUDA graph that captured NCCL work was released inside run_workload; tear the communicator down
+        # properly.  A watchdog ends the process if the teardown blocks (the measurement is complete and printed).
         torch.cuda.synchronize()
         dist.barrier()
         sys.stdout.flush()
         sys.stderr.flush()
-        os._exit(0)
+        dog = threading.Timer(60.0, lambda: os._exit(0))
+        dog.daemon = True
+        dog.start()
+        dist.destroy_process_group()
+        dog.cancel()
 
 
 if __name__ == "__main__":

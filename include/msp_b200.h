@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define MSP_ABI_VERSION 2
+#define MSP_ABI_VERSION 3
 
 const char* msp_last_error(void);
 int msp_version(void);
@@ -63,6 +63,9 @@ typedef struct msp_conv_desc {
  * pair: 0 never use the cta_group::2 CTA-pair tap-GEMM, 1 for >= 128 output channels per tile, 2 also for 64;
  * halo: 0 never use the halo-reuse kernel, 1 when the weights stay resident in shared memory, 2 whenever it applies. */
 int msp_conv_set_policy(int pair, int halo);
+/* Name of the kernel variant the calling thread's last msp_conv_* call launched ("tapgemm_kernel<256>",
+ * "tapgemm_halo_kernel<16>", "wgrad_kernel", ...): lets the benchmark attribute device time per kernel. */
+const char* msp_conv_last_kernel(void);
 
 /* OIHW fp32 master weights -> bf16 [K][KH*KW][Cpad] (fprop/wgrad operand) and, if w_dgrad != NULL,
  * bf16 [Cpad][KH*KW][Kpad] (dgrad operand).  Cpad/Kpad >= C/K, multiples of 8, padding zero-filled. */
@@ -317,11 +320,16 @@ int msp_p2p_allreduce_sum_f32(float* data, int n, int rank, int world, int max_n
  * torch.nn.utils.clip_grad_norm_ (train_model.py:93-98) and torch.optim.SGD / AdamW .step() (train_model.py:107 via
  * optim/optimizer.py:41-48).  Each call takes 1..32 fp32 contiguous tensors as host arrays of device pointers + element
  * counts (the pointer table travels in the kernel's parameter space); callers chunk longer lists.
- * msp_optim_sqnorm ADDS sum(g^2) of its tensors to the device double `sq_accum` (zero it first);
+ * msp_optim_sqnorm ADDS sum(g^2) of its tensors to the device double `sq_accum` (`zero_first`: cleared before this launch);
  * msp_optim_clip: g *= min(1, max_norm / (sqrt(*sq) + 1e-6)); msp_optim_sgd / msp_optim_adamw: torch's update formulas
  * (`first_step`: momentum buffers are initialised to the gradient; `step_dev`: device float, the 1-based step count).
  * ------------------------------------------------------------------------------------------ */
-int msp_optim_sqnorm(int n, void* const* grads, const long long* numel, double* sq_accum, void* stream);
+int msp_optim_sqnorm(int n, void* const* grads, const long long* numel, double* sq_accum, int zero_first,
+                     void* stream);
+/* *norm_out = (float)sqrt(*sq): the value clip_grad_norm_ returns ('gradient_magnitude', train_model.py:100) */
+int msp_optim_norm(const double* sq, float* norm_out, void* stream);
+/* *scalars[i] += value for 1..32 device floats: the AdamW step counters (one shared counter per parameter age) */
+int msp_optim_add_scalar(int n, void* const* scalars, float value, void* stream);
 int msp_optim_clip(int n, void* const* grads, const long long* numel, const double* sq, float max_norm, void* stream);
 int msp_optim_sgd(int n, void* const* params, void* const* grads, void* const* momentum_bufs, const long long* numel,
                   float lr, float momentum, float dampening, float weight_decay, int nesterov, int first_step,

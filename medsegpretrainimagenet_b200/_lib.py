@@ -41,6 +41,7 @@ SIGNATURES = {
     "msp_version": [],
     "msp_launch_count": [],
     "msp_conv_set_policy": [I, I],
+    "msp_conv_last_kernel": [],
     "msp_pack_weights": [P, I, I, I, I, I, I, P, P, P],
     "msp_conv_fprop": [C.POINTER(ConvDesc), P, P, P, P, P, P, P],
     "msp_conv_dgrad": [C.POINTER(ConvDesc), P, P, P, I, P],
@@ -86,7 +87,9 @@ SIGNATURES = {
     "msp_topk_hits": [P, P, I, I, LL, I, P, P],
     "msp_rowpair_distances": [P, P, I, LL, I, P, P],
     "msp_triplet_hinge": [P, I, P, I, P, P],
-    "msp_optim_sqnorm": [I, C.POINTER(C.c_void_p), C.POINTER(C.c_longlong), P, P],
+    "msp_optim_sqnorm": [I, C.POINTER(C.c_void_p), C.POINTER(C.c_longlong), P, I, P],
+    "msp_optim_norm": [P, P, P],
+    "msp_optim_add_scalar": [I, C.POINTER(C.c_void_p), F, P],
     "msp_optim_clip": [I, C.POINTER(C.c_void_p), C.POINTER(C.c_longlong), P, F, P],
     "msp_optim_sgd": [I, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_longlong),
                       F, F, F, F, I, I, P],
@@ -101,7 +104,7 @@ SIGNATURES = {
     "msp_p2p_free": [P],
     "msp_p2p_allreduce_sum_f32": [P, I, I, I, I, C.POINTER(C.c_void_p), P, P],
 }
-_RESTYPES = {"msp_last_error": C.c_char_p, "msp_launch_count": C.c_longlong, "msp_p2p_buffer_bytes": C.c_longlong}
+_RESTYPES = {"msp_last_error": C.c_char_p, "msp_conv_last_kernel": C.c_char_p, "msp_launch_count": C.c_longlong, "msp_p2p_buffer_bytes": C.c_longlong}
 
 
 class MspError(RuntimeError):

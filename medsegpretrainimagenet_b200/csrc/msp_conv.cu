@@ -40,6 +40,9 @@ extern void msp_count_launch(int n);
 
 namespace {
 
+// name of the kernel variant the calling thread launched last (bench.py's per-kernel roofline list)
+thread_local const char* g_last_kernel = "";
+
 constexpr int kMaxTaps = 49;
 constexpr int kBM = 128;  // UMMA M (rows of the output tile)
 constexpr int kBK = 64;   // contraction elements per pipeline stage (= one 128-byte swizzle row)
@@ -1234,6 +1237,8 @@ int launch_tapgemm(const CUtensorMap& tmA, const CUtensorMap& tmB, TapGemmParams
   MSP_CHECK_CUDA(msp_launch_pdl(tapgemm_kernel<BN_>, dim3(grid), dim3(kTapThreads), Cfg::kSmemBytes, st, tmA, tmB, p));
   MSP_CHECK_LAUNCH();
   msp_count_launch(1);
+  g_last_kernel = BN_ == 256 ? "tapgemm_kernel<256>" : BN_ == 128 ? "tapgemm_kernel<128>" : BN_ == 64 ? "tapgemm_kernel<64>"
+                  : BN_ == 32 ? "tapgemm_kernel<32>" : "tapgemm_kernel<16>";
   return MSP_OK;
 }
 
@@ -1262,6 +1267,7 @@ int launch_tapgemm2(const CUtensorMap& tmA, const CUtensorMap& tmB, TapGemmParam
   tapgemm2_kernel<BN_><<<grid, kTapThreads, Cfg2::kSmemBytes, st>>>(tmA, tmB, p);
   MSP_CHECK_LAUNCH();
   msp_count_launch(1);
+  g_last_kernel = BN_ == 256 ? "tapgemm2_kernel<256>" : BN_ == 128 ? "tapgemm2_kernel<128>" : "tapgemm2_kernel<64>";
   return MSP_OK;
 }
 
@@ -1401,6 +1407,8 @@ int launch_halo(const CUtensorMap& tmA, const CUtensorMap& tmB, TapGemmParams& p
   MSP_CHECK_CUDA(msp_launch_pdl(tapgemm_halo_kernel<BN_>, dim3(grid), dim3(kTapThreads), (size_t)smem, st, tmA, tmB, p));
   MSP_CHECK_LAUNCH();
   msp_count_launch(1);
+  g_last_kernel = BN_ == 256 ? "tapgemm_halo_kernel<256>" : BN_ == 128 ? "tapgemm_halo_kernel<128>"
+                  : BN_ == 64 ? "tapgemm_halo_kernel<64>" : BN_ == 32 ? "tapgemm_halo_kernel<32>" : "tapgemm_halo_kernel<16>";
   return MSP_OK;
 }
 
@@ -1472,6 +1480,8 @@ inline bool is_flat(const msp_conv_desc* d) {
 }
 
 }  // namespace
+
+extern "C" const char* msp_conv_last_kernel(void) { return g_last_kernel; }
 
 extern "C" int msp_conv_set_policy(int pair, int halo) {
   MSP_REQUIRE(pair >= -1 && pair <= 2 && halo >= -1 && halo <= 2, "conv_set_policy: values are -1 (default) .. 2");
@@ -1785,6 +1795,7 @@ extern "C" int msp_conv_wgrad(const msp_conv_desc* d, const void* x, const void*
   MSP_CHECK_CUDA(msp_launch_pdl(wgrad_kernel, dim3(grid), dim3(kConvThreads), (size_t)kWgSmemBytes, st, tmDY, tmX, p));
   MSP_CHECK_LAUNCH();
   msp_count_launch(1);
+  g_last_kernel = "wgrad_kernel";
   return MSP_OK;
 }
 

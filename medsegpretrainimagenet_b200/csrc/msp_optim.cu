@@ -129,6 +129,18 @@ __global__ void __launch_bounds__(kOptThreads) optim_adamw_kernel(const OptList 
   }
 }
 
+// sqrt of the accumulated sum of squares as the fp32 scalar clip_grad_norm_ returns
+__global__ void optim_norm_kernel(const double* __restrict__ sq, float* __restrict__ out) { *out = (float)sqrt(*sq); }
+
+// AdamW step counters (fp32 scalars shared by all parameters of the same age): += value
+struct ScalarList {
+  float* s[kOptMaxTensors];
+  int n;
+};
+__global__ void optim_add_scalar_kernel(const ScalarList L, float value) {
+  if ((int)threadIdx.x < L.n) *L.s[threadIdx.x] += value;
+}
+
 int fill_list(OptList* L, int n, void* const* p, void* const* g, void* const* a, void* const* b, const long long* numel,
               int* total_blocks) {
   MSP_REQUIRE(n >= 1 && n <= kOptMaxTensors && g && numel, "optim: 1..%d tensors per call (got %d)", kOptMaxTensors, n);
@@ -154,16 +166,41 @@ int fill_list(OptList* L, int n, void* const* p, void* const* g, void* const* a,
 
 }  // namespace
 
-extern "C" int msp_optim_sqnorm(int n, void* const* grads, const long long* numel, double* sq_accum, void* stream) {
+extern "C" int msp_optim_sqnorm(int n, void* const* grads, const long long* numel, double* sq_accum, int zero_first,
+                                void* stream) {
   MSP_REQUIRE(sq_accum, "optim_sqnorm: null accumulator");
   OptList L;
   int blocks = 0;
   int rc = fill_list(&L, n, nullptr, grads, nullptr, nullptr, numel, &blocks);
   if (rc) return rc;
+  if (zero_first) MSP_CHECK_CUDA(cudaMemsetAsync(sq_accum, 0, sizeof(double), (cudaStream_t)stream));
   OptHyper h;
   memset(&h, 0, sizeof(h));
   h.sq = sq_accum;
   optim_sqnorm_kernel<<<blocks, kOptThreads, 0, (cudaStream_t)stream>>>(L, h);
+  MSP_CHECK_LAUNCH();
+  msp_count_launch(1);
+  return MSP_OK;
+}
+
+extern "C" int msp_optim_norm(const double* sq, float* norm_out, void* stream) {
+  MSP_REQUIRE(sq && norm_out, "optim_norm: null pointer");
+  optim_norm_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(sq, norm_out);
+  MSP_CHECK_LAUNCH();
+  msp_count_launch(1);
+  return MSP_OK;
+}
+
+extern "C" int msp_optim_add_scalar(int n, void* const* scalars, float value, void* stream) {
+  MSP_REQUIRE(n >= 1 && n <= kOptMaxTensors && scalars, "optim_add_scalar: 1..%d scalars per call (got %d)", kOptMaxTensors, n);
+  ScalarList L;
+  memset(&L, 0, sizeof(L));
+  for (int i = 0; i < n; ++i) {
+    MSP_REQUIRE(scalars[i], "optim_add_scalar: null scalar %d", i);
+    L.s[i] = (float*)scalars[i];
+  }
+  L.n = n;
+  optim_add_scalar_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(L, value);
   MSP_CHECK_LAUNCH();
   msp_count_launch(1);
   return MSP_OK;

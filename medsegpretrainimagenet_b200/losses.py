@@ -160,3 +160,57 @@ class BCELoss(nn.Module):
         label = _f32c(label.reshape(prediction.shape))
         scale = 1.0 / prediction.numel() if self.reduction == "mean" else 1.0
         return _SumLoss.apply(prediction, label, "bce", self.clamp, scale)
+
+
+class Loss:
+    """Host-side mirror of the reference's `Loss` wrapper (loss/loss.py:8-114) for use WITHOUT the checkout (with it,
+    `patch.install()` leaves the reference's own wrapper in place and only re-routes the criteria): picks
+    `batch['prediction']` and `batch[label_type]`, divides by the accumulation scale, reads the value with `.item()`
+    (:85, the step's one host read), runs `.backward()` in training (:86-87) and keeps the running sums the epoch logs
+    are made of."""
+
+    def __init__(self, criterion, name=None, label_type="mask", accumulate=True):
+        import re
+        self.calculator = criterion
+        cls = type(criterion).__name__
+        snake = re.sub("([a-z0-9])([A-Z])", r"\1_\2", re.sub("(.)([A-Z][a-z]+)", r"\1_\2", cls)).lower()
+        self.name = name or getattr(criterion, "name", snake)
+        self.label_type = label_type
+        self.accumulate = accumulate
+        self.value, self.num_batches = 0, 0
+        self.acc_value, self.num_batch_fragments = 0, 0
+        self.train = True
+
+    def calculate_batch(self, batch, cumulate=True, train=True, average=True, accumulation_scale=1, last=False):
+        self.train = train
+        loss = self.calculator(batch["prediction"], batch[self.label_type])
+        if average:
+            loss = loss / accumulation_scale
+        value = loss.item()
+        if train and not last:
+            loss.backward()
+        if cumulate:
+            if self.accumulate:
+                self.acc_value += value
+                self.num_batch_fragments += 1
+            else:
+                self.value += value
+                self.num_batches += 1
+        return {self.name: value}
+
+    def evaluate_batch(self, *args, cumulate=True, flush=True, **kwargs):
+        value = self.acc_value if self.accumulate else self.value
+        if flush:
+            self.num_batch_fragments, self.acc_value = 0, 0
+        if cumulate:
+            self.value += value
+            self.num_batches += 1
+        return {self.name: value}
+
+    def evaluate_epoch(self, *args, flush=True, average=True, **kwargs):
+        value = self.value
+        if average and self.num_batches > 0:
+            value = value / self.num_batches
+        if flush:
+            self.value, self.num_batches = 0, 0
+        return {self.name: value}

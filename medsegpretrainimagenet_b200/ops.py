@@ -189,8 +189,8 @@ def conv_out_size(h: int, w: int, kh: int, kw: int, stride: int, padding) -> Tup
 
 
 # Optional per-call device timing of the convolution kernels (bench.py roofline): when a list is
-# installed, every conv call appends (kind, algorithmic_flops, start_event, end_event), the events being
-# recorded on the launching stream.
+# installed, every conv call appends (kind, algorithmic_flops, start_event, end_event, algorithmic_bytes,
+# kernel variant name), the events being recorded on the launching stream.
 _CONV_TIMELINE = None
 
 
@@ -200,8 +200,8 @@ def set_conv_timeline(lst):
 
 
 class _timed:
-    def __init__(self, kind, flops):
-        self.kind, self.flops = kind, flops
+    def __init__(self, kind, flops, nbytes=0.0):
+        self.kind, self.flops, self.nbytes = kind, flops, nbytes
 
     def __enter__(self):
         if _CONV_TIMELINE is not None:
@@ -213,7 +213,8 @@ class _timed:
     def __exit__(self, *exc):
         if _CONV_TIMELINE is not None:
             self.e1.record()
-            _CONV_TIMELINE.append((self.kind, self.flops, self.e0, self.e1))
+            name = (_lib.lib.msp_conv_last_kernel() or b"").decode()
+            _CONV_TIMELINE.append((self.kind, self.flops, self.e0, self.e1, self.nbytes, name))
         return False
 
 
@@ -235,7 +236,8 @@ def conv_fprop(x, wf, bias, k, kh, kw, stride, pad_t, pad_l, ho, wo, relu=False,
     s1 = s2 = None
     if stats is not None:
         s1, s2 = stats[0].data_ptr(), stats[1].data_ptr()
-    with _timed("fprop", 2.0 * n * ho * wo * k * (c_true or c) * kh * kw):
+    with _timed("fprop", 2.0 * n * ho * wo * k * (c_true or c) * kh * kw,
+                2.0 * (n * h * w * c + n * ho * wo * k + k * c * kh * kw)):
         call("msp_conv_fprop", C.byref(d), _p(x), _p(wf), _p(bias), _p(out), s1, s2, _stream())
     return out
 
@@ -249,19 +251,20 @@ def conv_dgrad(dy, wd, x_shape, kh, kw, stride, pad_t, pad_l, out=None, accumula
         accumulate = False
     _, _, _, _, x_cs = _chk_nhwc(out, "conv_dgrad(out)")
     d = _conv_desc(n, h, w, c, x_cs, ho, wo, k, y_cs, kh, kw, stride, pad_t, pad_l)
-    with _timed("dgrad", 2.0 * n * ho * wo * k * (c_true or c) * kh * kw):
+    with _timed("dgrad", 2.0 * n * ho * wo * k * (c_true or c) * kh * kw,
+                2.0 * (n * h * w * c + n * ho * wo * k + k * c * kh * kw)):
         call("msp_conv_dgrad", C.byref(d), _p(dy), _p(wd), _p(out), int(accumulate), _stream())
     return out
 
 
-def _wgrad(d: ConvDesc, x, dy, c_true, flops) -> torch.Tensor:
+def _wgrad(d: ConvDesc, x, dy, c_true, flops, nbytes=0.0) -> torch.Tensor:
     splits = _lib.lib.msp_conv_wgrad_splits(C.byref(d))
     _lib.check(0 if splits >= 1 else splits, "msp_conv_wgrad_splits")
     taps = d.KH if d.win_px else d.KH * d.KW
     cw = 64 if d.win_px else d.C
     part = torch.empty((splits, d.K, taps, cw), dtype=torch.float32, device=x.device)
     dw = torch.empty((d.K, c_true, d.KH, d.KW), dtype=torch.float32, device=x.device)
-    with _timed("wgrad", flops):
+    with _timed("wgrad", flops, nbytes):
         call("msp_conv_wgrad", C.byref(d), _p(x), _p(dy), _p(part), _stream())
         call("msp_unpack_wgrad", C.byref(d), _p(part), c_true, _p(dw), _stream())
     return dw
@@ -273,7 +276,8 @@ def conv_wgrad(x, dy, c_true, kh, kw, stride, pad_t, pad_l) -> torch.Tensor:
     n, h, w, c, x_cs = _chk_nhwc(x, "conv_wgrad(x)")
     _, ho, wo, k, y_cs = _chk_nhwc(dy, "conv_wgrad(dy)")
     d = _conv_desc(n, h, w, c, x_cs, ho, wo, k, y_cs, kh, kw, stride, pad_t, pad_l)
-    return _wgrad(d, x, dy, c_true, 2.0 * n * ho * wo * k * c_true * kh * kw)
+    return _wgrad(d, x, dy, c_true, 2.0 * n * ho * wo * k * c_true * kh * kw,
+                  2.0 * (n * h * w * c + n * ho * wo * k) + 4.0 * k * c_true * kh * kw)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -327,7 +331,8 @@ def conv_fprop_rowwin(xw, w_img, wr, bias, k, kh, kw, stride, pad_t, pad_l, ho, 
     s1 = s2 = None
     if stats is not None:
         s1, s2 = stats[0].data_ptr(), stats[1].data_ptr()
-    with _timed("fprop", 2.0 * n * ho * wo * k * (c_true or xw.shape[3]) * kh * kw):
+    with _timed("fprop", 2.0 * n * ho * wo * k * (c_true or xw.shape[3]) * kh * kw,
+                2.0 * (xw.numel() + n * ho * wo * k)):
         call("msp_conv_fprop", C.byref(d), _p(xw), _p(wr), _p(bias), _p(out), s1, s2, _stream())
     return out
 

@@ -54,10 +54,11 @@ def _chunks(n: int):
 def grad_sqnorm(grads: List[torch.Tensor]) -> torch.Tensor:
     """Device double holding sum(g^2) over all tensors (one launch per 32 tensors)."""
     dev = grads[0].device
-    sq = torch.zeros(1, dtype=torch.float64, device=dev)
+    sq = torch.empty(1, dtype=torch.float64, device=dev)
     for lo, hi in _chunks(len(grads)):
         part = grads[lo:hi]
-        _lib.call("msp_optim_sqnorm", len(part), _ptr_array(part), _numel_array(part), sq.data_ptr(), _stream(dev))
+        _lib.call("msp_optim_sqnorm", len(part), _ptr_array(part), _numel_array(part), sq.data_ptr(), int(lo == 0),
+                  _stream(dev))
     return sq
 
 
@@ -78,7 +79,8 @@ def clip_grad_norm_(parameters: Iterable[torch.Tensor], max_norm: float, norm_ty
         _check(g, "every gradient")
     dev = grads[0].device
     sq = grad_sqnorm(grads)
-    total = sq.sqrt().to(torch.float32).reshape(())
+    total = torch.empty((), dtype=torch.float32, device=dev)
+    _lib.call("msp_optim_norm", sq.data_ptr(), total.data_ptr(), _stream(dev))
     if error_if_nonfinite and not bool(torch.isfinite(total)):
         raise RuntimeError("The total norm for gradients is non-finite, so it cannot be clipped")
     if max_norm != float("inf"):
@@ -150,6 +152,7 @@ class AdamW(torch.optim.Optimizer):
         and the host-side mirror of the step counts (one read per parameter, at load time only) is rebuilt."""
         super().load_state_dict(state_dict)
         self._host_steps = {}
+        shared = {}
         for group in self.param_groups:
             if group.get("amsgrad", False):
                 raise ValueError("medsegpretrainimagenet_b200.optim.AdamW: amsgrad state cannot be loaded")
@@ -159,7 +162,10 @@ class AdamW(torch.optim.Optimizer):
                     continue
                 step = st["step"]
                 host = float(step.item()) if isinstance(step, torch.Tensor) else float(step)
-                st["step"] = torch.full((), host, dtype=torch.float32, device=p.device)
+                key = (p.device, host)
+                if key not in shared:       # one counter per distinct age (see step())
+                    shared[key] = torch.full((), host, dtype=torch.float32, device=p.device)
+                st["step"] = shared[key]
                 self._host_steps[id(p)] = int(round(host))
                 for k in ("exp_avg", "exp_avg_sq"):
                     if k in st and (st[k].device != p.device or st[k].dtype != torch.float32 or not st[k].is_contiguous()):
@@ -171,6 +177,7 @@ class AdamW(torch.optim.Optimizer):
         if closure is not None:
             with torch.enable_grad():
                 loss = closure()
+        fresh_counters = {}
         for group in self.param_groups:
             plist = []
             for p in group["params"]:
@@ -180,13 +187,22 @@ class AdamW(torch.optim.Optimizer):
                 _check(p.grad, "every gradient")
                 st = self.state[p]
                 if "exp_avg" not in st:
-                    st["step"] = torch.zeros((), dtype=torch.float32, device=p.device)
+                    # parameters that start in the same step() share ONE step counter tensor (torch's state layout —
+                    # every state[p]['step'] is a 0-dim fp32 tensor — with one increment per step instead of one per
+                    # parameter)
+                    key = (p.device, "fresh")
+                    if key not in fresh_counters:
+                        fresh_counters[key] = torch.zeros((), dtype=torch.float32, device=p.device)
+                    st["step"] = fresh_counters[key]
                     st["exp_avg"] = torch.zeros_like(p, memory_format=torch.contiguous_format)
                     st["exp_avg_sq"] = torch.zeros_like(p, memory_format=torch.contiguous_format)
                 plist.append(p)
             if not plist:
                 continue
-            torch._foreach_add_([self.state[p]["step"] for p in plist], 1.0)
+            self._split_partial_counters(plist)
+            counters = list({self.state[p]["step"].data_ptr(): self.state[p]["step"] for p in plist}.values())
+            for lo, hi in _chunks(len(counters)):
+                _lib.call("msp_optim_add_scalar", hi - lo, _ptr_array(counters[lo:hi]), 1.0, _stream(plist[0].device))
             b1, b2 = group["betas"]
             for same_age in self._group_by_step(plist):
                 for lo, hi in _chunks(len(same_age)):
@@ -197,6 +213,23 @@ class AdamW(torch.optim.Optimizer):
                               float(group["lr"]), float(b1), float(b2), float(group["eps"]), float(group["weight_decay"]),
                               self.state[part[0]]["step"].data_ptr(), _stream(part[0].device))
         return loss
+
+    def _split_partial_counters(self, plist) -> None:
+        """A shared counter may only advance if ALL its parameters step: when some of them have no gradient this time,
+        the ones that do step move to a private copy of the counter (rare: frozen / unused branches)."""
+        stepping = {id(p) for p in plist}
+        owners = {}
+        for group in self.param_groups:
+            for p in group["params"]:
+                st = self.state.get(p)
+                if st and "step" in st:
+                    owners.setdefault(st["step"].data_ptr(), []).append(p)
+        for ptr, ps in owners.items():
+            movers = [p for p in ps if id(p) in stepping]
+            if movers and len(movers) != len(ps):
+                fresh = self.state[movers[0]]["step"].clone()
+                for p in movers:
+                    self.state[p]["step"] = fresh
 
     def _group_by_step(self, plist):
         """Lists of parameters with the same step count (normally one list): a launch reads ONE device counter.  The

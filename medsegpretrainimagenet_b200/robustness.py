@@ -94,9 +94,13 @@ def predict_w_model(model, imgs: torch.Tensor, batch_size: int = 32, device="cud
     is left to the distance kernel (pass `pool=` to Robustness / robustness_table) unless requested here,
     in which case the reference's (N, C) tensor is returned."""
     model = model.to(device)
+    # `model.layers[0]` is a `Model` wrapper whose forward drops every argument but x (model/model.py:65-70), so the
+    # reference's `model(x, return_skip_vals=True)` never reaches the encoder through it: call the wrapped network
+    from .converter import _unwrap
+    net = _unwrap(model)
     outs = []
     for i in range(0, len(imgs), batch_size):
-        y, inner = model(imgs[i:i + batch_size].to(device), return_skip_vals=True)
+        y, inner = net(imgs[i:i + batch_size].to(device), return_skip_vals=True)
         levels = list(inner) + [y]
         outs.append(levels[level])
     pred = torch.cat(outs)

@@ -21,7 +21,7 @@ def test_library_exports_every_declared_symbol():
     for n in names:
         assert hasattr(lib, n), f"{n} is declared in include/msp_b200.h but not exported"
     assert sorted(_lib.SIGNATURES) == names, "ctypes binding table and header disagree"
-    assert lib.msp_version() == 2
+    assert lib.msp_version() == 3
 
 
 def test_errors_are_reported_not_swallowed():

@@ -10,7 +10,15 @@ from medsegpretrainimagenet_b200 import optim
 
 def _patched(monkeypatch, allow_cpu=True):
     calls = []
-    monkeypatch.setattr(optim._lib, "call", lambda name, *a: calls.append((name, a)))
+
+    def record(name, *a):
+        if name == "msp_optim_add_scalar":      # the step-counter bump, emulated on the CPU tensors' memory
+            import ctypes
+            for i in range(a[0]):
+                ctypes.c_float.from_address(a[1][i]).value += a[2]
+            return
+        calls.append((name, a))
+    monkeypatch.setattr(optim._lib, "call", record)
     monkeypatch.setattr(optim, "_stream", lambda dev: 0)
     if allow_cpu:
         monkeypatch.setattr(optim, "_check", lambda t, what: None)
@@ -59,6 +67,14 @@ def test_adamw_state_layout_and_step_groups(monkeypatch):
     opt.step()
     assert sorted(c[1][0] for c in calls) == [1, 7, 32]                          # the late parameter has its own step count
     assert float(opt.state[ps[0]]["step"]) == 1.0 and float(opt.state[ps[1]]["step"]) == 2.0
+    # one shared counter per parameter age, not one per parameter
+    assert len({opt.state[p]["step"].data_ptr() for p in ps}) == 2
+    # a parameter that sits a step out leaves the shared counter: the others move to a private copy
+    calls.clear()
+    ps[7].grad = None
+    opt.step()
+    assert float(opt.state[ps[7]]["step"]) == 2.0 and float(opt.state[ps[1]]["step"]) == 3.0
+    assert float(opt.state[ps[0]]["step"]) == 2.0
     sd = opt.state_dict()
     assert len(sd["state"]) == 40 and sd["param_groups"][0]["betas"] == (0.9, 0.999)
     with pytest.raises(ValueError):
@@ -70,10 +86,11 @@ def test_clip_grad_norm_calls_and_refusals(monkeypatch):
     ps = _params(33)
     ps[3].grad = None
     optim.clip_grad_norm_(ps, float("inf"))
-    assert [c[0] for c in calls] == ["msp_optim_sqnorm"]                         # 32 gradients: measure only
+    assert [c[0] for c in calls] == ["msp_optim_sqnorm", "msp_optim_norm"]       # 32 gradients: measure only
+    assert calls[0][1][4] == 1                                                   # the first launch clears the accumulator
     calls.clear()
     optim.clip_grad_norm_(ps, 1.0)
-    assert [c[0] for c in calls] == ["msp_optim_sqnorm", "msp_optim_clip"]
+    assert [c[0] for c in calls] == ["msp_optim_sqnorm", "msp_optim_norm", "msp_optim_clip"]
     with pytest.raises(RuntimeError):
         optim.clip_grad_norm_(ps, 1.0, norm_type=1.0)
     assert optim.clip_grad_norm_([torch.nn.Parameter(torch.zeros(3))], 1.0).item() == 0.0   # no gradients at all
