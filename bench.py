@@ -231,6 +231,52 @@ def ncu_traffic(workload_name):
         return {}, None
 
 
+CONV_KERNELS = ("tapgemm", "wgrad_kernel")
+
+
+def conv_times_from_profiler(prof_events, timeline):
+    """Device time of every conv call from the profiler's kernel records: the conv kernels (tapgemm* / wgrad_kernel) of
+    the instrumented step in stream order, dealt out to the calls in call order by their launch counts."""
+    import re
+    ks = []
+    for ev in prof_events:
+        if ev.device_type.name != "CUDA":
+            continue
+        n = ev.name
+        if any(k in n for k in CONV_KERNELS):
+            ks.append((ev.time_range.start, ev.device_time / 1e3))      # us -> ms
+    ks.sort()
+    need = sum(t[6] for t in timeline)
+    if len(ks) != need:
+        return None
+    out, i = [], 0
+    for kind, f, a, b, nbytes, name, nl in timeline:
+        out.append((kind, f, sum(d for _, d in ks[i:i + nl]), nbytes, name))
+        i += nl
+    return out
+
+
+def step_kernel_table(prof_events, top=14):
+    import collections
+    import re
+    agg = collections.OrderedDict()
+    for ev in prof_events:
+        if ev.device_type.name != "CUDA":
+            continue
+        n = ev.name.replace("(anonymous namespace)::", "").replace("<unnamed>::", "")
+        n = re.sub(r"^void\s+", "", n)
+        m = re.match(r"([\w:]+)(<[^(]*>)?", n)
+        key = (m.group(1).split("::")[-1] + (m.group(2) or ""))[:48] if m else n[:48]
+        a = agg.setdefault(key, [0, 0.0])
+        a[0] += 1
+        a[1] += ev.device_time / 1e3
+    tot = sum(v[1] for v in agg.values()) or 1.0
+    rows = sorted(agg.items(), key=lambda kv: -kv[1][1])
+    return {"kernels": sum(v[0] for v in agg.values()), "device_ms": tot,
+            "top": [{"kernel": k, "launches": c, "ms": round(ms, 4), "share": round(ms / tot, 4)} for k, (c, ms) in rows[:top]],
+            "library_kernels_at_or_torch": sum(c for k, (c, ms) in rows if k.startswith(("at::", "vectorized_", "multi_tensor", "elementwise_kernel", "CatArray", "reduce_kernel", "lpnorm")) or "at::native" in k)}
+
+
 def conv_roofline(timeline, ms_per_step, workload_name):
     """`roofline` object: the dominant kernel (largest share of device time among the conv kernel variants, which are
     60 % of the step) with its algorithmic FLOPs or bytes over its CUDA-event time, plus the per-kernel list."""
@@ -240,8 +286,7 @@ def conv_roofline(timeline, ms_per_step, workload_name):
     traffic, traffic_src = ncu_traffic(workload_name)
     fam = {}
     by_kind = {}
-    for kind, f, a, b, nbytes, name in timeline:
-        t = a.elapsed_time(b)
+    for kind, f, t, nbytes, name in timeline:
         d = fam.setdefault(name or "conv", {"launches": 0, "ms": 0.0, "gflop": 0.0, "gbyte": 0.0, "ideal_ms": 0.0})
         d["launches"] += 1; d["ms"] += t; d["gflop"] += f / 1e9; d["gbyte"] += nbytes / 1e9
         d["ideal_ms"] += max(f / (peak_tf * 1e12), nbytes / (hbm * 1e9)) * 1e3
@@ -302,6 +347,11 @@ def run_workload(args, workload, steps, warm, world, rank, local, dev, group, wi
     batch = (args.batch or batch) if workload == args.workload else batch
     torch.manual_seed(0)
     torch_opt = args.optimizer == "torch"
+    # the reference's YAMLs: use_deterministic_algorithms true for every downstream U-Net config
+    # (config/downstream/acdc/resnet50_attention_unet.yaml:233), false for pretraining (pretraining/resnet50/simple.yaml:99)
+    det = (workload != "cfg2") if args.deterministic == "yaml" else (args.deterministic == "on")
+    torch.use_deterministic_algorithms(det, warn_only=True)
+    torch.utils.deterministic.fill_uninitialized_memory = False    # torch.empty stays uninitialised (no fill kernels)
     if workload == "cfg2":
         # the pretraining YAML's own model: the sequential [DeepResNet, AdaptiveAvgPool2d, Flatten, Linear]
         # (config/pretraining/resnet50/simple.yaml:23-33), executed as one pass of the B200 interpreter
@@ -327,6 +377,7 @@ def run_workload(args, workload, steps, warm, world, rank, local, dev, group, wi
             make_opt = lambda ps: mopt.SGD(ps, lr=0.05, momentum=0.9, weight_decay=1e-4)
     models.kaiming_init_(model)
     model.to(dev).train()
+    ops.set_wgrad_stream(torch.cuda.Stream(device=dev) if args.wgrad_stream else None)
     params = [p for p in model.parameters() if p.requires_grad]
     reducer = GradReducer(params, bucket_mb=32.0, group=group)
     opt = make_opt(params)
@@ -442,11 +493,29 @@ def run_workload(args, workload, steps, warm, world, rank, local, dev, group, wi
     ms, ms_e2e = t.tolist()
 
     # ---- instrumented step: device time of every convolution launch -----------------------------
-    timeline = []
+    # per-kernel device times from the profiler (CUPTI activity records) of one eagerly enqueued step; if the profiler is
+    # unavailable, CUDA-event pairs around every conv call (which include the host's launch gaps at small batch)
+    timeline, prof_events, step_kernels, timing_src = [], None, None, "cuda events around every conv call"
     ops.set_conv_timeline(timeline)
-    step_core(x_dev, y_dev)
-    torch.cuda.synchronize()
+    try:
+        from torch.profiler import ProfilerActivity, profile
+        with profile(activities=[ProfilerActivity.CUDA]) as prof:
+            step_core(x_dev, y_dev)
+            torch.cuda.synchronize()
+        prof_events = list(prof.events())
+    except Exception as e:   # noqa: BLE001
+        print(f"[bench] profiler unavailable ({e}); falling back to event pairs", file=sys.stderr)
+        timeline.clear()
+        step_core(x_dev, y_dev)
+        torch.cuda.synchronize()
     ops.set_conv_timeline(None)
+    timed = conv_times_from_profiler(prof_events, timeline) if prof_events else None
+    if timed is not None:
+        timing_src = "profiler (CUPTI) per-kernel device time of one eagerly enqueued step"
+        step_kernels = step_kernel_table(prof_events)
+    else:
+        timed = [(kind, f, a.elapsed_time(b), nbytes, name) for kind, f, a, b, nbytes, name, _ in timeline]
+    timeline = timed
 
     out = None
     if rank == 0:
@@ -463,7 +532,8 @@ def run_workload(args, workload, steps, warm, world, rank, local, dev, group, wi
                        "l2": "inputs_larger_than_l2 (batch + activations >> 126 MB)",
                        "step": "fwd+loss+bwd+allreduce+metrics+gradnorm+optimizer",
                        "syncbn_exchange": None if world == 1 else ("peer-memory kernel" if args.small_allreduce == "p2p" else "nccl"),
-                       "execution": "eager launches" if graphed is None else "one CUDA graph replay per step"},
+                       "execution": "eager launches" if graphed is None else "one CUDA graph replay per step",
+                       "wgrad_stream": bool(args.wgrad_stream), "deterministic_reductions": det},
             "e2e": {"value": total_images / (ms_e2e * 1e-3), "unit": "images/sec",
                     "h2d_bytes_per_step": h2d_bytes * world,
                     "d2h_bytes_per_step": 4 * world, "ms_per_step": ms_e2e / steps, "last_loss": last,
@@ -473,9 +543,13 @@ def run_workload(args, workload, steps, warm, world, rank, local, dev, group, wi
             "clocks": clocks,
             "roofline": conv_roofline(timeline, ms / steps, name),
         }
+        out["roofline"]["kernel_time_source"] = timing_src
+        if step_kernels is not None:
+            out["step_kernels"] = step_kernels
         if with_cpu_baseline:
             out["cpu_baseline"] = cpu_baseline(workload)
     # release this workload's graph, pools and model before the next one
+    ops.set_wgrad_stream(None)
     del graphed, feeder, reader, timeline, opt, reducer, model, params
     import gc
     gc.collect()
@@ -500,6 +574,10 @@ def main():
                     help="SyncBN statistic exchange (N>1): one-kernel all-reduce over NVLink peer memory, or NCCL")
     ap.add_argument("--optimizer", default="b200", choices=["b200", "torch"],
                     help="gradient norm + optimizer step: this repo's multi-tensor kernels (default) or torch.optim")
+    ap.add_argument("--wgrad-stream", type=int, default=int(os.environ.get("MSP_WGRAD_STREAM", "0")),
+                    help="1: weight-gradient kernels on a side stream (graph branch) next to the dgrad / BN-backward chain")
+    ap.add_argument("--deterministic", default="yaml", choices=["yaml", "on", "off"],
+                    help="fixed-order reductions (torch.use_deterministic_algorithms): as the workload's reference YAML says, or forced")
     ap.add_argument("--no-graph", action="store_true", help="enqueue every step from Python instead of replaying a CUDA graph")
     ap.add_argument("--no-parity-check", action="store_true", help="skip the N-rank == 1-rank pre-check (N > 1)")
     args = ap.parse_args()
@@ -543,7 +621,8 @@ def main():
                          sample_clocks=False)
         if rank == 0:
             out["secondary"] = {k: s[k] for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step",
-                                                  "config", "e2e", "gpu_launches", "host_enqueue_ms_per_step", "roofline")}
+                                                  "config", "e2e", "gpu_launches", "host_enqueue_ms_per_step", "roofline",
+                                                  "step_kernels") if k in s}
     if rank == 0:
         if parity is not None:
             out["parity_n"] = "ok" if parity["ok"] else "FAILED"

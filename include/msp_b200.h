@@ -57,6 +57,12 @@ typedef struct msp_conv_desc {
    * msp_nchw_f32_to_rowwin_bf16 with C = 64 / win_px channels per pixel (image column w at column
    * w + pad_l), and the weights come from msp_pack_weights_rowwin.  fprop and wgrad only.          */
   int32_t win_px, Wp;
+  /* BatchNorm statistics of fprop (ch_sum / ch_sqsum): stat_rows = 0 -> every CTA ADDS its per-channel partial sums to
+   * the [2][K] accumulators with float atomics (the order of the additions varies from run to run).  stat_rows > 0 ->
+   * DETERMINISTIC mode (torch.use_deterministic_algorithms, run_experiment.py:65; every downstream YAML sets it): ch_sum
+   * points to a zero-initialised [stat_rows][2][K] fp32 workspace (ch_sqsum = ch_sum + K), CTA b STORES its partial sums
+   * in row b (stat_rows >= number of SMs) and msp_bn_finalize / msp_reduce_rows add the rows in fixed order. */
+  int32_t stat_rows;
 } msp_conv_desc;
 
 /* Kernel-variant policy of fprop / dgrad (tuning and tests; -1 restores the default / environment):
@@ -102,6 +108,22 @@ int msp_conv_wgrad(const msp_conv_desc* d, const void* x, const void* dy, float*
 /* sum of the partials -> OIHW fp32 [K][C_true][KH][KW] (the layout of nn.Conv2d.weight.grad). */
 int msp_unpack_wgrad(const msp_conv_desc* d, const float* dw_partials, int C_true, float* dw_oihw,
                      void* stream);
+/* Every weight gradient of a backward pass in ONE launch: item i = the fixed-order sum over `splits` partials
+ * (msp_conv_wgrad's output, `split_stride` elements apart) written — or ADDED when `accumulate` (gradient
+ * accumulation, all-reduce bucket views) — to `dst` in the OIHW fp32 layout of nn.Conv2d.weight.grad.
+ * Generic layers: partials [K][taps][Cpad]; row-window layers (rowwin_KH > 0): partials [K][KH][64] with
+ * `rowwin_cpp` channels per window pixel.  `items` is a HOST array of 1..96 entries (it travels in the kernel's
+ * parameter space). */
+typedef struct msp_unpack_item {
+  const float* partials;
+  float* dst;
+  long long split_stride;
+  int32_t splits, K, C_true, taps, Cpad;
+  int32_t rowwin_KH, rowwin_KW, rowwin_cpp;
+  int32_t accumulate;
+  int32_t reserved;
+} msp_unpack_item;
+int msp_unpack_wgrad_batched(int n, const msp_unpack_item* items, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Layout conversion at the module boundary (reference tensors are NCHW fp32).
@@ -126,11 +148,16 @@ int msp_nchw_f32_grad_to_nhwc_bf16(const float* g, int N, int C, int H, int W, i
  * (classification/models.py:203-212, 277-290) and BN+ReLU of ConvBlock (blocks.py:458-488).
  * ------------------------------------------------------------------------------------------ */
 /* sums -> mean / invstd, running-stat update (momentum, unbiased var) like torch (eps 1e-5).
- * reset_sums != 0: the two accumulators are zeroed after they have been read (persistent per-layer
- * accumulators need no memset launch per step). */
+ * reset_sums != 0: the accumulators are zeroed after they have been read (persistent per-layer
+ * accumulators need no memset launch per step).  rows > 1: ch_sum is the [rows][2][C] per-CTA workspace of the
+ * deterministic mode (msp_conv_desc.stat_rows), summed here row by row in fixed order. */
 int msp_bn_finalize(float* ch_sum, float* ch_sqsum, int C, double count, float eps, float momentum,
                     float* mean, float* invstd, float* running_mean, float* running_var, int reset_sums,
-                    void* stream);
+                    int rows, void* stream);
+/* out[i] = ws[0][i] + ws[1][i] + ... + ws[rows-1][i] (fixed order, i < n); reset != 0 zeroes ws afterwards.  The
+ * fixed-order second stage of every deterministic reduction (SyncBN sums before their all-reduce, BatchNorm-backward
+ * sums, bias gradients). */
+int msp_reduce_rows(float* ws, int rows, int n, float* out, int reset, void* stream);
 
 #define MSP_ACT_NONE 0
 #define MSP_ACT_RELU 1
@@ -156,9 +183,12 @@ int msp_bn_act_fwd(const msp_bn_act_desc* d, const void* x, const float* mean, c
  * Backward pass 1: with g = dy * act'(y) (ReLU mask recomputed from y; sigmoid from y),
  * accumulates sum_g[c] += sum s[n]*g, sum_gx[c] += sum s[n]*g*xhat (fp32 [C]); if dres != NULL also
  * writes the residual-branch gradient (g itself) — strided / channel-truncated like the forward. */
+/* rows_ws != NULL (deterministic mode): fp32 workspace of ws_rows x 2C floats; every block stores its partial sums in
+ * its own row and a second launch adds the rows in fixed order into sum_g / sum_gx (= sum_g + C required). */
 int msp_bn_act_bwd_reduce(const msp_bn_act_desc* d, const void* x, const void* y, const void* dy,
                           const float* mean, const float* invstd, const float* gamma, const float* beta,
-                          const float* sample_scale, float* sum_g, float* sum_gx, void* stream);
+                          const float* sample_scale, float* sum_g, float* sum_gx, float* rows_ws, int ws_rows,
+                          void* stream);
 /* Backward pass 2: dx = gamma*invstd*( s*g - sum_g/M - xhat*sum_gx/M ); M = N*H*W (x world size
  * when the sums were all-reduced: pass the global count).  dres (optional, same shape as the
  * residual tensor) receives g added into the sub-sampled positions (others untouched).          */
@@ -189,8 +219,9 @@ int msp_avgpool_fwd(const void* x, int N, int HW, int C, int x_cs, void* y, void
 int msp_avgpool_bwd(const void* dy, int N, int HW, int C, void* dx, int dx_cs, void* stream);
 /* y[.., off:off+C] = x (channel-slice copy into a concat buffer) and its inverse for gradients. */
 int msp_copy_channels(const void* x, long long P, int C, int x_cs, void* y, int y_cs, void* stream);
-/* out[c] = sum over P pixels of x[p][c] (fp32; conv bias gradients). out is zeroed by the call. */
-int msp_channel_sum(const void* x, long long P, int C, int cs, float* out, void* stream);
+/* out[c] = sum over P pixels of x[p][c] (fp32; conv bias gradients). out is zeroed by the call.  rows_ws != NULL:
+ * deterministic mode, as in msp_bn_act_bwd_reduce (workspace of ws_rows x C floats). */
+int msp_channel_sum(const void* x, long long P, int C, int cs, float* out, float* rows_ws, int ws_rows, void* stream);
 /* generic elementwise helpers on NHWC bf16 */
 int msp_add_relu_fwd(const void* a, const void* b, long long P, int C, int a_cs, int b_cs, void* y,
                      int y_cs, void* stream);
@@ -214,10 +245,11 @@ int msp_final_conv_act_fwd(const void* x, int N, int H, int W, int C, int x_cs, 
                            const float* bias, int K, int act, float* logits_nchw, float* prob_nchw,
                            void* stream);
 /* given dL/dprob (NCHW fp32) -> dlogits (through act), dx (NHWC bf16), dw [K][C], db [K] (atomics,
- * zeroed by the call) */
+ * zeroed by the call).  rows_ws != NULL: deterministic mode — workspace of ws_rows x (K*C + K) floats, the blocks'
+ * partial rows are added in fixed order into the contiguous result dw | db (db = dw + K*C required). */
 int msp_final_conv_act_bwd(const void* x, int N, int H, int W, int C, int x_cs, const float* w,
                            int K, int act, const float* prob_nchw, const float* dprob_nchw,
-                           void* dx, int dx_cs, float* dw, float* db, void* stream);
+                           void* dx, int dx_cs, float* dw, float* db, float* rows_ws, int ws_rows, void* stream);
 
 /* Dice loss (segmentation/losses/losses.py:34-58).  For each (group g, class c):
  *   I = sum y*p, Y = sum y, S = sum p^2   with y = (mask == c + label_offset),

@@ -27,7 +27,13 @@ D = C.c_double
 class ConvDesc(C.Structure):
     _fields_ = [(n, C.c_int32) for n in (
         "N", "H", "W", "C", "x_cs", "Ho", "Wo", "K", "y_cs", "KH", "KW", "stride", "pad_t", "pad_l",
-        "relu", "win_px", "Wp")]
+        "relu", "win_px", "Wp", "stat_rows")]
+
+
+class UnpackItem(C.Structure):
+    _fields_ = [("partials", C.c_void_p), ("dst", C.c_void_p), ("split_stride", C.c_longlong)] + \
+               [(n, C.c_int32) for n in ("splits", "K", "C_true", "taps", "Cpad", "rowwin_KH", "rowwin_KW", "rowwin_cpp",
+                                         "accumulate", "reserved")]
 
 
 class BnActDesc(C.Structure):
@@ -48,6 +54,7 @@ SIGNATURES = {
     "msp_conv_wgrad_splits": [C.POINTER(ConvDesc)],
     "msp_conv_wgrad": [C.POINTER(ConvDesc), P, P, P, P],
     "msp_unpack_wgrad": [C.POINTER(ConvDesc), P, I, P, P],
+    "msp_unpack_wgrad_batched": [I, C.POINTER(UnpackItem), P],
     "msp_pack_weights_rowwin": [P, I, I, I, I, I, P, P],
     "msp_pack_weights_batched": [P, I, I, P],
     "msp_nchw_f32_to_rowwin_bf16": [P, I, I, I, I, I, I, I, P, P],
@@ -55,9 +62,10 @@ SIGNATURES = {
     "msp_nchw_f32_to_nhwc_bf16": [P, I, I, I, I, I, P, P],
     "msp_nhwc_bf16_to_nchw_f32": [P, I, I, I, I, I, P, P],
     "msp_nchw_f32_grad_to_nhwc_bf16": [P, I, I, I, I, I, P, P],
-    "msp_bn_finalize": [P, P, I, D, F, F, P, P, P, P, I, P],
+    "msp_bn_finalize": [P, P, I, D, F, F, P, P, P, P, I, I, P],
+    "msp_reduce_rows": [P, I, I, P, I, P],
     "msp_bn_act_fwd": [C.POINTER(BnActDesc), P, P, P, P, P, P, P, P, P],
-    "msp_bn_act_bwd_reduce": [C.POINTER(BnActDesc), P, P, P, P, P, P, P, P, P, P, P],
+    "msp_bn_act_bwd_reduce": [C.POINTER(BnActDesc), P, P, P, P, P, P, P, P, P, P, P, I, P],
     "msp_bn_act_bwd_apply": [C.POINTER(BnActDesc), P, P, P, P, P, P, P, P, P, P, D, P, P, I, P],
     "msp_bn_eval_prepare": [P, I, F, P, P],
     "msp_maxpool_fwd": [P, I, I, I, I, I, I, I, I, P, P, I, I, I, P],
@@ -67,14 +75,14 @@ SIGNATURES = {
     "msp_avgpool_fwd": [P, I, I, I, I, P, P],
     "msp_avgpool_bwd": [P, I, I, I, P, I, P],
     "msp_copy_channels": [P, LL, I, I, P, I, P],
-    "msp_channel_sum": [P, LL, I, I, P, P],
+    "msp_channel_sum": [P, LL, I, I, P, P, I, P],
     "msp_add_relu_fwd": [P, P, LL, I, I, I, P, I, P],
     "msp_relu_bwd": [P, P, LL, I, I, I, P, I, P],
     "msp_add": [P, P, LL, I, I, I, P, I, P],
     "msp_gate_mul_fwd": [P, P, I, I, I, I, I, I, P, I, P],
     "msp_gate_mul_bwd": [P, P, P, I, I, I, I, I, I, I, P, I, I, P, I, P],
     "msp_final_conv_act_fwd": [P, I, I, I, I, I, P, P, I, I, P, P, P],
-    "msp_final_conv_act_bwd": [P, I, I, I, I, I, P, I, I, P, P, P, I, P, P, P],
+    "msp_final_conv_act_bwd": [P, I, I, I, I, I, P, I, I, P, P, P, I, P, P, P, I, P],
     "msp_dice_sums": [P, P, I, I, LL, I, I, I, P, P],
     "msp_dice_finalize": [P, I, I, I, F, P, P, P],
     "msp_dice_bwd": [P, P, I, I, LL, I, I, I, P, F, P, P, P],

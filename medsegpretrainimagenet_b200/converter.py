@@ -52,8 +52,9 @@ class ExecContext:
         by msp_bn_finalize after every use)."""
         buf = getattr(bn, "_msp_stats", None)
         dev = bn.weight.device if bn.weight is not None else bn.running_mean.device
-        if buf is None or buf.device != dev or buf.shape[1] != bn.num_features:
-            buf = torch.zeros((2, bn.num_features), dtype=torch.float32, device=dev)
+        if buf is None or buf.device != dev or buf.shape[-1] != bn.num_features or \
+                (buf.dim() == 3) != ops.deterministic():
+            buf = ops.new_stats(bn.num_features, dev)      # [2, C], or [SMs, 2, C] rows in deterministic mode
             bn._msp_stats = buf
         return buf
 

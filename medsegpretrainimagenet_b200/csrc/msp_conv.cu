@@ -77,6 +77,7 @@ struct TapGemmParams {
   const float* bias;
   float* ch_sum;
   float* ch_sqsum;
+  long long stat_row;  // deterministic statistics: elements between the rows of the per-CTA workspace (0: float atomics)
   int8_t tap_dh[kMaxTaps];
   int8_t tap_dw[kMaxTaps];
   uint8_t tap_w[kMaxTaps];
@@ -357,7 +358,11 @@ __device__ __forceinline__ void tap_epilogue(const TapGemmParams& p, uint8_t* st
                              (uint32_t)(st * 32 + (cw >> 1)) * 16 + (uint32_t)(which * 2 + (cw & 1)) * 4;
           const float tot = lds_f32(a) + lds_f32(a + E::kSlabBytes) + lds_f32(a + 2 * E::kSlabBytes) +
                             lds_f32(a + 3 * E::kSlabBytes);
-          atomicAdd((which ? p.ch_sqsum : p.ch_sum) + col, tot);
+          float* dst = (which ? p.ch_sqsum : p.ch_sum) + col;
+          // deterministic mode: this CTA's own row of the workspace (a CTA leaves every channel block once), added up
+          // in fixed order by msp_bn_finalize; otherwise one float atomic per CTA, statistic and channel
+          if (p.stat_row) dst[(long long)blockIdx.x * p.stat_row] = tot;
+          else atomicAdd(dst, tot);
         }
       }
       named_bar_sync(kEpiBarrier, kEpiThreads);
@@ -658,6 +663,193 @@ tapgemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 }
 
 // ------------------------------------------------------------------------------------------------
+// Narrow-channel epilogue of the halo kernel (TN = 16 or 32 output channels per tile; the full-resolution decoder layers
+// of the U-Nets: 16 / 32 channels at 256 x 256, HBM bound).  With one 128 x TN accumulator per hand-off the kernel ran at
+// 6-20 % of its HBM roofline (profiles/r01_convbench_unet50_b24.txt: 205 us for 15 us of traffic): nine N = 16 MMAs per
+// tile take ~600 cycles, the per-tile epilogue chain (barrier wait -> tcgen05.ld -> pack -> slab -> stores -> statistics)
+// ~2400 cycles of pure latency whatever the tile's width.  Here G = 64 / TN pixel tiles share one ACCUMULATOR SET of
+// 64 TMEM columns (two sets, double buffered): the MMA warp fills the set tile by tile and commits once, the epilogue
+// drains all G tiles with ONE pass of the chain — columns [g*TN, (g+1)*TN) of the set belong to tile g, so every 16-byte
+// piece of a row carries its own tile origin.  Same slab layout and statistics read-back as tap_epilogue<64>.
+// ------------------------------------------------------------------------------------------------
+constexpr int kMultiW = 64;  // accumulator set width (TMEM columns)
+
+template <int TN>
+__device__ __forceinline__ void halo_multi_epilogue(const TapGemmParams& p, uint8_t* staging, uint32_t tmem_base,
+                                                    uint64_t* tfull_bar, uint64_t* tempty_bar, int warp, int lane) {
+  constexpr int G = kMultiW / TN;   // pixel tiles per accumulator set
+  constexpr int CW = 32, P = 4;     // accumulator columns per warp, 16-byte pieces per slab row
+  constexpr int TPW = CW / TN;      // tiles spanned by one warp's columns: 2 (TN = 16) or 1 (TN = 32)
+  constexpr int PPT = TN / 8;       // 16-byte pieces per tile and row
+  constexpr int kSlabBytes = 32 * CW * 2;
+  static_assert(TN == 16 || TN == 32, "narrow tiles only");
+  static_assert(kEpiWarps == 8 && kEpiWarps * kSlabBytes <= TapGemmCfg<TN>::kStageBufs * kATileBytes, "slab budget");
+  const int et = threadIdx.x - 64;
+  const int ew = et >> 5;
+  const int q = warp & 3;        // TMEM lane quarter of this warp
+  const int part = ew >> 2;      // column half of the set
+  const int row = q * 32 + lane;
+  const bool do_stats = p.ch_sum != nullptr && !(p.debug & 2);
+  const bool has_bias = p.bias != nullptr;
+  const uint32_t slab_s = smem_u32(staging) + ew * kSlabBytes;
+  const int cl0 = part * CW;     // first accumulator column of this warp within the set
+  const int g0 = cl0 / TN;       // first tile (within the set) its columns belong to
+  float st_acc[4] = {0.f, 0.f, 0.f, 0.f};
+  const int my_wi = row % p.bw, my_hi = row / p.bw;  // halo tiles hold one image: row -> (hi, wi) with the halo pitch
+  const bool my_row_ok = row < p.rows && my_wi < p.bw_valid;
+  int o_wi[P], o_hi[P], o_tile[P], o_ch[P];
+  uint32_t o_lds[P];
+  long long o_rel[P];
+#pragma unroll
+  for (int j = 0; j < P; ++j) {
+    const int u = j * 32 + lane, rl = u / P, gp = u % P, r = q * 32 + rl;
+    o_wi[j] = r % p.bw;
+    o_hi[j] = r / p.bw;
+    o_tile[j] = gp / PPT;
+    o_ch[j] = (gp % PPT) * 8;
+    o_lds[j] = (uint32_t)((u >> 3) * 128 + (((u & 7) ^ ((u >> 3) & 7)) << 4));
+    o_rel[j] = (r < p.rows && o_wi[j] < p.bw_valid)
+                   ? (long long)o_hi[j] * p.y_h_stride + (long long)o_wi[j] * p.y_w_stride + o_ch[j]
+                   : -1;
+  }
+  uint32_t sts_off[P];
+#pragma unroll
+  for (int g = 0; g < P; ++g) {
+    const int u = lane * P + g;
+    sts_off[g] = (uint32_t)((u >> 3) * 128 + (((u & 7) ^ ((u >> 3) & 7)) << 4));
+  }
+  const uint32_t st_off0 = (uint32_t)((((lane >> 2) & 7) << 4) + (lane & 3) * 4);
+  const int my_tiles = (int)blockIdx.x < p.total_tiles ? (p.total_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+  const int nsets = (my_tiles + G - 1) / G;
+  for (int u = 0; u < nsets; ++u) {
+    // the (up to) TPW tiles this warp's columns belong to
+    int w0[TPW], h0[TPW];
+    long long tile_off[TPW];
+    bool t_ok[TPW], valid[TPW];
+#pragma unroll
+    for (int k = 0; k < TPW; ++k) {
+      const int tl = u * G + g0 + k;  // CTA-local tile index
+      t_ok[k] = tl < my_tiles;
+      const int tm = (int)blockIdx.x + (t_ok[k] ? tl : 0) * (int)gridDim.x;  // one output-channel block: tile = tm
+      const int tw = (int)((uint32_t)tm % (uint32_t)p.tiles_w);
+      const uint32_t rest = (uint32_t)tm / (uint32_t)p.tiles_w;
+      const int th = (int)(rest % (uint32_t)p.tiles_h), tn = (int)(rest / (uint32_t)p.tiles_h);
+      w0[k] = tw * p.bw_valid;
+      h0[k] = th * p.bh;
+      tile_off[k] = p.y_off + (long long)tn * p.y_n_stride + (long long)h0[k] * p.y_h_stride +
+                    (long long)w0[k] * p.y_w_stride;
+      valid[k] = t_ok[k] && my_row_ok && (w0[k] + my_wi) < p.OWs && (h0[k] + my_hi) < p.OHs;
+    }
+    __nv_bfloat16* o_ptr[P];
+#pragma unroll
+    for (int j = 0; j < P; ++j) {
+      const int k = o_tile[j];
+      const bool ok = t_ok[k] && o_rel[j] >= 0 && (w0[k] + o_wi[j]) < p.OWs && (h0[k] + o_hi[j]) < p.OHs &&
+                      o_ch[j] < p.Kout;
+      o_ptr[j] = ok ? p.y + tile_off[k] + o_rel[j] : nullptr;
+    }
+    const uint32_t as = (uint32_t)u & 1u;
+    if (lane == 0) mbar_wait(&tfull_bar[as], ((uint32_t)u >> 1) & 1u);
+    __syncwarp();
+    tc_fence_after();
+    uint32_t v[CW];
+    tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + as * kMultiW + cl0, v);
+    uint4 old[P];
+    if (p.accumulate) {
+#pragma unroll
+      for (int j = 0; j < P; ++j)
+        old[j] = o_ptr[j] != nullptr ? __ldg(reinterpret_cast<const uint4*>(o_ptr[j])) : make_uint4(0u, 0u, 0u, 0u);
+    }
+    tmem_ld_wait();
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&tempty_bar[as]);  // the set is in registers: hand it back to the MMA warp
+    float x[CW];
+#pragma unroll
+    for (int j = 0; j < CW; ++j) x[j] = __uint_as_float(v[j]);
+    if (has_bias) {
+#pragma unroll
+      for (int j = 0; j < CW; ++j)
+        if ((j % TN) < p.Kout) x[j] += __ldg(p.bias + (j % TN));
+    }
+    if (p.relu) {
+#pragma unroll
+      for (int j = 0; j < CW; ++j) x[j] = fmaxf(x[j], 0.f);
+    }
+#pragma unroll
+    for (int j = 0; j < CW; ++j)
+      if (!valid[j / TN]) x[j] = 0.f;
+    __syncwarp();  // the previous set's slab reads are done
+#pragma unroll
+    for (int g = 0; g < P; ++g)
+      sts_v4(slab_s + sts_off[g], pack_bf16x2(x[8 * g], x[8 * g + 1]), pack_bf16x2(x[8 * g + 2], x[8 * g + 3]),
+             pack_bf16x2(x[8 * g + 4], x[8 * g + 5]), pack_bf16x2(x[8 * g + 6], x[8 * g + 7]));
+    __syncwarp();
+    uint4 o[P];
+#pragma unroll
+    for (int j = 0; j < P; ++j) o[j] = lds_v4(slab_s + o_lds[j]);
+    if (p.accumulate) {
+#pragma unroll
+      for (int j = 0; j < P; ++j) {
+        const uint32_t ov[4] = {old[j].x, old[j].y, old[j].z, old[j].w};
+        const uint32_t nv[4] = {o[j].x, o[j].y, o[j].z, o[j].w};
+        uint32_t rv[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float2 a = unpack_bf16x2(ov[e]), b2 = unpack_bf16x2(nv[e]);
+          rv[e] = pack_bf16x2(a.x + b2.x, a.y + b2.y);
+        }
+        o[j] = make_uint4(rv[0], rv[1], rv[2], rv[3]);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < P; ++j)
+      if (o_ptr[j] != nullptr) st_v4(o_ptr[j], o[j]);
+    if (do_stats) {
+      float s1a = 0.f, s2a = 0.f, s1b = 0.f, s2b = 0.f;
+#pragma unroll
+      for (int j = 0; j < 4 * P; ++j) {
+        const float2 f = unpack_bf16x2(lds_u32(slab_s + j * 128 + (st_off0 ^ (uint32_t)((j & 7) << 4))));
+        s1a += f.x;
+        s2a = fmaf(f.x, f.x, s2a);
+        s1b += f.y;
+        s2b = fmaf(f.y, f.y, s2b);
+      }
+      st_acc[0] += s1a;
+      st_acc[1] += s1b;
+      st_acc[2] += s2a;
+      st_acc[3] += s2b;
+    }
+  }
+  if (do_stats) {
+    // one flush per launch: lanes l and l + 16 hold the same column pair (even / odd rows); the warps park their sums
+    // in their slabs, 2 * TN threads add the G tiles' columns of the four lane quarters: one atomic per channel and sum
+#pragma unroll
+    for (int e = 0; e < 4; ++e) st_acc[e] += __shfl_xor_sync(0xffffffffu, st_acc[e], 16);
+    __syncwarp();
+    sts_v4(slab_s + (uint32_t)lane * 16, __float_as_uint(st_acc[0]), __float_as_uint(st_acc[1]),
+           __float_as_uint(st_acc[2]), __float_as_uint(st_acc[3]));
+    named_bar_sync(kEpiBarrier, kEpiThreads);
+    for (int i = et; i < 2 * TN; i += kEpiThreads) {
+      const int which = i / TN, c = i - which * TN;
+      if (c < p.Kout) {
+        float tot = 0.f;
+#pragma unroll
+        for (int g = 0; g < G; ++g) {
+          const int cl = g * TN + c, prt = cl / CW, cw = cl - prt * CW;
+          const uint32_t a = smem_u32(staging) + (uint32_t)(prt * 4) * kSlabBytes + (uint32_t)(cw >> 1) * 16 +
+                             (uint32_t)(which * 2 + (cw & 1)) * 4;
+          tot += lds_f32(a) + lds_f32(a + kSlabBytes) + lds_f32(a + 2 * kSlabBytes) + lds_f32(a + 3 * kSlabBytes);
+        }
+        float* dst = (which ? p.ch_sqsum : p.ch_sum) + c;
+        if (p.stat_row) dst[(long long)blockIdx.x * p.stat_row] = tot;
+        else atomicAdd(dst, tot);
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // Halo variant of the tap-GEMM for stride-1 filters on feature maps up to 126 pixels wide.  The tap-GEMM above
 // fetches the A box once per tap (9x for a 3x3 filter) and is L2->SM bandwidth bound on those layers.  Here the
 // output tile is `bh` full-width rows stored with the HALO pitch bw = W + KW - 1, so that the input window of tap
@@ -670,11 +862,14 @@ tapgemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 constexpr int kHaloABytes = 32768;  // 256 rows x 128 B
 constexpr int kHaloMaxB = 12;
 
-template <int BN_>
+template <int BN_, bool MULTI = false>
 __global__ void __launch_bounds__(kTapThreads, 1)
 tapgemm_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const TapGemmParams p) {
   using Cfg = TapGemmCfg<BN_>;
+  constexpr int kTmemCols = MULTI ? 2 * kMultiW : Cfg::kTmemCols;
+  constexpr int kG = MULTI ? kMultiW / BN_ : 1;   // pixel tiles per accumulator set (halo_multi_epilogue)
+  constexpr int kSetW = MULTI ? kMultiW : BN_;
   extern __shared__ uint8_t smem_raw[];
   pdl_trigger();
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
@@ -716,7 +911,7 @@ tapgemm_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
     mbar_fence_init();
   }
-  if (warp == 1) tmem_alloc<Cfg::kTmemCols>(&tmem_base_s);
+  if (warp == 1) tmem_alloc<kTmemCols>(&tmem_base_s);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -782,10 +977,14 @@ tapgemm_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       }
       uint32_t sa = 0, pha = 0, sb = 0, phb = 0, t = 0;
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++t) {
-        const uint32_t as = t & 1u;
-        mbar_wait(&tempty_bar[as], ((t >> 1) & 1u) ^ 1u);
-        tc_fence_after();
-        const uint32_t tmem_d = tmem_base + as * BN_;
+        // accumulator set `as` (double buffered); MULTI: kG consecutive tiles of this CTA fill one set side by side
+        const uint32_t su = t / (uint32_t)kG, sg = t % (uint32_t)kG;
+        const uint32_t as = su & 1u;
+        if (sg == 0) {
+          mbar_wait(&tempty_bar[as], ((su >> 1) & 1u) ^ 1u);
+          tc_fence_after();
+        }
+        const uint32_t tmem_d = tmem_base + as * kSetW + sg * BN_;
         uint32_t acc = 0;
         for (int ch = 0; ch < chunks; ++ch) {
           mbar_wait(&a_full[sa], pha);
@@ -829,17 +1028,20 @@ tapgemm_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             pha ^= 1u;
           }
         }
-        umma_commit(&tfull_bar[as]);
+        if (sg == (uint32_t)(kG - 1) || tile + (int)gridDim.x >= p.total_tiles) umma_commit(&tfull_bar[as]);
       }
     }
     __syncwarp();
   } else {
-    tap_epilogue<BN_>(p, staging, scratch, tmem_base, tfull_bar, tempty_bar, warp, lane, (int)blockIdx.x,
-                      (int)gridDim.x, p.total_tiles, p.tiles_m, -1);
+    if constexpr (MULTI)
+      halo_multi_epilogue<BN_>(p, staging, tmem_base, tfull_bar, tempty_bar, warp, lane);
+    else
+      tap_epilogue<BN_>(p, staging, scratch, tmem_base, tfull_bar, tempty_bar, warp, lane, (int)blockIdx.x,
+                        (int)gridDim.x, p.total_tiles, p.tiles_m, -1);
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc<Cfg::kTmemCols>(tmem_base);
+  if (warp == 1) tmem_dealloc<kTmemCols>(tmem_base);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1089,6 +1291,8 @@ __global__ void pack_w_both_kernel(const float* __restrict__ w, int K, int C, in
 // per ResNet-50 step, 79 per U-Net step.
 constexpr int kPackItemWords = 10;
 constexpr int kPackElemsPerBlock = 256 * 8;
+constexpr int kPackTile = 32;       // tiled mode (taps <= 9): one block = 32 output x 32 input channels x all taps
+constexpr int kPackTiledMaxTaps = 9;
 __global__ void __launch_bounds__(256)
 pack_w_batched_kernel(const long long* __restrict__ items, int n_items) {
   int lo = 0, hi = n_items - 1;  // last item whose first block <= blockIdx.x
@@ -1103,6 +1307,40 @@ pack_w_batched_kernel(const long long* __restrict__ items, int n_items) {
   __nv_bfloat16* __restrict__ wd = reinterpret_cast<__nv_bfloat16*>(it[2]);
   const int K = (int)it[3], C = (int)it[4], taps = (int)it[5], Cpad = (int)it[6], Kpad = (int)it[7];
   const long long blk = (long long)blockIdx.x - it[8], nblk = it[9];
+  if (taps <= kPackTiledMaxTaps) {
+    // Tiled transposition through shared memory: the fp32 OIHW source is read in contiguous runs of 32 x taps floats
+    // per output channel, both bf16 destinations are written in 64-byte runs (the element-wise version below read the
+    // source with a stride of `taps` floats and spent 450 us per R50 U-Net step on 0.45 GB of traffic).
+    __shared__ float tile[kPackTile * (kPackTile * kPackTiledMaxTaps + 1)];
+    const int pitch = kPackTile * taps + 1;  // odd pitch: the output-channel-major read below is conflict free
+    const int tiles_c = (Cpad + kPackTile - 1) / kPackTile;
+    const int tk = (int)(blk / tiles_c), tc = (int)(blk - (long long)tk * tiles_c);
+    const int k0 = tk * kPackTile, c0 = tc * kPackTile;
+    const int run = kPackTile * taps;
+    for (int i = threadIdx.x; i < kPackTile * run; i += 256) {
+      const int kk = i / run, rem = i - kk * run;
+      const int cc = rem / taps;
+      float v = 0.f;
+      if (k0 + kk < K && c0 + cc < C) v = w[((long long)(k0 + kk) * C + c0) * taps + rem];
+      tile[kk * pitch + rem] = v;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < kPackTile * run; i += 256) {  // wf[k][tap][c], c fastest
+      const int cc = i % kPackTile, r = i / kPackTile;
+      const int tap = r % taps, kk = r / taps;
+      if (k0 + kk < K && c0 + cc < Cpad)
+        wf[((long long)(k0 + kk) * taps + tap) * Cpad + c0 + cc] = __float2bfloat16_rn(tile[kk * pitch + cc * taps + tap]);
+    }
+    if (wd != nullptr) {
+      for (int i = threadIdx.x; i < kPackTile * run; i += 256) {  // wd[c][tap][k], k fastest
+        const int kk = i % kPackTile, r = i / kPackTile;
+        const int tap = r % taps, cc = r / taps;
+        if (c0 + cc < Cpad && k0 + kk < Kpad)
+          wd[((long long)(c0 + cc) * taps + tap) * Kpad + k0 + kk] = __float2bfloat16_rn(tile[kk * pitch + cc * taps + tap]);
+      }
+    }
+    return;
+  }
   const long long nf = (long long)K * taps * Cpad, nd = wd ? (long long)Cpad * taps * Kpad : 0;
   for (long long i = blk * blockDim.x + threadIdx.x; i < nf + nd; i += nblk * blockDim.x) {
     if (i < nf) {
@@ -1170,6 +1408,60 @@ __global__ void unpack_wgrad_rowwin_kernel(const float* __restrict__ dwp, int sp
     float acc = 0.f;
     for (int s = 0; s < splits; ++s) acc += src[(long long)s * split_stride];
     out[i] = acc;
+  }
+}
+
+// Every weight gradient of a backward pass in ONE launch (msp_unpack_wgrad_batched): per item the fixed-order sum of
+// the split-K partials, written (or added) in the OIHW layout of nn.Conv2d.weight.grad.  The per-layer launches above
+// cost ~8 us each for microseconds of work: 50 of them per ResNet-50 step, 80 per U-Net step (5 % of the cfg3 step).
+// The item table travels in the kernel's parameter space (no device table to keep in sync with the allocator).
+constexpr int kUnpackMaxItems = 96;
+struct UnpackList {
+  msp_unpack_item it[kUnpackMaxItems];
+  int first_block[kUnpackMaxItems + 1];
+  int n;
+};
+__global__ void __launch_bounds__(256) unpack_wgrad_batched_kernel(const __grid_constant__ UnpackList L) {
+  int lo = 0, hi = L.n - 1;  // last item whose first block <= blockIdx.x
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (L.first_block[mid] <= (int)blockIdx.x) lo = mid;
+    else hi = mid - 1;
+  }
+  const msp_unpack_item& it = L.it[lo];
+  const long long blk = (long long)blockIdx.x - L.first_block[lo], nblk = L.first_block[lo + 1] - L.first_block[lo];
+  const float* __restrict__ dwp = it.partials;
+  float* __restrict__ out = it.dst;
+  const int splits = it.splits;
+  const long long ss = it.split_stride;
+  if (it.rowwin_KH > 0) {
+    const int KH = it.rowwin_KH, KW = it.rowwin_KW, cpp = it.rowwin_cpp, C = it.C_true;
+    const long long total = (long long)it.K * C * KH * KW;
+    for (long long i = blk * 256 + threadIdx.x; i < total; i += nblk * 256) {
+      const int q = (int)(i % KW);
+      long long t = i / KW;
+      const int r = (int)(t % KH);
+      t /= KH;
+      const int c = (int)(t % C);
+      const int k = (int)(t / C);
+      const float* src = dwp + ((long long)k * KH + r) * 64 + q * cpp + c;
+      float acc = 0.f;
+      for (int sp = 0; sp < splits; ++sp) acc += src[(long long)sp * ss];
+      out[i] = it.accumulate ? out[i] + acc : acc;
+    }
+  } else {
+    const int taps = it.taps, C = it.C_true, Cpad = it.Cpad;
+    const long long total = (long long)it.K * C * taps;
+    for (long long i = blk * 256 + threadIdx.x; i < total; i += nblk * 256) {
+      const int tap = (int)(i % taps);
+      const long long t = i / taps;
+      const int c = (int)(t % C);
+      const int k = (int)(t / C);
+      const float* src = dwp + ((long long)k * taps + tap) * Cpad + c;
+      float acc = 0.f;
+      for (int sp = 0; sp < splits; ++sp) acc += src[(long long)sp * ss];
+      out[i] = it.accumulate ? out[i] + acc : acc;
+    }
   }
 }
 
@@ -1300,8 +1592,34 @@ struct WMapArgs {  // packed weights [rows][taps][inner] (make_w_map)
 };
 int make_w_map(CUtensorMap* m, const void* base, int inner, int taps, int rows, int box_rows);
 
+// Output-channel tile width of the tap kernel by a makespan estimate.  The natural width (bn_tile_for) minimises the A
+// re-reads, but a launch with fewer tiles than SMs leaves most of the GPU idle: the deep layers of the R50 U-Net at batch
+// 24 have M = 1536 pixels = 12 row tiles, i.e. 24 CTAs of 148 at BN = 256 (profiles/r01_convbench_unet50_b24.txt:
+// 39 us for 5 us of work).  Model per CTA, in cycles: main loop = k-blocks x max(MMA issue, L2 -> SM operand feed at
+// ~74 B/clk), epilogue ~ 24 cycles per accumulator column, the two overlap from the second tile on (TMEM double
+// buffering).  Ties keep the wider tile.  MSP_CONV_BNPOL=0 restores the fixed choice.
+int pick_bn(int Kout, long long tiles_m, int kblocks) {
+  const int natural = bn_tile_for(Kout);
+  static int pol = -1;
+  if (pol < 0) { const char* e = getenv("MSP_CONV_BNPOL"); pol = e ? atoi(e) : 1; }
+  if (pol == 0 || natural <= 64) return natural;
+  const int sms = msp_num_sms();
+  int best = natural;
+  double best_t = 1e30;
+  for (int bn = natural; bn >= 64; bn >>= 1) {
+    const long long tiles = tiles_m * msp_cdiv(Kout, bn);
+    const double n = (double)((tiles + sms - 1) / sms);
+    const double mma = 4.0 * (bn >= 256 ? 128.0 : 64.0), load = (16384.0 + bn * 128.0) / 74.0;
+    const double main = kblocks * (mma > load ? mma : load), epi = 24.0 * bn;
+    const double t = main + (n - 1.0) * (main > epi ? main : epi) + epi;
+    if (t < best_t * 0.97) { best_t = t; best = bn; }   // a narrower tile must win by 3 %
+  }
+  return best;
+}
+
 int dispatch_tapgemm(const CUtensorMap& tmA, const WMapArgs& w, TapGemmParams& p, cudaStream_t st) {
-  const int bn = bn_tile_for(p.Kout);
+  const int bn = p.halo ? bn_tile_for(p.Kout)
+                        : pick_bn(p.Kout, (long long)p.tiles_w * p.tiles_h * p.tiles_n, p.ntaps * msp_cdiv(p.C, kBK));
   const int pol = pair_policy();
   CUtensorMap tmB;
   if (p.tiles_w * p.tiles_h * p.tiles_n >= 2 && !p.halo && ((bn >= 128 && pol >= 1) || (bn == 64 && pol >= 2))) {
@@ -1381,14 +1699,22 @@ bool plan_halo(TapGemmParams& p, int OW, int OH, int N, int BN, Box* box, int* h
   return true;
 }
 
-template <int BN_>
+// narrow tiles (16 / 32 output channels): several pixel tiles per TMEM accumulator set (halo_multi_epilogue).
+// MSP_CONV_MULTI=0 keeps one tile per hand-off.
+bool multi_policy() {
+  static int on = -1;
+  if (on < 0) { const char* e = getenv("MSP_CONV_MULTI"); on = e ? atoi(e) : 1; }
+  return on != 0;
+}
+
+template <int BN_, bool MULTI = false>
 int launch_halo(const CUtensorMap& tmA, const CUtensorMap& tmB, TapGemmParams& p, cudaStream_t st) {
   using Cfg = TapGemmCfg<BN_>;
   const int smem = p.a_stages * kHaloABytes + p.b_stages * Cfg::kBTileBytes + Cfg::kStageBufs * kATileBytes +
                    Cfg::kScratchBytes + 1024;
   static int attr_smem = 0;
   if (smem > attr_smem) {
-    MSP_CHECK_CUDA(cudaFuncSetAttribute(tapgemm_halo_kernel<BN_>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    MSP_CHECK_CUDA(cudaFuncSetAttribute(tapgemm_halo_kernel<BN_, MULTI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         232448 - 1024));
     attr_smem = 232448;
   }
@@ -1404,18 +1730,21 @@ int launch_halo(const CUtensorMap& tmA, const CUtensorMap& tmB, TapGemmParams& p
   p.total_tiles = (int)total;
   const int sms = msp_num_sms();
   const int grid = p.total_tiles < sms ? p.total_tiles : sms;
-  MSP_CHECK_CUDA(msp_launch_pdl(tapgemm_halo_kernel<BN_>, dim3(grid), dim3(kTapThreads), (size_t)smem, st, tmA, tmB, p));
+  MSP_CHECK_CUDA(msp_launch_pdl(tapgemm_halo_kernel<BN_, MULTI>, dim3(grid), dim3(kTapThreads), (size_t)smem, st, tmA, tmB, p));
   MSP_CHECK_LAUNCH();
   msp_count_launch(1);
   g_last_kernel = BN_ == 256 ? "tapgemm_halo_kernel<256>" : BN_ == 128 ? "tapgemm_halo_kernel<128>"
-                  : BN_ == 64 ? "tapgemm_halo_kernel<64>" : BN_ == 32 ? "tapgemm_halo_kernel<32>" : "tapgemm_halo_kernel<16>";
+                  : BN_ == 64 ? "tapgemm_halo_kernel<64>"
+                  : BN_ == 32 ? (MULTI ? "tapgemm_halo_kernel<32, multi>" : "tapgemm_halo_kernel<32>")
+                              : (MULTI ? "tapgemm_halo_kernel<16, multi>" : "tapgemm_halo_kernel<16>");
   return MSP_OK;
 }
 
 int dispatch_halo(const CUtensorMap& tmA, const CUtensorMap& tmB, TapGemmParams& p, cudaStream_t st) {
+  const bool multi = multi_policy() && p.Kout <= 32 && p.bn == 1;
   switch (bn_tile_for(p.Kout)) {
-    case 16: return launch_halo<16>(tmA, tmB, p, st);
-    case 32: return launch_halo<32>(tmA, tmB, p, st);
+    case 16: return multi ? launch_halo<16, true>(tmA, tmB, p, st) : launch_halo<16>(tmA, tmB, p, st);
+    case 32: return multi ? launch_halo<32, true>(tmA, tmB, p, st) : launch_halo<32>(tmA, tmB, p, st);
     case 64: return launch_halo<64>(tmA, tmB, p, st);
     case 128: return launch_halo<128>(tmA, tmB, p, st);
     default: return launch_halo<256>(tmA, tmB, p, st);
@@ -1588,6 +1917,11 @@ extern "C" int msp_conv_fprop(const msp_conv_desc* d, const void* x, const void*
   p.Kout = d->K; p.relu = d->relu;
   p.y = (__nv_bfloat16*)y; p.y_off = 0;
   p.bias = bias; p.ch_sum = ch_sum; p.ch_sqsum = ch_sqsum;
+  if (d->stat_rows > 0 && ch_sum != nullptr) {
+    MSP_REQUIRE(d->stat_rows >= msp_num_sms() && ch_sqsum == ch_sum + d->K,
+                "conv_fprop: deterministic statistics need a [rows >= %d][2][K] workspace (ch_sqsum = ch_sum + K)", msp_num_sms());
+    p.stat_row = 2ll * d->K;
+  }
   if (d->win_px) {
     p.C = 64; p.ntaps = d->KH;
     for (int r = 0; r < d->KH; ++r) {
@@ -1816,6 +2150,32 @@ extern "C" int msp_unpack_wgrad(const msp_conv_desc* d, const float* dw_partials
   else
     MSP_CHECK_CUDA(msp_launch_pdl(unpack_wgrad_kernel, dim3(blocks), dim3(256), 0, (cudaStream_t)stream, dw_partials,
                                   pl.splits, split_stride, d->K, C_true, d->KH * d->KW, d->C, dw_oihw));
+  MSP_CHECK_LAUNCH();
+  msp_count_launch(1);
+  return MSP_OK;
+}
+
+extern "C" int msp_unpack_wgrad_batched(int n, const msp_unpack_item* items, void* stream) {
+  MSP_REQUIRE(items != nullptr && n >= 1 && n <= kUnpackMaxItems, "unpack_wgrad_batched: 1..%d items per call (got %d)",
+              kUnpackMaxItems, n);
+  UnpackList L;
+  memset(&L, 0, sizeof(L));
+  int first = 0;
+  for (int i = 0; i < n; ++i) {
+    const msp_unpack_item& it = items[i];
+    MSP_REQUIRE(it.partials && it.dst && it.splits >= 1 && it.K > 0 && it.C_true > 0, "unpack_wgrad_batched: bad item %d", i);
+    MSP_REQUIRE(it.rowwin_KH > 0 ? (it.rowwin_KW > 0 && it.rowwin_cpp > 0) : (it.taps > 0 && it.Cpad >= it.C_true),
+                "unpack_wgrad_batched: bad geometry in item %d", i);
+    L.it[i] = it;
+    const long long total = (long long)it.K * it.C_true * (it.rowwin_KH > 0 ? it.rowwin_KH * it.rowwin_KW : it.taps);
+    long long nb = (total + 2047) / 2048;
+    nb = nb < 1 ? 1 : (nb > 128 ? 128 : nb);
+    L.first_block[i] = first;
+    first += (int)nb;
+  }
+  L.first_block[n] = first;
+  L.n = n;
+  unpack_wgrad_batched_kernel<<<(unsigned)first, 256, 0, (cudaStream_t)stream>>>(L);
   MSP_CHECK_LAUNCH();
   msp_count_launch(1);
   return MSP_OK;

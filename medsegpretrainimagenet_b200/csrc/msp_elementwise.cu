@@ -141,18 +141,47 @@ __global__ void nhwc_to_nchw_kernel(const __nv_bfloat16* __restrict__ x, int C, 
 // ---------------------------------------------------------------------------------------------
 // BatchNorm
 // ---------------------------------------------------------------------------------------------
-__global__ void bn_finalize_kernel(float* s1, float* s2, int C, double count, float eps, float momentum,
-                                   float* mean, float* invstd, float* rmean, float* rvar, int reset) {
+// out[i] = sum over rows of ws[r][i], the rows added in FIXED order: 8 row groups per column run in parallel (row r in
+// group r % 8, ascending), their partial sums are added in group order.  The second stage of the deterministic reductions.
+constexpr int kRowGroups = 8;
+__device__ __forceinline__ float sum_rows_fixed(float* ws, int rows, long long row_stride, int col, int grp, int reset,
+                                                float (*part)[33]) {
+  float acc = 0.f;
+  for (int r = grp; r < rows; r += kRowGroups) {
+    float* a = ws + (long long)r * row_stride + col;
+    acc += *a;
+    if (reset) *a = 0.f;
+  }
+  part[grp][threadIdx.x & 31] = acc;
+  __syncthreads();
+  float tot = 0.f;
+#pragma unroll
+  for (int g = 0; g < kRowGroups; ++g) tot += part[g][threadIdx.x & 31];
+  __syncthreads();
+  return tot;
+}
+__global__ void __launch_bounds__(32 * kRowGroups) reduce_rows_kernel(float* ws, int rows, int n, float* out, int reset) {
+  __shared__ float part[kRowGroups][33];
+  const int col = blockIdx.x * 32 + (threadIdx.x & 31), grp = threadIdx.x >> 5;
+  const float tot = sum_rows_fixed(ws, rows, n, col < n ? col : n - 1, grp, reset && col < n, part);
+  if (grp == 0 && col < n) out[col] = tot;
+}
+
+// block = 32 channels x 8 row groups; rows == 1: the plain [2][C] accumulators
+__global__ void __launch_bounds__(32 * kRowGroups)
+bn_finalize_kernel(float* s1, float* s2, int C, double count, float eps, float momentum,
+                   float* mean, float* invstd, float* rmean, float* rvar, int reset, int rows) {
   pdl_trigger();
   pdl_wait();
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
-  const double m = (double)s1[c] / count;
-  double var = (double)s2[c] / count - m * m;
-  if (reset) {  // self-cleaning accumulators: ready for the next forward without a memset launch
-    s1[c] = 0.f;
-    s2[c] = 0.f;
-  }
+  __shared__ float part[kRowGroups][33];
+  const int c = blockIdx.x * 32 + (threadIdx.x & 31), grp = threadIdx.x >> 5;
+  const int cc = c < C ? c : C - 1;
+  const long long stride = 2ll * C;
+  const float t1 = sum_rows_fixed(s1, rows, stride, cc, grp, reset && c < C, part);
+  const float t2 = sum_rows_fixed(s2, rows, stride, cc, grp, reset && c < C, part);
+  if (grp != 0 || c >= C) return;
+  const double m = (double)t1 / count;
+  double var = (double)t2 / count - m * m;
   if (var < 0) var = 0;
   mean[c] = (float)m;
   invstd[c] = (float)(1.0 / sqrt(var + (double)eps));
@@ -268,7 +297,7 @@ bn_act_bwd_reduce_kernel(const msp_bn_act_desc d, const __nv_bfloat16* __restric
                          const __nv_bfloat16* __restrict__ y, const __nv_bfloat16* __restrict__ dy,
                          const float* __restrict__ mean, const float* __restrict__ invstd,
                          const float* __restrict__ sscale, float* sum_g, float* sum_gx,
-                         const float* __restrict__ gamma, const float* __restrict__ beta) {
+                         const float* __restrict__ gamma, const float* __restrict__ beta, float* rows_ws) {
   pdl_trigger();
   pdl_wait();
   extern __shared__ float red[];
@@ -338,7 +367,9 @@ bn_act_bwd_reduce_kernel(const msp_bn_act_desc d, const __nv_bfloat16* __restric
     float acc = 0.f;
     for (int l = 0; l < ppb; ++l) acc += red[(long long)l * V * 16 + col];
     const int ch = (col >> 4) * 8 + (col & 7);
-    atomicAdd(((col & 8) ? sum_gx : sum_g) + ch, acc);
+    // deterministic mode: this block's own row [2][C] of the workspace (added in fixed order by reduce_rows_kernel)
+    if (rows_ws) rows_ws[(long long)blockIdx.x * 2 * d.C + ((col & 8) ? d.C : 0) + ch] = acc;
+    else atomicAdd(((col & 8) ? sum_gx : sum_g) + ch, acc);
   }
 }
 
@@ -830,7 +861,7 @@ __global__ void gate_mul_bwd_kernel(const __nv_bfloat16* __restrict__ skip,
 
 // per-channel sum over pixels of an NHWC bf16 tensor -> fp32 (bias gradients)
 __global__ void channel_sum_kernel(const __nv_bfloat16* __restrict__ x, long long P, int C, int cs,
-                                   float* out) {
+                                   float* out, float* rows_ws) {
   extern __shared__ float red[];
   const int V = C >> 3;
   const int cg = threadIdx.x % V, pl = threadIdx.x / V, ppb = blockDim.x / V;
@@ -853,7 +884,10 @@ __global__ void channel_sum_kernel(const __nv_bfloat16* __restrict__ x, long lon
       for (int j = 0; j < 8; ++j) a[j] += o[j];
     }
 #pragma unroll
-    for (int j = 0; j < 8; ++j) atomicAdd(out + cg * 8 + j, a[j]);
+    for (int j = 0; j < 8; ++j) {
+      if (rows_ws) rows_ws[(long long)blockIdx.x * C + cg * 8 + j] = a[j];   // deterministic mode: fixed-order second stage
+      else atomicAdd(out + cg * 8 + j, a[j]);
+    }
   }
 }
 
@@ -916,12 +950,21 @@ extern "C" int msp_nchw_f32_grad_to_nhwc_bf16(const float* g, int N, int C, int 
 
 extern "C" int msp_bn_finalize(float* ch_sum, float* ch_sqsum, int C, double count, float eps,
                                float momentum, float* mean, float* invstd, float* running_mean,
-                               float* running_var, int reset_sums, void* stream) {
+                               float* running_var, int reset_sums, int rows, void* stream) {
   MSP_REQUIRE(ch_sum && ch_sqsum && mean && invstd && C > 0 && count > 0, "bn_finalize: bad arguments");
   MSP_REQUIRE((running_mean == nullptr) == (running_var == nullptr),
               "bn_finalize: need both running buffers or none");
-  MSP_CHECK_CUDA(msp_launch_pdl(bn_finalize_kernel, dim3((C + 127) / 128), dim3(128), 0, ST, ch_sum, ch_sqsum, C, count,
-                                eps, momentum, mean, invstd, running_mean, running_var, reset_sums));
+  MSP_REQUIRE(rows >= 1 && (rows == 1 || ch_sqsum == ch_sum + C),
+              "bn_finalize: the per-CTA workspace is [rows][2][C] (ch_sqsum = ch_sum + C)");
+  MSP_CHECK_CUDA(msp_launch_pdl(bn_finalize_kernel, dim3((C + 31) / 32), dim3(32 * kRowGroups), 0, ST, ch_sum, ch_sqsum, C,
+                                count, eps, momentum, mean, invstd, running_mean, running_var, reset_sums, rows));
+  MSP_CHECK_LAUNCH();
+  msp_count_launch(1);
+  return MSP_OK;
+}
+extern "C" int msp_reduce_rows(float* ws, int rows, int n, float* out, int reset, void* stream) {
+  MSP_REQUIRE(ws && out && rows >= 1 && n >= 1, "reduce_rows: bad arguments");
+  reduce_rows_kernel<<<(n + 31) / 32, 32 * kRowGroups, 0, ST>>>(ws, rows, n, out, reset);
   MSP_CHECK_LAUNCH();
   msp_count_launch(1);
   return MSP_OK;
@@ -975,7 +1018,7 @@ static int check_mask_from_x(const msp_bn_act_desc* d, const void* y, const floa
 extern "C" int msp_bn_act_bwd_reduce(const msp_bn_act_desc* d, const void* x, const void* y,
                                      const void* dy, const float* mean, const float* invstd,
                                      const float* gamma, const float* beta, const float* sample_scale,
-                                     float* sum_g, float* sum_gx, void* stream) {
+                                     float* sum_g, float* sum_gx, float* rows_ws, int ws_rows, void* stream) {
   int rc = check_bn_desc(d);
   if (rc) return rc;
   MSP_REQUIRE(x && dy && mean && invstd && sum_g && sum_gx, "bn_act_bwd_reduce: null pointer");
@@ -983,7 +1026,9 @@ extern "C" int msp_bn_act_bwd_reduce(const msp_bn_act_desc* d, const void* x, co
   if (rc) return rc;
   const int V = d->C / 8, T = threads_for_vecs(V), ppb = T / V;
   const long long P = (long long)d->N * d->H * d->W;
-  if (sum_gx == sum_g + d->C) {  // the usual [2][C] buffer: one memset node
+  if (rows_ws != nullptr) {
+    MSP_REQUIRE(ws_rows >= 1 && sum_gx == sum_g + d->C, "bn_act_bwd_reduce: deterministic mode needs sum_gx = sum_g + C");
+  } else if (sum_gx == sum_g + d->C) {  // the usual [2][C] buffer: one memset node
     MSP_CHECK_CUDA(cudaMemsetAsync(sum_g, 0, sizeof(float) * 2 * d->C, ST));
   } else {
     MSP_CHECK_CUDA(cudaMemsetAsync(sum_g, 0, sizeof(float) * d->C, ST));
@@ -993,16 +1038,24 @@ extern "C" int msp_bn_act_bwd_reduce(const msp_bn_act_desc* d, const void* x, co
   MSP_REQUIRE(P < (1ll << 31), "bn_act: too many pixels");
   static int ured = -1;
   if (ured < 0) { const char* e = getenv("MSP_BN_RED_U"); ured = e ? atoi(e) : 4; }  // 4 loads per tensor in flight: 3.61 -> 3.11 ms over the ResNet-50 layers
+  int grid = ured == 4 ? resident_grid(bn_act_bwd_reduce_kernel<4>, T, smem, P, ppb * 4)
+                       : resident_grid(bn_act_bwd_reduce_kernel<2>, T, smem, P, ppb * 2);
+  if (rows_ws != nullptr && grid > ws_rows) grid = ws_rows;
   if (ured == 4)
-    bn_act_bwd_reduce_kernel<4><<<resident_grid(bn_act_bwd_reduce_kernel<4>, T, smem, P, ppb * 4), T, smem, ST>>>(
+    bn_act_bwd_reduce_kernel<4><<<grid, T, smem, ST>>>(
         *d, (const __nv_bfloat16*)x, (const __nv_bfloat16*)y, (const __nv_bfloat16*)dy, mean, invstd,
-        sample_scale, sum_g, sum_gx, gamma, beta);
+        sample_scale, sum_g, sum_gx, gamma, beta, rows_ws);
   else
-    bn_act_bwd_reduce_kernel<2><<<resident_grid(bn_act_bwd_reduce_kernel<2>, T, smem, P, ppb * 2), T, smem, ST>>>(
+    bn_act_bwd_reduce_kernel<2><<<grid, T, smem, ST>>>(
         *d, (const __nv_bfloat16*)x, (const __nv_bfloat16*)y, (const __nv_bfloat16*)dy, mean, invstd,
-        sample_scale, sum_g, sum_gx, gamma, beta);
+        sample_scale, sum_g, sum_gx, gamma, beta, rows_ws);
   MSP_CHECK_LAUNCH();
   msp_count_launch(1);
+  if (rows_ws != nullptr) {  // second stage: the blocks' rows in fixed order
+    reduce_rows_kernel<<<(2 * d->C + 31) / 32, 32 * kRowGroups, 0, ST>>>(rows_ws, grid, 2 * d->C, sum_g, 0);
+    MSP_CHECK_LAUNCH();
+    msp_count_launch(1);
+  }
   return MSP_OK;
 }
 
@@ -1175,14 +1228,25 @@ extern "C" int msp_gate_mul_bwd(const void* skip, const void* p, const void* dy,
   msp_count_launch(1);
   return MSP_OK;
 }
-extern "C" int msp_channel_sum(const void* x, long long P, int C, int cs, float* out, void* stream) {
+extern "C" int msp_channel_sum(const void* x, long long P, int C, int cs, float* out, float* rows_ws, int ws_rows,
+                               void* stream) {
   REQ_C8(C, cs, "channel_sum");
   MSP_REQUIRE(C <= 2048 && out && x, "channel_sum: bad arguments");
   const int V = C / 8, T = threads_for_vecs(V), ppb = T / V;
-  MSP_CHECK_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * C, ST));
-  channel_sum_kernel<<<grid_for(P, ppb * 8, 4), T, (size_t)T * 8 * sizeof(float), ST>>>(
-      (const __nv_bfloat16*)x, P, C, cs, out);
+  int grid = grid_for(P, ppb * 8, 4);
+  if (rows_ws != nullptr) {
+    MSP_REQUIRE(ws_rows >= 1, "channel_sum: empty row workspace");
+    if (grid > ws_rows) grid = ws_rows;
+  } else {
+    MSP_CHECK_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * C, ST));
+  }
+  channel_sum_kernel<<<grid, T, (size_t)T * 8 * sizeof(float), ST>>>((const __nv_bfloat16*)x, P, C, cs, out, rows_ws);
   MSP_CHECK_LAUNCH();
   msp_count_launch(1);
+  if (rows_ws != nullptr) {
+    reduce_rows_kernel<<<(C + 31) / 32, 32 * kRowGroups, 0, ST>>>(rows_ws, grid, C, out, 0);
+    MSP_CHECK_LAUNCH();
+    msp_count_launch(1);
+  }
   return MSP_OK;
 }

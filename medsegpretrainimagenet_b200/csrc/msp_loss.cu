@@ -92,7 +92,8 @@ __global__ void final_conv_act_bwd_kernel(const __nv_bfloat16* __restrict__ x, l
                                           int K, int act, const float* __restrict__ prob,
                                           const float* __restrict__ dprob,
                                           __nv_bfloat16* __restrict__ dx, int dx_cs,
-                                          float* __restrict__ dw, float* __restrict__ db) {
+                                          float* __restrict__ dw, float* __restrict__ db,
+                                          float* __restrict__ rows_ws) {
   extern __shared__ __align__(16) uint8_t sraw[];
   float* ws = reinterpret_cast<float*>(sraw);                    // [K][C]
   float* dls = ws + K * C;                                       // [K][256]
@@ -182,6 +183,11 @@ __global__ void final_conv_act_bwd_kernel(const __nv_bfloat16* __restrict__ x, l
       dwacc[i] += a;
     }
     __syncthreads();
+  }
+  if (rows_ws) {  // deterministic mode: this block's row [K*C + K], added in fixed order by msp_reduce_rows
+    float* row = rows_ws + (long long)blockIdx.x * (K * C + K);
+    for (int i = threadIdx.x; i < K * C + K; i += blockDim.x) row[i] = dwacc[i];
+    return;
   }
   for (int i = threadIdx.x; i < K * C; i += blockDim.x) atomicAdd(dw + i, dwacc[i]);
   if (db)
@@ -641,14 +647,18 @@ extern "C" int msp_final_conv_act_fwd(const void* x, int N, int H, int W, int C,
 extern "C" int msp_final_conv_act_bwd(const void* x, int N, int H, int W, int C, int x_cs,
                                       const float* w, int K, int act, const float* prob_nchw,
                                       const float* dprob_nchw, void* dx, int dx_cs, float* dw,
-                                      float* db, void* stream) {
+                                      float* db, float* rows_ws, int ws_rows, void* stream) {
   MSP_REQUIRE(x && w && prob_nchw && dprob_nchw && dw, "final_conv_act_bwd: null pointer");
+  MSP_REQUIRE(rows_ws == nullptr || (ws_rows >= 1 && db == dw + (long long)K * C),
+              "final_conv_act_bwd: deterministic mode needs db = dw + K*C (one [K*C + K] result vector)");
   MSP_REQUIRE(K >= 1 && K <= kMaxHeadK, "final_conv_act_bwd: K=%d outside [1,8]", K);
   MSP_REQUIRE(C > 0 && C % 8 == 0 && x_cs % 8 == 0 && x_cs >= C, "final_conv_act_bwd: C/x_cs %% 8");
   MSP_REQUIRE(dx == nullptr || (dx_cs % 8 == 0 && dx_cs >= C), "final_conv_act_bwd: dx_cs");
   const long long HW = (long long)H * W, P = (long long)N * HW;
-  MSP_CHECK_CUDA(cudaMemsetAsync(dw, 0, sizeof(float) * K * C, ST));
-  if (db) MSP_CHECK_CUDA(cudaMemsetAsync(db, 0, sizeof(float) * K, ST));
+  if (rows_ws == nullptr || P == 0) {
+    MSP_CHECK_CUDA(cudaMemsetAsync(dw, 0, sizeof(float) * K * C, ST));
+    if (db) MSP_CHECK_CUDA(cudaMemsetAsync(db, 0, sizeof(float) * K, ST));
+  }
   if (P == 0) return MSP_OK;
   const size_t smem = (size_t)((2 * K * C + K * 256 + K + 3) & ~3) * sizeof(float) + (size_t)256 * C * 2;
   MSP_REQUIRE(smem <= 200 * 1024, "final_conv_act_bwd: C=%d too large for the staged tile", C);
@@ -660,11 +670,13 @@ extern "C" int msp_final_conv_act_bwd(const void* x, int N, int H, int W, int C,
   }
   long long blocks = (P + 255) / 256;
   if (blocks > (long long)msp_num_sms() * 4) blocks = (long long)msp_num_sms() * 4;
+  if (rows_ws != nullptr && blocks > ws_rows) blocks = ws_rows;
   final_conv_act_bwd_kernel<<<(int)blocks, 256, smem, ST>>>(
       (const __nv_bfloat16*)x, P, HW, C, x_cs, w, K, act, prob_nchw, dprob_nchw, (__nv_bfloat16*)dx,
-      dx_cs, dw, db);
+      dx_cs, dw, db, rows_ws);
   MSP_CHECK_LAUNCH();
   msp_count_launch(1);
+  if (rows_ws != nullptr) return msp_reduce_rows(rows_ws, (int)blocks, K * C + K, dw, 0, stream);
   return MSP_OK;
 }
 

@@ -73,7 +73,7 @@ def _stats_buffer(want_stats, k, device):
     if want_stats is False or want_stats is None:
         return None
     if want_stats is True:
-        return torch.zeros((2, k), dtype=torch.float32, device=device)
+        return ops.new_stats(k, device)
     return want_stats
 
 
@@ -94,6 +94,7 @@ class _Conv(torch.autograd.Function):
                            ho, wo, relu=relu, out=out, stats=stats, c_true=c_true)
         ctx.geom = (kh, kw, stride, pt, pl, c_true, relu, bias is not None)
         ctx.x_shape = tuple(x.shape)
+        ctx.weight_param = weight if (weight.is_leaf and weight.requires_grad) else None
         ctx.save_for_backward(x, wd, y if relu else None)
         if stats is not None:
             ctx.mark_non_differentiable(stats)
@@ -119,7 +120,11 @@ class _Conv(torch.autograd.Function):
             else:
                 dx = ops.conv_dgrad(dy, wd, ctx.x_shape, kh, kw, stride, pt, pl, c_true=c_true)
         if ctx.needs_input_grad[1]:
-            dw = ops.conv_wgrad(x, dy, c_true, kh, kw, stride, pt, pl)
+            # a leaf Parameter's gradient goes straight into `weight.grad` (one unpack kernel per backward pass,
+            # ops._WgradQueue); autograd gets None for it
+            wp = ctx.weight_param
+            if wp is None or not ops.conv_wgrad_param(x, dy, wp, kh, kw, stride, pt, pl):
+                dw = ops.conv_wgrad(x, dy, c_true, kh, kw, stride, pt, pl)
         if has_bias and ctx.needs_input_grad[2]:
             db = ops.channel_sum(dy)
         return dx, dw, db, None, None, None, None, None, None
@@ -144,6 +149,7 @@ class _InputConv(torch.autograd.Function):
         y = ops.conv_fprop_rowwin(xw, w, wr, bias.detach() if bias is not None else None, k, kh, kw, stride,
                                   pt, pl, ho, wo, win_px, relu=relu, stats=stats, c_true=c_true)
         ctx.geom = (kh, kw, stride, pt, pl, c_true, relu, bias is not None, win_px, w)
+        ctx.weight_param = weight if (weight.is_leaf and weight.requires_grad) else None
         ctx.save_for_backward(xw, y if relu else None)
         if stats is not None:
             ctx.mark_non_differentiable(stats)
@@ -163,7 +169,9 @@ class _InputConv(torch.autograd.Function):
             dy = ops.relu_bwd(y, dy)
         dw = db = None
         if ctx.needs_input_grad[1]:
-            dw = ops.conv_wgrad_rowwin(xw, w_img, dy, c_true, kh, kw, stride, pt, pl, win_px)
+            wp = ctx.weight_param
+            if wp is None or not ops.conv_wgrad_rowwin_param(xw, w_img, dy, wp, kh, kw, stride, pt, pl, win_px):
+                dw = ops.conv_wgrad_rowwin(xw, w_img, dy, c_true, kh, kw, stride, pt, pl, win_px)
         if has_bias and ctx.needs_input_grad[2]:
             db = ops.channel_sum(dy)
         return None, dw, db, None, None, None, None, None
@@ -198,7 +206,11 @@ class _BnAct(torch.autograd.Function):
         count = n * h * w
         if training:
             if group is not None and dist.is_initialized() and dist.get_world_size(group) > 1:
-                # SyncBN: [2C] fp32 sums over NCCL; every rank holds the same per-GPU batch (weak scaling)
+                # SyncBN: [2C] fp32 sums over NVLink peer memory / NCCL; every rank holds the same per-GPU batch (weak
+                # scaling).  Deterministic mode: the per-CTA rows are first added in fixed order on this rank.
+                if stats.dim() == 3:
+                    stats = ops.reduce_rows(stats, reset=persistent_stats)
+                    persistent_stats = False
                 _allreduce_sum(stats, group)
                 count = count * dist.get_world_size(group)
             mi = ops.bn_finalize(stats, count, eps, momentum, running_mean, running_var, reset=persistent_stats)

@@ -42,6 +42,52 @@ def _chk_nhwc(t: torch.Tensor, name: str) -> Tuple[int, int, int, int, int]:
     return n, h, w, c, cs
 
 
+def deterministic() -> bool:
+    """torch.use_deterministic_algorithms (run_experiment.py:65; every downstream YAML of the reference sets it): the
+    floating-point reductions that normally finish with atomics (BatchNorm statistics in the conv epilogue, BatchNorm
+    backward sums, bias gradients) then store per-CTA partial rows and add them in a fixed order."""
+    return torch.are_deterministic_algorithms_enabled()
+
+
+_SMS = {}
+
+
+def sm_count(device) -> int:
+    idx = torch.device(device).index
+    idx = torch.cuda.current_device() if idx is None else idx
+    if idx not in _SMS:
+        _SMS[idx] = torch.cuda.get_device_properties(idx).multi_processor_count
+    return _SMS[idx]
+
+
+def new_stats(k: int, device) -> torch.Tensor:
+    """Zeroed BatchNorm statistic accumulators of a conv epilogue: [2, K], or the per-CTA row workspace
+    [SMs, 2, K] of the deterministic mode."""
+    if deterministic():
+        return torch.zeros((sm_count(device), 2, k), dtype=torch.float32, device=device)
+    return torch.zeros((2, k), dtype=torch.float32, device=device)
+
+
+def stats_total(stats: torch.Tensor) -> torch.Tensor:
+    """[2, K] totals of either layout (tests / inspection; the step itself uses bn_finalize / reduce_rows)."""
+    return stats if stats.dim() == 2 else stats.sum(0)
+
+
+def _stat_args(stats):
+    if stats is None:
+        return None, None, 0
+    if stats.dim() == 3:
+        return stats[0, 0].data_ptr(), stats[0, 1].data_ptr(), stats.shape[0]
+    return stats[0].data_ptr(), stats[1].data_ptr(), 0
+
+
+def reduce_rows(ws: torch.Tensor, reset: bool = False) -> torch.Tensor:
+    """[rows, *shape] fp32 -> [*shape]: the rows added in fixed order (second stage of the deterministic reductions)."""
+    out = torch.empty(ws.shape[1:], dtype=torch.float32, device=ws.device)
+    call("msp_reduce_rows", _p(ws), ws.shape[0], out.numel(), _p(out), int(reset), _stream())
+    return out
+
+
 def new_act(n: int, h: int, w: int, c: int, device, zero: bool = False) -> torch.Tensor:
     f = torch.zeros if zero else torch.empty
     return f((n, h, w, c), dtype=_BF16, device=device)
@@ -131,8 +177,11 @@ class WeightPackCache:
         rows, first = [], 0
         for w, wf, wd in self.entries.values():
             k, c, kh, kw = w.shape
-            elems = k * kh * kw * ceil8(c) * (2 if wd is not None else 1)
-            nblk = max(1, min(1024, (elems + 2047) // 2048))       # ~8 elements per thread
+            if kh * kw <= 9:      # tiled transposing mode of the kernel: one block per 32 x 32 channel tile (all taps)
+                nblk = ((ceil8(k) + 31) // 32) * ((ceil8(c) + 31) // 32)
+            else:
+                elems = k * kh * kw * ceil8(c) * (2 if wd is not None else 1)
+                nblk = max(1, min(1024, (elems + 2047) // 2048))       # ~8 elements per thread
             rows.append([w.data_ptr(), wf.data_ptr(), wd.data_ptr() if wd is not None else 0, k, c, kh * kw,
                          ceil8(c), ceil8(k), first, nblk])
             first += nblk
@@ -207,6 +256,7 @@ class _timed:
         if _CONV_TIMELINE is not None:
             self.e0 = torch.cuda.Event(enable_timing=True)
             self.e1 = torch.cuda.Event(enable_timing=True)
+            self.l0 = _lib.launch_count()
             self.e0.record()
         return self
 
@@ -214,13 +264,17 @@ class _timed:
         if _CONV_TIMELINE is not None:
             self.e1.record()
             name = (_lib.lib.msp_conv_last_kernel() or b"").decode()
-            _CONV_TIMELINE.append((self.kind, self.flops, self.e0, self.e1, self.nbytes, name))
+            # last field: number of kernels this call launched (bench.py matches them, in stream order, with the
+            # profiler's per-kernel device times: event pairs around a 10 us kernel of an eagerly enqueued step mostly
+            # measure the host's launch gaps)
+            _CONV_TIMELINE.append((self.kind, self.flops, self.e0, self.e1, self.nbytes, name,
+                                   _lib.launch_count() - self.l0))
         return False
 
 
 def _conv_desc(n, h, w, c, x_cs, ho, wo, k, y_cs, kh, kw, stride, pad_t, pad_l, relu=0, win_px=0,
-               wp=0) -> ConvDesc:
-    return ConvDesc(n, h, w, c, x_cs, ho, wo, k, y_cs, kh, kw, stride, pad_t, pad_l, relu, win_px, wp)
+               wp=0, stat_rows=0) -> ConvDesc:
+    return ConvDesc(n, h, w, c, x_cs, ho, wo, k, y_cs, kh, kw, stride, pad_t, pad_l, relu, win_px, wp, stat_rows)
 
 
 def conv_fprop(x, wf, bias, k, kh, kw, stride, pad_t, pad_l, ho, wo, relu=False, out=None, stats=None,
@@ -232,10 +286,8 @@ def conv_fprop(x, wf, bias, k, kh, kw, stride, pad_t, pad_l, ho, wo, relu=False,
         out = new_act(n, ho, wo, k, x.device)
     _, _, _, ko, y_cs = _chk_nhwc(out, "conv_fprop(out)")
     assert ko == k and wf.shape[2] == c, (ko, k, tuple(wf.shape), c)
-    d = _conv_desc(n, h, w, c, x_cs, ho, wo, k, y_cs, kh, kw, stride, pad_t, pad_l, int(relu))
-    s1 = s2 = None
-    if stats is not None:
-        s1, s2 = stats[0].data_ptr(), stats[1].data_ptr()
+    s1, s2, rows = _stat_args(stats)
+    d = _conv_desc(n, h, w, c, x_cs, ho, wo, k, y_cs, kh, kw, stride, pad_t, pad_l, int(relu), stat_rows=rows)
     with _timed("fprop", 2.0 * n * ho * wo * k * (c_true or c) * kh * kw,
                 2.0 * (n * h * w * c + n * ho * wo * k + k * c * kh * kw)):
         call("msp_conv_fprop", C.byref(d), _p(x), _p(wf), _p(bias), _p(out), s1, s2, _stream())
@@ -268,6 +320,130 @@ def _wgrad(d: ConvDesc, x, dy, c_true, flops, nbytes=0.0) -> torch.Tensor:
         call("msp_conv_wgrad", C.byref(d), _p(x), _p(dy), _p(part), _stream())
         call("msp_unpack_wgrad", C.byref(d), _p(part), c_true, _p(dw), _stream())
     return dw
+
+
+# ------------------------------------------------------------------------------------------------
+# weight gradients straight into `param.grad`, unpacked by ONE kernel per backward pass
+# ------------------------------------------------------------------------------------------------
+class _WgradQueue:
+    """Split-K partials of the wgrad launches of the running backward pass, waiting for msp_unpack_wgrad_batched.
+
+    Per-layer unpack launches cost ~8 us each for microseconds of work (5 % of the R50 U-Net step).  A convolution whose
+    weight is a leaf Parameter therefore writes its gradient into `weight.grad` itself (allocated here when absent, ADDED
+    to when present: gradient accumulation, all-reduce bucket views) instead of returning it to autograd, and only
+    queues the fixed-order split sum; `flush()` — queued as an end-of-backward callback of the autograd engine, and called
+    by parallel.GradReducer before it reduces a bucket — issues one kernel for everything queued.  Nobody can read
+    `weight.grad` in between: autograd never sees these gradients."""
+
+    def __init__(self):
+        self.items, self.keep, self.callback_queued = [], [], False
+
+    def push(self, d: ConvDesc, part, dst, c_true, accumulate):
+        it = _lib.UnpackItem()
+        it.partials, it.dst = part.data_ptr(), dst.data_ptr()
+        it.splits, it.K, it.C_true = part.shape[0], d.K, c_true
+        it.split_stride = part.stride(0)
+        if d.win_px:
+            it.rowwin_KH, it.rowwin_KW, it.rowwin_cpp, it.taps, it.Cpad = d.KH, d.KW, d.C, d.KH, 64
+        else:
+            it.rowwin_KH, it.taps, it.Cpad = 0, d.KH * d.KW, d.C
+        it.accumulate = int(accumulate)
+        self.items.append(it)
+        self.keep.append((part, dst))
+        if not self.callback_queued:
+            try:
+                torch.autograd.Variable._execution_engine.queue_callback(self.flush)
+                self.callback_queued = True
+            except RuntimeError:
+                self.flush()                    # not inside a backward pass: nothing to defer to
+
+    def flush(self):
+        self.callback_queued = False
+        items, self.items = self.items, []
+        keep, self.keep = self.keep, []
+        if items and _WGRAD_STREAM is not None:
+            cur = torch.cuda.current_stream()
+            cur.wait_stream(_WGRAD_STREAM)          # every queued wgrad kernel has finished before the unpack starts
+            for part, _ in keep:
+                part.record_stream(cur)
+        for lo in range(0, len(items), 96):
+            chunk = items[lo:lo + 96]
+            arr = (_lib.UnpackItem * len(chunk))(*chunk)
+            call("msp_unpack_wgrad_batched", len(chunk), arr, _stream())
+        del keep
+
+
+_WGRAD_QUEUE = _WgradQueue()
+_WGRAD_SINK = os.environ.get("MSP_WGRAD_SINK", "1") != "0"    # 0: return dW to autograd, one unpack launch per layer
+_WGRAD_STREAM: Optional[torch.cuda.Stream] = None
+
+
+def set_wgrad_stream(stream: Optional[torch.cuda.Stream]) -> None:
+    """Run the wgrad kernels of the sink path on `stream` (None: the current stream).  The weight gradients are leaves
+    of the backward pass: nothing downstream waits for them, while the dgrad / BatchNorm-backward chain is serial.  On
+    a side stream they fill the SMs the chain's small kernels leave idle (small batches: most launches of the R50
+    U-Net at batch 24 use a fraction of the 148 SMs).  The stream forks from the current stream before every launch
+    and is joined by `flush_wgrad()`; CUDA-graph capture records the fork / join as graph branches."""
+    global _WGRAD_STREAM
+    flush_wgrad()
+    _WGRAD_STREAM = stream
+
+
+def flush_wgrad() -> None:
+    _WGRAD_QUEUE.flush()
+
+
+def wgrad_into_param(d: ConvDesc, x, dy, weight: torch.Tensor, c_true, flops, nbytes=0.0) -> bool:
+    """Launch the wgrad kernel of one convolution and queue the unpack into `weight.grad`.  Returns False when the
+    parameter does not qualify (the caller then takes the autograd route)."""
+    if not _WGRAD_SINK or not weight.is_leaf or weight.dtype != torch.float32 or not weight.is_contiguous():
+        return False
+    g = weight.grad
+    if g is not None and (g.dtype != torch.float32 or not g.is_contiguous() or g.shape != weight.shape
+                          or g.device != weight.device):
+        return False
+    splits = _lib.lib.msp_conv_wgrad_splits(C.byref(d))
+    _lib.check(0 if splits >= 1 else splits, "msp_conv_wgrad_splits")
+    taps = d.KH if d.win_px else d.KH * d.KW
+    cw = 64 if d.win_px else d.C
+    side = _WGRAD_STREAM if _CONV_TIMELINE is None else None     # instrumented runs time every kernel in stream order
+    if side is not None:
+        side.wait_stream(torch.cuda.current_stream())             # x and dy are complete
+        with torch.cuda.stream(side):
+            part = torch.empty((splits, d.K, taps, cw), dtype=torch.float32, device=x.device)
+            call("msp_conv_wgrad", C.byref(d), _p(x), _p(dy), _p(part), side.cuda_stream)
+        x.record_stream(side)
+        dy.record_stream(side)
+    else:
+        part = torch.empty((splits, d.K, taps, cw), dtype=torch.float32, device=x.device)
+        with _timed("wgrad", flops, nbytes):
+            call("msp_conv_wgrad", C.byref(d), _p(x), _p(dy), _p(part), _stream())
+    accumulate = g is not None
+    if g is None:
+        g = torch.empty_like(weight, memory_format=torch.contiguous_format)
+        weight.grad = g
+    _WGRAD_QUEUE.push(d, part, g, c_true, accumulate)
+    ready = getattr(weight, "_msp_grad_ready", None)      # parallel.GradReducer: this bucket member is complete
+    if ready is not None:
+        ready(weight)
+    return True
+
+
+def conv_wgrad_param(x, dy, weight, kh, kw, stride, pad_t, pad_l) -> bool:
+    n, h, w, c, x_cs = _chk_nhwc(x, "conv_wgrad(x)")
+    _, ho, wo, k, y_cs = _chk_nhwc(dy, "conv_wgrad(dy)")
+    c_true = weight.shape[1]
+    d = _conv_desc(n, h, w, c, x_cs, ho, wo, k, y_cs, kh, kw, stride, pad_t, pad_l)
+    return wgrad_into_param(d, x, dy, weight, c_true, 2.0 * n * ho * wo * k * c_true * kh * kw,
+                            2.0 * (n * h * w * c + n * ho * wo * k) + 4.0 * k * c_true * kh * kw)
+
+
+def conv_wgrad_rowwin_param(xw, w_img, dy, weight, kh, kw, stride, pad_t, pad_l, win_px) -> bool:
+    n, ho, wo, k, y_cs = _chk_nhwc(dy, "conv_wgrad_rowwin(dy)")
+    d = _rowwin_desc(xw, w_img, k, kh, kw, stride, pad_t, pad_l, ho, wo, y_cs, win_px)
+    c_true = weight.shape[1]
+    return wgrad_into_param(d, xw, dy, weight, c_true, 2.0 * n * ho * wo * k * c_true * kh * kw,
+                            2.0 * (xw.numel() + n * ho * wo * k) + 4.0 * k * c_true * kh * kw)
 
 
 def conv_wgrad(x, dy, c_true, kh, kw, stride, pad_t, pad_l) -> torch.Tensor:
@@ -316,9 +492,10 @@ def pack_weights_rowwin(w: torch.Tensor, win_px: int) -> torch.Tensor:
     return out
 
 
-def _rowwin_desc(xw, w_img, k, kh, kw, stride, pad_t, pad_l, ho, wo, y_cs, win_px, relu=0):
+def _rowwin_desc(xw, w_img, k, kh, kw, stride, pad_t, pad_l, ho, wo, y_cs, win_px, relu=0, stat_rows=0):
     n, h, wp, cpp = xw.shape
-    return _conv_desc(n, h, w_img, cpp, cpp, ho, wo, k, y_cs, kh, kw, stride, pad_t, pad_l, relu, win_px, wp)
+    return _conv_desc(n, h, w_img, cpp, cpp, ho, wo, k, y_cs, kh, kw, stride, pad_t, pad_l, relu, win_px, wp,
+                      stat_rows)
 
 
 def conv_fprop_rowwin(xw, w_img, wr, bias, k, kh, kw, stride, pad_t, pad_l, ho, wo, win_px, relu=False,
@@ -327,10 +504,8 @@ def conv_fprop_rowwin(xw, w_img, wr, bias, k, kh, kw, stride, pad_t, pad_l, ho, 
     if out is None:
         out = new_act(n, ho, wo, k, xw.device)
     _, _, _, _, y_cs = _chk_nhwc(out, "conv_fprop_rowwin(out)")
-    d = _rowwin_desc(xw, w_img, k, kh, kw, stride, pad_t, pad_l, ho, wo, y_cs, win_px, int(relu))
-    s1 = s2 = None
-    if stats is not None:
-        s1, s2 = stats[0].data_ptr(), stats[1].data_ptr()
+    s1, s2, rows = _stat_args(stats)
+    d = _rowwin_desc(xw, w_img, k, kh, kw, stride, pad_t, pad_l, ho, wo, y_cs, win_px, int(relu), stat_rows=rows)
     with _timed("fprop", 2.0 * n * ho * wo * k * (c_true or xw.shape[3]) * kh * kw,
                 2.0 * (xw.numel() + n * ho * wo * k)):
         call("msp_conv_fprop", C.byref(d), _p(xw), _p(wr), _p(bias), _p(out), s1, s2, _stream())
@@ -346,7 +521,11 @@ def conv_wgrad_rowwin(xw, w_img, dy, c_true, kh, kw, stride, pad_t, pad_l, win_p
 def channel_sum(x: torch.Tensor) -> torch.Tensor:
     n, h, w, c, cs = _chk_nhwc(x, "channel_sum")
     out = torch.empty((c,), dtype=torch.float32, device=x.device)
-    call("msp_channel_sum", _p(x), n * h * w, c, cs, _p(out), _stream())
+    ws, rows = None, 0
+    if deterministic():
+        rows = 4 * sm_count(x.device)
+        ws = torch.empty((rows, c), dtype=torch.float32, device=x.device)
+    call("msp_channel_sum", _p(x), n * h * w, c, cs, _p(out), _p(ws), rows, _stream())
     return out
 
 
@@ -354,11 +533,13 @@ def channel_sum(x: torch.Tensor) -> torch.Tensor:
 # BatchNorm (+ activation + residual)
 # ------------------------------------------------------------------------------------------------
 def bn_finalize(stats, count, eps, momentum, running_mean=None, running_var=None, reset=False):
-    c = stats.shape[1]
+    """`stats`: [2, C] sums, or the [rows, 2, C] per-CTA workspace of the deterministic mode (rows added in fixed order)."""
+    c = stats.shape[-1]
+    s1, s2, rows = _stat_args(stats)
     mi = torch.empty((2, c), dtype=torch.float32, device=stats.device)
-    call("msp_bn_finalize", stats[0].data_ptr(), stats[1].data_ptr(), c, float(count), float(eps),
+    call("msp_bn_finalize", s1, s2, c, float(count), float(eps),
          float(momentum), mi[0].data_ptr(), mi[1].data_ptr(), _p(running_mean), _p(running_var), int(reset),
-         _stream())
+         max(rows, 1), _stream())
     return mi
 
 
@@ -396,8 +577,12 @@ def bn_act_bwd_reduce(x, y, dy, mi, act, sample_scale=None, gamma=None, beta=Non
     if y is not None:
         assert dy.stride(2) == y.stride(2), "dy must share the pixel stride of y"
     sums = torch.empty((2, x.shape[3]), dtype=torch.float32, device=x.device)
+    ws, rows = None, 0
+    if deterministic():
+        rows = 2 * sm_count(x.device)
+        ws = torch.empty((rows, 2, x.shape[3]), dtype=torch.float32, device=x.device)
     call("msp_bn_act_bwd_reduce", C.byref(d), _p(x), _p(y), _p(dy), mi[0].data_ptr(), mi[1].data_ptr(),
-         _p(gamma), _p(beta), _p(sample_scale), sums[0].data_ptr(), sums[1].data_ptr(), _stream())
+         _p(gamma), _p(beta), _p(sample_scale), sums[0].data_ptr(), sums[1].data_ptr(), _p(ws), rows, _stream())
     return sums
 
 
@@ -535,10 +720,20 @@ def final_conv_act_bwd(x, w2d, act: int, prob, dprob, need_dx=True, has_bias=Tru
     n, h, w, c, cs = _chk_nhwc(x, "final_conv_bwd(x)")
     k = w2d.shape[0]
     dx = new_act(n, h, w, c, x.device) if need_dx else None
+    ws, rows = None, 0
+    if deterministic():
+        # one contiguous [K*C + K] result (dw | db) so that the fixed-order row reduction is a single launch
+        flat = torch.empty((k * c + k,), dtype=torch.float32, device=x.device)
+        dw, db_all = flat[:k * c].view(k, c), flat[k * c:]
+        rows = 4 * sm_count(x.device)
+        ws = torch.empty((rows, k * c + k), dtype=torch.float32, device=x.device)
+        call("msp_final_conv_act_bwd", _p(x), n, h, w, c, cs, _p(w2d), k, act, _p(prob), _p(dprob), _p(dx), c,
+             _p(dw), _p(db_all), _p(ws), rows, _stream())
+        return dx, dw, (db_all if has_bias else None)
     dw = torch.empty((k, c), dtype=torch.float32, device=x.device)
     db = torch.empty((k,), dtype=torch.float32, device=x.device) if has_bias else None
     call("msp_final_conv_act_bwd", _p(x), n, h, w, c, cs, _p(w2d), k, act, _p(prob), _p(dprob), _p(dx), c,
-         _p(dw), _p(db), _stream())
+         _p(dw), _p(db), None, 0, _stream())
     return dx, dw, db
 
 

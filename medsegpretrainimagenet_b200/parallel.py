@@ -77,6 +77,9 @@ class GradReducer:
             for p in b.params:
                 self._bucket_of[p] = b
                 self._hooks.append(p.register_post_accumulate_grad_hook(self._on_grad))
+                # convolution weights bypass autograd's accumulation (ops._WgradQueue adds their gradient into the
+                # bucket view itself): they report here instead of through the hook
+                p._msp_grad_ready = self._on_grad
         self.zero_grad()
 
     def _close(self, params):
@@ -139,6 +142,8 @@ class GradReducer:
                                "call finish() after the last one")
         b.pending -= 1
         if b.pending == 0 and self.world > 1:
+            from . import ops
+            ops.flush_wgrad()           # the queued weight-gradient unpacks of this bucket's convolutions
             self._launch(b)
 
     def finish(self) -> None:
@@ -146,6 +151,8 @@ class GradReducer:
         gradient this step, e.g. frozen branches), waits for all of them and re-arms the buckets."""
         if self.world == 1:
             return
+        from . import ops
+        ops.flush_wgrad()
         for b in self.buckets:
             if b.work is None:
                 self._launch(b)
@@ -160,6 +167,9 @@ class GradReducer:
         for h in self._hooks:
             h.remove()
         self._hooks = []
+        for p in self._bucket_of:
+            if getattr(p, "_msp_grad_ready", None) is not None:
+                p._msp_grad_ready = None
 
 
 def shard_rows(n_global: int, rank: int, world: int):

@@ -95,6 +95,11 @@ def install(group=None, convert_models: bool = True) -> None:
     if _installed:
         return
     _shim_randint()
+    # run_experiment.py:65 switches torch.use_deterministic_algorithms on for the downstream YAMLs; torch then FILLS every
+    # torch.empty() buffer with NaNs (one extra kernel per allocation).  Every buffer this path allocates is fully written
+    # by its producing kernel, so the fill is pure overhead here.
+    import torch
+    _set(torch.utils.deterministic, "fill_uninitialized_memory", False)
     model_mod = importlib.import_module("model")
     model_impl = importlib.import_module("model.model")
     loss_mod = importlib.import_module("loss")

@@ -32,7 +32,21 @@ def _bn_buffers(model):
     return [b for n, b in model.named_buffers() if n.endswith("running_mean") or n.endswith("running_var")]
 
 
-def n_rank_parity(group=None, device=None, per_rank_batch: int = 2, size: int = 64, seed: int = 0) -> dict:
+def n_rank_parity(group=None, device=None, per_rank_batch: int = 4, size: int = 128, seed: int = 0) -> dict:
+    """Runs in deterministic mode (torch.use_deterministic_algorithms, as the reference's downstream YAMLs do): the
+    reductions then have a fixed order, so a difference between the two steps is a property of the data-parallel
+    path (statistics added per rank first, then across ranks), not run-to-run noise — `repeat_grad_cosine` (the
+    single-device step executed twice) documents that."""
+    was = torch.are_deterministic_algorithms_enabled()
+    warn = torch.is_deterministic_algorithms_warn_only_enabled()
+    torch.use_deterministic_algorithms(True, warn_only=True)
+    try:
+        return _n_rank_parity(group, device, per_rank_batch, size, seed)
+    finally:
+        torch.use_deterministic_algorithms(was, warn_only=warn)
+
+
+def _n_rank_parity(group, device, per_rank_batch, size, seed) -> dict:
     world = dist.get_world_size(group) if (group is not None and dist.is_initialized()) else 1
     rank = dist.get_rank(group) if world > 1 else 0
     device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
@@ -78,10 +92,18 @@ def n_rank_parity(group=None, device=None, per_rank_batch: int = 2, size: int = 
     cnt_f = metrics.binary_confusion_counts(pred_f.detach(), y.to(device), 0.5)
     counts_f = torch.stack([cnt_f[k] for k in ("TP", "TN", "FP", "FN")])
 
+    # the single-device step once more: run-to-run reproducibility of the reference point itself
+    m_rep = build(None)
+    loss_r = losses.DiceLoss()(m_rep(x.to(device)), y.to(device))
+    loss_r.backward()
+    gr = _flat([p.grad for p in m_rep.parameters() if p.requires_grad])
+
     gd, gf = _flat([p.grad for p in params_d]), _flat([p.grad for p in params_f])
+    rep_cos = float(torch.dot(gr, gf) / (gr.norm() * gf.norm()).clamp_min(1e-30))
+    rep_equal = bool(torch.equal(gr, gf)) and float(loss_r.detach()) == float(loss_f.detach())
     cos = float(torch.dot(gd, gf) / (gd.norm() * gf.norm()).clamp_min(1e-30))
     norm_rel = float((gd.norm() - gf.norm()).abs() / gf.norm().clamp_min(1e-30))
-    loss_rel = abs(float(loss_d) - float(loss_f)) / max(abs(float(loss_f)), 1e-30)
+    loss_rel = abs(float(loss_d.detach()) - float(loss_f.detach())) / max(abs(float(loss_f.detach())), 1e-30)
     bn_rel = 0.0
     for a, b in zip(_bn_buffers(m_dist), _bn_buffers(m_full)):
         bn_rel = max(bn_rel, float((a - b).abs().max() / b.abs().max().clamp_min(1e-6)))
@@ -90,7 +112,8 @@ def n_rank_parity(group=None, device=None, per_rank_batch: int = 2, size: int = 
     cnt_dev = float((counts_d - counts_f).abs().max()) / n_pix
     res = {"world": world, "loss_rel": loss_rel, "grad_cosine": cos, "grad_norm_rel": norm_rel, "bn_running_rel": bn_rel,
            "counters_exchange_bit_exact": exact, "counters_vs_single_device_frac": cnt_dev,
-           "loss": float(loss_d), "loss_single_device": float(loss_f)}
+           "loss": float(loss_d.detach()), "loss_single_device": float(loss_f.detach()),
+           "repeat_grad_cosine": rep_cos, "repeat_bit_identical": rep_equal}
     res["ok"] = bool(loss_rel <= 1e-3 and cos >= 0.999 and norm_rel <= 1e-2 and bn_rel <= 1e-3 and exact
                      and cnt_dev <= 2e-3)
     if world > 1:                                                   # the ranks agree on the verdict

@@ -418,3 +418,123 @@ def test_final_conv_act(k, act, c):
     _close(_from_nhwc(dx), x.grad, 6e-3, "final conv dx")
     _close(dw.cpu(), wt.grad, 1e-4, "final conv dw")
     _close(db.cpu(), b.grad, 1e-4, "final conv db")
+
+
+# ------------------------------------------------------------------------------------------------
+# deterministic mode (torch.use_deterministic_algorithms; every downstream YAML of the reference sets it)
+# ------------------------------------------------------------------------------------------------
+@pytest.fixture()
+def deterministic_mode():
+    torch.use_deterministic_algorithms(True, warn_only=True)
+    try:
+        yield
+    finally:
+        torch.use_deterministic_algorithms(False)
+
+
+@pytest.mark.parametrize("cin, cout, ks, hw, n", [(64, 64, 3, 28, 16), (256, 512, 1, 14, 32), (16, 16, 3, 64, 4),
+                                                  (32, 32, 3, 48, 3)])
+def test_deterministic_statistics_rows_match_the_atomics_and_repeat_exactly(deterministic_mode, cin, cout, ks, hw, n):
+    """Conv epilogue statistics as per-CTA rows [SMs, 2, K] added in fixed order == the float-atomics accumulators
+    (to fp32 rounding), and two runs give the same BITS; the narrow layers go through the multi-tile epilogue."""
+    from medsegpretrainimagenet_b200 import ops
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn((n, hw, hw, cin), generator=g).to(torch.bfloat16).to(DEV)
+    w = (torch.randn((cout, cin, ks, ks), generator=g) * 0.1).to(DEV)
+    wf, _ = ops.pack_weights(w, need_dgrad=False)
+    pad = ks // 2
+    totals, outs = [], []
+    for _ in range(2):
+        stats = ops.new_stats(cout, DEV)
+        assert stats.dim() == 3 and stats.shape[0] == ops.sm_count(DEV)
+        y = ops.conv_fprop(x, wf, None, cout, ks, ks, 1, pad, pad, hw, hw, stats=stats)
+        totals.append(ops.reduce_rows(stats).clone())
+        outs.append(y.clone())
+        mi = ops.bn_finalize(stats, n * hw * hw, 1e-5, 0.1, reset=True)
+        assert float(stats.abs().max()) == 0.0                       # self-cleaning rows
+    assert torch.equal(totals[0], totals[1]) and torch.equal(outs[0], outs[1])
+    yf = outs[0].float().reshape(-1, cout)
+    ref = torch.stack([yf.sum(0), (yf * yf).sum(0)])
+    assert ((totals[0] - ref).abs().max() / ref.abs().max()).item() <= 1e-3
+    m_ref = yf.mean(0)
+    assert ((mi[0] - m_ref).abs().max()).item() <= 1e-3 * max(1.0, m_ref.abs().max().item())
+    torch.use_deterministic_algorithms(False)
+    st = torch.zeros((2, cout), device=DEV)
+    ops.conv_fprop(x, wf, None, cout, ks, ks, 1, pad, pad, hw, hw, stats=st)
+    assert ((st - totals[0]).abs().max() / totals[0].abs().max()).item() <= 1e-5
+
+
+def test_deterministic_bn_backward_sums_bias_and_head_gradients(deterministic_mode):
+    from medsegpretrainimagenet_b200 import ops
+    g = torch.Generator().manual_seed(1)
+    n, hw, c = 6, 40, 64
+    x = torch.randn((n, hw, hw, c), generator=g).to(torch.bfloat16).to(DEV)
+    dy = torch.randn((n, hw, hw, c), generator=g).to(torch.bfloat16).to(DEV)
+    mi = torch.stack([torch.zeros(c), torch.ones(c)]).to(DEV)
+    gamma, beta = torch.ones(c, device=DEV), torch.zeros(c, device=DEV)
+    a = ops.bn_act_bwd_reduce(x, None, dy, mi, ops.ACT_RELU, gamma=gamma, beta=beta).clone()
+    b = ops.bn_act_bwd_reduce(x, None, dy, mi, ops.ACT_RELU, gamma=gamma, beta=beta).clone()
+    assert torch.equal(a, b)
+    gm = (dy.float() * (x.float() > 0)).reshape(-1, c)
+    ref = torch.stack([gm.sum(0), (gm * x.float().reshape(-1, c)).sum(0)])
+    assert ((a - ref).abs().max() / ref.abs().max()).item() <= 1e-3
+    s1, s2 = ops.channel_sum(dy).clone(), ops.channel_sum(dy).clone()
+    assert torch.equal(s1, s2)
+    assert ((s1 - dy.float().reshape(-1, c).sum(0)).abs().max()).item() <= 1e-2
+    k = 4
+    w2d, prob = torch.randn((k, c), generator=g).to(DEV), torch.softmax(torch.randn((n, k, hw, hw), generator=g), 1).to(DEV)
+    dprob = torch.randn((n, k, hw, hw), generator=g).to(DEV)
+    r1 = ops.final_conv_act_bwd(x, w2d, 2, prob, dprob)
+    r2 = ops.final_conv_act_bwd(x, w2d, 2, prob, dprob)
+    assert torch.equal(r1[1], r2[1]) and torch.equal(r1[2], r2[2]) and torch.equal(r1[0], r2[0])
+    torch.use_deterministic_algorithms(False)
+    r0 = ops.final_conv_act_bwd(x, w2d, 2, prob, dprob)
+    assert ((r0[1] - r1[1]).abs().max() / r0[1].abs().max()).item() <= 1e-4
+    assert ((r0[2] - r1[2]).abs().max() / r0[2].abs().max()).item() <= 1e-4
+
+
+def test_batched_weight_gradient_unpack_and_tiled_pack_match_the_per_layer_kernels():
+    """ops._WgradQueue (one unpack launch per backward, straight into param.grad, accumulate mode) against the per-layer
+    path, and the tiled transposing weight pack against the element-wise one."""
+    import os
+    from medsegpretrainimagenet_b200 import functional as Fn, ops
+    g = torch.Generator().manual_seed(2)
+    x = torch.randn((3, 20, 20, 24), generator=g).to(torch.bfloat16).to(DEV).requires_grad_(True)
+    ws = [torch.nn.Parameter((torch.randn(s, generator=g) * 0.1).to(DEV)) for s in ((40, 24, 3, 3), (16, 40, 1, 1),
+                                                                                   (32, 16, 2, 2))]
+
+    def run():
+        for w in ws:
+            w.grad = None
+        y, _ = Fn.conv2d(x, ws[0], None, 1, 1)
+        y, _ = Fn.conv2d(y, ws[1], None, 1, 0)
+        y, _ = Fn.conv2d(y, ws[2], None, 1, "same")
+        y.float().square().mean().backward()
+        return [w.grad.clone() for w in ws]
+    sink = run()
+    twice = None
+    for w in ws:                       # accumulate mode: a second backward adds into the existing gradients
+        pass
+    y, _ = Fn.conv2d(x, ws[0], None, 1, 1)
+    y, _ = Fn.conv2d(y, ws[1], None, 1, 0)
+    y, _ = Fn.conv2d(y, ws[2], None, 1, "same")
+    y.float().square().mean().backward()
+    twice = [w.grad.clone() for w in ws]
+    ops._WGRAD_SINK = False
+    try:
+        plain = run()
+    finally:
+        ops._WGRAD_SINK = True
+    for a, b, c2 in zip(sink, plain, twice):
+        assert torch.equal(a, b)
+        assert torch.allclose(c2, 2 * a, rtol=1e-6, atol=1e-8)
+    # weight packing: batched tiled kernel == per-layer kernel
+    cache = ops.WeightPackCache()
+    per_layer = [ops.pack_weights(w) for w in ws]
+    for w in ws:
+        cache.lookup(w, True)
+    cache.build_table()
+    cache.begin_step()
+    for w, (wf, wd) in zip(ws, per_layer):
+        bf, bd = cache.lookup(w, True)
+        assert torch.equal(bf, wf) and torch.equal(bd, wd)

@@ -28,6 +28,9 @@ def test_world_size_1_leg_runs_the_same_code():
     res = n_rank_parity(None)
     assert res["world"] == 1 and res["ok"], res
     assert res["counters_exchange_bit_exact"] and res["loss_rel"] <= 1e-3 and res["grad_cosine"] >= 0.999
+    # deterministic mode: the same step twice is the same bits (fixed-order BatchNorm statistics, BatchNorm-backward
+    # sums, bias and head gradients; split-K wgrad partials summed in order)
+    assert res["repeat_bit_identical"], res
 
 
 @pytest.mark.parametrize("exchange", ["p2p", "nccl"])
