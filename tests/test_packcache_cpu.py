@@ -34,8 +34,9 @@ def test_pack_cache_protocol(monkeypatch):
     first, nblk = t[:, 8].tolist(), t[:, 9].tolist()
     assert first[0] == 0 and all(first[i + 1] == first[i] + nblk[i] for i in range(3))
     assert cache.total_blocks == first[-1] + nblk[-1]
-    elems = [64 * 49 * 8, 2 * 256 * 64, 2 * 512 * 9 * 512, 2 * 16 * 9 * 32]
-    assert nblk == [max(1, min(1024, (e + 2047) // 2048)) for e in elems]
+    # > 9 taps: element-wise mode, ~8 elements per thread; <= 9 taps: one block per 32 x 32 channel tile (all taps)
+    assert nblk == [max(1, min(1024, (64 * 49 * 8 + 2047) // 2048)), (256 // 32) * (64 // 32), (512 // 32) * (512 // 32),
+                    1 * 1]
     # forwards 2, 3: exactly one batched call, the same buffers, although no version counter moved
     for _ in range(2):
         calls.clear()
