@@ -96,6 +96,13 @@ int msp_conv_fprop(const msp_conv_desc* d, const void* x, const void* w_fprop, c
  * msp_pack_weights.  dx has d->C channels at pixel stride d->x_cs; dy has d->K channels at d->y_cs. */
 int msp_conv_dgrad(const msp_conv_desc* d, const void* dy, const void* w_dgrad, void* dx,
                    int accumulate /* dx += result (residual gradient already in dx) */, void* stream);
+/* nn.ConvTranspose2d forward (north star: "conv/transposed-conv layers"; the reference's own up-sampling is nearest x2 +
+ * Conv2d, segmentation/models/blocks.py:531-535) = the data gradient of the convolution it transposes, with bias and
+ * ReLU in the same epilogue.  `d` describes that convolution: (N, H, W, C) = the transposed conv's OUTPUT,
+ * (Ho, Wo, K) = its input x; w_dgrad = the [C][tap][K] packing of the (in_channels = K, out_channels = C, kh, kw)
+ * weight.  Its backward passes are msp_conv_fprop (data) and msp_conv_wgrad with the two tensors swapped (weights). */
+int msp_conv_transpose_fprop(const msp_conv_desc* d, const void* x, const void* w_dgrad, const float* bias, int relu,
+                             void* y, void* stream);
 
 /* Weight gradient, split-K over pixel tiles WITHOUT atomics (deterministic): split s writes its partial
  * sum, packed like w_fprop ([K][KH*KW][C] fp32; [K][KH][64] in row-window mode), at
@@ -215,6 +222,13 @@ int msp_upsample2x_fwd(const void* x, int N, int H, int W, int C, int x_cs, void
                        void* stream);
 int msp_upsample2x_bwd(const void* dy, int N, int H, int W, int C, int dy_cs, void* dx, int dx_cs,
                        void* stream);
+/* nn.Upsample(scale_factor=2, mode='bilinear', align_corners=False) forward / backward on NHWC bf16 (north star
+ * "bilinear/nearest upsampling"; the reference's blocks instantiate the nearest mode, blocks.py:532).  x (N,H,W,C) ->
+ * y (N,2H,2W,C); the backward is the gather form of the transpose (no atomics). */
+int msp_upsample_bilinear2x_fwd(const void* x, int N, int H, int W, int C, int x_cs, void* y, int y_cs,
+                                void* stream);
+int msp_upsample_bilinear2x_bwd(const void* dy, int N, int H, int W, int C, int dy_cs, void* dx, int dx_cs,
+                                void* stream);
 int msp_avgpool_fwd(const void* x, int N, int HW, int C, int x_cs, void* y, void* stream);
 int msp_avgpool_bwd(const void* dy, int N, int HW, int C, void* dx, int dx_cs, void* stream);
 /* y[.., off:off+C] = x (channel-slice copy into a concat buffer) and its inverse for gradients. */
@@ -289,6 +303,14 @@ int msp_bce_fwd_bwd(const float* prob, const float* target, long long numel, int
 int msp_softmax_ce_fwd_bwd(const float* logits, const int64_t* label, int N, int C, float smooth,
                            float gscale, const float* gscale_dev, double* loss_sum, float* dlogits,
                            void* stream);
+/* torch.nn.CrossEntropyLoss with class-PROBABILITY targets (Mixup / CutMix, config/pretraining/resnet50/advanced.yaml:17,48):
+ * target fp32 [N][C]; t' = (1 - smooth) t + smooth / C, loss_sum += sum_n (lse_n sum_c t'_c - sum_c t'_c z_c). */
+int msp_softmax_ce_soft_fwd_bwd(const float* logits, const float* target, int N, int C, float smooth, float gscale,
+                                const float* gscale_dev, double* loss_sum, float* dlogits, void* stream);
+/* F.cross_entropy on spatial logits fp32 [N][C][HW] with class-index targets int64 [N][HW] (classification/losses.py:24-25
+ * applied to a segmentation map), label smoothing as in msp_softmax_ce_fwd_bwd; loss_sum accumulates over all N*HW pixels. */
+int msp_softmax_ce_spatial_fwd_bwd(const float* logits, const int64_t* label, int N, int C, long long HW, float smooth,
+                                   float gscale, const float* gscale_dev, double* loss_sum, float* dlogits, void* stream);
 /* out[0] = (float)(in[0] * scale): turns a loss sum into the mean without a host round trip. */
 int msp_scale_to_float(const double* in, double scale, float* out, void* stream);
 

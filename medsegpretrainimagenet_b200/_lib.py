@@ -51,6 +51,7 @@ SIGNATURES = {
     "msp_pack_weights": [P, I, I, I, I, I, I, P, P, P],
     "msp_conv_fprop": [C.POINTER(ConvDesc), P, P, P, P, P, P, P],
     "msp_conv_dgrad": [C.POINTER(ConvDesc), P, P, P, I, P],
+    "msp_conv_transpose_fprop": [C.POINTER(ConvDesc), P, P, P, I, P, P],
     "msp_conv_wgrad_splits": [C.POINTER(ConvDesc)],
     "msp_conv_wgrad": [C.POINTER(ConvDesc), P, P, P, P],
     "msp_unpack_wgrad": [C.POINTER(ConvDesc), P, I, P, P],
@@ -72,6 +73,8 @@ SIGNATURES = {
     "msp_maxpool_bwd": [P, P, I, I, I, I, I, I, I, I, I, I, P, I, I, P],
     "msp_upsample2x_fwd": [P, I, I, I, I, I, P, I, P],
     "msp_upsample2x_bwd": [P, I, I, I, I, I, P, I, P],
+    "msp_upsample_bilinear2x_fwd": [P, I, I, I, I, I, P, I, P],
+    "msp_upsample_bilinear2x_bwd": [P, I, I, I, I, I, P, I, P],
     "msp_avgpool_fwd": [P, I, I, I, I, P, P],
     "msp_avgpool_bwd": [P, I, I, I, P, I, P],
     "msp_copy_channels": [P, LL, I, I, P, I, P],
@@ -90,6 +93,8 @@ SIGNATURES = {
     "msp_ce_prob_fwd_bwd": [P, P, I, I, LL, F, F, P, P, P, P],
     "msp_bce_fwd_bwd": [P, P, LL, I, F, P, P, P, P],
     "msp_softmax_ce_fwd_bwd": [P, P, I, I, F, F, P, P, P, P],
+    "msp_softmax_ce_soft_fwd_bwd": [P, P, I, I, F, F, P, P, P, P],
+    "msp_softmax_ce_spatial_fwd_bwd": [P, P, I, I, LL, F, F, P, P, P, P],
     "msp_confusion_binary": [P, P, I, I, I, LL, F, I, P, P],
     "msp_confusion_multiclass": [P, P, I, I, I, LL, P, P],
     "msp_topk_hits": [P, P, I, I, LL, I, P, P],

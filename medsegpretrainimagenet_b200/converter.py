@@ -12,7 +12,8 @@ reference modules and the oracle restatement in oracle/ref_models.py):
   ConvBlock / UpConvBlock / AttentionBlock / ConcatBlock             segmentation/models/blocks.py:419-635
   Model wrapper (`.model`)                                           model/model.py:18-75
   FeedForwardModel (sequential `.layers`: encoder + pooled linear head)  config/pretraining/*/*.yaml
-  nn.Conv2d / BatchNorm2d / ReLU / Sigmoid / MaxPool2d / Upsample(nearest, x2) / Sequential / Identity
+  nn.Conv2d / ConvTranspose2d / BatchNorm2d / ReLU / Sigmoid / MaxPool2d / Upsample(nearest | bilinear, x2) /
+  Sequential / Identity
 Anything else raises UnsupportedModule: there is no PyTorch fallback on this path.
 """
 from __future__ import annotations
@@ -158,8 +159,10 @@ def _is_noop(m) -> bool:
 
 
 def conv_bn_act(ctx: ExecContext, x, conv: nn.Conv2d, bn: Optional[nn.BatchNorm2d] = None, act: int = 0,
-                residual=None, r_stride: int = 1, sample_scale=None, link_in=None, link_out=None):
-    """Conv2d [-> BatchNorm2d] [-> ReLU | Sigmoid], with optional fused residual / per-sample scale."""
+                residual=None, r_stride: int = 1, sample_scale=None, link_in=None, link_out=None, out=None):
+    """Conv2d [-> BatchNorm2d] [-> ReLU | Sigmoid], with optional fused residual / per-sample scale.
+    `out` (conv without BatchNorm only): channel slice of a wider NHWC buffer the epilogue writes into (zero-copy
+    torch.cat)."""
     _check_conv(conv)
     stride, padding = conv.stride[0], _pad_of(conv)
     if isinstance(x, RawInput):
@@ -171,8 +174,10 @@ def conv_bn_act(ctx: ExecContext, x, conv: nn.Conv2d, bn: Optional[nn.BatchNorm2
     if bn is None:
         if residual is not None or sample_scale is not None or act == ops.ACT_SIGMOID:
             raise UnsupportedModule("residual / sigmoid epilogue without BatchNorm")
-        y, _ = conv2d(x, conv.weight, conv.bias, stride, padding, relu=(act == ops.ACT_RELU))
+        y, _ = conv2d(x, conv.weight, conv.bias, stride, padding, relu=(act == ops.ACT_RELU), out=out)
         return y
+    if out is not None:
+        raise UnsupportedModule("conv_bn_act(out=...) with BatchNorm")
     training = bn.training or bn.running_mean is None
     # the conv adds its bias in the epilogue, but the bias *gradient* is produced by the BatchNorm node
     bias = conv.bias.detach() if conv.bias is not None else None
@@ -204,6 +209,19 @@ def run_sequence(ctx: ExecContext, mods: List[nn.Module], x):
                 j += 1
             x = conv_bn_act(ctx, x, m, bn, act)
             i = j
+        elif nm == "ConvTranspose2d":
+            # north star "conv/transposed-conv layers" (the reference's own up-sampling is nearest + Conv2d): the data
+            # gradient kernel of the convolution it transposes, bias / ReLU in the epilogue
+            if m.groups != 1 or tuple(m.dilation) != (1, 1) or tuple(m.output_padding) != (0, 0) or \
+                    m.stride[0] != m.stride[1] or m.stride[0] not in (1, 2) or m.kernel_size[0] != m.kernel_size[1] or \
+                    m.padding[0] != m.padding[1] or m.kernel_size[0] < m.stride[0] or m.out_channels % 8 or \
+                    m.in_channels % 8:
+                raise UnsupportedModule(f"{m} is outside the B200 path")
+            j, relu = i + 1, False
+            if j < n and _name(_unwrap(mods[j])) == "ReLU":
+                relu, j = True, j + 1
+            x = Fn.conv_transpose2d(x, m.weight, m.bias, m.stride[0], m.padding[0], relu=relu)
+            i = j
         elif nm == "MaxPool2d":
             k = m.kernel_size if isinstance(m.kernel_size, int) else m.kernel_size[0]
             s = m.stride if isinstance(m.stride, int) else m.stride[0]
@@ -213,10 +231,15 @@ def run_sequence(ctx: ExecContext, mods: List[nn.Module], x):
             x = Fn.maxpool2d(x, k, s or k, p)
             i += 1
         elif nm == "Upsample":
-            if m.mode != "nearest" or float(m.scale_factor if not isinstance(m.scale_factor, tuple)
-                                            else m.scale_factor[0]) != 2.0:
-                raise UnsupportedModule(f"{m}: only nearest x2 up-sampling is on the B200 path")
-            x = Fn.upsample2x(x)
+            sf = m.scale_factor if not isinstance(m.scale_factor, tuple) else m.scale_factor[0]
+            if sf is None or float(sf) != 2.0 or (isinstance(m.scale_factor, tuple) and len(set(m.scale_factor)) != 1):
+                raise UnsupportedModule(f"{m}: only x2 up-sampling is on the B200 path")
+            if m.mode == "nearest":
+                x = Fn.upsample2x(x)
+            elif m.mode == "bilinear" and not m.align_corners:
+                x = Fn.upsample_bilinear2x(x)
+            else:
+                raise UnsupportedModule(f"{m}: nearest and bilinear (align_corners=False) x2 up-sampling only")
             i += 1
         elif nm == "Sequential":
             x = run_sequence(ctx, list(m.children()), x)
@@ -321,12 +344,25 @@ def run_conv_block(ctx, m, x):
     return run_sequence(ctx, list(m.block.children()), x)
 
 
-def run_upconv_block(ctx, m, x):
-    return run_sequence(ctx, list(m.convup.children()), x)
+def run_upconv_block(ctx, m, x, out=None):
+    """UpConvBlock.forward (blocks.py:537-539): nearest x2 -> Conv2d(k=2, 'same') -> ReLU.  `out`: the leading channel
+    slice of the level's concat buffer — the conv epilogue writes x_up where torch.cat (blocks.py:628,635) would copy it."""
+    mods = [_unwrap(c) for c in m.convup.children()]
+    if out is not None and [_name(c) for c in mods] == ["Upsample", "Conv2d", "ReLU"]:
+        xu = run_sequence(ctx, [mods[0]], x)
+        return conv_bn_act(ctx, xu, mods[1], None, ops.ACT_RELU, out=out)
+    return run_sequence(ctx, mods, x)
 
 
-def run_attention_block(ctx, m, x, x_up, skip):
-    """AttentionBlock.forward (blocks.py:620-628)."""
+def _upconv_out_channels(m) -> Optional[int]:
+    mods = [_unwrap(c) for c in m.convup.children()] if hasattr(m, "convup") else []
+    if [_name(c) for c in mods] == ["Upsample", "Conv2d", "ReLU"] and mods[1].out_channels % 8 == 0:
+        return mods[1].out_channels
+    return None
+
+
+def run_attention_block(ctx, m, x, x_up, skip, buf=None):
+    """AttentionBlock.forward (blocks.py:620-628).  `buf`: the concat buffer whose leading slice already IS x_up."""
     g = run_module(ctx, _unwrap(m.gs_block), x)
     wg_conv, wg_bn = list(m.W_g.children())
     ws_conv, ws_bn = list(m.W_s.children())
@@ -337,7 +373,7 @@ def run_attention_block(ctx, m, x, x_up, skip):
     # relu(BN(W_s(skip)) + g1): the add + ReLU ride on the BN-apply kernel
     p = conv_bn_act(ctx, skip, ws_conv, ws_bn, ops.ACT_RELU, residual=g1)
     p = conv_bn_act(ctx, p, psi[0], psi[1], ops.ACT_SIGMOID)
-    return Fn.gate_concat(x_up, skip, p)
+    return Fn.gate_concat(x_up, skip, p, buf=buf)
 
 
 def run_unet_encoder(ctx, m, x, return_skip_vals=False):
@@ -364,18 +400,26 @@ def run_unet_decoder(ctx, m, x, skips: list, final_act=None):
         raise UnsupportedModule("U-Net residual connections / layer scaling are not on the B200 path")
     skips = list(skips)
     for i, unit in enumerate(m.up_layers):
-        x_up = run_module(ctx, _unwrap(unit["upsampl"]), x)
+        up = _unwrap(unit["upsampl"])
         if i < m.skip_con_nr:
             skip = skips.pop()
             mix = _unwrap(unit["mixing"])
-            if _name(mix) == "ConcatBlock":
-                x = Fn.concat(x_up, skip)
-            elif _name(mix) == "AttentionBlock":
-                x = run_attention_block(ctx, mix, x, x_up, skip)
-            else:
+            if _name(mix) not in ("ConcatBlock", "AttentionBlock"):
                 raise UnsupportedModule(f"mixing block {_name(mix)}")
+            # zero-copy torch.cat((x_up, .), dim=1) (blocks.py:628,635): the up-conv's epilogue writes x_up straight into
+            # the leading channel slice of the concat buffer, the gate product / the skip goes into the trailing slice
+            buf, ca = None, _upconv_out_channels(up) if _name(up) == "UpConvBlock" else None
+            if ca is not None and skip.shape[3] % 8 == 0:
+                buf = ops.new_act(skip.shape[0], skip.shape[1], skip.shape[2], ca + skip.shape[3], skip.device)
+                x_up = run_upconv_block(ctx, up, x, out=buf[..., :ca])
+            else:
+                x_up = run_module(ctx, up, x)
+            if _name(mix) == "ConcatBlock":
+                x = Fn.concat(x_up, skip, buf=buf)
+            else:
+                x = run_attention_block(ctx, mix, x, x_up, skip, buf=buf)
         else:
-            x = x_up
+            x = run_module(ctx, up, x)
         for j in range(m.width):
             x = run_module(ctx, _unwrap(unit[f"conv{j}"]), x)
     fb = _unwrap(m.final_block)
@@ -412,7 +456,7 @@ def run_module(ctx, m, x, **kw):
     nm = _name(m)
     if nm in _RUNNERS:
         return _RUNNERS[nm](ctx, m, x, **kw)
-    if nm in ("Conv2d", "MaxPool2d", "Upsample", "Sequential", "Identity"):
+    if nm in ("Conv2d", "ConvTranspose2d", "MaxPool2d", "Upsample", "Sequential", "Identity"):
         return run_sequence(ctx, [m], x)
     raise UnsupportedModule(f"module {nm} has no B200 implementation (no PyTorch fallback on this path)")
 

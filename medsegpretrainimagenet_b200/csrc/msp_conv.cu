@@ -1953,8 +1953,24 @@ extern "C" int msp_conv_fprop(const msp_conv_desc* d, const void* x, const void*
   return dispatch_tapgemm(tmA, wm, p, (cudaStream_t)stream);
 }
 
+namespace {
+int dgrad_impl(const msp_conv_desc* d, const void* dy, const void* w_dgrad, void* dx, int accumulate,
+               const float* bias, int relu, void* stream);
+}
 extern "C" int msp_conv_dgrad(const msp_conv_desc* d, const void* dy, const void* w_dgrad, void* dx,
                               int accumulate, void* stream) {
+  return dgrad_impl(d, dy, w_dgrad, dx, accumulate, nullptr, 0, stream);
+}
+// nn.ConvTranspose2d forward IS the data gradient of the convolution it transposes: y = dgrad(x) (+ bias, ReLU in the
+// same epilogue).  `d` describes that convolution: (N, H, W, C) = the OUTPUT of the transposed conv, (Ho, Wo, K) = its
+// input; w_dgrad = msp_pack_weights' [C][tap][K] copy of the (K = in_channels, C = out_channels, kh, kw) weight.
+extern "C" int msp_conv_transpose_fprop(const msp_conv_desc* d, const void* x, const void* w_dgrad, const float* bias,
+                                        int relu, void* y, void* stream) {
+  return dgrad_impl(d, x, w_dgrad, y, 0, bias, relu, stream);
+}
+namespace {
+int dgrad_impl(const msp_conv_desc* d, const void* dy, const void* w_dgrad, void* dx, int accumulate,
+               const float* bias, int relu, void* stream) {
   int rc = check_desc(d);
   if (rc) return rc;
   MSP_REQUIRE(dy && w_dgrad && dx, "conv_dgrad: null pointer");
@@ -2009,7 +2025,8 @@ extern "C" int msp_conv_dgrad(const msp_conv_desc* d, const void* dy, const void
       p.bw = b.bw; p.bh = b.bh; p.bn = b.bn; p.rows = b.bw * b.bh * b.bn;
       p.tiles_w = msp_cdiv(p.OWs, b.bw); p.tiles_h = msp_cdiv(p.OHs, b.bh);
       p.tiles_n = msp_cdiv(p.N, b.bn);
-      p.sxw = 1; p.sxh = 1; p.C = d->K; p.ntaps = nt; p.Kout = d->C; p.relu = 0; p.accumulate = accumulate;
+      p.sxw = 1; p.sxh = 1; p.C = d->K; p.ntaps = nt; p.Kout = d->C; p.relu = relu; p.accumulate = accumulate;
+      p.bias = bias;
       p.y = (__nv_bfloat16*)dx;
       if (!flat && s == 1) {
         Box hb;
@@ -2029,6 +2046,7 @@ extern "C" int msp_conv_dgrad(const msp_conv_desc* d, const void* dy, const void
     }
   return MSP_OK;
 }
+}  // namespace
 
 namespace {
 struct WgradPlan {

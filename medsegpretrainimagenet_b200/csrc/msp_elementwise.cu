@@ -698,6 +698,85 @@ __global__ void upsample2x_fwd_kernel(const __nv_bfloat16* __restrict__ x, int N
     *reinterpret_cast<uint4*>(y + (((long long)n * H2 + h) * W2 + w) * y_cs + cg * 8) = v;
   }
 }
+
+// nn.Upsample(scale_factor=2, mode='bilinear', align_corners=False) (north star: "bilinear/nearest upsampling"; the
+// reference's blocks use nearest, blocks.py:532).  torch's source index: max(0, (dst + 0.5) / 2 - 0.5), i.e. per axis
+//   dst = 2i   -> 0.25 * x[i-1] + 0.75 * x[i]   (i = 0: x[0]),   dst = 2i+1 -> 0.75 * x[i] + 0.25 * x[min(i+1, H-1)]
+// evaluated like ATen: h0 * (w0 * x00 + w1 * x01) + h1 * (w0 * x10 + w1 * x11) in fp32 on the bf16 inputs.
+__device__ __forceinline__ void bilin_src(int dst, int size, int* i0, int* i1, float* l0, float* l1) {
+  float real = (dst + 0.5f) * 0.5f - 0.5f;
+  real = real < 0.f ? 0.f : real;
+  const int a = (int)real;
+  *i0 = a;
+  *i1 = a + 1 < size ? a + 1 : size - 1;
+  *l1 = real - (float)a;
+  *l0 = 1.f - *l1;
+}
+__global__ void upsample_bilinear2x_fwd_kernel(const __nv_bfloat16* __restrict__ x, int N, int H, int W, int C,
+                                               int x_cs, __nv_bfloat16* __restrict__ y, int y_cs) {
+  const int V = C >> 3;
+  const int H2 = 2 * H, W2 = 2 * W;
+  const long long total = (long long)N * H2 * W2 * V;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int cg = (int)(i % V);
+    long long p = i / V;
+    const int w = (int)(p % W2); p /= W2;
+    const int h = (int)(p % H2);
+    const int n = (int)(p / H2);
+    int h0, h1, w0, w1;
+    float lh0, lh1, lw0, lw1;
+    bilin_src(h, H, &h0, &h1, &lh0, &lh1);
+    bilin_src(w, W, &w0, &w1, &lw0, &lw1);
+    const __nv_bfloat16* b = x + (long long)n * H * W * x_cs + cg * 8;
+    const F8 a00 = load_bf16x8(b + ((long long)h0 * W + w0) * x_cs), a01 = load_bf16x8(b + ((long long)h0 * W + w1) * x_cs),
+             a10 = load_bf16x8(b + ((long long)h1 * W + w0) * x_cs), a11 = load_bf16x8(b + ((long long)h1 * W + w1) * x_cs);
+    F8 o;
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      o.v[j] = lh0 * (lw0 * a00.v[j] + lw1 * a01.v[j]) + lh1 * (lw0 * a10.v[j] + lw1 * a11.v[j]);
+    store_bf16x8(y + (((long long)n * H2 + h) * W2 + w) * y_cs + cg * 8, o);
+  }
+}
+// gather form of the transpose: source pixel (i, j) collects, per axis, from outputs 2i-1 (0.25), 2i (0.75; 1 at i = 0),
+// 2i+1 (0.75; 1 at i = H-1) and 2i+2 (0.25) - no atomics, one thread per 8 channels of a source pixel
+__device__ __forceinline__ int bilin_taps(int i, int size, int* dst, float* wgt) {
+  int n = 0;
+  if (i >= 1) { dst[n] = 2 * i - 1; wgt[n++] = 0.25f; }
+  dst[n] = 2 * i; wgt[n++] = i == 0 ? 1.0f : 0.75f;
+  dst[n] = 2 * i + 1; wgt[n++] = i == size - 1 ? 1.0f : 0.75f;
+  if (i + 1 < size) { dst[n] = 2 * i + 2; wgt[n++] = 0.25f; }
+  return n;
+}
+__global__ void upsample_bilinear2x_bwd_kernel(const __nv_bfloat16* __restrict__ dy, int N, int H, int W, int C,
+                                               int dy_cs, __nv_bfloat16* __restrict__ dx, int dx_cs) {
+  const int V = C >> 3;
+  const int H2 = 2 * H, W2 = 2 * W;
+  const long long total = (long long)N * H * W * V;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int cg = (int)(i % V);
+    long long p = i / V;
+    const int w = (int)(p % W); p /= W;
+    const int h = (int)(p % H);
+    const int n = (int)(p / H);
+    int hd[4], wd[4];
+    float hw_[4], ww[4];
+    const int nh = bilin_taps(h, H, hd, hw_), nw = bilin_taps(w, W, wd, ww);
+    F8 o;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) o.v[j] = 0.f;
+    const __nv_bfloat16* b = dy + (long long)n * H2 * W2 * dy_cs + cg * 8;
+    for (int a = 0; a < nh; ++a)
+      for (int c = 0; c < nw; ++c) {
+        const F8 g = load_bf16x8(b + ((long long)hd[a] * W2 + wd[c]) * dy_cs);
+        const float f = hw_[a] * ww[c];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o.v[j] = fmaf(f, g.v[j], o.v[j]);
+      }
+    store_bf16x8(dx + (((long long)n * H + h) * W + w) * dx_cs + cg * 8, o);
+  }
+}
 __global__ void upsample2x_bwd_kernel(const __nv_bfloat16* __restrict__ dy, int N, int H, int W, int C,
                                       int dy_cs, __nv_bfloat16* __restrict__ dx, int dx_cs) {
   const int V = C >> 3;
@@ -1146,6 +1225,28 @@ extern "C" int msp_upsample2x_bwd(const void* dy, int N, int H, int W, int C, in
   const long long total = (long long)N * H * W * (C / 8);
   upsample2x_bwd_kernel<<<grid_for(total, 256), 256, 0, ST>>>((const __nv_bfloat16*)dy, N, H, W, C,
                                                               dy_cs, (__nv_bfloat16*)dx, dx_cs);
+  MSP_CHECK_LAUNCH();
+  msp_count_launch(1);
+  return MSP_OK;
+}
+extern "C" int msp_upsample_bilinear2x_fwd(const void* x, int N, int H, int W, int C, int x_cs, void* y, int y_cs,
+                                           void* stream) {
+  REQ_C8(C, x_cs, "upsample_bilinear2x_fwd(x)");
+  REQ_C8(C, y_cs, "upsample_bilinear2x_fwd(y)");
+  const long long total = (long long)N * 4 * H * W * (C / 8);
+  upsample_bilinear2x_fwd_kernel<<<grid_for(total, 256), 256, 0, ST>>>((const __nv_bfloat16*)x, N, H, W, C, x_cs,
+                                                                       (__nv_bfloat16*)y, y_cs);
+  MSP_CHECK_LAUNCH();
+  msp_count_launch(1);
+  return MSP_OK;
+}
+extern "C" int msp_upsample_bilinear2x_bwd(const void* dy, int N, int H, int W, int C, int dy_cs, void* dx,
+                                           int dx_cs, void* stream) {
+  REQ_C8(C, dy_cs, "upsample_bilinear2x_bwd(dy)");
+  REQ_C8(C, dx_cs, "upsample_bilinear2x_bwd(dx)");
+  const long long total = (long long)N * H * W * (C / 8);
+  upsample_bilinear2x_bwd_kernel<<<grid_for(total, 256), 256, 0, ST>>>((const __nv_bfloat16*)dy, N, H, W, C,
+                                                                       dy_cs, (__nv_bfloat16*)dx, dx_cs);
   MSP_CHECK_LAUNCH();
   msp_count_launch(1);
   return MSP_OK;

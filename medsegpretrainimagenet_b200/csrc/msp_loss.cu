@@ -620,6 +620,111 @@ inline int strip_grid(long long work, int threads, int rows) {
   return (int)b;
 }
 
+
+// torch.nn.CrossEntropyLoss with CLASS-PROBABILITY targets (Mixup / CutMix of config/pretraining/resnet50/advanced.yaml:17,48):
+// t' = (1 - smooth) t + smooth / C;  loss_n = lse * sum(t') - sum_c t'_c z_c;  dz_c = p_c * sum(t') - t'_c.  One block per row.
+__global__ void softmax_ce_soft_kernel(const float* __restrict__ logits, const float* __restrict__ target, int C,
+                                       float smooth, float gscale, const float* __restrict__ gdev,
+                                       double* __restrict__ loss_sum, float* __restrict__ dlogits) {
+  gscale *= gdev ? __ldg(gdev) : 1.f;
+  const int n = blockIdx.x;
+  const float* z = logits + (long long)n * C;
+  const float* t = target + (long long)n * C;
+  __shared__ float red[3][8];
+  __shared__ float bc[4];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  float m = -INFINITY;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) m = fmaxf(m, z[c]);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if (lane == 0) red[0][warp] = m;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float a = red[0][0];
+    for (int w = 1; w < nw; ++w) a = fmaxf(a, red[0][w]);
+    bc[0] = a;
+  }
+  __syncthreads();
+  m = bc[0];
+  const float off = smooth / (float)C;
+  float s = 0.f, st = 0.f, stz = 0.f;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const float tp = fmaf(1.f - smooth, t[c], off);
+    s += expf(z[c] - m);
+    st += tp;
+    stz = fmaf(tp, z[c], stz);
+  }
+  s = warp_sum(s);
+  st = warp_sum(st);
+  stz = warp_sum(stz);
+  __syncthreads();
+  if (lane == 0) { red[0][warp] = s; red[1][warp] = st; red[2][warp] = stz; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float a = 0.f, b = 0.f, c2 = 0.f;
+    for (int w = 0; w < nw; ++w) { a += red[0][w]; b += red[1][w]; c2 += red[2][w]; }
+    bc[1] = a; bc[2] = b; bc[3] = c2;
+  }
+  __syncthreads();
+  const float lse = m + logf(bc[1]), sum_t = bc[2];
+  if (threadIdx.x == 0 && loss_sum) atomicAdd(loss_sum, (double)(lse * sum_t - bc[3]));
+  if (dlogits) {
+    float* d = dlogits + (long long)n * C;
+    for (int c = threadIdx.x; c < C; c += blockDim.x)
+      d[c] = (expf(z[c] - lse) * sum_t - fmaf(1.f - smooth, t[c], off)) * gscale;
+  }
+}
+
+// F.cross_entropy on SPATIAL logits (N, C, HW) with class-index targets (N, HW), label smoothing as above: one thread per
+// pixel, the class loop strides by HW (coalesced across the pixels of a warp); targets outside [0, C) contribute nothing
+// to the NLL term (ignore_index is not implemented and is refused by the host wrapper).
+__global__ void __launch_bounds__(256)
+softmax_ce_spatial_kernel(const float* __restrict__ logits, const long long* __restrict__ label, int C, long long HW,
+                          long long P, float smooth, float gscale, const float* __restrict__ gdev,
+                          double* __restrict__ loss_sum, float* __restrict__ dlogits) {
+  gscale *= gdev ? __ldg(gdev) : 1.f;
+  double acc = 0.0;
+  const float off = smooth / (float)C;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < P; i += (long long)gridDim.x * blockDim.x) {
+    const long long n = i / HW, hw = i - n * HW;
+    const float* z = logits + n * C * HW + hw;
+    float m = -INFINITY;
+    for (int c = 0; c < C; ++c) m = fmaxf(m, z[(long long)c * HW]);
+    float s = 0.f, sz = 0.f;
+    for (int c = 0; c < C; ++c) {
+      const float v = z[(long long)c * HW];
+      s += expf(v - m);
+      sz += v;
+    }
+    const float lse = m + logf(s);
+    const long long y = label[i];
+    const bool ok = y >= 0 && y < C;
+    if (loss_sum) {
+      const float nll = ok ? lse - z[y * HW] : 0.f;
+      acc += (double)((1.f - smooth) * nll + smooth * (lse - sz / (float)C));
+    }
+    if (dlogits) {
+      float* d = dlogits + n * C * HW + hw;
+      for (int c = 0; c < C; ++c) {
+        const float p = expf(z[(long long)c * HW] - lse);
+        const float t = off + ((ok && c == y) ? (1.f - smooth) : 0.f);
+        d[(long long)c * HW] = (p - t) * gscale;
+      }
+    }
+  }
+  if (loss_sum) {
+    acc = warp_sum_d(acc);
+    __shared__ double part[8];
+    if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double t = 0.0;
+      for (int w = 0; w < 8; ++w) t += part[w];
+      atomicAdd(loss_sum, t);
+    }
+  }
+}
+
 }  // namespace
 
 #define ST ((cudaStream_t)stream)
@@ -759,6 +864,32 @@ extern "C" int msp_bce_fwd_bwd(const float* prob, const float* target, long long
   else
     bce_kernel<<<strip_grid(numel, 256, 1), 256, 0, ST>>>(prob, target, numel, clamp_log, gscale, gscale_dev, loss_sum,
                                                           dprob);
+  MSP_CHECK_LAUNCH();
+  msp_count_launch(1);
+  return MSP_OK;
+}
+
+extern "C" int msp_softmax_ce_soft_fwd_bwd(const float* logits, const float* target, int N, int C, float smooth,
+                                           float gscale, const float* gscale_dev, double* loss_sum, float* dlogits,
+                                           void* stream) {
+  MSP_REQUIRE(logits && target && (loss_sum || dlogits) && N > 0 && C > 0, "softmax_ce_soft: bad arguments");
+  if (loss_sum) MSP_CHECK_CUDA(cudaMemsetAsync(loss_sum, 0, sizeof(double), ST));
+  softmax_ce_soft_kernel<<<N, 256, 0, ST>>>(logits, target, C, smooth, gscale, gscale_dev, loss_sum, dlogits);
+  MSP_CHECK_LAUNCH();
+  msp_count_launch(1);
+  return MSP_OK;
+}
+
+extern "C" int msp_softmax_ce_spatial_fwd_bwd(const float* logits, const int64_t* label, int N, int C, long long HW,
+                                              float smooth, float gscale, const float* gscale_dev, double* loss_sum,
+                                              float* dlogits, void* stream) {
+  MSP_REQUIRE(logits && label && (loss_sum || dlogits) && N > 0 && C > 0 && HW > 0, "softmax_ce_spatial: bad arguments");
+  if (loss_sum) MSP_CHECK_CUDA(cudaMemsetAsync(loss_sum, 0, sizeof(double), ST));
+  const long long P = (long long)N * HW;
+  long long blocks = (P + 255) / 256;
+  if (blocks > (long long)msp_num_sms() * 8) blocks = (long long)msp_num_sms() * 8;
+  softmax_ce_spatial_kernel<<<(int)blocks, 256, 0, ST>>>(logits, (const long long*)label, C, HW, P, smooth, gscale,
+                                                         gscale_dev, loss_sum, dlogits);
   MSP_CHECK_LAUNCH();
   msp_count_launch(1);
   return MSP_OK;

@@ -190,6 +190,52 @@ def conv2d(x, weight, bias=None, stride=1, padding=0, relu=False, want_stats=Fal
     return _Conv.apply(x, weight, bias, stride, padding, relu, want_stats, out, link)
 
 
+class _ConvTranspose(torch.autograd.Function):
+    """y = conv_transpose2d(x, weight, bias) (+ReLU), weight (in_channels, out_channels, kh, kw) as nn.ConvTranspose2d
+    keeps it.  The transposed convolution is the data gradient of the convolution `parent` with OIHW weight = this very
+    tensor (O = in_channels): forward = parent's dgrad kernel (bias / ReLU in its epilogue), input gradient = parent's
+    fprop, weight gradient = parent's wgrad with the roles of the two activations swapped — all three the same tcgen05
+    tap-GEMM kernels the convolutions use."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, stride, padding, relu):
+        cin, cout, kh, kw = weight.shape
+        if cout % 8:
+            raise ValueError("conv_transpose2d: out_channels must be a multiple of 8 on the B200 path")
+        wf, wd = ops.packed_weights(weight, need_dgrad=True)      # parent conv: K = cin, C = cout
+        y = ops.conv_transpose_fprop(x, wd, bias.detach() if bias is not None else None, ops.ceil8(cout), kh, kw, stride,
+                                     padding, relu=relu, k_true=cin)
+        ctx.geom = (kh, kw, stride, padding, cin, cout, relu, bias is not None)
+        ctx.x_shape = tuple(x.shape)
+        ctx.weight_param = weight if (weight.is_leaf and weight.requires_grad) else None
+        ctx.save_for_backward(x, wf, y if relu else None)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        kh, kw, stride, pad, cin, cout, relu, has_bias = ctx.geom
+        x, wf, y = ctx.saved_tensors
+        if dy.stride(3) != 1:
+            dy = dy.contiguous()
+        if relu:
+            dy = ops.relu_bwd(y, dy)
+        n, hi, wi, k8 = ctx.x_shape
+        dx = dw = db = None
+        if ctx.needs_input_grad[0]:
+            dx = ops.conv_fprop(dy, wf, None, k8, kh, kw, stride, pad, pad, hi, wi, c_true=cout)
+        if ctx.needs_input_grad[1]:
+            wp = ctx.weight_param
+            if wp is None or not ops.conv_wgrad_param(dy, x, wp, kh, kw, stride, pad, pad):
+                dw = ops.conv_wgrad(dy, x, cout, kh, kw, stride, pad, pad)[:cin]
+        if has_bias and ctx.needs_input_grad[2]:
+            db = ops.channel_sum(dy)[:cout]
+        return dx, dw, db, None, None, None
+
+
+def conv_transpose2d(x, weight, bias=None, stride=1, padding=0, relu=False):
+    return _ConvTranspose.apply(x, weight, bias, stride, padding, relu)
+
+
 # ------------------------------------------------------------------------------------------------
 # BatchNorm + activation + residual + per-sample scale
 # ------------------------------------------------------------------------------------------------
@@ -329,6 +375,24 @@ def upsample2x(x):
     return _Upsample2x.apply(x)
 
 
+class _UpsampleBilinear2x(torch.autograd.Function):
+    """nn.Upsample(scale_factor=2, mode='bilinear', align_corners=False)."""
+
+    @staticmethod
+    def forward(ctx, x):
+        return ops.upsample_bilinear2x_fwd(x)
+
+    @staticmethod
+    def backward(ctx, dy):
+        if dy.stride(3) != 1:
+            dy = dy.contiguous()
+        return ops.upsample_bilinear2x_bwd(dy)
+
+
+def upsample_bilinear2x(x):
+    return _UpsampleBilinear2x.apply(x)
+
+
 class _AvgPool(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x):
@@ -344,37 +408,50 @@ def global_avgpool(x):
     return _AvgPool.apply(x)
 
 
+def _is_leading_slice(a, buf, ca) -> bool:
+    return buf is not None and a.data_ptr() == buf.data_ptr() and a.stride() == buf.stride() and a.shape[3] == ca
+
+
 class _Concat(torch.autograd.Function):
-    """torch.cat along channels (blocks.py:628,635).  Backward hands out channel-slice views of dy."""
+    """torch.cat along channels (blocks.py:628,635).  `buf`: a preallocated (N, H, W, Ca + Cb) buffer whose leading
+    channel slice already holds `a` (its producer wrote there): only `b` is copied.  Backward hands out channel-slice
+    views of dy."""
 
     @staticmethod
-    def forward(ctx, a, b):
+    def forward(ctx, a, b, buf):
         n, h, w, ca = a.shape
         cb = b.shape[3]
-        out = ops.new_act(n, h, w, ca + cb, a.device)
-        ops.copy_channels(a, out[..., :ca])
+        if _is_leading_slice(a, buf, ca):
+            out = buf
+        else:
+            out = ops.new_act(n, h, w, ca + cb, a.device)
+            ops.copy_channels(a, out[..., :ca])
         ops.copy_channels(b, out[..., ca:])
         ctx.ca = ca
         return out
 
     @staticmethod
     def backward(ctx, dy):
-        return dy[..., : ctx.ca], dy[..., ctx.ca:]
+        return dy[..., : ctx.ca], dy[..., ctx.ca:], None
 
 
-def concat(a, b):
-    return _Concat.apply(a, b)
+def concat(a, b, buf=None):
+    return _Concat.apply(a, b, buf)
 
 
 class _GateConcat(torch.autograd.Function):
-    """cat(x_up, skip * up2(p)) (blocks.py:625-628): the product is written straight into its slice."""
+    """cat(x_up, skip * up2(p)) (blocks.py:625-628): the product is written straight into its slice; with `buf` (the
+    concat buffer whose leading slice the up-conv's epilogue already filled) nothing is copied at all."""
 
     @staticmethod
-    def forward(ctx, x_up, skip, p):
+    def forward(ctx, x_up, skip, p, buf):
         n, h, w, ca = x_up.shape
         cb = skip.shape[3]
-        out = ops.new_act(n, h, w, ca + cb, x_up.device)
-        ops.copy_channels(x_up, out[..., :ca])
+        if _is_leading_slice(x_up, buf, ca):
+            out = buf
+        else:
+            out = ops.new_act(n, h, w, ca + cb, x_up.device)
+            ops.copy_channels(x_up, out[..., :ca])
         ops.gate_mul_fwd(skip, p, out=out[..., ca:])
         ctx.ca = ca
         ctx.save_for_backward(skip, p)
@@ -384,11 +461,11 @@ class _GateConcat(torch.autograd.Function):
     def backward(ctx, dy):
         skip, p = ctx.saved_tensors
         dskip, dp = ops.gate_mul_bwd(skip, p, dy[..., ctx.ca:])
-        return dy[..., : ctx.ca], dskip, dp
+        return dy[..., : ctx.ca], dskip, dp, None
 
 
-def gate_concat(x_up, skip, p):
-    return _GateConcat.apply(x_up, skip, p)
+def gate_concat(x_up, skip, p, buf=None):
+    return _GateConcat.apply(x_up, skip, p, buf)
 
 
 # ------------------------------------------------------------------------------------------------

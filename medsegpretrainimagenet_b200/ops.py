@@ -309,6 +309,22 @@ def conv_dgrad(dy, wd, x_shape, kh, kw, stride, pad_t, pad_l, out=None, accumula
     return out
 
 
+def conv_transpose_fprop(x, wd, bias, c_out, kh, kw, stride, pad, relu=False, out=None, k_true=None):
+    """nn.ConvTranspose2d forward = data gradient of the conv it transposes (msp_conv_transpose_fprop).
+    x (N, Hi, Wi, K8) -> (N, Ho, Wo, C8) with Ho = (Hi - 1) * stride - 2 * pad + kh."""
+    n, hi, wi, k, x_cs = _chk_nhwc(x, "conv_transpose(x)")
+    ho, wo = (hi - 1) * stride - 2 * pad + kh, (wi - 1) * stride - 2 * pad + kw
+    if out is None:
+        out = new_act(n, ho, wo, c_out, x.device)
+    _, _, _, _, y_cs = _chk_nhwc(out, "conv_transpose(out)")
+    # descriptor of the transposed convolution's "parent": input (N, ho, wo, c_out) -> output (N, hi, wi, k)
+    d = _conv_desc(n, ho, wo, c_out, y_cs, hi, wi, k, x_cs, kh, kw, stride, pad, pad)
+    with _timed("dgrad", 2.0 * n * hi * wi * (k_true or k) * c_out * kh * kw,
+                2.0 * (n * hi * wi * k + n * ho * wo * c_out + k * c_out * kh * kw)):
+        call("msp_conv_transpose_fprop", C.byref(d), _p(x), _p(wd), _p(bias), int(relu), _p(out), _stream())
+    return out
+
+
 def _wgrad(d: ConvDesc, x, dy, c_true, flops, nbytes=0.0) -> torch.Tensor:
     splits = _lib.lib.msp_conv_wgrad_splits(C.byref(d))
     _lib.check(0 if splits >= 1 else splits, "msp_conv_wgrad_splits")
@@ -636,6 +652,21 @@ def upsample2x_bwd(dy):
     return dx
 
 
+def upsample_bilinear2x_fwd(x, out=None):
+    n, h, w, c, cs = _chk_nhwc(x, "upsample_bilinear2x(x)")
+    if out is None:
+        out = new_act(n, 2 * h, 2 * w, c, x.device)
+    call("msp_upsample_bilinear2x_fwd", _p(x), n, h, w, c, cs, _p(out), out.stride(2), _stream())
+    return out
+
+
+def upsample_bilinear2x_bwd(dy):
+    n, h2, w2, c, cs = _chk_nhwc(dy, "upsample_bilinear2x_bwd(dy)")
+    dx = new_act(n, h2 // 2, w2 // 2, c, dy.device)
+    call("msp_upsample_bilinear2x_bwd", _p(dy), n, h2 // 2, w2 // 2, c, cs, _p(dx), c, _stream())
+    return dx
+
+
 def avgpool_fwd(x):
     n, h, w, c, cs = _chk_nhwc(x, "avgpool(x)")
     y = new_act(n, 1, 1, c, x.device)
@@ -794,6 +825,27 @@ def softmax_ce(logits, label, smooth, gscale=1.0, gscale_dev=None, want_loss=Tru
     ls = torch.empty((1,), dtype=torch.float64, device=logits.device) if want_loss else None
     dl = torch.empty_like(logits) if want_grad else None
     call("msp_softmax_ce_fwd_bwd", _p(logits), _p(label), n, c, float(smooth), float(gscale),
+         _p(gscale_dev), _p(ls), _p(dl), _stream())
+    return ls, dl
+
+
+def softmax_ce_soft(logits, target, smooth, gscale=1.0, gscale_dev=None, want_loss=True, want_grad=False):
+    """(N, C) logits against (N, C) class-probability targets."""
+    n, c = logits.shape
+    ls = torch.empty((1,), dtype=torch.float64, device=logits.device) if want_loss else None
+    dl = torch.empty_like(logits) if want_grad else None
+    call("msp_softmax_ce_soft_fwd_bwd", _p(logits), _p(target), n, c, float(smooth), float(gscale),
+         _p(gscale_dev), _p(ls), _p(dl), _stream())
+    return ls, dl
+
+
+def softmax_ce_spatial(logits, label, smooth, gscale=1.0, gscale_dev=None, want_loss=True, want_grad=False):
+    """(N, C, *spatial) logits against (N, prod(spatial)) class indices."""
+    n, c = logits.shape[0], logits.shape[1]
+    hw = logits[0, 0].numel()
+    ls = torch.empty((1,), dtype=torch.float64, device=logits.device) if want_loss else None
+    dl = torch.empty_like(logits) if want_grad else None
+    call("msp_softmax_ce_spatial_fwd_bwd", _p(logits), _p(label), n, c, hw, float(smooth), float(gscale),
          _p(gscale_dev), _p(ls), _p(dl), _stream())
     return ls, dl
 

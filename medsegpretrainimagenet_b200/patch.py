@@ -13,6 +13,8 @@ What is replaced, and nothing else (`uninstall()` puts every original back):
   * segmentation.losses.losses.DiceLoss, classification.losses.{CrossEntropyLoss, BCELoss}
                                    -> forward() routed to the fused loss kernels; options the kernels do not
                                       implement raise instead of being dropped
+  * utils.get_class_constr         -> the class paths `torch.nn.CrossEntropyLoss` / `torch.nn.BCELoss` (advanced.yaml:48,
+                                      utils/default_dict.py:10) resolve to fused-kernel classes with torch's signature
   * metrics.metrics.ConfusionMatrix.calculate_batch,
     metrics.multiclass_metrics.{MultiClassConfusionMatrix, Top5Accuracy}.calculate_batch
                                    -> single-pass counter kernels
@@ -162,6 +164,26 @@ def install(group=None, convert_models: bool = True) -> None:
     _set(rdist, "inv_pearson_corr", _robust.inv_pearson_corr)
     _set(rdist, "cosine_distance", _robust.cosine_distance)
     _set(reval, "cosine_distance", _robust.cosine_distance)
+
+    # criteria named by their TORCH class path in a YAML (`torch.nn.CrossEntropyLoss`: pretraining/resnet50/advanced.yaml:48;
+    # `torch.nn.BCELoss`: the framework default, utils/default_dict.py:10) resolve to the fused-kernel classes with
+    # torch's constructor signature; every other class path resolves as before
+    import torch
+    utils_impl = importlib.import_module("utils._utils")
+    utils_pkg = importlib.import_module("utils")
+    redirect = {torch.nn.CrossEntropyLoss: _losses.TorchCrossEntropyLoss, torch.nn.BCELoss: _losses.TorchBCELoss}
+    orig_get = utils_impl.get_class_constr
+
+    def get_class_constr(class_path):
+        cls = orig_get(class_path)
+        try:
+            return redirect.get(cls, cls)
+        except TypeError:               # unhashable
+            return cls
+
+    _set(utils_impl, "get_class_constr", get_class_constr)
+    if getattr(utils_pkg, "get_class_constr", None) is orig_get:
+        _set(utils_pkg, "get_class_constr", get_class_constr)
 
     def robustness_call(self, preds0, preds1):
         return _robust.Robustness(self.distance_fn, self.margin)(preds0, preds1)

@@ -538,3 +538,109 @@ def test_batched_weight_gradient_unpack_and_tiled_pack_match_the_per_layer_kerne
     for w, (wf, wd) in zip(ws, per_layer):
         bf, bd = cache.lookup(w, True)
         assert torch.equal(bf, wf) and torch.equal(bd, wd)
+
+
+@pytest.mark.parametrize("cin, cout, k, s, p, hw", [(32, 16, 2, 2, 0, 12), (64, 32, 4, 2, 1, 9), (16, 24, 3, 1, 1, 10),
+                                                    (128, 64, 2, 2, 0, 16)])
+def test_conv_transpose2d_matches_torch(cin, cout, k, s, p, hw):
+    """nn.ConvTranspose2d (north star: transposed-conv layers) on the dgrad / fprop / wgrad tap-GEMM kernels against
+    F.conv_transpose2d in fp32 on bf16-representable operands: output within 6e-3 of its range (bf16 storage), input /
+    weight / bias gradients within 1e-2 / 2e-3 / 2e-3 of theirs."""
+    from medsegpretrainimagenet_b200 import functional as Fn
+    g = torch.Generator().manual_seed(0)
+    n = 3
+    x = torch.randn((n, cin, hw, hw), generator=g).to(torch.bfloat16).float()
+    w = (torch.randn((cin, cout, k, k), generator=g) * 0.1).to(torch.bfloat16).float()
+    b = torch.randn((cout,), generator=g)
+    xr, wr, br = x.clone().requires_grad_(True), w.clone().requires_grad_(True), b.clone().requires_grad_(True)
+    yr = F.relu(F.conv_transpose2d(xr, wr, br, stride=s, padding=p))
+    gy = torch.randn(yr.shape, generator=g).to(torch.bfloat16).float()
+    yr.backward(gy)
+    xg = x.to(DEV).requires_grad_(True)
+    wg = torch.nn.Parameter(w.to(DEV))
+    bg = torch.nn.Parameter(b.to(DEV))
+    yn = Fn.conv_transpose2d(Fn.to_nhwc(xg), wg, bg, s, p, relu=True)
+    y = Fn.to_nchw(yn, cout)
+    assert y.shape == yr.shape
+    y.backward(gy.to(DEV))
+    _close(y.detach().cpu(), yr.detach(), 6e-3, "conv_transpose y")
+    _close(xg.grad.cpu(), xr.grad, 1e-2, "conv_transpose dx")
+    _close(wg.grad.cpu(), wr.grad, 2e-3, "conv_transpose dw")
+    _close(bg.grad.cpu(), br.grad, 2e-3, "conv_transpose db")
+
+
+def test_conv_transpose2d_module_is_converted():
+    """The converter maps nn.ConvTranspose2d (+ReLU) inside a reference-structured block."""
+    from medsegpretrainimagenet_b200 import converter as cv, functional as Fn
+    torch.manual_seed(0)
+    seq = torch.nn.Sequential(torch.nn.ConvTranspose2d(32, 16, 2, stride=2), torch.nn.ReLU()).to(DEV)
+    with torch.no_grad():
+        for prm in seq.parameters():
+            prm.copy_(prm.to(torch.bfloat16).float())
+    x = torch.randn((2, 32, 8, 8), generator=torch.Generator().manual_seed(1)).to(torch.bfloat16).float().to(DEV)
+    y = Fn.to_nchw(cv.run_sequence(cv.ExecContext(), list(seq.children()), Fn.to_nhwc(x)))
+    _close(y.detach().cpu(), seq(x).detach().cpu(), 6e-3, "ConvTranspose2d module")
+    with pytest.raises(cv.UnsupportedModule):
+        cv.run_sequence(cv.ExecContext(), [torch.nn.ConvTranspose2d(32, 16, 2, stride=2, output_padding=1).to(DEV)],
+                        Fn.to_nhwc(x))
+
+
+@pytest.mark.parametrize("n, c, h, w", [(2, 16, 5, 7), (1, 64, 1, 9), (3, 8, 12, 12)])
+def test_bilinear_upsample_matches_torch(n, c, h, w):
+    """nn.Upsample(scale_factor=2, mode='bilinear') forward and backward against F.interpolate (fp32) on
+    bf16-representable inputs: outputs within one bf16 rounding (2^-8 relative), gradients likewise."""
+    from medsegpretrainimagenet_b200 import converter as cv, functional as Fn
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn((n, c, h, w), generator=g).to(torch.bfloat16).float()
+    xr = x.clone().requires_grad_(True)
+    yr = F.interpolate(xr, scale_factor=2, mode="bilinear", align_corners=False)
+    gy = torch.randn(yr.shape, generator=g).to(torch.bfloat16).float()
+    yr.backward(gy)
+    xg = x.to(DEV).requires_grad_(True)
+    up = torch.nn.Upsample(scale_factor=2, mode="bilinear")
+    y = Fn.to_nchw(cv.run_sequence(cv.ExecContext(), [up], Fn.to_nhwc(xg)))
+    y.backward(gy.to(DEV))
+    _close(y.detach().cpu(), yr.detach(), 5e-3, "bilinear y")
+    _close(xg.grad.cpu(), xr.grad, 5e-3, "bilinear dx")
+    with pytest.raises(cv.UnsupportedModule):
+        cv.run_sequence(cv.ExecContext(), [torch.nn.Upsample(scale_factor=2, mode="bilinear", align_corners=True)],
+                        Fn.to_nhwc(xg))
+
+
+def test_softmax_ce_soft_labels_and_spatial_logits_match_torch():
+    """torch.nn.CrossEntropyLoss with class-probability targets (Mixup / CutMix, advanced.yaml:17,48) and
+    F.cross_entropy on spatial logits, both with label smoothing: loss rel <= 1e-5, gradients <= 1e-5 of their range."""
+    from medsegpretrainimagenet_b200 import losses
+    g = torch.Generator().manual_seed(0)
+    for smooth in (0.0, 0.1):
+        z = torch.randn((37, 1000), generator=g) * 3
+        t = torch.zeros((37, 1000))
+        a, b = torch.randint(0, 1000, (37,), generator=g), torch.randint(0, 1000, (37,), generator=g)
+        lam = torch.rand((37,), generator=g)
+        t[torch.arange(37), a] += lam
+        t[torch.arange(37), b] += 1 - lam                         # mixed one-hot pairs
+        zr = z.clone().requires_grad_(True)
+        lr_ = F.cross_entropy(zr, t, label_smoothing=smooth)
+        lr_.backward()
+        zg = z.to(DEV).requires_grad_(True)
+        lg = losses.TorchCrossEntropyLoss(label_smoothing=smooth)(zg, t.to(DEV))
+        (lg * 1.0).backward()
+        assert abs(lg.item() - lr_.item()) <= 1e-5 * abs(lr_.item())
+        _close(zg.grad.cpu(), zr.grad, 1e-5, "soft CE grad")
+        # spatial logits: (N, C, H, W) against (N, H, W) and (N, 1, H, W) class indices
+        zs = torch.randn((3, 4, 19, 23), generator=g) * 2
+        ys = torch.randint(0, 4, (3, 19, 23), generator=g)
+        zsr = zs.clone().requires_grad_(True)
+        ls_ = F.cross_entropy(zsr, ys, label_smoothing=smooth)
+        ls_.backward()
+        for lab in (ys, ys.unsqueeze(1)):
+            zsg = zs.to(DEV).requires_grad_(True)
+            lsg = losses.CrossEntropyLoss(smooth, apply_softmax=True)(zsg, lab.to(DEV))
+            lsg.backward()
+            assert abs(lsg.item() - ls_.item()) <= 1e-5 * abs(ls_.item())
+            _close(zsg.grad.cpu(), zsr.grad, 1e-5, "spatial CE grad")
+        # the hard-label (N, C) / (N, 1) form keeps working through the same entry
+        y1 = torch.randint(0, 1000, (37, 1), generator=g)
+        want = F.cross_entropy(z, y1.squeeze(1), label_smoothing=smooth)
+        got = losses.CrossEntropyLoss(smooth, apply_softmax=True)(z.to(DEV), y1.to(DEV))
+        assert abs(got.item() - want.item()) <= 1e-5 * abs(want.item())

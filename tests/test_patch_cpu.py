@@ -117,3 +117,22 @@ def test_uninstall_restores_the_reference():
     # and the unmodified reference still computes on the CPU
     crit = seg_losses.DiceLoss()
     assert torch.isfinite(crit(torch.rand(2, 1, 8, 8), torch.zeros(2, 1, 8, 8, dtype=torch.long)))
+
+
+def test_advanced_pretraining_yaml_resolves_torch_criterion_to_the_fused_class(patched):
+    """config/pretraining/resnet50/advanced.yaml:48 names `torch.nn.CrossEntropyLoss` (soft Mixup / CutMix labels); the
+    class path resolves to the fused-kernel class with torch's constructor, other torch classes resolve unchanged."""
+    import utils
+    from medsegpretrainimagenet_b200 import losses
+    assert utils.get_class_constr("torch.nn.CrossEntropyLoss") is losses.TorchCrossEntropyLoss
+    assert utils.get_class_constr("torch.nn.BCELoss") is losses.TorchBCELoss
+    assert utils.get_class_constr("torch.nn.Conv2d") is torch.nn.Conv2d
+    cd = H.load_config("pretraining/resnet50/advanced.yaml")
+    loss_fn = H.build_loss(cd)
+    assert isinstance(loss_fn.calculator, losses.TorchCrossEntropyLoss)
+    assert loss_fn.calculator.label_smoothing == pytest.approx(0.1) and loss_fn.label_type == "label"
+    with pytest.raises(NotImplementedError):
+        losses.TorchCrossEntropyLoss(ignore_index=0)
+    model = H.build_model(cd, seed=0)          # stochastic_depth_rate 0.1 sequential model
+    import medsegpretrainimagenet_b200 as b200
+    assert b200.is_converted(model) and type(model.model).__name__ == "FeedForwardModel"
