@@ -121,6 +121,28 @@ int msp_unpack_wgrad(const msp_conv_desc* d, const float* dw_partials, int C_tru
  * Generic layers: partials [K][taps][Cpad]; row-window layers (rowwin_KH > 0): partials [K][KH][64] with
  * `rowwin_cpp` channels per window pixel.  `items` is a HOST array of 1..96 entries (it travels in the kernel's
  * parameter space). */
+/* ------------------------------------------------------------------------------------------
+ * Folded up-convolution: nn.Upsample(scale_factor=2) (nearest) -> Conv2d(k=2, padding='same') of UpConvBlock
+ * (segmentation/models/blocks.py:531-535) computed on the LOW-RES input: output pixel (2i+a, 2j+b) only ever reads
+ * low-res rows i (a = 0) or i, i+1 (a = 1), so the layer is four output-parity classes of 1x1 / 1x2 / 2x1 / 2x2
+ * convolutions with pre-summed weights — 9 instead of 16 taps per 2x2 output block, no x4 tensor, no up-sample kernels.
+ * Folded weights: fp32 [K][C][9], tap order class (a,b) = (0,0),(0,1),(1,0),(1,1) at 0,1,3,5, (dr,dq) row-major inside;
+ * pack them with msp_pack_weights as a 1x9 filter.  `d` everywhere: (N,H,W,C,x_cs) = the low-res input, (Ho,Wo) = (2H,2W),
+ * K, y_cs (relu: fprop epilogue).  The weight gradient runs per class (msp_upconv2x_wgrad_class with the class's own
+ * descriptor KH = 1+a, KW = 1+b, pad 0, Ho = H, Wo = W; msp_upconv2x_wgrad_splits sizes its partials), is unpacked per
+ * class ([K][C][1+a][1+b]) and mapped back to the 2x2 filter by msp_unfold_upconv_wgrad (the fold is linear).
+ * ------------------------------------------------------------------------------------------ */
+int msp_fold_upconv_weights(const float* w, int K, int C, float* w_folded, void* stream);
+int msp_unfold_upconv_wgrad(const float* g00, const float* g01, const float* g10, const float* g11, int K, int C,
+                            float* dw, int accumulate, void* stream);
+int msp_upconv2x_fprop(const msp_conv_desc* d, const void* x, const void* w_folded_fprop, const float* bias, void* y,
+                       void* stream);
+int msp_upconv2x_dgrad(const msp_conv_desc* d, const void* dy, const void* w_folded_dgrad, void* dx, int accumulate,
+                       void* stream);
+int msp_upconv2x_wgrad_splits(const msp_conv_desc* d);
+int msp_upconv2x_wgrad_class(const msp_conv_desc* d, const void* x, const void* dy, int a, int b, float* dw_partials,
+                             void* stream);
+
 typedef struct msp_unpack_item {
   const float* partials;
   float* dst;

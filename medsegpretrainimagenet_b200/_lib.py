@@ -56,6 +56,12 @@ SIGNATURES = {
     "msp_conv_wgrad": [C.POINTER(ConvDesc), P, P, P, P],
     "msp_unpack_wgrad": [C.POINTER(ConvDesc), P, I, P, P],
     "msp_unpack_wgrad_batched": [I, C.POINTER(UnpackItem), P],
+    "msp_fold_upconv_weights": [P, I, I, P, P],
+    "msp_unfold_upconv_wgrad": [P, P, P, P, I, I, P, I, P],
+    "msp_upconv2x_fprop": [C.POINTER(ConvDesc), P, P, P, P, P],
+    "msp_upconv2x_dgrad": [C.POINTER(ConvDesc), P, P, P, I, P],
+    "msp_upconv2x_wgrad_splits": [C.POINTER(ConvDesc)],
+    "msp_upconv2x_wgrad_class": [C.POINTER(ConvDesc), P, P, I, I, P, P],
     "msp_pack_weights_rowwin": [P, I, I, I, I, I, P, P],
     "msp_pack_weights_batched": [P, I, I, P],
     "msp_nchw_f32_to_rowwin_bf16": [P, I, I, I, I, I, I, I, P, P],

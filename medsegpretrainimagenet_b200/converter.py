@@ -18,6 +18,7 @@ Anything else raises UnsupportedModule: there is no PyTorch fallback on this pat
 """
 from __future__ import annotations
 
+import os
 import types
 from typing import List, Optional, Tuple
 
@@ -30,6 +31,9 @@ from . import ops
 
 class UnsupportedModule(NotImplementedError):
     pass
+
+
+_UPCONV_FOLD = os.environ.get("MSP_UPCONV_FOLD", "1") != "0"    # 0: materialise the x4 tensor like the reference
 
 
 class ExecContext:
@@ -348,9 +352,19 @@ def run_upconv_block(ctx, m, x, out=None):
     """UpConvBlock.forward (blocks.py:537-539): nearest x2 -> Conv2d(k=2, 'same') -> ReLU.  `out`: the leading channel
     slice of the level's concat buffer — the conv epilogue writes x_up where torch.cat (blocks.py:628,635) would copy it."""
     mods = [_unwrap(c) for c in m.convup.children()]
-    if out is not None and [_name(c) for c in mods] == ["Upsample", "Conv2d", "ReLU"]:
-        xu = run_sequence(ctx, [mods[0]], x)
-        return conv_bn_act(ctx, xu, mods[1], None, ops.ACT_RELU, out=out)
+    if [_name(c) for c in mods] == ["Upsample", "Conv2d", "ReLU"]:
+        up, conv = mods[0], mods[1]
+        sf = up.scale_factor if not isinstance(up.scale_factor, tuple) else up.scale_factor[0]
+        foldable = (_UPCONV_FOLD and up.mode == "nearest" and sf is not None and float(sf) == 2.0
+                    and tuple(conv.kernel_size) == (2, 2) and tuple(conv.stride) == (1, 1) and conv.padding == "same"
+                    and conv.groups == 1 and tuple(conv.dilation) == (1, 1) and conv.out_channels % 8 == 0
+                    and not isinstance(x, RawInput))
+        if foldable:
+            # nearest x2 -> 2x2 'same' conv -> ReLU folded onto the low-res input (functional._UpConv2x)
+            return Fn.upconv2x(x, conv.weight, conv.bias, relu=True, out=out)
+        if out is not None:
+            xu = run_sequence(ctx, [up], x)
+            return conv_bn_act(ctx, xu, conv, None, ops.ACT_RELU, out=out)
     return run_sequence(ctx, mods, x)
 
 

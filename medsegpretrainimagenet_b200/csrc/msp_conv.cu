@@ -1057,6 +1057,7 @@ struct WgradParams {
   int csub, tsub;            // ... = csub 64-channel chunks x tsub filter taps (narrow layers batch taps)
   int rowwin;
   int splits;
+  int dys;                 // element stride of dY's W / H coordinates (2: the folded up-conv reads a parity class of dY)
   long long split_stride;  // elements between the partial dW of consecutive splits
   float* dw;
 };
@@ -1144,8 +1145,8 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant__ C
         const int w0 = tw * p.bw, h0 = th * p.bh, n0 = tn * p.bn;
         uint8_t* a_s = smem + s * kWgStageBytes;
         mbar_expect_tx(&full_bar[s], tx_bytes);
-        tma_load_4d(a_s, &tmDY, &full_bar[s], co0, w0, h0, n0);
-        tma_load_4d(a_s + kWgAtomBytes, &tmDY, &full_bar[s], co0 + 64, w0, h0, n0);
+        tma_load_4d(a_s, &tmDY, &full_bar[s], co0, w0 * p.dys, h0 * p.dys, n0);
+        tma_load_4d(a_s + kWgAtomBytes, &tmDY, &full_bar[s], co0 + 64, w0 * p.dys, h0 * p.dys, n0);
         const int xw0 = w0 * p.sxw, xh0 = h0 * p.sxh;
 #pragma unroll
         for (int j = 0; j < kWgMaxSub; ++j)
@@ -1408,6 +1409,40 @@ __global__ void unpack_wgrad_rowwin_kernel(const float* __restrict__ dwp, int sp
     float acc = 0.f;
     for (int s = 0; s < splits; ++s) acc += src[(long long)s * split_stride];
     out[i] = acc;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Folded up-convolution: nn.Upsample(scale_factor=2) (nearest) -> Conv2d(k=2, padding='same') (UpConvBlock,
+// segmentation/models/blocks.py:531-535) WITHOUT the x4 tensor.  Output pixel (2i+a, 2j+b) reads the up-sampled rows
+// 2i+a+r, r in {0,1}, i.e. the LOW-RES rows i (a = 0: both taps) or i, i+1 (a = 1): four output-parity classes of
+// 1x1 / 1x2 / 2x1 / 2x2 convolutions on the low-res input with pre-summed weights — 9 taps instead of 16 per 2x2 output
+// block (9/16 of the FLOPs), the A operand 4x smaller, and no up-sample kernels in either direction.
+// Folded tap order: class (a,b) = (0,0),(0,1),(1,0),(1,1) at bases 0,1,3,5; inside a class (dr,dq) row-major.
+// ------------------------------------------------------------------------------------------------
+__constant__ int kFoldBase[4] = {0, 1, 3, 5};
+__global__ void fold_upconv_kernel(const float* __restrict__ w, long long KC, float* __restrict__ wf) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < KC; i += (long long)gridDim.x * blockDim.x) {
+    const float w00 = w[i * 4], w01 = w[i * 4 + 1], w10 = w[i * 4 + 2], w11 = w[i * 4 + 3];
+    float* o = wf + i * 9;
+    o[0] = (w00 + w01) + (w10 + w11);                 // (0,0): all four taps land on (i, j)
+    o[1] = w00 + w10;  o[2] = w01 + w11;              // (0,1): columns j, j+1
+    o[3] = w00 + w01;  o[4] = w10 + w11;              // (1,0): rows i, i+1
+    o[5] = w00; o[6] = w01; o[7] = w10; o[8] = w11;   // (1,1)
+  }
+}
+// gradient of the fold: dW[r][q] = sum over classes of the folded tap that (r, q) was summed into
+__global__ void unfold_upconv_kernel(const float* __restrict__ g00, const float* __restrict__ g01,
+                                     const float* __restrict__ g10, const float* __restrict__ g11, long long KC,
+                                     float* __restrict__ dw, int accumulate) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < KC; i += (long long)gridDim.x * blockDim.x) {
+    const float a = g00[i];
+    const float b0 = g01[i * 2], b1 = g01[i * 2 + 1];
+    const float c0 = g10[i * 2], c1 = g10[i * 2 + 1];
+    const float d00 = g11[i * 4], d01 = g11[i * 4 + 1], d10 = g11[i * 4 + 2], d11 = g11[i * 4 + 3];
+    float r[4] = {((a + b0) + c0) + d00, ((a + b1) + c0) + d01, ((a + b0) + c1) + d10, ((a + b1) + c1) + d11};
+#pragma unroll
+    for (int t = 0; t < 4; ++t) dw[i * 4 + t] = accumulate ? dw[i * 4 + t] + r[t] : r[t];
   }
 }
 
@@ -1759,6 +1794,16 @@ int make_act_map(CUtensorMap* m, const void* base, int C, int W, int H, int N, i
   uint32_t es[4] = {1, (uint32_t)s, (uint32_t)s, 1};
   return msp_encode_tmap_bf16(m, base, 4, dims, strides, box, es, 128);
 }
+// Same over a SUB-GRID view: base already points at the first element, (W, H) are the view's extents in elements of the
+// parent tensor, row / image strides are the parent's (the folded up-conv reads the parity class (a, b) of dY).
+int make_act_map_view(CUtensorMap* m, const void* base, int C, int W, int H, int N, int cs, long long row_stride,
+                      long long img_stride, Box b, int s) {
+  uint64_t dims[4] = {(uint64_t)C, (uint64_t)W, (uint64_t)H, (uint64_t)N};
+  uint64_t strides[3] = {(uint64_t)cs * 2, (uint64_t)row_stride * 2, (uint64_t)img_stride * 2};
+  uint32_t box[4] = {64, (uint32_t)(b.bw * s), (uint32_t)(b.bh * s), (uint32_t)b.bn};
+  uint32_t es[4] = {1, (uint32_t)s, (uint32_t)s, 1};
+  return msp_encode_tmap_bf16(m, base, 4, dims, strides, box, es, 128);
+}
 // Row-window map over the W-padded input [N][H][Wp][cpp]: dim 0 = 64 contiguous elements (the KW taps of
 // one filter row), dim 1 = output column (stride = conv stride x pixel, OVERLAPPING windows), dim 2 = input
 // row (element stride = conv stride), dim 3 = image.
@@ -2053,8 +2098,8 @@ struct WgradPlan {
   Box b;
   int OW, OH, N, tiles_m, nsub, csub, tsub, cchunks, gx, gy, splits, Cw, ntaps;
 };
-int plan_wgrad(const msp_conv_desc* d, WgradPlan* pl) {
-  const bool flat = is_flat(d);
+int plan_wgrad(const msp_conv_desc* d, WgradPlan* pl, bool force_2d = false) {
+  const bool flat = is_flat(d) && !force_2d;
   if (flat) {
     const long long P = (long long)d->N * d->H * d->W;
     MSP_REQUIRE(P < (1ll << 31), "conv_wgrad: too many pixels");
@@ -2095,8 +2140,27 @@ extern "C" int msp_conv_wgrad_splits(const msp_conv_desc* d) {
   return pl.splits;
 }
 
+namespace {
+int wgrad_impl(const msp_conv_desc* d, const void* x, const void* dy, float* dw_partials, int dy_es, int dy_oh,
+               int dy_ow, void* stream);
+}
 extern "C" int msp_conv_wgrad(const msp_conv_desc* d, const void* x, const void* dy,
                               float* dw_partials, void* stream) {
+  return wgrad_impl(d, x, dy, dw_partials, 1, 0, 0, stream);
+}
+// One output-parity class of the folded up-convolution: `d` = the class's convolution on the LOW-RES input (KH = 1 + a,
+// KW = 1 + b, pad 0, stride 1, Ho = H, Wo = W) whose output gradient is the parity class (a, b) of the full-resolution
+// dy (2H x 2W, pixel stride d->y_cs): dY(i, j) = dy[2i + a][2j + b].
+extern "C" int msp_upconv2x_wgrad_class(const msp_conv_desc* d, const void* x, const void* dy, int a, int b,
+                                        float* dw_partials, void* stream) {
+  MSP_REQUIRE(d && (a == 0 || a == 1) && (b == 0 || b == 1) && d->KH == 1 + a && d->KW == 1 + b && d->stride == 1 &&
+                  d->pad_t == 0 && d->pad_l == 0 && d->Ho == d->H && d->Wo == d->W && d->win_px == 0,
+              "upconv2x_wgrad_class: descriptor does not describe parity class (%d,%d)", a, b);
+  return wgrad_impl(d, x, dy, dw_partials, 2, a, b, stream);
+}
+namespace {
+int wgrad_impl(const msp_conv_desc* d, const void* x, const void* dy, float* dw_partials, int dy_es, int dy_oh,
+               int dy_ow, void* stream) {
   int rc = check_desc(d);
   if (rc) return rc;
   MSP_REQUIRE(x && dy && dw_partials, "conv_wgrad: null pointer");
@@ -2108,14 +2172,25 @@ extern "C" int msp_conv_wgrad(const msp_conv_desc* d, const void* x, const void*
     attr_set = true;
   }
   WgradPlan pl;
-  rc = plan_wgrad(d, &pl);
+  rc = plan_wgrad(d, &pl, dy_es != 1);
   if (rc) return rc;
   WgradParams p;
   memset(&p, 0, sizeof(p));
-  const bool flat = is_flat(d);
+  const bool flat = is_flat(d) && dy_es == 1;
   CUtensorMap tmDY, tmX;
   const Box b = pl.b;
-  if (flat) {
+  p.dys = dy_es;
+  if (dy_es != 1) {
+    // dY = parity class (dy_oh, dy_ow) of a (dy_es*Ho x dy_es*Wo) tensor: view from its first element, parent strides
+    const int Wf = dy_es * d->Wo, Hf = dy_es * d->Ho;
+    const __nv_bfloat16* base = (const __nv_bfloat16*)dy + ((long long)dy_oh * Wf + dy_ow) * d->y_cs;
+    rc = make_act_map_view(&tmDY, base, d->K, Wf - dy_ow, Hf - dy_oh, d->N, d->y_cs, (long long)Wf * d->y_cs,
+                           (long long)Hf * Wf * d->y_cs, b, dy_es);
+    if (rc) return rc;
+    rc = make_act_map(&tmX, x, d->C, d->W, d->H, d->N, d->x_cs, b, d->stride);
+    if (rc) return rc;
+    p.sxw = p.sxh = d->stride;
+  } else if (flat) {
     rc = make_act_map(&tmDY, dy, d->K, pl.OW, 1, 1, d->y_cs, b, 1);
     if (rc) return rc;
     rc = make_act_map(&tmX, x, d->C, pl.OW, 1, 1, d->x_cs, b, 1);
@@ -2149,6 +2224,126 @@ extern "C" int msp_conv_wgrad(const msp_conv_desc* d, const void* x, const void*
   msp_count_launch(1);
   g_last_kernel = "wgrad_kernel";
   return MSP_OK;
+}
+}  // namespace
+
+extern "C" int msp_upconv2x_wgrad_splits(const msp_conv_desc* d) {
+  int rc = check_desc(d);
+  if (rc) return rc;
+  WgradPlan pl;
+  rc = plan_wgrad(d, &pl, true);
+  if (rc) return rc;
+  return pl.splits;
+}
+
+extern "C" int msp_fold_upconv_weights(const float* w, int K, int C, float* w_folded, void* stream) {
+  MSP_REQUIRE(w && w_folded && K > 0 && C > 0, "fold_upconv_weights: bad arguments");
+  const long long KC = (long long)K * C;
+  const int blocks = (int)((KC + 255) / 256 < 2048 ? (KC + 255) / 256 : 2048);
+  fold_upconv_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(w, KC, w_folded);
+  MSP_CHECK_LAUNCH();
+  msp_count_launch(1);
+  return MSP_OK;
+}
+
+extern "C" int msp_unfold_upconv_wgrad(const float* g00, const float* g01, const float* g10, const float* g11, int K,
+                                       int C, float* dw, int accumulate, void* stream) {
+  MSP_REQUIRE(g00 && g01 && g10 && g11 && dw && K > 0 && C > 0, "unfold_upconv_wgrad: bad arguments");
+  const long long KC = (long long)K * C;
+  const int blocks = (int)((KC + 255) / 256 < 2048 ? (KC + 255) / 256 : 2048);
+  unfold_upconv_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(g00, g01, g10, g11, KC, dw, accumulate);
+  MSP_CHECK_LAUNCH();
+  msp_count_launch(1);
+  return MSP_OK;
+}
+
+// y = ReLU?(upconv(x) + bias): four stride-1 tap-GEMMs on the low-res input, class (a, b) writing the output sub-grid
+// (2i + a, 2j + b).  `d`: (N, H, W, C, x_cs) = the LOW-RES input, (Ho, Wo) = (2H, 2W), K, y_cs, relu.
+extern "C" int msp_upconv2x_fprop(const msp_conv_desc* d, const void* x, const void* w_folded_fprop, const float* bias,
+                                  void* y, void* stream) {
+  int rc = check_desc(d);
+  if (rc) return rc;
+  MSP_REQUIRE(x && w_folded_fprop && y, "upconv2x_fprop: null pointer");
+  MSP_REQUIRE(d->Ho == 2 * d->H && d->Wo == 2 * d->W && d->win_px == 0, "upconv2x_fprop: output must be 2H x 2W");
+  cudaStream_t st = (cudaStream_t)stream;
+  const WMapArgs wm{w_folded_fprop, d->C, 9, d->K};
+  for (int a = 0; a < 2; ++a)
+    for (int b2 = 0; b2 < 2; ++b2) {
+      TapGemmParams p;
+      memset(&p, 0, sizeof(p));
+      const int cls = a * 2 + b2, base = cls == 0 ? 0 : (cls == 1 ? 1 : (cls == 2 ? 3 : 5));
+      int nt = 0;
+      for (int dr = 0; dr <= a; ++dr)
+        for (int dq = 0; dq <= b2; ++dq) {
+          p.tap_dh[nt] = (int8_t)dr;
+          p.tap_dw[nt] = (int8_t)dq;
+          p.tap_w[nt] = (uint8_t)(base + nt);
+          ++nt;
+        }
+      Box b = pick_box(d->W, d->H, d->N);
+      CUtensorMap tmA, tmB;
+      rc = make_act_map(&tmA, x, d->C, d->W, d->H, d->N, d->x_cs, b, 1);
+      if (rc) return rc;
+      p.OWs = d->W; p.OHs = d->H; p.N = d->N;
+      p.y_n_stride = (long long)d->Ho * d->Wo * d->y_cs;
+      p.y_h_stride = 2ll * d->Wo * d->y_cs;
+      p.y_w_stride = 2ll * d->y_cs;
+      p.y_off = ((long long)a * d->Wo + b2) * d->y_cs;
+      p.bw = b.bw; p.bh = b.bh; p.bn = b.bn; p.rows = b.bw * b.bh * b.bn;
+      p.tiles_w = msp_cdiv(p.OWs, b.bw); p.tiles_h = msp_cdiv(p.OHs, b.bh); p.tiles_n = msp_cdiv(p.N, b.bn);
+      p.sxw = 1; p.sxh = 1; p.C = d->C; p.ntaps = nt; p.Kout = d->K; p.relu = d->relu;
+      p.y = (__nv_bfloat16*)y;
+      p.bias = bias;
+      Box hb;
+      int hw = 0;
+      if (plan_halo(p, d->W, d->H, d->N, bn_tile_for(d->K), &hb, &hw)) {
+        rc = make_act_map(&tmA, x, d->C, d->W, d->H, d->N, d->x_cs, hb, 1);
+        if (rc) return rc;
+        rc = make_w_map(&tmB, wm.base, wm.inner, wm.taps, wm.rows, bn_tile_for(d->K));
+        if (rc) return rc;
+        rc = dispatch_halo(tmA, tmB, p, st);
+      } else {
+        rc = dispatch_tapgemm(tmA, wm, p, st);
+      }
+      if (rc) return rc;
+    }
+  return MSP_OK;
+}
+
+// dx (low-res) = sum over the 9 folded taps of dy[2(i - dr) + a][2(j - dq) + b] * Wfold^T: ONE tap-GEMM whose A operand is
+// dy read through a stride-2 tensor map (as a stride-2 forward convolution reads its input).
+extern "C" int msp_upconv2x_dgrad(const msp_conv_desc* d, const void* dy, const void* w_folded_dgrad, void* dx,
+                                  int accumulate, void* stream) {
+  int rc = check_desc(d);
+  if (rc) return rc;
+  MSP_REQUIRE(dy && w_folded_dgrad && dx, "upconv2x_dgrad: null pointer");
+  MSP_REQUIRE(d->Ho == 2 * d->H && d->Wo == 2 * d->W && d->win_px == 0, "upconv2x_dgrad: dy must be 2H x 2W");
+  TapGemmParams p;
+  memset(&p, 0, sizeof(p));
+  int nt = 0;
+  for (int a = 0; a < 2; ++a)
+    for (int b2 = 0; b2 < 2; ++b2)
+      for (int dr = 0; dr <= a; ++dr)
+        for (int dq = 0; dq <= b2; ++dq) {
+          p.tap_dh[nt] = (int8_t)(a - 2 * dr);   // dy row 2(i - dr) + a = 2i + (a - 2 dr)
+          p.tap_dw[nt] = (int8_t)(b2 - 2 * dq);
+          p.tap_w[nt] = (uint8_t)nt;            // folded tap order == this enumeration
+          ++nt;
+        }
+  Box b = pick_box(d->W, d->H, d->N);
+  CUtensorMap tmA;
+  rc = make_act_map(&tmA, dy, d->K, d->Wo, d->Ho, d->N, d->y_cs, b, 2);
+  if (rc) return rc;
+  p.OWs = d->W; p.OHs = d->H; p.N = d->N;
+  p.y_n_stride = (long long)d->H * d->W * d->x_cs;
+  p.y_h_stride = (long long)d->W * d->x_cs;
+  p.y_w_stride = d->x_cs;
+  p.bw = b.bw; p.bh = b.bh; p.bn = b.bn; p.rows = b.bw * b.bh * b.bn;
+  p.tiles_w = msp_cdiv(p.OWs, b.bw); p.tiles_h = msp_cdiv(p.OHs, b.bh); p.tiles_n = msp_cdiv(p.N, b.bn);
+  p.sxw = 2; p.sxh = 2; p.C = d->K; p.ntaps = nt; p.Kout = d->C; p.accumulate = accumulate;
+  p.y = (__nv_bfloat16*)dx;
+  const WMapArgs wm{w_folded_dgrad, d->K, 9, d->C};
+  return dispatch_tapgemm(tmA, wm, p, (cudaStream_t)stream);
 }
 
 extern "C" int msp_unpack_wgrad(const msp_conv_desc* d, const float* dw_partials, int C_true,

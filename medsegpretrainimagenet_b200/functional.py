@@ -190,6 +190,46 @@ def conv2d(x, weight, bias=None, stride=1, padding=0, relu=False, want_stats=Fal
     return _Conv.apply(x, weight, bias, stride, padding, relu, want_stats, out, link)
 
 
+class _UpConv2x(torch.autograd.Function):
+    """UpConvBlock's nn.Upsample(scale_factor=2) -> Conv2d(k=2, padding='same') [-> ReLU] (blocks.py:531-539) as ONE
+    folded operation on the low-res input (csrc/msp_conv.cu, "Folded up-convolution"): the x4 tensor of the reference is
+    never formed, 9/16 of its FLOPs run, forward / dgrad / wgrad are the same tap-GEMM and wgrad kernels."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, relu, out):
+        k, c_true, kh, kw = weight.shape
+        assert (kh, kw) == (2, 2)
+        wf9, wd9 = ops.packed_folded_weights(weight)
+        y = ops.upconv2x_fprop(x, wf9, bias.detach() if bias is not None else None, k, relu=relu, out=out,
+                               c_true=c_true)
+        ctx.cfg = (c_true, relu, bias is not None)
+        ctx.x_shape = tuple(x.shape)
+        ctx.weight_ref = weight
+        ctx.save_for_backward(x, wd9, y if relu else None)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        c_true, relu, has_bias = ctx.cfg
+        x, wd9, y = ctx.saved_tensors
+        if dy.stride(3) != 1:
+            dy = dy.contiguous()
+        if relu:
+            dy = ops.relu_bwd(y, dy)
+        dx = dw = db = None
+        if ctx.needs_input_grad[0]:
+            dx = ops.upconv2x_dgrad(dy, wd9, ctx.x_shape, c_true=c_true)
+        if ctx.needs_input_grad[1]:
+            dw = ops.upconv2x_wgrad(x, dy, ctx.weight_ref)        # None when it went straight into weight.grad
+        if has_bias and ctx.needs_input_grad[2]:
+            db = ops.channel_sum(dy)
+        return dx, dw, db, None, None
+
+
+def upconv2x(x, weight, bias=None, relu=True, out=None):
+    return _UpConv2x.apply(x, weight, bias, relu, out)
+
+
 class _ConvTranspose(torch.autograd.Function):
     """y = conv_transpose2d(x, weight, bias) (+ReLU), weight (in_channels, out_channels, kh, kw) as nn.ConvTranspose2d
     keeps it.  The transposed convolution is the data gradient of the convolution `parent` with OIHW weight = this very

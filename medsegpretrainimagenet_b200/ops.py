@@ -146,7 +146,8 @@ class WeightPackCache:
     first time (or while the table is being rebuilt) is packed on the spot, as before."""
 
     def __init__(self):
-        self.entries = {}       # data_ptr -> [weight alias, wf, wd]
+        self.entries = {}       # data_ptr -> [weight alias (OIHW fp32 source of the pack), wf, wd]
+        self.folds = {}         # data_ptr of an up-conv weight -> (weight alias, folded fp32 [K, C, 1, 9] buffer)
         self.table = None
         self.total_blocks = 0
         self.dirty = False
@@ -191,8 +192,25 @@ class WeightPackCache:
         self.in_table = set(self.entries.keys())
         self.dirty = False
 
+    def lookup_folded(self, w: torch.Tensor):
+        """Operand copies of the FOLDED weights of an up-convolution (fold_upconv_weight): the fold kernel refreshes a
+        persistent fp32 [K, C, 1, 9] buffer at the top of every forward, which then takes part in the batched pack."""
+        if w.dtype != torch.float32 or not w.is_contiguous():
+            return pack_weights(fold_upconv_weight(w), True)
+        key = w.data_ptr()
+        f = self.folds.get(key)
+        if f is None or f[0].shape != w.shape:
+            f = (w.detach(), torch.empty((w.shape[0], w.shape[1], 1, 9), dtype=torch.float32, device=w.device))
+            self.folds[key] = f
+            fold_upconv_weight(w, out=f[1])
+        elif not self.packed:
+            fold_upconv_weight(w, out=f[1])             # begin_step() has not refreshed it (table being rebuilt)
+        return self.lookup(f[1], True)
+
     def begin_step(self) -> None:
         self.packed = False
+        for w, buf in self.folds.values():              # up-conv weights: fold first, the batched pack reads the result
+            fold_upconv_weight(w, out=buf)
         if self.table is None:
             return                                      # first forward: lookup() packs layer by layer
         call("msp_pack_weights_batched", self.table.data_ptr(), self.table.shape[0], self.total_blocks, _stream())
@@ -209,6 +227,26 @@ _PACK_ENABLED = os.environ.get("MSP_PACK_CACHE", "1") != "0"     # 0: pack layer
 def set_active_pack_cache(cache: Optional[WeightPackCache]) -> None:
     global _PACK
     _PACK = cache
+
+
+def fold_upconv_weight(w: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """(K, C, 2, 2) weights of nearest-x2 -> Conv2d(k=2, 'same') -> the (K, C, 1, 9) pre-summed taps of the four
+    output-parity classes on the low-res input (msp_fold_upconv_weights; see include/msp_b200.h)."""
+    w = w.detach()
+    if w.dtype != torch.float32 or not w.is_contiguous():
+        w = w.float().contiguous()
+    k, c, kh, kw = w.shape
+    assert (kh, kw) == (2, 2)
+    if out is None:
+        out = torch.empty((k, c, 1, 9), dtype=torch.float32, device=w.device)
+    call("msp_fold_upconv_weights", _p(w), k, c, _p(out), _stream())
+    return out
+
+
+def packed_folded_weights(w: torch.Tensor):
+    if _PACK is not None and _PACK_ENABLED:
+        return _PACK.lookup_folded(w)
+    return pack_weights(fold_upconv_weight(w), True)
 
 
 def packed_weights(w: torch.Tensor, need_dgrad: bool = True):
@@ -309,6 +347,87 @@ def conv_dgrad(dy, wd, x_shape, kh, kw, stride, pad_t, pad_l, out=None, accumula
     return out
 
 
+def upconv2x_fprop(x, wf9, bias, k, relu=True, out=None, c_true=None):
+    """nearest x2 -> conv 2x2 'same' (+bias, ReLU) on the LOW-RES x (N, H, W, C8) -> (N, 2H, 2W, K)."""
+    n, h, w, c, x_cs = _chk_nhwc(x, "upconv2x(x)")
+    if out is None:
+        out = new_act(n, 2 * h, 2 * w, k, x.device)
+    _, _, _, ko, y_cs = _chk_nhwc(out, "upconv2x(out)")
+    assert ko == k and wf9.shape[2] == c and wf9.shape[1] == 9
+    d = _conv_desc(n, h, w, c, x_cs, 2 * h, 2 * w, k, y_cs, 2, 2, 1, 0, 0, int(relu))
+    # 9 folded taps per 2x2 output block = 9/4 per output pixel: the FLOPs actually executed
+    with _timed("fprop", 2.0 * n * h * w * 9 * k * (c_true or c), 2.0 * (n * h * w * c + 4 * n * h * w * k + 9 * k * c)):
+        call("msp_upconv2x_fprop", C.byref(d), _p(x), _p(wf9), _p(bias), _p(out), _stream())
+    return out
+
+
+def upconv2x_dgrad(dy, wd9, x_shape, c_true=None):
+    n, h2, w2, k, y_cs = _chk_nhwc(dy, "upconv2x_dgrad(dy)")
+    _, h, w, c = x_shape
+    dx = new_act(n, h, w, c, dy.device)
+    d = _conv_desc(n, h, w, c, c, h2, w2, k, y_cs, 2, 2, 1, 0, 0)
+    with _timed("dgrad", 2.0 * n * h * w * 9 * k * (c_true or c), 2.0 * (n * h * w * c + 4 * n * h * w * k + 9 * k * c)):
+        call("msp_upconv2x_dgrad", C.byref(d), _p(dy), _p(wd9), _p(dx), 0, _stream())
+    return dx
+
+
+def upconv2x_wgrad(x, dy, weight: torch.Tensor):
+    """Weight gradient of the folded up-conv in the layout of the ORIGINAL (K, C, 2, 2) filter: one wgrad launch per
+    output-parity class on the low-res x, the class gradients unpacked ([K, C, 1+a, 1+b]) and mapped back through the
+    (linear) fold.  With a leaf Parameter the result goes straight into `weight.grad` at the end of the backward pass
+    (ops._WgradQueue); otherwise it is returned."""
+    n, h, w, c, x_cs = _chk_nhwc(x, "upconv2x_wgrad(x)")
+    _, h2, w2, k, y_cs = _chk_nhwc(dy, "upconv2x_wgrad(dy)")
+    c_true = weight.shape[1]
+    sink = _WGRAD_SINK and weight.is_leaf and weight.dtype == torch.float32 and weight.is_contiguous() and \
+        (weight.grad is None or (weight.grad.dtype == torch.float32 and weight.grad.is_contiguous()))
+    side = _WGRAD_STREAM if (_CONV_TIMELINE is None and sink) else None
+    classes = []
+    if side is not None:
+        side.wait_stream(torch.cuda.current_stream())
+    for a in (0, 1):
+        for b in (0, 1):
+            d = _conv_desc(n, h, w, c, x_cs, h, w, k, y_cs, 1 + a, 1 + b, 1, 0, 0)
+            splits = _lib.lib.msp_upconv2x_wgrad_splits(C.byref(d))
+            _lib.check(0 if splits >= 1 else splits, "msp_upconv2x_wgrad_splits")
+            taps = (1 + a) * (1 + b)
+            flops, nbytes = 2.0 * n * h * w * taps * k * c_true, 2.0 * (n * h * w * c + n * h * w * k) + 4.0 * k * c_true * taps
+            if side is not None:
+                with torch.cuda.stream(side):
+                    part = torch.empty((splits, k, taps, c), dtype=torch.float32, device=x.device)
+                    call("msp_upconv2x_wgrad_class", C.byref(d), _p(x), _p(dy), a, b, _p(part), side.cuda_stream)
+            else:
+                part = torch.empty((splits, k, taps, c), dtype=torch.float32, device=x.device)
+                with _timed("wgrad", flops, nbytes):
+                    call("msp_upconv2x_wgrad_class", C.byref(d), _p(x), _p(dy), a, b, _p(part), _stream())
+            g = torch.empty((k, c_true, 1 + a, 1 + b), dtype=torch.float32, device=x.device)
+            classes.append((d, part, g))
+    if side is not None:
+        x.record_stream(side)
+        dy.record_stream(side)
+    if sink:
+        acc = weight.grad is not None
+        if not acc:
+            weight.grad = torch.empty_like(weight, memory_format=torch.contiguous_format)
+        dst = weight.grad
+        for d, part, g in classes:
+            _WGRAD_QUEUE.push(d, part, g, c_true, False)
+        gs = [g for _, _, g in classes]
+        _WGRAD_QUEUE.after_unpack(lambda: call("msp_unfold_upconv_wgrad", _p(gs[0]), _p(gs[1]), _p(gs[2]), _p(gs[3]), k,
+                                               c_true, _p(dst), int(acc), _stream()), keep=(gs, dst))
+        ready = getattr(weight, "_msp_grad_ready", None)
+        if ready is not None:
+            ready(weight)
+        return None
+    for d, part, g in classes:
+        it = _WGRAD_QUEUE.make_item(d, part, g, c_true, False)
+        call("msp_unpack_wgrad_batched", 1, (_lib.UnpackItem * 1)(it), _stream())
+    dw = torch.empty((k, c_true, 2, 2), dtype=torch.float32, device=x.device)
+    call("msp_unfold_upconv_wgrad", _p(classes[0][2]), _p(classes[1][2]), _p(classes[2][2]), _p(classes[3][2]), k, c_true,
+         _p(dw), 0, _stream())
+    return dw
+
+
 def conv_transpose_fprop(x, wd, bias, c_out, kh, kw, stride, pad, relu=False, out=None, k_true=None):
     """nn.ConvTranspose2d forward = data gradient of the conv it transposes (msp_conv_transpose_fprop).
     x (N, Hi, Wi, K8) -> (N, Ho, Wo, C8) with Ho = (Hi - 1) * stride - 2 * pad + kh."""
@@ -353,8 +472,24 @@ class _WgradQueue:
 
     def __init__(self):
         self.items, self.keep, self.callback_queued = [], [], False
+        self.post = []          # calls issued after the unpack launches of a flush (the up-conv's unfold)
+
+    def after_unpack(self, fn, keep=None):
+        self.post.append(fn)
+        self.keep.append(keep)
 
     def push(self, d: ConvDesc, part, dst, c_true, accumulate):
+        self.items.append(self.make_item(d, part, dst, c_true, accumulate))
+        self.keep.append((part, dst))
+        if not self.callback_queued:
+            try:
+                torch.autograd.Variable._execution_engine.queue_callback(self.flush)
+                self.callback_queued = True
+            except RuntimeError:
+                self.flush()                    # not inside a backward pass: nothing to defer to
+
+    @staticmethod
+    def make_item(d: ConvDesc, part, dst, c_true, accumulate):
         it = _lib.UnpackItem()
         it.partials, it.dst = part.data_ptr(), dst.data_ptr()
         it.splits, it.K, it.C_true = part.shape[0], d.K, c_true
@@ -364,28 +499,25 @@ class _WgradQueue:
         else:
             it.rowwin_KH, it.taps, it.Cpad = 0, d.KH * d.KW, d.C
         it.accumulate = int(accumulate)
-        self.items.append(it)
-        self.keep.append((part, dst))
-        if not self.callback_queued:
-            try:
-                torch.autograd.Variable._execution_engine.queue_callback(self.flush)
-                self.callback_queued = True
-            except RuntimeError:
-                self.flush()                    # not inside a backward pass: nothing to defer to
+        return it
 
     def flush(self):
         self.callback_queued = False
         items, self.items = self.items, []
         keep, self.keep = self.keep, []
+        post, self.post = self.post, []
         if items and _WGRAD_STREAM is not None:
             cur = torch.cuda.current_stream()
             cur.wait_stream(_WGRAD_STREAM)          # every queued wgrad kernel has finished before the unpack starts
-            for part, _ in keep:
-                part.record_stream(cur)
+            for kp in keep:
+                if kp is not None and isinstance(kp[0], torch.Tensor):
+                    kp[0].record_stream(cur)
         for lo in range(0, len(items), 96):
             chunk = items[lo:lo + 96]
             arr = (_lib.UnpackItem * len(chunk))(*chunk)
             call("msp_unpack_wgrad_batched", len(chunk), arr, _stream())
+        for fn in post:
+            fn()
         del keep
 
 

@@ -131,3 +131,47 @@ def eval_encoder(model, imgs: torch.Tensor, scorer: Robustness, level: int, pool
     if pool:
         preds0, preds1 = torch.mean(preds0.flatten(2), dim=2), torch.mean(preds1.flatten(2), dim=2)
     return scorer(preds0, preds1)
+
+
+def symmetric_chunks(n: int, rows: int):
+    """Row sets closed under the negative permutation perm = [1, 0, n-1, n-2, ..., 2] (robustness/eval.py:22-23), each
+    a list of ascending global index ranges whose concatenation, taken as a LOCAL array, has the same permutation
+    structure: local rows 0, 1 are the global pair (0, 1) and local row j >= 2 pairs with local row m + 1 - j (m = the
+    chunk's length), exactly as global row i >= 2 pairs with n + 1 - i.  A chunk is therefore scored by the same kernel
+    as the whole array; rows 0 and 1 ride along in every chunk (their scores are taken from the first one).
+    Used to stream representations that do not fit in HBM at once: cfg5's unpooled levels 1-3 are 160 GB per tensor."""
+    if n <= max(4, rows):
+        return [[(0, n)]]
+    chunks, lo, hi = [], 2, n            # rows [lo, hi) of the tail are still unassigned; lo + (hi - 1) == n + 1
+    half = max(1, (rows - 2) // 2)
+    while lo < hi:
+        take = min(half, (hi - lo + 1) // 2)
+        a_lo, a_hi = lo, lo + take                      # ascending block from the front ...
+        b_lo, b_hi = n + 2 - a_hi, n + 2 - a_lo         # ... and its partners n + 1 - i, also ascending
+        if b_lo <= a_hi:                                # the two blocks meet: one contiguous, self-paired range
+            chunks.append([(0, 2), (a_lo, hi)])
+            break
+        chunks.append([(0, 2), (a_lo, a_hi), (b_lo, b_hi)])
+        lo, hi = a_hi, b_lo
+    return chunks
+
+
+def robustness_table_streamed(rep_fn, n: int, rows_per_chunk: int, margins: Sequence[float] = (0.0, 0.25, 0.5, 0.75, 1.0),
+                              pool: bool = False) -> torch.Tensor:
+    """`robustness_table` for representations too large to hold at once: `rep_fn(lo, hi) -> (reps0, reps1)` produces the
+    two views' representations of global rows [lo, hi) (e.g. an encoder forward over those images); the rows are
+    visited in permutation-closed chunks (`symmetric_chunks`), each scored by the same single-pass kernel.
+    -> fp32 (len(margins), 3, n), identical to the unstreamed result."""
+    out = None
+    for chunk in symmetric_chunks(n, rows_per_chunk):
+        parts = [rep_fn(lo, hi) for lo, hi in chunk]
+        r0 = torch.cat([p[0] for p in parts])
+        r1 = torch.cat([p[1] for p in parts])
+        t = robustness_table(r0, r1, margins, pool=pool)            # (M, 3, rows of this chunk)
+        if out is None:
+            out = torch.empty((t.shape[0], 3, n), dtype=torch.float32, device=t.device)
+        pos = 0
+        for lo, hi in chunk:            # (rows 0 and 1 are rewritten by every chunk with the same values)
+            out[:, :, lo:hi] = t[:, :, pos:pos + (hi - lo)]
+            pos += hi - lo
+    return out

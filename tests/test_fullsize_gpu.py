@@ -181,3 +181,50 @@ def test_cfg2_resnet50_eval_batch_256_equals_batch_8():
     with torch.no_grad():
         y_bf = gpu(x[:8].to(torch.bfloat16))
     assert _rel(y_bf, gpu(x[:8].to(torch.bfloat16).float())) == 0.0
+
+
+def test_cfg5_unpooled_levels_streamed_equals_resident():
+    """cfg5: unpooled level-5 representations (D = 100 352 = 2048 x 7 x 7) resident, scored (a) in one launch
+    and (b) streamed in permutation-closed chunks {i, perm(i)} as the 160 GB levels 1-3 have to be: identical scores.
+    Also level 4 (D = 200 704) through the pooled-in-kernel path against pooling first."""
+    import medsegpretrainimagenet_b200 as b
+    from medsegpretrainimagenet_b200 import robustness as R
+    g = torch.Generator(device=DEV).manual_seed(0)
+    n, d = 4001, 100352                                      # odd n: the permutation has a fixed point
+    q = torch.relu(torch.randn((n, d), device=DEV, generator=g))
+    k = torch.relu(q + 0.1 * torch.randn((n, d), device=DEV, generator=g))
+    whole = R.robustness_table(q, k)
+    streamed = R.robustness_table_streamed(lambda lo, hi: (q[lo:hi], k[lo:hi]), n, rows_per_chunk=514)
+    assert torch.equal(whole, streamed)
+    chunks = R.symmetric_chunks(n, 514)
+    assert len(chunks) >= 8 and all(sum(hi - lo for lo, hi in c) <= 516 for c in chunks)
+    del q, k
+    # level 4 unpooled maps (1024 x 14 x 14): pool=True inside the kernel == spatial mean first, rel <= 1e-4
+    f0 = torch.relu(torch.randn((600, 1024, 14, 14), device=DEV, generator=g))
+    f1 = torch.relu(f0 + 0.1 * torch.randn((600, 1024, 14, 14), device=DEV, generator=g))
+    fused = R.all_distances(f0, f1, pool=True)
+    first = R.all_distances(f0.flatten(2).mean(2), f1.flatten(2).mean(2))
+    assert ((fused - first).abs().max() / first.abs().max()).item() <= 1e-4
+    # and the unpooled level-4 row length through the plain path: d(q, q) = 0 for all three distances
+    same = R.all_distances(f0, f0)
+    assert same[0].abs().max().item() <= 1e-6 and same[2].abs().max().item() == 0.0 and same[4].abs().max().item() <= 1e-6
+
+
+def test_predict_w_model_levels_and_pooling():
+    """robustness/eval.py:30-54 (with its missing torch.cat): every level of a ResNet-50 encoder, pooled and unpooled,
+    batched; D of the unpooled levels as SURVEY a19 lists them for 224 x 224 inputs."""
+    from medsegpretrainimagenet_b200 import models, robustness as R
+    torch.manual_seed(0)
+    enc = models.kaiming_init_(models.DeepResNet(bias=False)).to(DEV).eval()
+    imgs = torch.rand((5, 3, 224, 224))
+    want_d = [802816, 802816, 401408, 200704, 100352]
+    want_c = [64, 256, 512, 1024, 2048]
+    for level in range(5):
+        un = R.predict_w_model(enc, imgs, batch_size=2, device=DEV, level=level, pool=False)
+        po = R.predict_w_model(enc, imgs, batch_size=2, device=DEV, level=level, pool=True)
+        assert un.shape[0] == 5 and un[0].numel() == want_d[level] and tuple(po.shape) == (5, want_c[level])
+        assert torch.allclose(po, un.flatten(2).mean(2), rtol=1e-5, atol=1e-6)
+    # batching does not change the representation (eval mode: running statistics)
+    a = R.predict_w_model(enc, imgs, batch_size=5, device=DEV, level=-1, pool=True)
+    b2 = R.predict_w_model(enc, imgs, batch_size=1, device=DEV, level=-1, pool=True)
+    assert torch.allclose(a, b2, rtol=2e-2, atol=1e-3)

@@ -205,3 +205,19 @@ def test_one_vs_rest_counts_from_the_matrix():
         tp, tn, fp, fn = M.binary_counts_of_class(cm, idx)
         assert tp == cm[idx, idx] and fn == cm[idx].sum() - tp and fp == cm[:, idx].sum() - tp
         assert tp + tn + fp + fn == cm.sum()
+
+
+def test_symmetric_chunks_are_closed_under_the_negative_permutation():
+    """Streaming cfg5's unpooled levels: every chunk, read as a local array, must pair its rows exactly as the global
+    permutation [1, 0, n-1, ..., 2] (robustness/eval.py:22-23) does, and the chunks must cover every row."""
+    from medsegpretrainimagenet_b200.robustness import negative_permutation, symmetric_chunks
+    for n in (2, 3, 5, 10, 11, 50, 51, 1000, 1001):
+        for rows in (6, 8, 16, 33):
+            perm, seen = negative_permutation(n), set()
+            for chunk in symmetric_chunks(n, rows):
+                idx = [i for lo, hi in chunk for i in range(lo, hi)]
+                local = negative_permutation(len(idx))
+                assert all(idx[local[j]] == perm[i] for j, i in enumerate(idx)), (n, rows, chunk)
+                assert len(idx) <= max(rows, 4) + 2
+                seen |= set(idx)
+            assert seen == set(range(n))

@@ -644,3 +644,75 @@ def test_softmax_ce_soft_labels_and_spatial_logits_match_torch():
         want = F.cross_entropy(z, y1.squeeze(1), label_smoothing=smooth)
         got = losses.CrossEntropyLoss(smooth, apply_softmax=True)(z.to(DEV), y1.to(DEV))
         assert abs(got.item() - want.item()) <= 1e-5 * abs(want.item())
+
+
+@pytest.mark.parametrize("n, cin, cout, h, w", [(2, 64, 32, 7, 9), (1, 2048, 1024, 4, 4), (3, 32, 16, 33, 20),
+                                                (2, 128, 64, 16, 16)])
+def test_folded_upconv_matches_upsample_then_conv(n, cin, cout, h, w):
+    """UpConvBlock (blocks.py:531-539): nearest x2 -> Conv2d(k=2, padding='same') -> ReLU, folded onto the low-res input
+    (four output-parity classes with pre-summed weights), against torch in fp32 on bf16-representable operands:
+    output within 6e-3 of its range, dx 1e-2, dW 3e-3, db 2e-3 — and no x4 tensor / up-sample kernel is involved."""
+    from medsegpretrainimagenet_b200 import functional as Fn, ops
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn((n, cin, h, w), generator=g).to(torch.bfloat16).float()
+    wt = (torch.randn((cout, cin, 2, 2), generator=g) * (1.0 / (4 * cin)) ** 0.5).to(torch.bfloat16).float()
+    b = torch.randn((cout,), generator=g) * 0.1
+    xr, wr, br = x.clone().requires_grad_(True), wt.clone().requires_grad_(True), b.clone().requires_grad_(True)
+    up = F.interpolate(xr, scale_factor=2, mode="nearest")
+    yr = F.relu(F.conv2d(F.pad(up, (0, 1, 0, 1)), wr, br))
+    gy = torch.randn(yr.shape, generator=g).to(torch.bfloat16).float()
+    yr.backward(gy)
+    xg = x.to(DEV).requires_grad_(True)
+    wg, bg = torch.nn.Parameter(wt.to(DEV)), torch.nn.Parameter(b.to(DEV))
+    l0 = ops.launch_count()
+    y = Fn.to_nchw(Fn.upconv2x(Fn.to_nhwc(xg), wg, bg, relu=True), cout)
+    assert y.shape == yr.shape
+    y.backward(gy.to(DEV))
+    _close(y.detach().cpu(), yr.detach(), 6e-3, "folded up-conv y")
+    _close(xg.grad.cpu(), xr.grad, 1e-2, "folded up-conv dx")
+    _close(wg.grad.cpu(), wr.grad, 3e-3, "folded up-conv dW")
+    _close(bg.grad.cpu(), br.grad, 2e-3, "folded up-conv db")
+    # accumulate into an existing gradient (second backward) and the autograd-returned path agree
+    y2 = Fn.to_nchw(Fn.upconv2x(Fn.to_nhwc(xg), wg, bg, relu=True), cout)
+    y2.backward(gy.to(DEV))
+    _close(wg.grad.cpu(), 2 * wr.grad, 3e-3, "folded up-conv dW accumulated")
+    wv = wt.to(DEV).requires_grad_(True)
+    y3 = Fn.to_nchw(Fn.upconv2x(Fn.to_nhwc(xg), wv * 1.0, None, relu=False), cout)     # non-leaf weight: returned to autograd
+    y3.backward(gy.to(DEV))
+    yr3 = F.conv2d(F.pad(F.interpolate(x, scale_factor=2, mode="nearest"), (0, 1, 0, 1)), wr.detach().requires_grad_(True))
+    w3 = wt.clone().requires_grad_(True)
+    F.conv2d(F.pad(F.interpolate(x, scale_factor=2, mode="nearest"), (0, 1, 0, 1)), w3).backward(gy)
+    _close(wv.grad.cpu(), w3.grad, 3e-3, "folded up-conv dW (autograd route)")
+
+
+def test_unet_with_folded_upconvs_and_zero_copy_concat_equals_the_materialising_path():
+    """The attention U-Net with the up-convs folded and x_up written straight into the concat buffers against the same
+    network with the x4 tensors materialised (MSP_UPCONV_FOLD=0 path): predictions within bf16 noise (the folded weights
+    are summed before their bf16 rounding), gradients aligned."""
+    import medsegpretrainimagenet_b200 as b200
+    from medsegpretrainimagenet_b200 import converter as cv, models
+    torch.manual_seed(0)
+    m = models.kaiming_init_(models.resnet18_attention_unet()).to(DEV).train()
+    x = torch.rand((4, 1, 64, 64), device=DEV)
+    y = (torch.rand((4, 1, 64, 64), device=DEV) < 0.3).long()
+    torch.use_deterministic_algorithms(True, warn_only=True)
+
+    def run():
+        for p in m.parameters():
+            p.grad = None
+        for bn in [mod for mod in m.modules() if isinstance(mod, torch.nn.BatchNorm2d)]:
+            bn.reset_running_stats()
+        pred = m(x)
+        loss = b200.losses.DiceLoss()(pred, y)
+        loss.backward()
+        return pred.detach().clone(), loss.item(), torch.cat([p.grad.flatten() for p in m.parameters()]).double()
+    try:
+        p1, l1, g1 = run()
+        cv._UPCONV_FOLD = False
+        p0, l0, g0 = run()
+    finally:
+        cv._UPCONV_FOLD = True
+        torch.use_deterministic_algorithms(False)
+    rms = ((p1 - p0).double().pow(2).mean().sqrt() / p0.double().pow(2).mean().sqrt()).item()
+    cos = (g1 @ g0 / (g1.norm() * g0.norm())).item()
+    assert rms <= 1e-2 and abs(l1 - l0) <= 5e-3 * abs(l0) and cos >= 0.98, (rms, l1, l0, cos)
