@@ -170,7 +170,9 @@ def conv_bn_act(ctx: ExecContext, x, conv: nn.Conv2d, bn: Optional[nn.BatchNorm2
     _check_conv(conv)
     stride, padding = conv.stride[0], _pad_of(conv)
     if isinstance(x, RawInput):
-        conv2d = lambda _x, *a, **k: Fn.input_conv2d(x.t, *a, **k)
+        if out is not None:
+            raise UnsupportedModule("the network's first convolution cannot write into a concat slice")
+        conv2d = lambda _x, *a, out=None, **k: Fn.input_conv2d(x.t, *a, **k)
     elif link_in is not None:
         conv2d = lambda *a, **k: Fn.conv2d(*a, link=link_in, **k)
     else:

@@ -941,8 +941,12 @@ tapgemm_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         const int co0 = tco * BN_;
         for (int ch = 0; ch < chunks; ++ch) {
           mbar_wait(&a_empty[sa], pha ^ 1u);
-          mbar_expect_tx(&a_full[sa], a_bytes);
-          tma_load_4d(a_ring + sa * kHaloABytes, &tmA, &a_full[sa], ch * kBK, w0 + p.org_dw, h0 + p.org_dh, tn);
+          if (p.debug & 128) {  // timing experiment: MMA / epilogue side alone (no A loads, garbage operands)
+            mbar_arrive(&a_full[sa]);
+          } else {
+            mbar_expect_tx(&a_full[sa], a_bytes);
+            tma_load_4d(a_ring + sa * kHaloABytes, &tmA, &a_full[sa], ch * kBK, w0 + p.org_dw, h0 + p.org_dh, tn);
+          }
           if (++sa == (uint32_t)p.a_stages) {
             sa = 0;
             pha ^= 1u;
@@ -1004,7 +1008,8 @@ tapgemm_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             // the TMA write; measured on B200), so the window of tap (r', q') needs only the start address shifted
             // by r'*bw + q' rows of 128 B — the descriptor's "matrix base offset" field stays 0.
             const uint32_t ta_lo = a_lo + tap_lo_s[tap];
-            if (nk == 4) {
+            if (p.debug & 256) {  // timing experiment: load + epilogue side alone (no MMAs)
+            } else if (nk == 4) {
               umma_bf16_lohi(tmem_d, ta_lo, desc_hi, b_lo, desc_hi, idesc, acc);
               umma_bf16_lohi(tmem_d, ta_lo + 2, desc_hi, b_lo + 2, desc_hi, idesc, 1u);
               umma_bf16_lohi(tmem_d, ta_lo + 4, desc_hi, b_lo + 4, desc_hi, idesc, 1u);
@@ -1318,26 +1323,33 @@ pack_w_batched_kernel(const long long* __restrict__ items, int n_items) {
     const int tk = (int)(blk / tiles_c), tc = (int)(blk - (long long)tk * tiles_c);
     const int k0 = tk * kPackTile, c0 = tc * kPackTile;
     const int run = kPackTile * taps;
-    for (int i = threadIdx.x; i < kPackTile * run; i += 256) {
-      const int kk = i / run, rem = i - kk * run;
-      const int cc = rem / taps;
-      float v = 0.f;
-      if (k0 + kk < K && c0 + cc < C) v = w[((long long)(k0 + kk) * C + c0) * taps + rem];
-      tile[kk * pitch + rem] = v;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 8 warps: no per-element division anywhere below
+    for (int kk = ty; kk < kPackTile; kk += 8) {              // warp = one output channel: contiguous source run
+      const bool kok = k0 + kk < K;
+      const float* src = w + ((long long)(k0 + kk) * C + c0) * taps;
+      int cc = tx / taps, tap = tx - cc * taps;               // element r = tx, tx + 32, ... of the run: (cc, tap)
+      const int dcc = 32 / taps, dtap = 32 - dcc * taps;
+      for (int r = tx; r < run; r += 32) {
+        tile[kk * pitch + r] = (kok && c0 + cc < C) ? src[r] : 0.f;
+        cc += dcc; tap += dtap;
+        if (tap >= taps) { tap -= taps; ++cc; }
+      }
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < kPackTile * run; i += 256) {  // wf[k][tap][c], c fastest
-      const int cc = i % kPackTile, r = i / kPackTile;
-      const int tap = r % taps, kk = r / taps;
-      if (k0 + kk < K && c0 + cc < Cpad)
-        wf[((long long)(k0 + kk) * taps + tap) * Cpad + c0 + cc] = __float2bfloat16_rn(tile[kk * pitch + cc * taps + tap]);
+    if (c0 + tx < Cpad) {                                     // wf[k][tap][c]: lane = input channel (64-byte runs)
+      for (int kk = ty; kk < kPackTile; kk += 8) {
+        if (k0 + kk >= K) break;
+        __nv_bfloat16* dst = wf + (long long)(k0 + kk) * taps * Cpad + c0 + tx;
+        const float* srow = tile + kk * pitch + tx * taps;
+        for (int tap = 0; tap < taps; ++tap) dst[(long long)tap * Cpad] = __float2bfloat16_rn(srow[tap]);
+      }
     }
-    if (wd != nullptr) {
-      for (int i = threadIdx.x; i < kPackTile * run; i += 256) {  // wd[c][tap][k], k fastest
-        const int kk = i % kPackTile, r = i / kPackTile;
-        const int tap = r % taps, cc = r / taps;
-        if (c0 + cc < Cpad && k0 + kk < Kpad)
-          wd[((long long)(c0 + cc) * taps + tap) * Kpad + k0 + kk] = __float2bfloat16_rn(tile[kk * pitch + cc * taps + tap]);
+    if (wd != nullptr && k0 + tx < Kpad) {                    // wd[c][tap][k]: lane = output channel
+      for (int cc = ty; cc < kPackTile; cc += 8) {
+        if (c0 + cc >= Cpad) break;
+        __nv_bfloat16* dst = wd + (long long)(c0 + cc) * taps * Kpad + k0 + tx;
+        const float* scol = tile + tx * pitch + cc * taps;
+        for (int tap = 0; tap < taps; ++tap) dst[(long long)tap * Kpad] = __float2bfloat16_rn(scol[tap]);
       }
     }
     return;
