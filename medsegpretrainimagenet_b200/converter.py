@@ -33,7 +33,13 @@ class UnsupportedModule(NotImplementedError):
     pass
 
 
-_UPCONV_FOLD = os.environ.get("MSP_UPCONV_FOLD", "1") != "0"    # 0: materialise the x4 tensor like the reference
+# Folded up-convolution (functional._UpConv2x): 0 = never (materialise the x4 tensor like the reference), 2 = always,
+# 1 (default) = when the layer is large enough to pay for its extra launches: the fold runs 9/16 of the FLOPs on a 4x
+# smaller operand but as 4 + 1 + 4 kernels instead of 1 + 1 + 1 (+ 2 up-sample kernels); at the R50 U-Net's batch 24 every
+# up-conv is a 15-30 us launch for a few us of work and the fold measured 3 % SLOWER over the step (2 033 vs 2 094 img/s,
+# profiles/r02_experiments.txt), on the 1024^2 basic U-Net the up-convs are the largest tensors of the network.
+_UPCONV_FOLD = int(os.environ.get("MSP_UPCONV_FOLD", "1"))
+_UPCONV_FOLD_MIN_FLOPS = 1.5e11      # unfused forward FLOPs (2 * 4NHW * K * 4C) above which the fold is used in mode 1
 
 
 class ExecContext:
@@ -357,7 +363,10 @@ def run_upconv_block(ctx, m, x, out=None):
     if [_name(c) for c in mods] == ["Upsample", "Conv2d", "ReLU"]:
         up, conv = mods[0], mods[1]
         sf = up.scale_factor if not isinstance(up.scale_factor, tuple) else up.scale_factor[0]
-        foldable = (_UPCONV_FOLD and up.mode == "nearest" and sf is not None and float(sf) == 2.0
+        big = isinstance(x, torch.Tensor) and \
+            2.0 * 4 * x.shape[0] * x.shape[1] * x.shape[2] * conv.out_channels * 4 * conv.in_channels >= _UPCONV_FOLD_MIN_FLOPS
+        foldable = ((_UPCONV_FOLD == 2 or (_UPCONV_FOLD == 1 and big)) and up.mode == "nearest"
+                    and sf is not None and float(sf) == 2.0
                     and tuple(conv.kernel_size) == (2, 2) and tuple(conv.stride) == (1, 1) and conv.padding == "same"
                     and conv.groups == 1 and tuple(conv.dilation) == (1, 1) and conv.out_channels % 8 == 0
                     and not isinstance(x, RawInput))
