@@ -425,21 +425,30 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       tma_prefetch_desc(&tmA);
       tma_prefetch_desc(&tmB);
       const uint32_t tx_bytes = (uint32_t)p.rows * 128u + (uint32_t)Cfg::kBTileBytes;
-      uint32_t it = 0;
+      // ring slot / phase advance incrementally: `it % nst`, `it / nst` with a run-time ring depth were two integer
+      // divisions per k-block in this one thread (~200 cycles against the 256 cycles of four N <= 128 MMAs)
+      const uint32_t nst = p.dbg_stages ? (uint32_t)p.dbg_stages : (uint32_t)Cfg::kStages;
+      uint32_t ps = 0, pph = 0;
+      const bool flat_tiles = p.tiles_h == 1 && p.tiles_n == 1;  // 1x1 "flat" convolutions: no (w, h, n) split
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-        const int tco = tile / p.tiles_m;
+        const int tco = p.tiles_co == 1 ? 0 : tile / p.tiles_m;
         const int tm = tile - tco * p.tiles_m;
-        const int tw = tm % p.tiles_w;
-        const int th = (tm / p.tiles_w) % p.tiles_h;
-        const int tn = tm / (p.tiles_w * p.tiles_h);
+        int tw = tm, th = 0, tn = 0;
+        if (!flat_tiles) {
+          tw = tm % p.tiles_w;
+          th = (tm / p.tiles_w) % p.tiles_h;
+          tn = tm / (p.tiles_w * p.tiles_h);
+        }
         const int w0 = tw * p.bw * p.sxw, h0 = th * p.bh * p.sxh, n0 = tn * p.bn;
         const int co0 = tco * BN_;
         for (int tap = 0; tap < p.ntaps; ++tap) {
           const int cw = w0 + p.tap_dw[tap], chh = h0 + p.tap_dh[tap], wt = (int)p.tap_w[tap];
-          for (int ch = 0; ch < chunks; ++ch, ++it) {
-            const uint32_t nst = p.dbg_stages ? (uint32_t)p.dbg_stages : (uint32_t)Cfg::kStages;
-            const int s = it % nst;
-            const uint32_t ph = (it / nst) & 1u;
+          for (int ch = 0; ch < chunks; ++ch) {
+            const uint32_t s = ps, ph = pph;
+            if (++ps == nst) {
+              ps = 0;
+              pph ^= 1u;
+            }
             mbar_wait(&empty_bar[s], ph ^ 1u);
             uint8_t* a_s = smem + s * Cfg::kStageBytes;
             if (p.debug & 128) {  // timing experiment: MMA side alone (no loads, garbage operands)
@@ -939,12 +948,25 @@ tapgemm_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                         (int)p.tap_w[tap], 0);
       }
       uint32_t sa = 0, pha = 0, sb = 0, phb = 0;
+      // Tile coordinates advance INCREMENTALLY (tile += gridDim.x = (s_w, s_h, s_n) with carries): five integer divisions
+      // per tile in this single thread cost 13 us of a 200 us launch on the 16-channel 256 x 256 layers
+      // (profiles/r02_narrow_layer_decomposition.txt).  One output-channel block only; otherwise the plain arithmetic.
+      const bool inc = p.tiles_co == 1 && !(p.debug & 8);
+      int tw = 0, th = 0, tn = 0, tco = 0;
+      int s_w = 0, s_h = 0, s_n = 0;
+      if (inc) {
+        const int t0 = (int)blockIdx.x, st = (int)gridDim.x;
+        tw = t0 % p.tiles_w; th = (t0 / p.tiles_w) % p.tiles_h; tn = t0 / (p.tiles_w * p.tiles_h);
+        s_w = st % p.tiles_w; s_h = (st / p.tiles_w) % p.tiles_h; s_n = st / (p.tiles_w * p.tiles_h);
+      }
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-        const int tco = tile / p.tiles_m;
-        const int tm = tile - tco * p.tiles_m;
-        const int tw = tm % p.tiles_w;
-        const int th = (tm / p.tiles_w) % p.tiles_h;
-        const int tn = tm / (p.tiles_w * p.tiles_h);
+        if (!inc && !(p.debug & 8)) {
+          tco = tile / p.tiles_m;
+          const int tm = tile - tco * p.tiles_m;
+          tw = tm % p.tiles_w;
+          th = (tm / p.tiles_w) % p.tiles_h;
+          tn = tm / (p.tiles_w * p.tiles_h);
+        }
         const int h0 = th * p.bh, w0 = tw * p.bw_valid;
         const int co0 = tco * BN_;
         for (int ch = 0; ch < chunks; ++ch) {
@@ -971,6 +993,15 @@ tapgemm_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             }
           }
         }
+        if (inc) {
+          tw += s_w;
+          const int c1 = tw >= p.tiles_w;
+          tw -= c1 ? p.tiles_w : 0;
+          th += s_h + c1;
+          const int c2 = th >= p.tiles_h;
+          th -= c2 ? p.tiles_h : 0;
+          tn += s_n + c2;
+        }
       }
     }
   } else if (warp == 1) {
@@ -988,6 +1019,52 @@ tapgemm_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         tc_fence_after();
       }
       uint32_t sa = 0, pha = 0, sb = 0, phb = 0, t = 0;
+      // FAST PATH (resident weights, one channel chunk, <= 9 taps: every narrow decoder layer): the per-tap descriptor
+      // words live in registers and the tap loop is straight-line code.  The generic loop below spends ~150 cycles of
+      // scalar work per tap (shared-memory look-up, index arithmetic, branches) in the ONE issuing thread — invisible
+      // next to a 128-cycle N = 256 MMA, but 2.5x the 64-cycle floor of the N = 16 / 32 MMAs: on the 16-channel
+      // 256 x 256 layer the loop alone (MMAs removed) took 66 us of the 198 us launch
+      // (profiles/r02_narrow_layer_decomposition.txt).
+      if (p.b_resident && chunks == 1 && p.ntaps <= 9 && !(p.debug & (16 | 256))) {
+        uint32_t ta[9], tb[9];
+#pragma unroll
+        for (int i = 0; i < 9; ++i) {
+          ta[i] = i < p.ntaps ? tap_lo_s[i] : 0u;
+          tb[i] = b_lo0 + (uint32_t)i * kBLo;
+        }
+        const int nk = nk_tail;
+        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++t) {
+          const uint32_t su = t / (uint32_t)kG, sg = t % (uint32_t)kG;
+          const uint32_t as = su & 1u;
+          if (sg == 0) {
+            mbar_wait(&tempty_bar[as], ((su >> 1) & 1u) ^ 1u);
+            tc_fence_after();
+          }
+          const uint32_t tmem_d = tmem_base + as * kSetW + sg * BN_;
+          mbar_wait(&a_full[sa], pha);
+          tc_fence_after();
+          const uint32_t a_lo = a_lo0 + sa * kALo;
+          uint32_t acc = 0;
+#pragma unroll
+          for (int i = 0; i < 9; ++i) {
+            if (i < p.ntaps) {
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                if (k < nk) {
+                  umma_bf16_lohi(tmem_d, a_lo + ta[i] + 2 * k, desc_hi, tb[i] + 2 * k, desc_hi, idesc, acc);
+                  acc = 1u;
+                }
+              }
+            }
+          }
+          umma_commit(&a_empty[sa]);
+          if (++sa == (uint32_t)p.a_stages) {
+            sa = 0;
+            pha ^= 1u;
+          }
+          if (sg == (uint32_t)(kG - 1) || tile + (int)gridDim.x >= p.total_tiles) umma_commit(&tfull_bar[as]);
+        }
+      } else
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++t) {
         // accumulator set `as` (double buffered); MULTI: kG consecutive tiles of this CTA fill one set side by side
         const uint32_t su = t / (uint32_t)kG, sg = t % (uint32_t)kG;
@@ -1003,7 +1080,7 @@ tapgemm_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           tc_fence_after();
           const uint32_t a_lo = a_lo0 + sa * kALo;
           const int nk = (ch + 1 < chunks) ? 4 : nk_tail;
-          for (int tap = 0; tap < p.ntaps; ++tap) {
+          for (int tap = 0; tap < ((p.debug & 16) ? 0 : p.ntaps); ++tap) {  // (timing experiment 16: no tap loop at all)
             uint32_t b_lo;
             if (p.b_resident) {
               b_lo = b_lo0 + (uint32_t)(tap * chunks + ch) * kBLo;
@@ -1147,15 +1224,26 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant__ C
         sub_dh[j] = r - p.pad_t;
         sub_c[j] = ci0 + 64 * cj;
       }
+      // pixel-tile coordinates advance incrementally (tm += splits) instead of three integer divisions per 64-pixel
+      // tile in this one thread: ~500 cycles of scalar work against 512 cycles of MMAs made the PRODUCER the bound of
+      // the narrow-layer wgrads (profiles/r02_narrow_layer_decomposition.txt)
+      int tw = split % p.tiles_w, th = (split / p.tiles_w) % p.tiles_h, tn = split / (p.tiles_w * p.tiles_h);
+      const int s_w = p.splits % p.tiles_w, s_h = (p.splits / p.tiles_w) % p.tiles_h,
+                s_n = p.splits / (p.tiles_w * p.tiles_h);
       for (int it = 0; it < my_tiles; ++it) {
         const int s = it % kWgStages;
         const uint32_t ph = (uint32_t)(it / kWgStages) & 1u;
         mbar_wait(&empty_bar[s], ph ^ 1u);
-        const int tm = split + it * p.splits;
-        const int tw = tm % p.tiles_w;
-        const int th = (tm / p.tiles_w) % p.tiles_h;
-        const int tn = tm / (p.tiles_w * p.tiles_h);
         const int w0 = tw * p.bw, h0 = th * p.bh, n0 = tn * p.bn;
+        {
+          tw += s_w;
+          const int c1 = tw >= p.tiles_w;
+          tw -= c1 ? p.tiles_w : 0;
+          th += s_h + c1;
+          const int c2 = th >= p.tiles_h;
+          th -= c2 ? p.tiles_h : 0;
+          tn += s_n + c2;
+        }
         uint8_t* a_s = smem + s * kWgStageBytes;
         mbar_expect_tx(&full_bar[s], tx_bytes);
         tma_load_4d(a_s, &tmDY, &full_bar[s], co0, w0 * p.dys, h0 * p.dys, n0);
@@ -1734,6 +1822,8 @@ bool plan_halo(TapGemmParams& p, int OW, int OH, int N, int BN, Box* box, int* h
   if (p.b_resident) {
     p.b_stages = p.ntaps * chunks;
     p.a_stages = (res_bytes + 3 * kHaloABytes <= budget) ? 3 : 2;
+    { static int cap = -1; if (cap < 0) { const char* e = getenv("MSP_HALO_ASTAGES"); cap = e ? atoi(e) : 3; }
+      if (cap >= 1 && cap < p.a_stages) p.a_stages = cap; }   // timing experiments: ring depth
   } else {
     p.a_stages = BN >= 256 ? 2 : 3;
     long long nb = (budget - (long long)p.a_stages * kHaloABytes) / bt;
