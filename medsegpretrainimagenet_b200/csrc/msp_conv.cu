@@ -1735,18 +1735,20 @@ struct WMapArgs {  // packed weights [rows][taps][inner] (make_w_map)
 };
 int make_w_map(CUtensorMap* m, const void* base, int inner, int taps, int rows, int box_rows);
 
-// Output-channel tile width of the tap kernel by a makespan estimate.  The natural width (bn_tile_for) minimises the A
-// re-reads, but a launch with fewer tiles than SMs leaves most of the GPU idle: the deep layers of the R50 U-Net at batch
-// 24 have M = 1536 pixels = 12 row tiles, i.e. 24 CTAs of 148 at BN = 256 (profiles/r01_convbench_unet50_b24.txt:
-// 39 us for 5 us of work).  Model per CTA, in cycles: main loop = k-blocks x max(MMA issue, L2 -> SM operand feed at
-// ~74 B/clk), epilogue ~ 24 cycles per accumulator column, the two overlap from the second tile on (TMEM double
-// buffering).  Ties keep the wider tile.  MSP_CONV_BNPOL=0 restores the fixed choice.
+// Output-channel tile width of the tap kernel.  The natural width (bn_tile_for) minimises the A re-reads and the per-tile
+// epilogue overhead, and it is kept whenever it yields at least one tile per SM.  A launch with FEWER tiles than SMs leaves
+// most of the GPU idle: the deep layers of the R50 U-Net at batch 24 have M = 1536 pixels = 12 row tiles, i.e. 24 CTAs of
+// 148 at BN = 256 (profiles/r01_convbench_unet50_b24.txt: 39 us for 5 us of work).  Only then narrower tiles are
+// considered, by a makespan estimate per CTA in cycles: main loop = k-blocks x max(MMA issue, L2 -> SM operand feed at
+// ~74 B/clk), epilogue ~ 24 cycles per accumulator column.  (Applied to well-filled launches as well, the same estimate
+// picked 64-wide tiles for ResNet-50's 1x1 layers at batch 256 and made them up to 2x slower — it underestimates the
+// per-tile cost of narrow tiles — profiles/r02_experiments.txt.)  MSP_CONV_BNPOL=0 restores the fixed choice.
 int pick_bn(int Kout, long long tiles_m, int kblocks) {
   const int natural = bn_tile_for(Kout);
   static int pol = -1;
   if (pol < 0) { const char* e = getenv("MSP_CONV_BNPOL"); pol = e ? atoi(e) : 1; }
-  if (pol == 0 || natural <= 64) return natural;
   const int sms = msp_num_sms();
+  if (pol == 0 || natural <= 64 || tiles_m * msp_cdiv(Kout, natural) >= sms) return natural;
   int best = natural;
   double best_t = 1e30;
   for (int bn = natural; bn >= 64; bn >>= 1) {

@@ -415,9 +415,6 @@ def upconv2x_wgrad(x, dy, weight: torch.Tensor):
         gs = [g for _, _, g in classes]
         _WGRAD_QUEUE.after_unpack(lambda: call("msp_unfold_upconv_wgrad", _p(gs[0]), _p(gs[1]), _p(gs[2]), _p(gs[3]), k,
                                                c_true, _p(dst), int(acc), _stream()), keep=(gs, dst))
-        ready = getattr(weight, "_msp_grad_ready", None)
-        if ready is not None:
-            ready(weight)
         return None
     for d, part, g in classes:
         it = _WGRAD_QUEUE.make_item(d, part, g, c_true, False)
@@ -571,9 +568,6 @@ def wgrad_into_param(d: ConvDesc, x, dy, weight: torch.Tensor, c_true, flops, nb
         g = torch.empty_like(weight, memory_format=torch.contiguous_format)
         weight.grad = g
     _WGRAD_QUEUE.push(d, part, g, c_true, accumulate)
-    ready = getattr(weight, "_msp_grad_ready", None)      # parallel.GradReducer: this bucket member is complete
-    if ready is not None:
-        ready(weight)
     return True
 
 

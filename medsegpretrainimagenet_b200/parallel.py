@@ -76,10 +76,10 @@ class GradReducer:
         for b in self.buckets:
             for p in b.params:
                 self._bucket_of[p] = b
+                # the hook also fires for the convolution weights, whose gradient bypasses autograd's accumulation
+                # (ops._WgradQueue adds it into the bucket view itself and hands autograd None): AccumulateGrad runs its
+                # post hooks for an undefined gradient too (torch 2.11; tests/test_parallel_cpu.py pins that behaviour)
                 self._hooks.append(p.register_post_accumulate_grad_hook(self._on_grad))
-                # convolution weights bypass autograd's accumulation (ops._WgradQueue adds their gradient into the
-                # bucket view itself): they report here instead of through the hook
-                p._msp_grad_ready = self._on_grad
         self.zero_grad()
 
     def _close(self, params):
@@ -167,9 +167,6 @@ class GradReducer:
         for h in self._hooks:
             h.remove()
         self._hooks = []
-        for p in self._bucket_of:
-            if getattr(p, "_msp_grad_ready", None) is not None:
-                p._msp_grad_ready = None
 
 
 def shard_rows(n_global: int, rank: int, world: int):

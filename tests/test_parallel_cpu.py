@@ -109,6 +109,28 @@ def test_grad_reducer_and_statistics_world2_gloo():
     assert dict(out) == {0: True, 1: True}
 
 
+def test_post_accumulate_hook_fires_for_gradients_that_bypass_autograd():
+    """parallel.GradReducer counts a bucket's parameters through post-accumulate-grad hooks; convolution weights hand
+    autograd None (their gradient is written into `param.grad` by ops._WgradQueue).  The hook must still fire for them."""
+    class Bypass(torch.autograd.Function):
+        @staticmethod
+        def forward(ctx, x, w):
+            ctx.w = w
+            return x * w.detach()
+
+        @staticmethod
+        def backward(ctx, g):
+            ctx.w.grad.add_(1.0)            # "written by the kernel"
+            return g, None
+
+    w = torch.nn.Parameter(torch.ones(3))
+    w.grad = torch.zeros(3)
+    fired = []
+    w.register_post_accumulate_grad_hook(lambda p: fired.append(p.grad.clone()))
+    Bypass.apply(torch.ones(3, requires_grad=True), w).sum().backward()
+    assert len(fired) == 1 and torch.equal(fired[0], torch.ones(3))
+
+
 def test_shard_rows():
     from medsegpretrainimagenet_b200.parallel import shard_rows
     assert [shard_rows(48, r, 4) for r in range(4)] == [(0, 12), (12, 24), (24, 36), (36, 48)]
