@@ -607,8 +607,10 @@ def main():
         if not args.no_parity_check:
             # SURVEY.md §4 tier 6: the N-rank step (SyncBN, global Dice, averaged gradients) == the single-device
             # step on the concatenated batch, checked on these very GPUs before anything is timed
-            from medsegpretrainimagenet_b200.selfcheck import n_rank_parity
+            from medsegpretrainimagenet_b200.selfcheck import exchange_parity, n_rank_parity
             parity = n_rank_parity(group, dev)
+            parity["exchange"] = exchange_parity(group, dev)
+            parity["ok"] = bool(parity["ok"] and parity["exchange"]["ok"])
     warm = max(args.warmup, 3)
 
     out = run_workload(args, args.workload, args.steps, warm, world, rank, local, dev, group,

@@ -24,7 +24,9 @@ def _free_port():
 
 
 def test_world_size_1_leg_runs_the_same_code():
-    from medsegpretrainimagenet_b200.selfcheck import n_rank_parity
+    from medsegpretrainimagenet_b200.selfcheck import exchange_parity, n_rank_parity
+    ex = exchange_parity(None)
+    assert ex["world"] == 1 and ex["ok"], ex
     res = n_rank_parity(None)
     assert res["world"] == 1 and res["ok"], res
     assert res["counters_exchange_bit_exact"] and res["loss_rel"] <= 1e-3 and res["grad_cosine"] >= 0.999
@@ -47,5 +49,10 @@ def test_n_ranks_equal_one_rank_on_the_concatenated_batch(exchange):
     assert r.returncode == 0 and lines, (r.returncode, r.stdout[-2000:], r.stderr[-2000:])
     res = json.loads(lines[-1])
     assert res["world"] == world and res["ok"], res
-    assert res["loss_rel"] <= 1e-3 and res["grad_cosine"] >= 0.999 and res["bn_running_rel"] <= 1e-3
-    assert res["counters_exchange_bit_exact"]
+    # the exchanges themselves, teacher-forced one layer deep: tight bounds
+    ex = res["exchange"]
+    assert ex["ok"] and ex["syncbn_y_rms_rel"] <= 1e-4 and ex["syncbn_dx_rms_rel"] <= 1e-4, ex
+    assert ex["reduced_dw_rel"] <= 1e-4 and ex["dice_loss_rel"] <= 1e-6 and ex["dice_grad_rel"] <= 1e-5, ex
+    # the whole step: as close to the single-device step as that step is to itself under another summation order
+    assert res["loss_rel"] <= 1e-3 and res["counters_exchange_bit_exact"]
+    assert res["grad_cosine"] >= min(0.999, res["noise_floor_cosine"] - 0.05), res
