@@ -260,11 +260,14 @@ def step_kernel_table(prof_events, top=14):
     import collections
     import re
     agg = collections.OrderedDict()
+    lib_full = collections.Counter()
     for ev in prof_events:
         if ev.device_type.name != "CUDA":
             continue
         n = ev.name.replace("(anonymous namespace)::", "").replace("<unnamed>::", "")
         n = re.sub(r"^void\s+", "", n)
+        if "at::" in n or "nccl" in n or "Memset" in n or "Memcpy" in n:
+            lib_full[re.sub(r"\s+", " ", n)[:140]] += 1
         m = re.match(r"([\w:]+)(<[^(]*>)?", n)
         key = (m.group(1).split("::")[-1] + (m.group(2) or ""))[:48] if m else n[:48]
         a = agg.setdefault(key, [0, 0.0])
@@ -274,6 +277,7 @@ def step_kernel_table(prof_events, top=14):
     rows = sorted(agg.items(), key=lambda kv: -kv[1][1])
     return {"kernels": sum(v[0] for v in agg.values()), "device_ms": tot,
             "top": [{"kernel": k, "launches": c, "ms": round(ms, 4), "share": round(ms / tot, 4)} for k, (c, ms) in rows[:top]],
+            "library_kernel_names": [[k, c] for k, c in lib_full.most_common(10)],
             "library_kernels_at_or_torch": sum(c for k, (c, ms) in rows if k.startswith(("at::", "vectorized_", "multi_tensor", "elementwise_kernel", "CatArray", "reduce_kernel", "lpnorm")) or "at::native" in k)}
 
 
@@ -452,7 +456,7 @@ def run_workload(args, workload, steps, warm, world, rank, local, dev, group, wi
     if graphed is not None:
         launches = graphed.launches_per_replay * steps
     ms = e0.elapsed_time(e1)
-    clocks = sampler.stop() if (rank == 0 and sample_clocks) else None
+    clocks = None      # the sampler keeps running through the end-to-end timed region below (both are under load)
 
     # ---- timed region 2: end to end through the public API with host batches --------------------
     barrier()
@@ -475,6 +479,22 @@ def run_workload(args, workload, steps, warm, world, rank, local, dev, group, wi
     e3.record()
     barrier()
     ms_e2e = e2.elapsed_time(e3)
+    if sample_clocks:
+        # nvidia-smi needs ~0.1-0.3 s to deliver its first sample: if the two timed regions were shorter than that,
+        # keep the same step running (untimed, every rank the same count) until samples under load exist
+        extra = 0
+        if rank == 0 and len(sampler.lines) < 2 and sampler.proc is not None:
+            extra = int(min(200, max(1, 700.0 / max(ms / steps, 0.05))))
+        if world > 1:
+            te = torch.tensor([extra], dtype=torch.int64, device=dev)
+            dist.broadcast(te, src=0)
+            extra = int(te.item())
+        for _ in range(extra):
+            step(x_dev, y_dev)
+        barrier()
+    if rank == 0 and sample_clocks:
+        clocks = sampler.stop()
+        clocks["sampled_over"] = "both timed regions" + (f" + {extra} extra untimed steps" if extra else "")
 
     # the host -> device copy of one batch by itself (explains e2e when the PCIe link, not the step, is the limit)
     h0, h1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -574,7 +594,7 @@ def main():
                     help="SyncBN statistic exchange (N>1): one-kernel all-reduce over NVLink peer memory, or NCCL")
     ap.add_argument("--optimizer", default="b200", choices=["b200", "torch"],
                     help="gradient norm + optimizer step: this repo's multi-tensor kernels (default) or torch.optim")
-    ap.add_argument("--wgrad-stream", type=int, default=int(os.environ.get("MSP_WGRAD_STREAM", "0")),
+    ap.add_argument("--wgrad-stream", type=int, default=int(os.environ.get("MSP_WGRAD_STREAM", "1")),
                     help="1: weight-gradient kernels on a side stream (graph branch) next to the dgrad / BN-backward chain")
     ap.add_argument("--deterministic", default="yaml", choices=["yaml", "on", "off"],
                     help="fixed-order reductions (torch.use_deterministic_algorithms): as the workload's reference YAML says, or forced")

@@ -218,6 +218,11 @@ int msp_bn_act_bwd_reduce(const msp_bn_act_desc* d, const void* x, const void* y
                           const float* mean, const float* invstd, const float* gamma, const float* beta,
                           const float* sample_scale, float* sum_g, float* sum_gx, float* rows_ws, int ws_rows,
                           void* stream);
+/* First stage only: block b's partial sums in row b of the [ws_rows][2][C] workspace, *rows_used (host int) = the
+ * number of rows written; the caller adds them (msp_p2p_stats_exchange does it inside the SyncBN exchange). */
+int msp_bn_act_bwd_reduce_rows(const msp_bn_act_desc* d, const void* x, const void* y, const void* dy,
+                               const float* mean, const float* invstd, const float* gamma, const float* beta,
+                               const float* sample_scale, float* rows_ws, int ws_rows, int* rows_used, void* stream);
 /* Backward pass 2: dx = gamma*invstd*( s*g - sum_g/M - xhat*sum_gx/M ); M = N*H*W (x world size
  * when the sums were all-reduced: pass the global count).  dres (optional, same shape as the
  * residual tensor) receives g added into the sub-sampled positions (others untouched).          */
@@ -390,6 +395,19 @@ int msp_p2p_close(void* ptr);
 int msp_p2p_free(void* ptr);
 int msp_p2p_allreduce_sum_f32(float* data, int n, int rank, int world, int max_n, void* const* bufs,
                               unsigned* seq, void* stream);
+/* SyncBN statistic exchange in ONE launch (C / 32 blocks): `ws` = this rank's [rows][2][C] per-CTA rows (rows == 1: the
+ * plain [2][C] sums), added in fixed order (reset != 0: zeroed afterwards), optionally stored (local_add != 0: ADDED) to
+ * `local_a` [C] / `local_b` [C] (the rank-local halves = dbeta / dgamma of the backward pass, e.g. straight into
+ * param.grad), exchanged with every peer and added in rank order into
+ * `global_out` [2][C] (may be NULL when only the finalize is wanted).  mean != NULL: msp_bn_finalize's arithmetic on the
+ * global sums with the GLOBAL element count (mean, invstd, running statistics) — functional._BnAct forward.  Replaces
+ * msp_reduce_rows -> msp_p2p_allreduce_sum_f32 -> msp_bn_finalize (and the copies around them).  `ticket` = a second
+ * zero-initialised device uint32 of the communicator; 2 * C <= max_n. */
+int msp_p2p_stats_exchange(float* ws, int rows, int C, float* local_a, float* local_b, int local_add, float* global_out,
+                           int reset, double count,
+                           float eps, float momentum, float* mean, float* invstd, float* running_mean,
+                           float* running_var, int rank, int world, int max_n, void* const* bufs, unsigned* seq,
+                           unsigned* ticket, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Multi-tensor gradient norm / clip and optimizer step (csrc/msp_optim.cu).  Replaces

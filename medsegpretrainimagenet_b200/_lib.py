@@ -73,6 +73,7 @@ SIGNATURES = {
     "msp_reduce_rows": [P, I, I, P, I, P],
     "msp_bn_act_fwd": [C.POINTER(BnActDesc), P, P, P, P, P, P, P, P, P],
     "msp_bn_act_bwd_reduce": [C.POINTER(BnActDesc), P, P, P, P, P, P, P, P, P, P, P, I, P],
+    "msp_bn_act_bwd_reduce_rows": [C.POINTER(BnActDesc), P, P, P, P, P, P, P, P, P, I, C.POINTER(C.c_int), P],
     "msp_bn_act_bwd_apply": [C.POINTER(BnActDesc), P, P, P, P, P, P, P, P, P, P, D, P, P, I, P],
     "msp_bn_eval_prepare": [P, I, F, P, P],
     "msp_maxpool_fwd": [P, I, I, I, I, I, I, I, I, P, P, I, I, I, P],
@@ -122,6 +123,7 @@ SIGNATURES = {
     "msp_p2p_close": [P],
     "msp_p2p_free": [P],
     "msp_p2p_allreduce_sum_f32": [P, I, I, I, I, C.POINTER(C.c_void_p), P, P],
+    "msp_p2p_stats_exchange": [P, I, I, P, P, I, P, I, D, F, F, P, P, P, P, I, I, I, C.POINTER(C.c_void_p), P, P, P],
 }
 _RESTYPES = {"msp_last_error": C.c_char_p, "msp_conv_last_kernel": C.c_char_p, "msp_launch_count": C.c_longlong, "msp_p2p_buffer_bytes": C.c_longlong}
 

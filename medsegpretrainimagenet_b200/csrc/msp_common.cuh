@@ -162,6 +162,38 @@ __device__ __forceinline__ float2 unpack_bf16x2(uint32_t u) {
   return __bfloat1622float2(h);
 }
 
+// ---- fixed-order row sums (second stage of the deterministic reductions) ----
+// out[i] = sum over rows of ws[r][i], the rows added in FIXED order: 8 row groups per column run in parallel (row r in
+// group r % 8, ascending), their partial sums are added in group order.  The second stage of the deterministic reductions.
+constexpr int kRowGroups = 32;
+__device__ __forceinline__ float sum_rows_fixed(float* ws, int rows, long long row_stride, int col, int grp, int reset,
+                                                float (*part)[33]) {
+  // four independent accumulators per thread keep four loads in flight (a single dependent chain made the finalize of a
+  // 148-row workspace a 16 us kernel); the association is fixed by the code, hence run-to-run identical
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+  int r = grp;
+  for (; r + 3 * kRowGroups < rows; r += 4 * kRowGroups) {
+    const float v0 = ws[(long long)r * row_stride + col];
+    const float v1 = ws[(long long)(r + kRowGroups) * row_stride + col];
+    const float v2 = ws[(long long)(r + 2 * kRowGroups) * row_stride + col];
+    const float v3 = ws[(long long)(r + 3 * kRowGroups) * row_stride + col];
+    a0 += v0; a1 += v1; a2 += v2; a3 += v3;
+  }
+  for (; r < rows; r += kRowGroups) a0 += ws[(long long)r * row_stride + col];
+  if (reset)
+    for (int z = grp; z < rows; z += kRowGroups) ws[(long long)z * row_stride + col] = 0.f;
+  part[grp][threadIdx.x & 31] = (a0 + a1) + (a2 + a3);
+  __syncthreads();
+  float tot = 0.f;
+  if (grp == 0) {
+#pragma unroll
+    for (int g = 0; g < kRowGroups; ++g) tot += part[g][threadIdx.x & 31];
+  }
+  __syncthreads();
+  return tot;
+}
+
+
 // ----------------------------------------------------------------------------------------------
 // mbarrier
 // ----------------------------------------------------------------------------------------------

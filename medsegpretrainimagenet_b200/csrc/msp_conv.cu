@@ -2494,7 +2494,7 @@ extern "C" int msp_unpack_wgrad_batched(int n, const msp_unpack_item* items, voi
     L.it[i] = it;
     const long long total = (long long)it.K * it.C_true * (it.rowwin_KH > 0 ? it.rowwin_KH * it.rowwin_KW : it.taps);
     long long nb = (total + 2047) / 2048;
-    nb = nb < 1 ? 1 : (nb > 128 ? 128 : nb);
+    nb = nb < 1 ? 1 : (nb > 1024 ? 1024 : nb);  // (a 128-block cap left the largest layers of a per-bucket flush on 8 warps per SM)
     L.first_block[i] = first;
     first += (int)nb;
   }

@@ -141,35 +141,7 @@ __global__ void nhwc_to_nchw_kernel(const __nv_bfloat16* __restrict__ x, int C, 
 // ---------------------------------------------------------------------------------------------
 // BatchNorm
 // ---------------------------------------------------------------------------------------------
-// out[i] = sum over rows of ws[r][i], the rows added in FIXED order: 8 row groups per column run in parallel (row r in
-// group r % 8, ascending), their partial sums are added in group order.  The second stage of the deterministic reductions.
-constexpr int kRowGroups = 32;
-__device__ __forceinline__ float sum_rows_fixed(float* ws, int rows, long long row_stride, int col, int grp, int reset,
-                                                float (*part)[33]) {
-  // four independent accumulators per thread keep four loads in flight (a single dependent chain made the finalize of a
-  // 148-row workspace a 16 us kernel); the association is fixed by the code, hence run-to-run identical
-  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-  int r = grp;
-  for (; r + 3 * kRowGroups < rows; r += 4 * kRowGroups) {
-    const float v0 = ws[(long long)r * row_stride + col];
-    const float v1 = ws[(long long)(r + kRowGroups) * row_stride + col];
-    const float v2 = ws[(long long)(r + 2 * kRowGroups) * row_stride + col];
-    const float v3 = ws[(long long)(r + 3 * kRowGroups) * row_stride + col];
-    a0 += v0; a1 += v1; a2 += v2; a3 += v3;
-  }
-  for (; r < rows; r += kRowGroups) a0 += ws[(long long)r * row_stride + col];
-  if (reset)
-    for (int z = grp; z < rows; z += kRowGroups) ws[(long long)z * row_stride + col] = 0.f;
-  part[grp][threadIdx.x & 31] = (a0 + a1) + (a2 + a3);
-  __syncthreads();
-  float tot = 0.f;
-  if (grp == 0) {
-#pragma unroll
-    for (int g = 0; g < kRowGroups; ++g) tot += part[g][threadIdx.x & 31];
-  }
-  __syncthreads();
-  return tot;
-}
+// (sum_rows_fixed / kRowGroups: msp_common.cuh — shared with the peer-memory statistic exchange, msp_p2p.cu)
 __global__ void __launch_bounds__(32 * kRowGroups) reduce_rows_kernel(float* ws, int rows, int n, float* out, int reset) {
   __shared__ float part[kRowGroups][33];
   const int col = blockIdx.x * 32 + (threadIdx.x & 31), grp = threadIdx.x >> 5;
@@ -1104,10 +1076,10 @@ static int check_mask_from_x(const msp_bn_act_desc* d, const void* y, const floa
   return MSP_OK;
 }
 
-extern "C" int msp_bn_act_bwd_reduce(const msp_bn_act_desc* d, const void* x, const void* y,
-                                     const void* dy, const float* mean, const float* invstd,
-                                     const float* gamma, const float* beta, const float* sample_scale,
-                                     float* sum_g, float* sum_gx, float* rows_ws, int ws_rows, void* stream) {
+static int bn_bwd_reduce_impl(const msp_bn_act_desc* d, const void* x, const void* y,
+                              const void* dy, const float* mean, const float* invstd,
+                              const float* gamma, const float* beta, const float* sample_scale,
+                              float* sum_g, float* sum_gx, float* rows_ws, int ws_rows, int* rows_used, void* stream) {
   int rc = check_bn_desc(d);
   if (rc) return rc;
   MSP_REQUIRE(x && dy && mean && invstd && sum_g && sum_gx, "bn_act_bwd_reduce: null pointer");
@@ -1140,12 +1112,32 @@ extern "C" int msp_bn_act_bwd_reduce(const msp_bn_act_desc* d, const void* x, co
         sample_scale, sum_g, sum_gx, gamma, beta, rows_ws);
   MSP_CHECK_LAUNCH();
   msp_count_launch(1);
-  if (rows_ws != nullptr) {  // second stage: the blocks' rows in fixed order
+  if (rows_used != nullptr) {  // the caller adds the rows itself (msp_p2p_stats_exchange)
+    *rows_used = grid;
+  } else if (rows_ws != nullptr) {  // second stage: the blocks' rows in fixed order
     reduce_rows_kernel<<<(2 * d->C + 31) / 32, 32 * kRowGroups, 0, ST>>>(rows_ws, grid, 2 * d->C, sum_g, 0);
     MSP_CHECK_LAUNCH();
     msp_count_launch(1);
   }
   return MSP_OK;
+}
+
+extern "C" int msp_bn_act_bwd_reduce(const msp_bn_act_desc* d, const void* x, const void* y,
+                                     const void* dy, const float* mean, const float* invstd,
+                                     const float* gamma, const float* beta, const float* sample_scale,
+                                     float* sum_g, float* sum_gx, float* rows_ws, int ws_rows, void* stream) {
+  return bn_bwd_reduce_impl(d, x, y, dy, mean, invstd, gamma, beta, sample_scale, sum_g, sum_gx, rows_ws, ws_rows, nullptr,
+                            stream);
+}
+
+extern "C" int msp_bn_act_bwd_reduce_rows(const msp_bn_act_desc* d, const void* x, const void* y,
+                                          const void* dy, const float* mean, const float* invstd,
+                                          const float* gamma, const float* beta, const float* sample_scale,
+                                          float* rows_ws, int ws_rows, int* rows_used, void* stream) {
+  MSP_REQUIRE(rows_ws != nullptr && ws_rows >= 1 && rows_used != nullptr, "bn_act_bwd_reduce_rows: needs the row workspace");
+  // first stage only: block b's sums land in row b of the [ws_rows][2][C] workspace; *rows_used rows are valid
+  return bn_bwd_reduce_impl(d, x, y, dy, mean, invstd, gamma, beta, sample_scale, rows_ws, rows_ws + d->C, rows_ws, ws_rows,
+                            rows_used, stream);
 }
 
 extern "C" int msp_bn_act_bwd_apply(const msp_bn_act_desc* d, const void* x, const void* y,

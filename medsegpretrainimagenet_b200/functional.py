@@ -15,6 +15,21 @@ import torch.distributed as dist
 from . import ops
 
 
+def _peer(group):
+    """The peer-memory communicator of `group` when enabled (parallel.enable_peer_allreduce), else None."""
+    from .parallel import peer_allreduce_for
+    return peer_allreduce_for(group)
+
+
+def _grad_sink_ok(p) -> bool:
+    """True when a kernel may add this parameter's gradient into `p.grad` itself (None: nothing to write)."""
+    if p is None:
+        return True
+    g = p.grad
+    return (p.is_leaf and g is not None and g.dtype == torch.float32 and g.is_contiguous() and g.shape == p.shape
+            and g.device == p.device)
+
+
 def _allreduce_sum(t: torch.Tensor, group) -> None:
     """SyncBN / global-Dice exchange: a small NCCL all-reduce, only when a process group is active."""
     from .parallel import allreduce_small_sum_
@@ -84,6 +99,7 @@ class _Conv(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, weight, bias, stride, padding, relu, want_stats, out, link):
         ctx.link = link
+        ctx.set_materialize_grads(False)    # no zero-filled "gradient" of the statistics output per backward pass
         k, c_true, kh, kw = weight.shape
         n, h, w, c8 = x.shape
         ho, wo, pt, pl = ops.conv_out_size(h, w, kh, kw, stride, padding)
@@ -103,6 +119,8 @@ class _Conv(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, dy, _dstats):
+        if dy is None:
+            return (None,) * 9
         kh, kw, stride, pt, pl, c_true, relu, has_bias = ctx.geom
         x, wd, y = ctx.saved_tensors
         if dy.stride(3) != 1:
@@ -137,6 +155,7 @@ class _InputConv(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, weight, bias, stride, padding, relu, want_stats, geom):
+        ctx.set_materialize_grads(False)
         k, c_true, kh, kw = weight.shape
         n, _, h, w = x.shape
         win_px, cpp = geom
@@ -158,6 +177,8 @@ class _InputConv(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, dy, _dstats):
+        if dy is None:
+            return (None,) * 8
         kh, kw, stride, pt, pl, c_true, relu, has_bias, win_px, w_img = ctx.geom
         xw, y = ctx.saved_tensors
         if ctx.needs_input_grad[0]:
@@ -294,12 +315,22 @@ class _BnAct(torch.autograd.Function):
             if group is not None and dist.is_initialized() and dist.get_world_size(group) > 1:
                 # SyncBN: [2C] fp32 sums over NVLink peer memory / NCCL; every rank holds the same per-GPU batch (weak
                 # scaling).  Deterministic mode: the per-CTA rows are first added in fixed order on this rank.
-                if stats.dim() == 3:
-                    stats = ops.reduce_rows(stats, reset=persistent_stats)
-                    persistent_stats = False
-                _allreduce_sum(stats, group)
                 count = count * dist.get_world_size(group)
-            mi = ops.bn_finalize(stats, count, eps, momentum, running_mean, running_var, reset=persistent_stats)
+                par = _peer(group)
+                if par is not None and 2 * c <= par.max_floats:
+                    # ONE launch: rows -> local sums -> sums over the ranks (NVLink peer memory) -> mean / invstd /
+                    # running statistics (csrc/msp_p2p.cu), instead of reduce_rows -> all-reduce -> bn_finalize
+                    mi = torch.empty((2, c), dtype=torch.float32, device=x.device)
+                    par.stats_exchange(stats, stats.shape[0] if stats.dim() == 3 else 1, c, reset=persistent_stats,
+                                       finalize=(count, eps, momentum, mi, running_mean, running_var))
+                else:
+                    if stats.dim() == 3:
+                        stats = ops.reduce_rows(stats, reset=persistent_stats)
+                        persistent_stats = False
+                    _allreduce_sum(stats, group)
+                    mi = ops.bn_finalize(stats, count, eps, momentum, running_mean, running_var, reset=persistent_stats)
+            else:
+                mi = ops.bn_finalize(stats, count, eps, momentum, running_mean, running_var, reset=persistent_stats)
         else:
             mi = ops.bn_eval_stats(running_mean, running_var, eps)
         y = ops.bn_act_fwd(x, mi, gamma.detach() if gamma is not None else None,
@@ -310,6 +341,7 @@ class _BnAct(torch.autograd.Function):
         # BatchNorm -> ReLU without shortcut / sample scale: the backward recomputes the mask from x and never reads y
         mask_from_x = act == ops.ACT_RELU and residual is None and sample_scale is None
         ctx.y_stride = y.stride(2)
+        ctx.params = (gamma, beta)      # the Parameters themselves: the SyncBN path adds their gradients into `.grad`
         ctx.save_for_backward(x, None if mask_from_x else y, mi, gamma, sample_scale, beta if mask_from_x else None)
         return y
 
@@ -323,21 +355,41 @@ class _BnAct(torch.autograd.Function):
             dy = ops.copy_channels(dy if dy.stride(3) == 1 else dy.contiguous(), full)
         gd = gamma.detach() if gamma is not None else None
         bd = beta.detach() if beta is not None else None
-        sums = ops.bn_act_bwd_reduce(x, y, dy, mi, act, sample_scale=sscale, gamma=gd, beta=bd)
         synced = training and group is not None and dist.is_initialized() and dist.get_world_size(group) > 1
-        # dgamma / dbeta are the LOCAL sums (the gradient reducer averages parameters' gradients); only the
-        # SyncBN all-reduce below overwrites `sums` in place, so a copy is needed in that case alone
-        dbeta, dgamma = (sums[0].clone(), sums[1].clone()) if synced else (sums[0], sums[1])
+        par = _peer(group) if synced else None
+        fused = par is not None and 2 * c <= par.max_floats
+        # dgamma / dbeta are the LOCAL sums (the gradient reducer averages parameters' gradients)
+        if fused:
+            # per-block rows -> local sums + sums over the ranks in ONE launch (no reduce_rows, no copies)
+            ws, rows = ops.bn_act_bwd_reduce_rows(x, y, dy, mi, act, sample_scale=sscale, gamma=gd, beta=bd)
+            sums = torch.empty((2, c), dtype=torch.float32, device=x.device)
+            gamma_p, beta_p = ctx.params
+            want_g = gamma_p is not None and ctx.needs_input_grad[2]
+            want_b = beta_p is not None and ctx.needs_input_grad[3]
+            if _grad_sink_ok(gamma_p if want_g else None) and _grad_sink_ok(beta_p if want_b else None):
+                # dgamma / dbeta ADDED straight into param.grad (the reducer's bucket views, accumulated micro-batches):
+                # autograd gets None and launches no accumulate kernel per parameter (ops._WgradQueue's idea)
+                par.stats_exchange(ws, rows, c, global_out=sums, local_add=True,
+                                   local_halves=(beta_p.grad if want_b else None, gamma_p.grad if want_g else None))
+                dbeta = dgamma = None
+            else:
+                local = torch.empty((2, c), dtype=torch.float32, device=x.device)
+                par.stats_exchange(ws, rows, c, local_out=local, global_out=sums)
+                dbeta, dgamma = local[0], local[1]
+        else:
+            sums = ops.bn_act_bwd_reduce(x, y, dy, mi, act, sample_scale=sscale, gamma=gd, beta=bd)
+            # only the SyncBN all-reduce below overwrites `sums` in place, so a copy is needed in that case alone
+            dbeta, dgamma = (sums[0].clone(), sums[1].clone()) if synced else (sums[0], sums[1])
         dbias = None
         if ctx.needs_input_grad[14]:
             # gradient of the producing conv's bias = sum over pixels of dx.  Train mode: BatchNorm
             # removes the mean, so it is exactly zero; eval mode: gamma * invstd * sum(g).  Either way
             # it comes from the fp32 sums instead of a second pass over the bf16 dx.
             if training:
-                dbias = torch.zeros_like(dbeta)
+                dbias = torch.zeros(c, dtype=torch.float32, device=x.device)
             else:
                 dbias = dbeta * mi[1] if gamma is None else dbeta * mi[1] * gamma.detach()
-        if synced:
+        if synced and not fused:
             _allreduce_sum(sums, group)
         elif not training:
             # frozen statistics: dx = gamma * invstd * s * g (no mean / projection terms)
@@ -354,7 +406,7 @@ class _BnAct(torch.autograd.Function):
         if dres is not None and ctx.link is not None:
             ctx.link.dres, dres = dres, None    # consumed by the unit's first convolution (ResidualLink)
         return (dx, None, dgamma if gamma is not None and ctx.needs_input_grad[2] else None,
-                dbeta if ctx.needs_input_grad[3] else None, dres, None, None, None, None, None, None, None,
+                dbeta if dbeta is not None and ctx.needs_input_grad[3] else None, dres, None, None, None, None, None, None, None,
                 None, None, dbias, None, None)
 
 

@@ -728,6 +728,22 @@ def bn_act_bwd_reduce(x, y, dy, mi, act, sample_scale=None, gamma=None, beta=Non
     return sums
 
 
+def bn_act_bwd_reduce_rows(x, y, dy, mi, act, sample_scale=None, gamma=None, beta=None):
+    """First stage of the BatchNorm-backward sums only: ([rows, 2, C] workspace, rows written).  For the SyncBN path, whose
+    exchange kernel adds the rows itself (parallel.PeerAllReduce.stats_exchange) — in either reduction mode: the
+    per-block rows cost nothing extra and spare the atomics' memset."""
+    d = _bn_desc(x, dy if y is None else y, act, None, 1)
+    _chk_nhwc(dy, "bn_act_bwd(dy)")
+    if y is not None:
+        assert dy.stride(2) == y.stride(2), "dy must share the pixel stride of y"
+    rows = 2 * sm_count(x.device)
+    ws = torch.empty((rows, 2, x.shape[3]), dtype=torch.float32, device=x.device)
+    used = C.c_int(0)
+    call("msp_bn_act_bwd_reduce_rows", C.byref(d), _p(x), _p(y), _p(dy), mi[0].data_ptr(), mi[1].data_ptr(),
+         _p(gamma), _p(beta), _p(sample_scale), _p(ws), rows, C.byref(used), _stream())
+    return ws, used.value
+
+
 def bn_act_bwd_apply(x, y, dy, mi, gamma, act, sums, count, residual_like=None, r_stride=1,
                      sample_scale=None, dres=None, dres_accumulate=False, beta=None):
     n, h, w, c = x.shape

@@ -226,6 +226,7 @@ class PeerAllReduce:
             elif err is None:
                 err = RuntimeError("a peer rank could not allocate its communication buffer")
             self.seq = torch.zeros(1, dtype=torch.int32, device=self.device)
+            self.ticket = torch.zeros(1, dtype=torch.int32, device=self.device)   # msp_p2p_stats_exchange's block counter
             torch.cuda.synchronize()
             ok = torch.tensor([0 if err is not None else 1], dtype=torch.int32, device=self.device)
             if self.world > 1:
@@ -241,6 +242,34 @@ class PeerAllReduce:
         _lib.call("msp_p2p_allreduce_sum_f32", t.data_ptr(), t.numel(), self.rank, self.world, self.max_floats,
                   self._ptrs, self.seq.data_ptr(), torch.cuda.current_stream(self.device).cuda_stream)
         return t
+
+    def stats_exchange(self, ws: torch.Tensor, rows: int, c: int, local_out=None, global_out=None, reset: bool = False,
+                       finalize=None, local_halves=None, local_add: bool = False):
+        """SyncBN exchange in one launch (msp_p2p_stats_exchange): `ws` = this rank's [rows, 2, C] per-CTA rows (or the
+        [2, C] sums with rows = 1) -> rank-local sums (`local_out` [2, C], or `local_halves` = two [C] tensors that are
+        written / with `local_add` added to: param.grad) -> sums over the ranks (`global_out`), optionally
+        `finalize` = (global count, eps, momentum, mi [2, C], running_mean, running_var): mean / invstd / running stats."""
+        if ws.dtype != torch.float32 or not ws.is_contiguous() or 2 * c > self.max_floats:
+            raise ValueError(f"PeerAllReduce.stats_exchange: needs contiguous fp32 rows with 2C <= {self.max_floats}")
+        count, eps, mom, mean, invstd, rm, rv = 0.0, 0.0, 0.0, None, None, None, None
+        if finalize is not None:
+            count, eps, mom, mi, rm, rv = finalize
+            mean, invstd = mi[0].data_ptr(), mi[1].data_ptr()
+        la = lb = None
+        if local_out is not None:
+            la, lb = local_out[0].data_ptr(), local_out[1].data_ptr()
+        elif local_halves is not None:
+            for t in local_halves:
+                if t is not None and (t.dtype != torch.float32 or not t.is_contiguous() or t.numel() != c):
+                    raise ValueError("PeerAllReduce.stats_exchange: local halves must be contiguous fp32 [C]")
+            la = None if local_halves[0] is None else local_halves[0].data_ptr()
+            lb = None if local_halves[1] is None else local_halves[1].data_ptr()
+        _lib.call("msp_p2p_stats_exchange", ws.data_ptr(), int(rows), int(c), la, lb, int(local_add),
+                  None if global_out is None else global_out.data_ptr(),
+                  int(reset), float(count), float(eps), float(mom), mean, invstd,
+                  None if rm is None else rm.data_ptr(), None if rv is None else rv.data_ptr(),
+                  self.rank, self.world, self.max_floats, self._ptrs, self.seq.data_ptr(), self.ticket.data_ptr(),
+                  torch.cuda.current_stream(self.device).cuda_stream)
 
     def close(self) -> None:
         torch.cuda.synchronize()

@@ -86,6 +86,53 @@ def test_graphed_step_matches_eager():
         assert abs(a - c) <= 3e-2 * abs(a), losses
 
 
+def test_wgrad_side_stream_changes_no_bit():
+    """ops.set_wgrad_stream: the weight-gradient kernels run on a side stream next to the dgrad / BatchNorm-backward
+    chain (bench.py's default).  Scheduling only: in deterministic mode every gradient is bit-identical to the
+    single-stream step, eagerly launched and replayed from a CUDA graph."""
+    from medsegpretrainimagenet_b200 import ops
+    b = _b200()
+    g = torch.Generator().manual_seed(5)
+    x = torch.rand((4, 1, 64, 64), generator=g).to(DEV)
+    m = (torch.rand((4, 1, 64, 64), generator=g) < 0.3).long().to(DEV)
+    was, warn = torch.are_deterministic_algorithms_enabled(), torch.is_deterministic_algorithms_warn_only_enabled()
+    torch.use_deterministic_algorithms(True, warn_only=True)
+    try:
+        grads = {}
+        for mode in ("plain", "side", "side_graph"):
+            model = _make()
+            crit = b.losses.DiceLoss()
+            params = list(model.parameters())
+            ops.set_wgrad_stream(torch.cuda.Stream() if mode != "plain" else None)
+
+            def step(x_, m_):
+                for p_ in params:
+                    p_.grad = None
+                loss = crit(model(x_), m_)
+                loss.backward()
+                return loss.detach()
+
+            fn = step
+            if mode == "side_graph":
+                bufs = [t for t in model.buffers()]
+                saved = [t.detach().clone() for t in bufs]
+                fn = b.GraphedStep(step, (x, m), models=[model], warmup=2)
+                with torch.no_grad():                      # the capture's warm-up steps moved the running statistics
+                    for t, v in zip(bufs, saved):
+                        t.copy_(v)
+            loss = fn(x, m)
+            torch.cuda.synchronize()
+            grads[mode] = (float(loss), [p_.grad.detach().clone() for p_ in params])
+            ops.set_wgrad_stream(None)
+        for mode in ("side", "side_graph"):
+            assert grads[mode][0] == grads["plain"][0], (mode, grads[mode][0], grads["plain"][0])
+            for a, c in zip(grads[mode][1], grads["plain"][1]):
+                assert torch.equal(a, c), mode
+    finally:
+        ops.set_wgrad_stream(None)
+        torch.use_deterministic_algorithms(was, warn_only=warn)
+
+
 def test_batch_prefetcher_order_and_content():
     b = _b200()
     host = [(torch.full((2, 3, 8, 8), float(i)).pin_memory(), torch.full((2, 1), i, dtype=torch.int64).pin_memory())
@@ -129,6 +176,22 @@ def test_peer_allreduce_world_1_and_multi_gpu():
         par.allreduce_sum_(torch.zeros(2048, device=DEV))          # larger than the communicator's buffer
     with pytest.raises(ValueError):
         par.allreduce_sum_(torch.zeros(8, device=DEV, dtype=torch.float64))
+    # fused SyncBN statistic exchange, world 1: == reduce_rows -> bn_finalize bit for bit; rows reset; counter advances
+    from medsegpretrainimagenet_b200 import ops
+    g = torch.Generator(device=DEV).manual_seed(3)
+    for rows, c in ((1, 64), (148, 16), (296, 256), (37, 504)):
+        ws = torch.randn((rows, 2, c), device=DEV, generator=g).abs_()
+        rm, rv, rm2, rv2 = torch.zeros(c, device=DEV), torch.ones(c, device=DEV), torch.zeros(c, device=DEV), torch.ones(c, device=DEV)
+        loc = ops.reduce_rows(ws.clone())
+        mi_ref = ops.bn_finalize(loc.clone(), 777.0, 1e-5, 0.1, rm, rv)
+        mi, lo, gl, ws2 = torch.empty((2, c), device=DEV), torch.empty((2, c), device=DEV), torch.empty((2, c), device=DEV), ws.clone()
+        seq0 = int(par.seq.item())
+        par.stats_exchange(ws2, rows, c, local_out=lo, global_out=gl, reset=True, finalize=(777.0, 1e-5, 0.1, mi, rm2, rv2))
+        assert torch.equal(mi, mi_ref) and torch.equal(rm, rm2) and torch.equal(rv, rv2)
+        assert torch.equal(lo, loc) and torch.equal(gl, loc) and not ws2.any()
+        assert int(par.seq.item()) == seq0 + 1 and int(par.ticket.item()) == 0
+    with pytest.raises(ValueError):
+        par.stats_exchange(torch.zeros((1, 2, 1024), device=DEV), 1, 1024, global_out=torch.zeros((2, 1024), device=DEV))
     par.close()
     if torch.cuda.device_count() >= 2:
         root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))

@@ -53,6 +53,47 @@ for rep in range(5):
     for i, b in enumerate(bufs):
         exp = sum(float(r + 1 + i + rep) for r in range(world))
         assert torch.all(b == exp), (rep, i, b[:4], exp)
+# fused SyncBN statistic exchange (msp_p2p_stats_exchange): rows -> local sums -> global sums -> mean / invstd / running
+# stats in ONE launch == reduce_rows -> all-reduce -> bn_finalize, bit for bit (same row order, same rank order)
+from medsegpretrainimagenet_b200 import ops
+for it, (rows, c) in enumerate([(1, 64), (148, 16), (296, 256), (148, 2048), (37, 520), (1, 4096)]):
+    ws = torch.randn((rows, 2, c), device=dev, generator=g).abs_()
+    rm, rv = torch.zeros(c, device=dev), torch.ones(c, device=dev)
+    rm2, rv2 = rm.clone(), rv.clone()
+    count = 1000.0 * world
+    loc = ops.reduce_rows(ws.clone())
+    glob = loc.clone()
+    par.allreduce_sum_(glob.view(-1))
+    mi_ref = ops.bn_finalize(glob.clone(), count, 1e-5, 0.1, rm, rv)
+    mi = torch.empty((2, c), device=dev)
+    ws2 = ws.clone()
+    par.stats_exchange(ws2, rows, c, reset=True, finalize=(count, 1e-5, 0.1, mi, rm2, rv2))
+    assert torch.equal(mi, mi_ref) and torch.equal(rm, rm2) and torch.equal(rv, rv2), (rows, c)
+    assert not ws2.any()                                       # reset: the rows are zeroed for the next step
+    lo, gl = torch.empty((2, c), device=dev), torch.empty((2, c), device=dev)
+    par.stats_exchange(ws.clone(), rows, c, local_out=lo, global_out=gl)
+    assert torch.equal(lo, loc) and torch.equal(gl, glob), (rows, c)
+# ... captured in a graph and replayed (the exchange number advances inside the kernels: last block to finish)
+wss = [torch.zeros((148, 2, 256), device=dev) for _ in range(12)]
+outs = [torch.empty((2, 256), device=dev) for _ in range(12)]
+side.wait_stream(torch.cuda.current_stream())
+with torch.cuda.stream(side):
+    for w_, o_ in zip(wss, outs):
+        par.stats_exchange(w_, 148, 256, global_out=o_)
+torch.cuda.current_stream().wait_stream(side)
+torch.cuda.synchronize()
+g2 = torch.cuda.CUDAGraph()
+with torch.cuda.graph(g2):
+    for w_, o_ in zip(wss, outs):
+        par.stats_exchange(w_, 148, 256, global_out=o_)
+for rep in range(5):
+    for i, w_ in enumerate(wss):
+        w_.fill_(float(rank + 1 + i + rep))
+    g2.replay()
+    torch.cuda.synchronize()
+    for i, o_ in enumerate(outs):
+        exp = 148.0 * sum(float(r + 1 + i + rep) for r in range(world))
+        assert torch.all(o_ == exp), (rep, i, o_[0, :4], exp)
 # latency
 def timed(fn, iters=200):
     for _ in range(20):
