@@ -281,6 +281,59 @@ def step_kernel_table(prof_events, top=14):
             "library_kernels_at_or_torch": sum(c for k, (c, ms) in rows if k.startswith(("at::", "vectorized_", "multi_tensor", "elementwise_kernel", "CatArray", "reduce_kernel", "lpnorm")) or "at::native" in k)}
 
 
+def graph_timeline(path, replay, barrier):
+    """Diagnostic (--graph-timeline PREFIX): CUPTI records of ONE replay of the step's CUDA graph — span, time with at
+    least one kernel running, idle gaps and what surrounds the largest ones, per-kernel totals as they run inside the
+    graph (peer exchanges include their real waiting time here, unlike the eagerly enqueued profile)."""
+    import collections
+    import re
+    import torch
+    from torch.profiler import ProfilerActivity, profile
+    barrier()
+    with profile(activities=[ProfilerActivity.CUDA]) as prof:
+        replay()
+        torch.cuda.synchronize()
+    evs = []
+    for ev in prof.events():
+        if ev.device_type.name != "CUDA":
+            continue
+        n = re.sub(r"^void\s+", "", ev.name.replace("(anonymous namespace)::", "").replace("<unnamed>::", ""))
+        m = re.match(r"([\w:]+)(<[^(]*>)?", n)
+        key = (m.group(1).split("::")[-1] + (m.group(2) or ""))[:44] if m else n[:44]
+        evs.append((ev.time_range.start, ev.time_range.end, key))
+    evs.sort()
+    if not evs:
+        return
+    t0, t1 = evs[0][0], max(e[1] for e in evs)
+    busy, cur_end, gaps, last_name = 0.0, evs[0][0], [], "(start)"
+    for a, b, k in evs:             # union of the kernels' intervals (streams overlap)
+        if a > cur_end:
+            gaps.append((a - cur_end, last_name, k))
+            cur_end = a
+        if b > cur_end:
+            busy += b - cur_end
+            cur_end = b
+            last_name = k
+    agg = collections.OrderedDict()
+    for a, b, k in evs:
+        v = agg.setdefault(k, [0, 0.0])
+        v[0] += 1
+        v[1] += b - a
+    with open(path, "w") as f:
+        f.write(f"one graph replay: {len(evs)} kernels, span {(t1 - t0) / 1e3:.3f} ms, some kernel running "
+                f"{busy / 1e3:.3f} ms, idle {(t1 - t0 - busy) / 1e3:.3f} ms in {len(gaps)} gaps, sum of kernel durations "
+                f"{sum(v[1] for v in agg.values()) / 1e3:.3f} ms\n")
+        gsum = collections.Counter()
+        for g, a, b in gaps:
+            gsum[(a, b)] += g
+        f.write("idle time by (kernel before -> kernel after):\n")
+        for (a, b), g in gsum.most_common(25):
+            f.write(f"  {g:9.1f} us  {a} -> {b}\n")
+        f.write("kernels:\n")
+        for k, (c, us) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:40]:
+            f.write(f"  {k:46s} {c:5d} {us / 1e3:9.3f} ms {us / c:9.1f} us\n")
+
+
 def conv_roofline(timeline, ms_per_step, workload_name):
     """`roofline` object: the dominant kernel (largest share of device time among the conv kernel variants, which are
     60 % of the step) with its algorithmic FLOPs or bytes over its CUDA-event time, plus the per-kernel list."""
@@ -512,6 +565,9 @@ def run_workload(args, workload, steps, warm, world, rank, local, dev, group, wi
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms, ms_e2e = t.tolist()
 
+    if args.graph_timeline and graphed is not None:
+        graph_timeline(args.graph_timeline + (f".{workload}.rank{rank}.txt"), lambda: step(x_dev, y_dev), barrier)
+
     # ---- instrumented step: device time of every convolution launch -----------------------------
     # per-kernel device times from the profiler (CUPTI activity records) of one eagerly enqueued step; if the profiler is
     # unavailable, CUDA-event pairs around every conv call (which include the host's launch gaps at small batch)
@@ -598,6 +654,8 @@ def main():
                     help="1: weight-gradient kernels on a side stream (graph branch) next to the dgrad / BN-backward chain")
     ap.add_argument("--deterministic", default="yaml", choices=["yaml", "on", "off"],
                     help="fixed-order reductions (torch.use_deterministic_algorithms): as the workload's reference YAML says, or forced")
+    ap.add_argument("--graph-timeline", default="", help="diagnostic: write PREFIX.<workload>.rank<r>.txt with the CUPTI timeline "
+                                                          "summary of one graph replay")
     ap.add_argument("--no-graph", action="store_true", help="enqueue every step from Python instead of replaying a CUDA graph")
     ap.add_argument("--no-parity-check", action="store_true", help="skip the N-rank == 1-rank pre-check (N > 1)")
     args = ap.parse_args()

@@ -70,6 +70,10 @@ inline cudaError_t msp_launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 bloc
 static inline int msp_cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
 
 int msp_num_sms();
+// narrow-channel convolutions (msp_narrow.cu), dispatched from msp_conv.cu: 0 splits = layer not eligible
+struct msp_conv_desc;
+int msp_narrow_wgrad_splits(const msp_conv_desc* d);
+int msp_narrow_wgrad(const msp_conv_desc* d, const void* x, const void* dy, float* partials, void* stream);
 
 #ifdef __CUDACC__
 // ----------------------------------------------------------------------------------------------

@@ -1559,6 +1559,7 @@ __global__ void unfold_upconv_kernel(const float* __restrict__ g00, const float*
 // cost ~8 us each for microseconds of work: 50 of them per ResNet-50 step, 80 per U-Net step (5 % of the cfg3 step).
 // The item table travels in the kernel's parameter space (no device table to keep in sync with the allocator).
 constexpr int kUnpackMaxItems = 96;
+constexpr int kUnpackWideSplits = 48;   // items with at least this many partials: splits shared by 8 thread groups
 struct UnpackList {
   msp_unpack_item it[kUnpackMaxItems];
   int first_block[kUnpackMaxItems + 1];
@@ -1577,6 +1578,41 @@ __global__ void __launch_bounds__(256) unpack_wgrad_batched_kernel(const __grid_
   float* __restrict__ out = it.dst;
   const int splits = it.splits;
   const long long ss = it.split_stride;
+  if (it.rowwin_KH == 0 && splits >= kUnpackWideSplits) {
+    // many partials of a small gradient (the narrow-channel wgrad kernel: one partial per CTA, ~300 x 9 KB): a serial
+    // loop over the splits is ~300 dependent L2 round trips per thread.  Here 8 thread groups share the splits of 32
+    // elements, 4 independent accumulators each; the association is fixed by the code (deterministic).
+    __shared__ float part[8][33];
+    const int taps = it.taps, C = it.C_true, Cpad = it.Cpad;
+    const long long total = (long long)it.K * C * taps;
+    const int lane = threadIdx.x & 31, grp = threadIdx.x >> 5;
+    for (long long base = blk * 32; base < total; base += nblk * 32) {
+      const long long i = base + lane < total ? base + lane : total - 1;
+      const int tap = (int)(i % taps);
+      const long long t = i / taps;
+      const int c = (int)(t % C), k = (int)(t / C);
+      const float* src = dwp + ((long long)k * taps + tap) * Cpad + c;
+      float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+      int sp = grp;
+      for (; sp + 24 < splits; sp += 32) {
+        a0 += src[(long long)sp * ss];
+        a1 += src[(long long)(sp + 8) * ss];
+        a2 += src[(long long)(sp + 16) * ss];
+        a3 += src[(long long)(sp + 24) * ss];
+      }
+      for (; sp < splits; sp += 8) a0 += src[(long long)sp * ss];
+      part[grp][lane] = (a0 + a1) + (a2 + a3);
+      __syncthreads();
+      if (grp == 0 && base + lane < total) {
+        float acc = 0.f;
+#pragma unroll
+        for (int g = 0; g < 8; ++g) acc += part[g][lane];
+        out[i] = it.accumulate ? out[i] + acc : acc;
+      }
+      __syncthreads();
+    }
+    return;
+  }
   if (it.rowwin_KH > 0) {
     const int KH = it.rowwin_KH, KW = it.rowwin_KW, cpp = it.rowwin_cpp, C = it.C_true;
     const long long total = (long long)it.K * C * KH * KW;
@@ -2246,6 +2282,8 @@ int plan_wgrad(const msp_conv_desc* d, WgradPlan* pl, bool force_2d = false) {
 extern "C" int msp_conv_wgrad_splits(const msp_conv_desc* d) {
   int rc = check_desc(d);
   if (rc) return rc;
+  const int narrow = msp_narrow_wgrad_splits(d);   // 16 / 32-channel full-resolution layers: warp-level MMA kernel
+  if (narrow > 0) return narrow;
   WgradPlan pl;
   rc = plan_wgrad(d, &pl);
   if (rc) return rc;
@@ -2276,6 +2314,11 @@ int wgrad_impl(const msp_conv_desc* d, const void* x, const void* dy, float* dw_
   int rc = check_desc(d);
   if (rc) return rc;
   MSP_REQUIRE(x && dy && dw_partials, "conv_wgrad: null pointer");
+  if (dy_es == 1 && msp_narrow_wgrad_splits(d) > 0) {
+    rc = msp_narrow_wgrad(d, x, dy, dw_partials, stream);
+    g_last_kernel = "narrow_wgrad_kernel";
+    return rc;
+  }
   cudaStream_t st = (cudaStream_t)stream;
   static bool attr_set = false;
   if (!attr_set) {
@@ -2466,6 +2509,14 @@ extern "C" int msp_unpack_wgrad(const msp_conv_desc* d, const float* dw_partials
   WgradPlan pl;
   rc = plan_wgrad(d, &pl);
   if (rc) return rc;
+  const int narrow = msp_narrow_wgrad_splits(d);   // the narrow-channel kernel writes one partial per CTA
+  if (narrow > 0) {
+    msp_unpack_item it;
+    memset(&it, 0, sizeof(it));
+    it.partials = dw_partials; it.dst = dw_oihw; it.split_stride = (long long)d->K * pl.ntaps * pl.Cw;
+    it.splits = narrow; it.K = d->K; it.C_true = C_true; it.taps = pl.ntaps; it.Cpad = pl.Cw;
+    return msp_unpack_wgrad_batched(1, &it, stream);
+  }
   const long long split_stride = (long long)d->K * pl.ntaps * pl.Cw;
   const long long total = (long long)d->K * C_true * d->KH * d->KW;
   const int blocks = (int)((total + 255) / 256 < 4096 ? (total + 255) / 256 : 4096);
@@ -2493,7 +2544,7 @@ extern "C" int msp_unpack_wgrad_batched(int n, const msp_unpack_item* items, voi
                 "unpack_wgrad_batched: bad geometry in item %d", i);
     L.it[i] = it;
     const long long total = (long long)it.K * it.C_true * (it.rowwin_KH > 0 ? it.rowwin_KH * it.rowwin_KW : it.taps);
-    long long nb = (total + 2047) / 2048;
+    long long nb = (it.rowwin_KH == 0 && it.splits >= kUnpackWideSplits) ? (total + 31) / 32 : (total + 2047) / 2048;
     nb = nb < 1 ? 1 : (nb > 1024 ? 1024 : nb);  // (a 128-block cap left the largest layers of a per-bucket flush on 8 warps per SM)
     L.first_block[i] = first;
     first += (int)nb;

@@ -69,6 +69,12 @@ CONV_CASES = [
     (16, 1, 1, 2048, 1000, 1, 1, 0),
     (2, 20, 24, 96, 40, 3, 1, 1),
     (1, 130, 130, 16, 16, 3, 1, 1),
+    # >= 65536 output pixels with 16 / 32 channels: the warp-level MMA kernels of csrc/msp_narrow.cu (ragged tiles, all
+    # four channel combinations, even 'same' filter of the up-conv)
+    (2, 190, 200, 16, 16, 3, 1, 1),
+    (1, 256, 264, 32, 32, 3, 1, 1),
+    (2, 192, 176, 32, 16, 2, 1, "same"),
+    (1, 260, 256, 16, 32, 3, 1, 1),
 ]
 
 
@@ -117,6 +123,28 @@ def test_conv_fprop_dgrad_wgrad(case):
     dw = ops.conv_wgrad(xd, dyd, c, ks, ks, stride, pt, pl)
     # fp32 accumulation over up to N*Ho*Wo pixels, fixed-order fp32 sum of the split-K partials
     _close(dw.cpu(), wt.grad, 2e-3, "wgrad")
+
+
+def test_narrow_wgrad_on_channel_slices_and_last_kernel_name():
+    """csrc/msp_narrow.cu wgrad reading x and dy as channel slices of wider buffers (concat buffers: pixel stride >
+    channels), repeated bit for bit (fixed-order reduction), and reported under its own kernel name."""
+    from medsegpretrainimagenet_b200 import _lib
+    ops = _ops()
+    g = torch.Generator().manual_seed(77)
+    n, h, w, c, k = 2, 200, 190, 16, 32
+    x = _bf(torch.randn((n, c, h, w), generator=g))
+    dy = _bf(torch.randn((n, k, h, w), generator=g))
+    wt = torch.zeros((k, c, 3, 3), requires_grad=True)
+    F.conv2d(x, wt, None, padding=1).backward(dy)
+    xbuf = torch.zeros((n, h, w, 48), dtype=torch.bfloat16, device=DEV)
+    dybuf = torch.zeros((n, h, w, 40), dtype=torch.bfloat16, device=DEV)
+    xbuf[..., 16:32] = _to_nhwc(x)
+    dybuf[..., 8:40] = _to_nhwc(dy)
+    a = ops.conv_wgrad(xbuf[..., 16:32], dybuf[..., 8:40], c, 3, 3, 1, 1, 1)
+    assert _lib.lib.msp_conv_last_kernel().decode() == "narrow_wgrad_kernel"
+    b = ops.conv_wgrad(xbuf[..., 16:32], dybuf[..., 8:40], c, 3, 3, 1, 1, 1)
+    assert torch.equal(a, b)
+    _close(a.cpu(), wt.grad, 2e-3, "narrow wgrad on slices")
 
 
 ROWWIN_CASES = [
