@@ -74,6 +74,12 @@ int msp_num_sms();
 struct msp_conv_desc;
 int msp_narrow_wgrad_splits(const msp_conv_desc* d);
 int msp_narrow_wgrad(const msp_conv_desc* d, const void* x, const void* dy, float* partials, void* stream);
+bool msp_narrow_fprop_ok(const msp_conv_desc* d);
+bool msp_narrow_dgrad_ok(const msp_conv_desc* d);
+int msp_narrow_fprop(const msp_conv_desc* d, const void* x, const void* w_fprop, const float* bias, void* y, float* ch_sum,
+                     float* ch_sqsum, void* stream);
+int msp_narrow_dgrad(const msp_conv_desc* d, const void* dy, const void* w_dgrad, const float* bias, int relu, void* dx,
+                     void* stream);
 
 #ifdef __CUDACC__
 // ----------------------------------------------------------------------------------------------
@@ -478,6 +484,46 @@ __host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N, int a_mn_ma
                                                         int b_mn_major) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn_major << 15) |
          ((uint32_t)b_mn_major << 16) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+// Two columns at once (col and col + pair_off of the same rows: sum and sum of squares of one channel): one pass and one
+// pair of block barriers instead of two — the finalize / exchange kernels are pure latency (a few microseconds, 75-150
+// of them on the critical path of a U-Net step).  Same association as sum_rows_fixed per column.
+__device__ __forceinline__ float2 sum_rows_fixed2(float* ws, int rows, long long row_stride, int col, int pair_off, int grp,
+                                                  int reset, float (*part)[33], float (*part2)[33]) {
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f, b0 = 0.f, b1 = 0.f, b2 = 0.f, b3 = 0.f;
+  int r = grp;
+  for (; r + 3 * kRowGroups < rows; r += 4 * kRowGroups) {
+    const float* q0 = ws + (long long)r * row_stride + col;
+    const float* q1 = q0 + (long long)kRowGroups * row_stride;
+    const float* q2 = q1 + (long long)kRowGroups * row_stride;
+    const float* q3 = q2 + (long long)kRowGroups * row_stride;
+    const float v0 = q0[0], v1 = q1[0], v2 = q2[0], v3 = q3[0];
+    const float w0 = q0[pair_off], w1 = q1[pair_off], w2 = q2[pair_off], w3 = q3[pair_off];
+    a0 += v0; a1 += v1; a2 += v2; a3 += v3;
+    b0 += w0; b1 += w1; b2 += w2; b3 += w3;
+  }
+  for (; r < rows; r += kRowGroups) {
+    a0 += ws[(long long)r * row_stride + col];
+    b0 += ws[(long long)r * row_stride + col + pair_off];
+  }
+  if (reset)
+    for (int z = grp; z < rows; z += kRowGroups) {
+      ws[(long long)z * row_stride + col] = 0.f;
+      ws[(long long)z * row_stride + col + pair_off] = 0.f;
+    }
+  part[grp][threadIdx.x & 31] = (a0 + a1) + (a2 + a3);
+  part2[grp][threadIdx.x & 31] = (b0 + b1) + (b2 + b3);
+  __syncthreads();
+  float2 tot = make_float2(0.f, 0.f);
+  if (grp == 0) {
+#pragma unroll
+    for (int g = 0; g < kRowGroups; ++g) {
+      tot.x += part[g][threadIdx.x & 31];
+      tot.y += part2[g][threadIdx.x & 31];
+    }
+  }
+  __syncthreads();
+  return tot;
 }
 #endif  // __CUDACC__
 

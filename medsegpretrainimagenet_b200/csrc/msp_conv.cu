@@ -2075,6 +2075,11 @@ extern "C" int msp_conv_fprop(const msp_conv_desc* d, const void* x, const void*
   if (rc) return rc;
   MSP_REQUIRE(x && w_fprop && y, "conv_fprop: null pointer");
   MSP_REQUIRE((ch_sum == nullptr) == (ch_sqsum == nullptr), "conv_fprop: need both stat buffers");
+  if (msp_narrow_fprop_ok(d)) {   // 16 / 32-channel full-resolution layers: warp-level MMA kernel (msp_narrow.cu)
+    rc = msp_narrow_fprop(d, x, w_fprop, bias, y, ch_sum, ch_sqsum, stream);
+    g_last_kernel = "narrow_fprop_kernel";
+    return rc;
+  }
   const int taps = d->KH * d->KW;
   TapGemmParams p;
   memset(&p, 0, sizeof(p));
@@ -2168,6 +2173,11 @@ int dgrad_impl(const msp_conv_desc* d, const void* dy, const void* w_dgrad, void
   if (rc) return rc;
   MSP_REQUIRE(dy && w_dgrad && dx, "conv_dgrad: null pointer");
   MSP_REQUIRE(d->win_px == 0, "conv_dgrad: not available in row-window mode (the network input needs no gradient)");
+  if (!accumulate && msp_narrow_dgrad_ok(d)) {
+    rc = msp_narrow_dgrad(d, dy, w_dgrad, bias, relu, dx, stream);
+    g_last_kernel = "narrow_fprop_kernel";
+    return rc;
+  }
   const int taps = d->KH * d->KW;
   const int s = d->stride;
   cudaStream_t st = (cudaStream_t)stream;

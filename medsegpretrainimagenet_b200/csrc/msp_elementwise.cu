@@ -156,11 +156,19 @@ bn_finalize_kernel(float* s1, float* s2, int C, double count, float eps, float m
   pdl_trigger();
   pdl_wait();
   __shared__ float part[kRowGroups][33];
+  __shared__ float part2[kRowGroups][33];
   const int c = blockIdx.x * 32 + (threadIdx.x & 31), grp = threadIdx.x >> 5;
   const int cc = c < C ? c : C - 1;
   const long long stride = 2ll * C;
-  const float t1 = sum_rows_fixed(s1, rows, stride, cc, grp, reset && c < C, part);
-  const float t2 = sum_rows_fixed(s2, rows, stride, cc, grp, reset && c < C, part);
+  float t1, t2;
+  if (s2 == s1 + C) {   // the usual [rows][2][C] layout: both statistics in one pass
+    const float2 t = sum_rows_fixed2(s1, rows, stride, cc, C, grp, reset && c < C, part, part2);
+    t1 = t.x;
+    t2 = t.y;
+  } else {
+    t1 = sum_rows_fixed(s1, rows, stride, cc, grp, reset && c < C, part);
+    t2 = sum_rows_fixed(s2, rows, stride, cc, grp, reset && c < C, part);
+  }
   if (grp != 0 || c >= C) return;
   const double m = (double)t1 / count;
   double var = (double)t2 / count - m * m;

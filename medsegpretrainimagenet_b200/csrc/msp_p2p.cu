@@ -109,6 +109,7 @@ p2p_stats_kernel(float* __restrict__ ws, int rows, int C, float* __restrict__ lo
                  int local_add, float* __restrict__ global_out, int reset, int rank, int world, int max_n, P2PTable tbl, unsigned* __restrict__ seq_ptr,
                  unsigned* __restrict__ ticket, StatsFinalize fin) {
   __shared__ float part[kRowGroups][33];
+  __shared__ float part2[kRowGroups][33];
   __shared__ float mine_s[64];
   __shared__ float tot_s[64];
   __shared__ unsigned seq_s;
@@ -117,8 +118,8 @@ p2p_stats_kernel(float* __restrict__ ws, int rows, int C, float* __restrict__ lo
   const int nvalid = C - c0 < 32 ? C - c0 : 32;
   if (threadIdx.x == 0) seq_s = *reinterpret_cast<volatile unsigned*>(seq_ptr) + 1u;
   const long long stride = 2ll * C;
-  const float t1 = sum_rows_fixed(ws, rows, stride, cc, grp, reset && c < C, part);
-  const float t2 = sum_rows_fixed(ws + C, rows, stride, cc, grp, reset && c < C, part);
+  const float2 t12 = sum_rows_fixed2(ws, rows, stride, cc, C, grp, reset && c < C, part, part2);
+  const float t1 = t12.x, t2 = t12.y;
   if (grp == 0) {
     mine_s[lane] = t1;
     mine_s[32 + lane] = t2;

@@ -461,7 +461,7 @@ def deterministic_mode():
 
 
 @pytest.mark.parametrize("cin, cout, ks, hw, n", [(64, 64, 3, 28, 16), (256, 512, 1, 14, 32), (16, 16, 3, 64, 4),
-                                                  (32, 32, 3, 48, 3)])
+                                                  (32, 32, 3, 48, 3), (16, 16, 3, 136, 4), (32, 16, 3, 150, 3)])
 def test_deterministic_statistics_rows_match_the_atomics_and_repeat_exactly(deterministic_mode, cin, cout, ks, hw, n):
     """Conv epilogue statistics as per-CTA rows [SMs, 2, K] added in fixed order == the float-atomics accumulators
     (to fp32 rounding), and two runs give the same BITS; the narrow layers go through the multi-tile epilogue."""
