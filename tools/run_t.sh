@@ -1,6 +1,7 @@
-mkdir -p gpurun_out/r02t
-timeout 900 python -m pytest tests/ -x -q -m gpu > gpurun_out/r02t/tests.log 2>&1
-timeout 600 python tools/bench_conv.py --model unet50 --batch 24 --only d4_ > gpurun_out/r02t/conv.txt 2>&1
-timeout 600 python tools/bench_conv.py --model unet50 --batch 24 --only d3_ >> gpurun_out/r02t/conv.txt 2>&1
-timeout 600 python bench.py --steps 20 --warmup 3 --no-cpu-baseline > gpurun_out/r02t/bench.log 2> gpurun_out/r02t/bench.err
+mkdir -p gpurun_out/r02u
+python bench.py --workload cfg2 --steps 1 --warmup 3 --no-graph --no-cpu-baseline --secondary none > gpurun_out/r02u/plain_cfg2.log 2>&1 && \
+ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none -c 3200 --csv --log-file gpurun_out/r02u/ncu_traffic_cfg2.csv python bench.py --workload cfg2 --steps 1 --warmup 3 --no-graph --no-cpu-baseline --secondary none > gpurun_out/r02u/ncu_cfg2.log 2>&1
+python bench.py --workload cfg3 --steps 1 --warmup 3 --no-graph --no-cpu-baseline --secondary none > gpurun_out/r02u/plain_cfg3.log 2>&1 && \
+ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none -c 4400 --csv --log-file gpurun_out/r02u/ncu_traffic_cfg3.csv python bench.py --workload cfg3 --steps 1 --warmup 3 --no-graph --no-cpu-baseline --secondary none > gpurun_out/r02u/ncu_cfg3.log 2>&1
+timeout 600 python bench.py --steps 20 --warmup 3 --no-cpu-baseline > gpurun_out/r02u/bench.log 2> gpurun_out/r02u/bench.err
 true
