@@ -129,6 +129,22 @@ class GradReducer:
         op = dist.ReduceOp.AVG if (self.average and dist.get_backend(self.group) == "nccl") else dist.ReduceOp.SUM
         b.work = dist.all_reduce(b.flat, op=op, group=self.group, async_op=True)
 
+    def _flush_and_launch(self, b) -> None:
+        """The bucket's queued weight-gradient unpacks, then its all-reduce.  With the wgrad side stream (ops.
+        set_wgrad_stream) both go ON that stream — it first waits for the main stream (the bucket's BatchNorm / bias
+        gradients), then carries the unpack behind the wgrad kernels it depends on and hands the bucket to NCCL, while
+        the main stream's dgrad / BatchNorm-backward chain runs on without waiting for any of it."""
+        from . import ops
+        side = ops.wgrad_stream() if b.flat.is_cuda else None
+        if side is None:
+            ops.flush_wgrad()
+            self._launch(b)
+            return
+        side.wait_stream(torch.cuda.current_stream())
+        ops.flush_wgrad(on_side=True)
+        with torch.cuda.stream(side):
+            self._launch(b)
+
     def _on_grad(self, p) -> None:
         if p.grad is None or p.grad.data_ptr() != self._grad_ptr[p]:
             raise RuntimeError("GradReducer: param.grad no longer aliases the reduction bucket (was the gradient reset "
@@ -142,9 +158,7 @@ class GradReducer:
                                "call finish() after the last one")
         b.pending -= 1
         if b.pending == 0 and self.world > 1:
-            from . import ops
-            ops.flush_wgrad()           # the queued weight-gradient unpacks of this bucket's convolutions
-            self._launch(b)
+            self._flush_and_launch(b)   # the queued weight-gradient unpacks of this bucket's convolutions, then NCCL
 
     def finish(self) -> None:
         """Call after the (last) backward: launches every bucket that is not in flight yet (parameters without a
@@ -152,10 +166,11 @@ class GradReducer:
         if self.world == 1:
             return
         from . import ops
-        ops.flush_wgrad()
+        ops.flush_wgrad()               # joins the wgrad side stream when anything is still queued
         for b in self.buckets:
             if b.work is None:
                 self._launch(b)
+        ops.join_wgrad_stream()         # (a CUDA-graph capture must see every forked stream joined again)
         for b in self.buckets:
             b.work.wait()
             if self.average and dist.get_backend(self.group) != "nccl":
