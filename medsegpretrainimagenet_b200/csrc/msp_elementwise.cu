@@ -616,6 +616,129 @@ maxpool_bwd_fixed_kernel(const uint8_t* __restrict__ idx, const __nv_bfloat16* _
     }
   }
 }
+// ---- 3x3 / stride 2 / pad 1 (the ResNet stem's pool, classification/models.py:49), instruction-lean versions ----
+// ncu on the fixed-geometry kernels above at 256 x 112 x 112 x 64 (profiles/r02_maxpool.txt): DRAM traffic = algorithmic,
+// DRAM 30 % / 17 % of peak, issue slots 62 % / 67 % busy, 720 / 327 instructions per 8-channel item: INSTRUCTION bound
+// (fp32 compare + select per channel and tap; four candidate windows per input pixel, 2.25 of them real).
+// Forward: compare / select on packed bf16 pairs (mask from __hgt2_mask | NaN, value and tap index merged with the mask:
+// 5 instructions per pair and tap instead of ~16); work items flattened over the whole tensor.
+__device__ __forceinline__ uint32_t bf2_gt_or_nan_mask(uint32_t v, uint32_t best) {
+  const __nv_bfloat162 a = *reinterpret_cast<const __nv_bfloat162*>(&v), b = *reinterpret_cast<const __nv_bfloat162*>(&best);
+  return __hgt2_mask(a, b) | __hneu2_mask(a, a);   // v > best (ordered: a NaN best stays), or v is NaN (torch: NaN wins)
+}
+__global__ void __launch_bounds__(256)
+maxpool3s2_fwd_kernel(const __nv_bfloat16* __restrict__ x, int N, int H, int W, int C, int x_cs,
+                      __nv_bfloat16* __restrict__ y, uint8_t* __restrict__ idx, int Ho, int Wo, int y_cs) {
+  const uint32_t V = (uint32_t)C >> 3;
+  const long long total = (long long)N * Ho * Wo * V;
+  constexpr uint32_t kNegInf2 = 0xFF80FF80u;   // bf16 -inf pair: never wins, out-of-image taps
+  for (long long it = (long long)blockIdx.x * blockDim.x + threadIdx.x; it < total; it += (long long)gridDim.x * blockDim.x) {
+    const uint32_t cg = (uint32_t)(it % V);
+    const long long pix = it / V;
+    const int wo = (int)(pix % Wo);
+    const long long rowi = pix / Wo;
+    const int ho = (int)(rowi % Ho), n = (int)(rowi / Ho);
+    const int h_lo = ho * 2 - 1, w_lo = wo * 2 - 1;
+    const __nv_bfloat16* xn = x + ((long long)n * H * W) * x_cs + cg * 8;
+    uint4 raw[9];
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+      for (int q = 0; q < 3; ++q) {
+        const int h = h_lo + r, w = w_lo + q;
+        const bool ok = (unsigned)h < (unsigned)H && (unsigned)w < (unsigned)W;
+        raw[r * 3 + q] = ok ? *reinterpret_cast<const uint4*>(xn + ((long long)h * W + w) * x_cs)
+                            : make_uint4(kNegInf2, kNegInf2, kNegInf2, kNegInf2);
+      }
+    uint32_t best[4] = {kNegInf2, kNegInf2, kNegInf2, kNegInf2}, bi[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+    for (int e = 0; e < 9; ++e) {
+      const uint32_t v[4] = {raw[e].x, raw[e].y, raw[e].z, raw[e].w};
+      const uint32_t ee = (uint32_t)e * 0x00010001u;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const uint32_t m = bf2_gt_or_nan_mask(v[j], best[j]);
+        best[j] = (v[j] & m) | (best[j] & ~m);
+        bi[j] = (ee & m) | (bi[j] & ~m);
+      }
+    }
+    const long long op = pix;
+    *reinterpret_cast<uint4*>(y + op * y_cs + cg * 8) = make_uint4(best[0], best[1], best[2], best[3]);
+    if (idx) {
+      uint2 u;
+      u.x = __byte_perm(bi[0], bi[1], 0x6420);   // tap indices of channels 0..3, one byte each
+      u.y = __byte_perm(bi[2], bi[3], 0x6420);
+      *reinterpret_cast<uint2*>(idx + op * C + cg * 8) = u;
+    }
+  }
+}
+// Backward: one thread owns a 2 x 2 block of INPUT pixels (rows 2i, 2i+1; columns 2j, 2j+1) x 8 channels.  Only the
+// windows (i, i+1) x (j, j+1) can have their arg-max there: their 4 index / gradient vectors are loaded once and serve
+// the block's 9 real (pixel, window) pairs — instead of 4 candidate windows loaded and tested per pixel (16 per block).
+__global__ void __launch_bounds__(256)
+maxpool3s2_bwd_kernel(const uint8_t* __restrict__ idx, const __nv_bfloat16* __restrict__ dy, int N, int H, int W, int C,
+                      int Ho, int Wo, int dy_cs, __nv_bfloat16* __restrict__ dx, int dx_cs, int acc) {
+  const uint32_t V = (uint32_t)C >> 3;
+  const int Hb = (H + 1) >> 1, Wb = (W + 1) >> 1;
+  const long long total = (long long)N * Hb * Wb * V;
+  for (long long it = (long long)blockIdx.x * blockDim.x + threadIdx.x; it < total; it += (long long)gridDim.x * blockDim.x) {
+    const uint32_t cg = (uint32_t)(it % V);
+    const long long blk = it / V;
+    const int j = (int)(blk % Wb);
+    const long long rowi = blk / Wb;
+    const int i = (int)(rowi % Hb), n = (int)(rowi / Hb);
+    uint2 iu[4];
+    uint4 gu[4];
+#pragma unroll
+    for (int di = 0; di < 2; ++di)
+#pragma unroll
+      for (int dj = 0; dj < 2; ++dj) {
+        const int ho = i + di, wo = j + dj;
+        const bool ok = ho < Ho && wo < Wo;
+        const long long op = ((long long)n * Ho + ho) * Wo + wo;
+        iu[di * 2 + dj] = ok ? *reinterpret_cast<const uint2*>(idx + op * C + cg * 8) : make_uint2(0xFFFFFFFFu, 0xFFFFFFFFu);
+        gu[di * 2 + dj] = ok ? *reinterpret_cast<const uint4*>(dy + op * dy_cs + cg * 8) : make_uint4(0u, 0u, 0u, 0u);
+      }
+#pragma unroll
+    for (int a = 0; a < 2; ++a)
+#pragma unroll
+      for (int b = 0; b < 2; ++b) {
+        const int h = 2 * i + a, w = 2 * j + b;
+        if (h >= H || w >= W) continue;
+        __nv_bfloat16* o = dx + (((long long)n * H + h) * W + w) * dx_cs + cg * 8;
+        float s8[8];
+        if (acc) {
+          const F8 old = load_bf16x8(o);
+#pragma unroll
+          for (int c = 0; c < 8; ++c) s8[c] = old.v[c];
+        } else {
+#pragma unroll
+          for (int c = 0; c < 8; ++c) s8[c] = 0.f;
+        }
+        // pixel row 2i + a lies in window row i at filter row a + 1, and (a = 1 only) in window row i + 1 at filter row 0
+#pragma unroll
+        for (int di = 0; di < 2; ++di)
+#pragma unroll
+          for (int dj = 0; dj < 2; ++dj) {
+            const int r = a + 1 - 2 * di, q = b + 1 - 2 * dj;
+            if (r < 0 || q < 0) continue;              // compile-time after unrolling
+            const int wdw = di * 2 + dj;
+            const uint32_t me = (uint32_t)(r * 3 + q) * 0x01010101u;
+            const uint32_t m0 = __vcmpeq4(iu[wdw].x, me), m1 = __vcmpeq4(iu[wdw].y, me);   // 0xFF where this pixel won
+            const uint32_t g01 = gu[wdw].x & __byte_perm(m0, 0u, 0x1100), g23 = gu[wdw].y & __byte_perm(m0, 0u, 0x3322);
+            const uint32_t g45 = gu[wdw].z & __byte_perm(m1, 0u, 0x1100), g67 = gu[wdw].w & __byte_perm(m1, 0u, 0x3322);
+            s8[0] += __uint_as_float(g01 << 16); s8[1] += __uint_as_float(g01 & 0xFFFF0000u);
+            s8[2] += __uint_as_float(g23 << 16); s8[3] += __uint_as_float(g23 & 0xFFFF0000u);
+            s8[4] += __uint_as_float(g45 << 16); s8[5] += __uint_as_float(g45 & 0xFFFF0000u);
+            s8[6] += __uint_as_float(g67 << 16); s8[7] += __uint_as_float(g67 & 0xFFFF0000u);
+          }
+        F8 r8;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) r8.v[c] = s8[c];
+        store_bf16x8(o, r8);
+      }
+  }
+}
 // gather formulation (no atomics): every INPUT pixel sums dy of the windows whose arg-max it is; one block-iteration
 // per input row (n, h)
 __global__ void __launch_bounds__(256)
@@ -1185,7 +1308,7 @@ extern "C" int msp_maxpool_fwd(const void* x, int N, int H, int W, int C, int x_
   REQ_C8(C, y_cs, "maxpool_fwd(y)");
   MSP_REQUIRE(x && y && k >= 1 && k <= 15 && stride >= 1 && pad >= 0, "maxpool_fwd: bad arguments");
   if (k == 3 && stride == 2 && pad == 1)
-    maxpool_fwd_fixed_kernel<3, 2, 1><<<resident_grid(maxpool_fwd_fixed_kernel<3, 2, 1>, 256, 0, (long long)N * Ho, 1), 256, 0, ST>>>(
+    maxpool3s2_fwd_kernel<<<resident_grid(maxpool3s2_fwd_kernel, 256, 0, (long long)N * Ho * Wo * (C / 8), 256), 256, 0, ST>>>(
         (const __nv_bfloat16*)x, N, H, W, C, x_cs, (__nv_bfloat16*)y, (uint8_t*)idx, Ho, Wo, y_cs);
   else if (k == 2 && stride == 2 && pad == 0)
     maxpool_fwd_fixed_kernel<2, 2, 0><<<resident_grid(maxpool_fwd_fixed_kernel<2, 2, 0>, 256, 0, (long long)N * Ho, 1), 256, 0, ST>>>(
@@ -1203,7 +1326,11 @@ extern "C" int msp_maxpool_bwd(const void* idx, const void* dy, int N, int H, in
   REQ_C8(C, dy_cs, "maxpool_bwd(dy)");
   REQ_C8(C, dx_cs, "maxpool_bwd(dx)");
   MSP_REQUIRE(idx && dy && dx, "maxpool_bwd: null pointer");
-  if (k == 3 && stride == 2 && pad == 1)
+  if (k == 3 && stride == 2 && pad == 1 && Ho == (H - 1) / 2 + 1 && Wo == (W - 1) / 2 + 1)
+    maxpool3s2_bwd_kernel<<<resident_grid(maxpool3s2_bwd_kernel, 256, 0,
+                                          (long long)N * ((H + 1) / 2) * ((W + 1) / 2) * (C / 8), 256), 256, 0, ST>>>(
+        (const uint8_t*)idx, (const __nv_bfloat16*)dy, N, H, W, C, Ho, Wo, dy_cs, (__nv_bfloat16*)dx, dx_cs, accumulate);
+  else if (k == 3 && stride == 2 && pad == 1)
     maxpool_bwd_fixed_kernel<3, 2, 1><<<resident_grid(maxpool_bwd_fixed_kernel<3, 2, 1>, 256, 0, (long long)N * H, 1), 256, 0, ST>>>(
         (const uint8_t*)idx, (const __nv_bfloat16*)dy, N, H, W, C, Ho, Wo, dy_cs, (__nv_bfloat16*)dx, dx_cs, accumulate);
   else if (k == 2 && stride == 2 && pad == 0)
