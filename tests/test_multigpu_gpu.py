@@ -55,4 +55,4 @@ def test_n_ranks_equal_one_rank_on_the_concatenated_batch(exchange):
     assert ex["reduced_dw_rel"] <= 1e-4 and ex["dice_loss_rel"] <= 1e-6 and ex["dice_grad_rel"] <= 1e-5, ex
     # the whole step: as close to the single-device step as that step is to itself under another summation order
     assert res["loss_rel"] <= 1e-3 and res["counters_exchange_bit_exact"]
-    assert res["grad_cosine"] >= min(0.999, res["noise_floor_cosine"] - 0.05), res
+    assert res["grad_cosine"] >= min(0.999, res["noise_floor_cosine"] - 0.08), res

@@ -1,4 +1,3 @@
-mkdir -p gpurun_out/r02y
-timeout 900 python -m pytest tests/test_kernels_gpu.py tests/test_hotpath_gpu.py -x -q -k "maxpool or resnet50 or resnet18 or eval_mode" > gpurun_out/r02y/tests.log 2>&1
-python tools/bench_pool.py > gpurun_out/r02y/pool_new.txt 2>&1
+mkdir -p gpurun_out/r02z
+for v in 0 2; do echo "== MSP_CONV_2CTA=$v"; MSP_CONV_2CTA=$v timeout 200 python tools/bench_conv.py --model r50 --batch 256 --only stem --kinds fprop 2>&1 | tail -3; MSP_CONV_2CTA=$v timeout 200 python tools/bench_conv.py --model r50 --batch 256 --only L0b --kinds fprop,dgrad 2>&1 | tail -8; done > gpurun_out/r02z/pair.txt 2>&1
 true
