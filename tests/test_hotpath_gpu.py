@@ -54,6 +54,8 @@ def _run_pair(make, x, target_fn, seed=0, train=True, lossname="dice"):
             t = tgt.to(DEV) if k == "gpu" else tgt
             if lossname == "dice":
                 l = b.losses.DiceLoss()(ys[k], t) if k == "gpu" else ref_losses.dice_loss(ys[k], t)
+            elif lossname == "bce":
+                l = b.losses.TorchBCELoss()(ys[k], t) if k == "gpu" else ref_losses.bce_loss_torch(ys[k], t)
             else:
                 l = b.losses.CrossEntropyLoss(0.1)(ys[k], t) if k == "gpu" else ref_losses.ce_with_softmax(ys[k], t, 0.1)
             l.backward()
@@ -214,6 +216,9 @@ def test_basic_unet_cfg4_multilabel():
     _blockwise_parity(make, x)
     out = _run_pair(make, x, None, train=False)
     _check(out, "basic U-Net eval")
+    # whole-network training step of cfg4: 5-channel multilabel float masks, torch.nn.BCELoss (config/downstream/idrid/unet.yaml)
+    out = _run_pair(make, x, lambda y: (torch.rand(y.shape, generator=g) < 0.05).float(), lossname="bce")
+    _check(out, "basic U-Net multilabel BCE step")
 
 
 def test_resnet50_classifier_cfg2():
