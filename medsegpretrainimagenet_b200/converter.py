@@ -39,6 +39,8 @@ class UnsupportedModule(NotImplementedError):
 # up-conv is a 15-30 us launch for a few us of work and the fold measured 3 % SLOWER over the step (2 033 vs 2 094 img/s,
 # profiles/r02_experiments.txt), on the 1024^2 basic U-Net the up-convs are the largest tensors of the network.
 _UPCONV_FOLD = int(os.environ.get("MSP_UPCONV_FOLD", "1"))
+_BRANCH_STREAMS = os.environ.get("MSP_BRANCH_STREAMS", "1") != "0"
+_BRANCH_MAX_PIXELS = int(os.environ.get("MSP_BRANCH_MAX_PIXELS", "1000000000000"))   # (sweep: always on is best)
 _UPCONV_FOLD_MIN_FLOPS = 1.5e11      # unfused forward FLOPs (2 * 4NHW * K * 4C) above which the fold is used in mode 1
 
 
@@ -53,6 +55,23 @@ class ExecContext:
         self._replay = []
         self.counters = []       # num_batches_tracked buffers touched by the running forward
         self.pack_cache = ops.WeightPackCache()   # bf16 operand copies of the conv weights, one repack kernel per step
+        self._branch = {}        # device index -> (stream, stream) for independent decoder chains
+
+    def branch_streams(self, device, pixels: int):
+        """Two side streams for the independent chains of an attention decoder level (run_unet_decoder), or None:
+        off with MSP_BRANCH_STREAMS=0, on the CPU, while bench.py's per-kernel instrumentation attributes device time
+        to convolution calls in stream order, and — single process — on levels large enough to fill the GPU by
+        themselves (`pixels` = N * H * W of the level)."""
+        if not _BRANCH_STREAMS or torch.device(device).type != "cuda" or ops.conv_timeline_active():
+            return None
+        if self.group is None and pixels > _BRANCH_MAX_PIXELS:
+            return None
+        key = torch.device(device).index
+        st = self._branch.get(key)
+        if st is None:
+            st = (torch.cuda.Stream(device=device), torch.cuda.Stream(device=device))
+            self._branch[key] = st
+        return st
 
     def begin_forward(self):
         self.pack_cache.begin_step()
@@ -190,10 +209,12 @@ def _is_noop(m) -> bool:
 
 
 def conv_bn_act(ctx: ExecContext, x, conv: nn.Conv2d, bn: Optional[nn.BatchNorm2d] = None, act: int = 0,
-                residual=None, r_stride: int = 1, sample_scale=None, link_in=None, link_out=None, out=None):
+                residual=None, r_stride: int = 1, sample_scale=None, link_in=None, link_out=None, out=None,
+                conv_stream=None):
     """Conv2d [-> BatchNorm2d] [-> ReLU | Sigmoid], with optional fused residual / per-sample scale.
     `out` (conv without BatchNorm only): channel slice of a wider NHWC buffer the epilogue writes into (zero-copy
-    torch.cat)."""
+    torch.cat).  `conv_stream`: a side stream that already waits for x; the convolution is issued there and the current
+    stream joins it before the BatchNorm (the statistics exchange of a data-parallel run stays on the current stream)."""
     _check_conv(conv)
     stride, padding = conv.stride[0], _pad_of(conv)
     if isinstance(x, RawInput):
@@ -214,8 +235,16 @@ def conv_bn_act(ctx: ExecContext, x, conv: nn.Conv2d, bn: Optional[nn.BatchNorm2
     training = bn.training or bn.running_mean is None
     # the conv adds its bias in the epilogue, but the bias *gradient* is produced by the BatchNorm node
     bias = conv.bias.detach() if conv.bias is not None else None
-    y, stats = conv2d(x, conv.weight, bias, stride, padding, relu=False,
-                      want_stats=ctx.stats_for(bn) if training else False)
+    if conv_stream is not None:
+        cur = torch.cuda.current_stream()
+        with torch.cuda.stream(conv_stream):
+            y, stats = conv2d(x, conv.weight, bias, stride, padding, relu=False,
+                              want_stats=ctx.stats_for(bn) if training else False)
+        cur.wait_stream(conv_stream)
+        y.record_stream(cur)            # allocated on the side stream's pool, consumed here
+    else:
+        y, stats = conv2d(x, conv.weight, bias, stride, padding, relu=False,
+                          want_stats=ctx.stats_for(bn) if training else False)
     return Fn.bn_act(y, stats, bn, act=act, residual=residual, r_stride=r_stride,
                      sample_scale=sample_scale, group=ctx.group, conv_bias=conv.bias, persistent_stats=True,
                      counters=ctx.counters, link=link_out)
@@ -407,8 +436,13 @@ def _upconv_out_channels(m) -> Optional[int]:
     return None
 
 
-def run_attention_block(ctx, m, x, x_up, skip, buf=None):
-    """AttentionBlock.forward (blocks.py:620-628).  `buf`: the concat buffer whose leading slice already IS x_up."""
+def run_attention_block(ctx, m, x, x_up, skip, buf=None, ws_stream=None, up_stream=None):
+    """AttentionBlock.forward (blocks.py:620-628).  `buf`: the concat buffer whose leading slice already IS x_up.
+    `ws_stream` / `up_stream` (ExecContext.branch_streams): the W_s convolution of the skip tensor is issued on the first,
+    the up-convolution that produces x_up is still running on the second — the three chains of a decoder level
+    (up-conv; gating signal g -> W_g; W_s) are independent until the gate and fill the GPU side by side at small batch."""
+    if ws_stream is not None:
+        ws_stream.wait_stream(torch.cuda.current_stream())      # skip is complete
     g = run_module(ctx, _unwrap(m.gs_block), x)
     wg_conv, wg_bn = list(m.W_g.children())
     ws_conv, ws_bn = list(m.W_s.children())
@@ -417,8 +451,10 @@ def run_attention_block(ctx, m, x, x_up, skip, buf=None):
         raise UnsupportedModule(f"attention psi {m.psi}")
     g1 = conv_bn_act(ctx, g, wg_conv, wg_bn, ops.ACT_NONE)
     # relu(BN(W_s(skip)) + g1): the add + ReLU ride on the BN-apply kernel
-    p = conv_bn_act(ctx, skip, ws_conv, ws_bn, ops.ACT_RELU, residual=g1)
+    p = conv_bn_act(ctx, skip, ws_conv, ws_bn, ops.ACT_RELU, residual=g1, conv_stream=ws_stream)
     p = conv_bn_act(ctx, p, psi[0], psi[1], ops.ACT_SIGMOID)
+    if up_stream is not None:
+        torch.cuda.current_stream().wait_stream(up_stream)       # x_up is complete
     return Fn.gate_concat(x_up, skip, p, buf=buf)
 
 
@@ -455,13 +491,22 @@ def run_unet_decoder(ctx, m, x, skips: list, final_act=None):
             # zero-copy torch.cat((x_up, .), dim=1) (blocks.py:628,635): the up-conv's epilogue writes x_up straight into
             # the leading channel slice of the concat buffer, the gate product / the skip goes into the trailing slice
             buf, ca = None, _upconv_out_channels(up) if _name(up) == "UpConvBlock" else None
+            streams = ctx.branch_streams(skip.device, skip.shape[0] * skip.shape[1] * skip.shape[2]) \
+                if (_name(mix) == "AttentionBlock" and ca is not None and skip.shape[3] % 8 == 0) else None
             if ca is not None and skip.shape[3] % 8 == 0:
                 buf = ops.new_act(skip.shape[0], skip.shape[1], skip.shape[2], ca + skip.shape[3], skip.device)
-                x_up = run_upconv_block(ctx, up, x, out=buf[..., :ca])
+                if streams is not None:
+                    streams[0].wait_stream(torch.cuda.current_stream())      # x (and buf's allocation) are complete
+                    with torch.cuda.stream(streams[0]):
+                        x_up = run_upconv_block(ctx, up, x, out=buf[..., :ca])
+                else:
+                    x_up = run_upconv_block(ctx, up, x, out=buf[..., :ca])
             else:
                 x_up = run_module(ctx, up, x)
             if _name(mix) == "ConcatBlock":
                 x = Fn.concat(x_up, skip, buf=buf)
+            elif streams is not None:
+                x = run_attention_block(ctx, mix, x, x_up, skip, buf=buf, ws_stream=streams[1], up_stream=streams[0])
             else:
                 x = run_attention_block(ctx, mix, x, x_up, skip, buf=buf)
         else:

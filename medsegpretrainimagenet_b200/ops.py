@@ -281,6 +281,10 @@ def conv_out_size(h: int, w: int, kh: int, kw: int, stride: int, padding) -> Tup
 _CONV_TIMELINE = None
 
 
+def conv_timeline_active() -> bool:
+    return _CONV_TIMELINE is not None
+
+
 def set_conv_timeline(lst):
     global _CONV_TIMELINE
     _CONV_TIMELINE = lst
