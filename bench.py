@@ -518,6 +518,8 @@ def run_workload(args, workload, steps, warm, world, rank, local, dev, group, wi
     # of 2 x 77 MB inside it cost one run 6 ms per step over 20 steps)
     feeder = b200.BatchPrefetcher((x_host, y_host), dev)
     reader = b200.ScalarReader(depth=1)             # every step's loss is read back; the host waits one step late
+    if graphed is not None:
+        graphed.after_copy = feeder.release         # the feeder's buffer is free once it sits in the graph's static inputs
     barrier()
     e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e2.record()
@@ -567,8 +569,21 @@ def run_workload(args, workload, steps, warm, world, rank, local, dev, group, wi
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms, ms_e2e = t.tolist()
 
+    if graphed is not None:
+        graphed.after_copy = None
     if args.graph_timeline and graphed is not None:
         graph_timeline(args.graph_timeline + (f".{workload}.rank{rank}.txt"), lambda: step(x_dev, y_dev), barrier)
+        graphed.after_copy = feeder.release
+
+        def e2e_iters():        # six iterations of the end-to-end loop (steady state: the host runs ahead of the device)
+            feeder.put(x_host, y_host)
+            for i in range(6):
+                xb_, yb_ = feeder.get()
+                if i + 1 < 6:
+                    feeder.put(x_host, y_host)
+                reader.push(graphed(xb_, yb_))
+            reader.drain()
+        graph_timeline(args.graph_timeline + (f".{workload}.rank{rank}.e2e.txt"), e2e_iters, barrier)
 
     # ---- instrumented step: device time of every convolution launch -----------------------------
     # per-kernel device times from the profiler (CUPTI activity records) of one eagerly enqueued step; if the profiler is

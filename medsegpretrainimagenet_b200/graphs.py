@@ -27,6 +27,7 @@ class GraphedStep:
         """step_fn(*inputs) -> tensor or tuple of tensors; `models`: converted models whose DropPath masks must be
         refreshed per replay (may be empty)."""
         self.step_fn = step_fn
+        self.after_copy = None          # optional callable run after the inputs were copied into the static buffers
         self.static_in = [torch.empty_like(t) for t in example_inputs]
         for s, t in zip(self.static_in, example_inputs):
             s.copy_(t)
@@ -52,6 +53,8 @@ class GraphedStep:
         for s, t in zip(self.static_in, inputs):
             if s.data_ptr() != t.data_ptr():
                 s.copy_(t, non_blocking=True)
+        if self.after_copy is not None:
+            self.after_copy()           # e.g. host.BatchPrefetcher.release: the input buffers may be refilled from here on
         for c in self.ctxs:
             c.refresh_droppath()
         self.graph.replay()

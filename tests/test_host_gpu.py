@@ -148,6 +148,33 @@ def test_batch_prefetcher_order_and_content():
     assert seen == [(float(i), i) for i in range(5)]
 
 
+def test_batch_prefetcher_release_after_the_static_copy():
+    """GraphedStep.after_copy = feeder.release: the feeder's buffer is handed back as soon as it has been copied into the
+    consumer's own (static) tensors, so the refill does not wait for the whole step.  Same batches, same order, with a slow
+    consumer kernel between the copy and the next get()."""
+    b = _b200()
+    n = 12
+    host = [(torch.full((4, 3, 64, 64), float(i)).pin_memory(), torch.full((4, 1), i, dtype=torch.int64).pin_memory())
+            for i in range(n)]
+    feeder = b.BatchPrefetcher(host[0], DEV)
+    sx, sy = torch.empty_like(host[0][0], device=DEV), torch.empty_like(host[0][1], device=DEV)
+    big = torch.randn((2048, 2048), device=DEV)
+    feeder.put(*host[0])
+    seen = []
+    for i in range(n):
+        x, y = feeder.get()
+        if i + 1 < n:
+            feeder.put(*host[i + 1])
+        sx.copy_(x, non_blocking=True)
+        sy.copy_(y, non_blocking=True)
+        feeder.release()                                   # from here on the feeder may overwrite x / y
+        for _ in range(4):
+            big = big @ big * 1e-3                         # the "step": long enough for refills to overtake it
+        seen.append((sx.mean(), sy[0, 0].clone()))
+    torch.cuda.synchronize()
+    assert [(float(a), int(c)) for a, c in seen] == [(float(i), i) for i in range(n)]
+
+
 def test_scalar_reader_reads_every_step_one_late():
     b = _b200()
     reader = b.ScalarReader(depth=1)
