@@ -221,3 +221,33 @@ def test_symmetric_chunks_are_closed_under_the_negative_permutation():
                 assert len(idx) <= max(rows, 4) + 2
                 seen |= set(idx)
             assert seen == set(range(n))
+
+
+def test_gradient_sink_eligibility_and_branch_streams_off_the_gpu():
+    """Host rules of two round-2 paths.  functional._grad_sink_ok: a kernel may ADD a parameter's gradient into `p.grad`
+    itself only for a leaf with an existing fp32, contiguous, same-shape gradient (the reducer's bucket views, accumulated
+    micro-batches) — otherwise the gradient goes back through autograd.  ExecContext.branch_streams: no side streams on the
+    CPU, when switched off, or while bench.py's per-kernel instrumentation needs stream order."""
+    import torch
+    from medsegpretrainimagenet_b200 import converter, ops
+    from medsegpretrainimagenet_b200.functional import _grad_sink_ok
+    p = torch.nn.Parameter(torch.zeros(8))
+    assert _grad_sink_ok(None)
+    assert not _grad_sink_ok(p)                       # no gradient yet: autograd has to adopt one
+    p.grad = torch.zeros(8)
+    assert _grad_sink_ok(p)
+    p.grad = torch.zeros(16)[::2]
+    assert not _grad_sink_ok(p)                       # strided view
+    q = torch.nn.Parameter(torch.zeros(8, dtype=torch.float64))
+    q.grad = torch.zeros(8, dtype=torch.float64)
+    assert not _grad_sink_ok(q)
+    assert not _grad_sink_ok((p * 2.0))               # not a leaf
+    ctx = converter.ExecContext()
+    assert ctx.branch_streams("cpu", 1000) is None
+    tl = []
+    ops.set_conv_timeline(tl)
+    try:
+        assert ops.conv_timeline_active() and ops.wgrad_stream() is None
+    finally:
+        ops.set_conv_timeline(None)
+    assert not ops.conv_timeline_active()
