@@ -2340,6 +2340,36 @@ int plan_wgrad(const msp_conv_desc* d, WgradPlan* pl, bool force_2d = false) {
   int splits = msp_num_sms() / base;
   if (splits < 1) splits = 1;
   if (splits > pl->tiles_m) splits = pl->tiles_m;
+  {
+    // optional cap on the bytes of split-K partials per layer (MSP_WGRAD_PART_MB; 0 = none): every partial is written by
+    // the wgrad kernel and read again by the unpack, which runs exposed between the backward pass and the optimizer
+    static long long cap_bytes = -1;
+    if (cap_bytes < 0) {
+      const char* e = getenv("MSP_WGRAD_PART_MB");
+      cap_bytes = e ? (long long)atoi(e) << 20 : 0;
+    }
+    if (cap_bytes > 0) {
+      const long long wbytes = (long long)d->K * pl->ntaps * pl->Cw * 4;
+      long long smax = cap_bytes / (wbytes > 0 ? wbytes : 1);
+      if (smax < 1) smax = 1;
+      if (splits > smax) splits = (int)smax;
+    }
+    // ... or relative to the activations the launch reads anyway: partial bytes <= alpha x (x + dy bytes).  At batch 24 the
+    // U-Net's mid layers wrote 8-74 partials of their whole weight tensor (1.1 GB per step, written during the backward pass
+    // and read again by the unpack); at batch 256 the activations dominate and the rule changes nothing.
+    static double alpha = -1.0;
+    if (alpha < 0.0) {
+      const char* e = getenv("MSP_WGRAD_PART_ALPHA");
+      alpha = e ? atof(e) : 1.0;   // measured: cfg3 9.60 -> 9.38 ms (0.5: 9.27), cfg2 unchanged (a 6 MB byte cap: cfg2 +1.7 % slower)
+    }
+    if (alpha > 0.0) {
+      const double wbytes = (double)d->K * pl->ntaps * pl->Cw * 4.0;
+      const double abytes = 2.0 * (double)pl->OW * pl->OH * pl->N * ((double)d->C + d->K);
+      long long smax = (long long)(alpha * abytes / (wbytes > 0 ? wbytes : 1.0));
+      if (smax < 1) smax = 1;
+      if (splits > smax) splits = (int)smax;
+    }
+  }
   if (splits > 65535) splits = 65535;
   pl->splits = splits;
   return MSP_OK;
